@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- CIRIM 320x320x15-coil slices/sec (BASELINE.json metric) on N B200s, plus the DC-step HBM GB/s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                  # our arm (CUDA, through the public API)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # reference arm: the CPU oracle port
+
+A "step" = one pass of the hot path (CIRIM.forward: 5 cascades x 8 time steps, ConvGRU, SENSE) over one batch of
+`--batch` synthetic 15-coil 320x320 slices per GPU, followed by the gather of the reconstructions.  One process
+per GPU (torchrun for N > 1), slices sharded across ranks, no data-path collective, weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C, H, W = 15, 320, 320
+CHW8 = C * H * W * 8
+HW8 = H * W * 8
+# algorithmic bytes of one RIM data-consistency gradient per slice (+ mask bytes)
+DC_BYTES_PER_SLICE = 2 * CHW8 + HW8 + 2 * HW8
+# algorithmic FLOPs of the conv stack per time step per slice (2*MACs), SURVEY 8(d): 19.163 GFLOP
+CONV_FLOPS_PER_STEP = 2 * H * W * (4 * 64 * 25 + 2 * (64 * 192 * 2) + 64 * 64 * 9 + 64 * 2 * 9)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(batch, first_slice=0):
+    from mridc_b200 import synth
+
+    return synth.make_batch(batch, C, H, W, centered=False, normalization="backward", first_slice=first_slice)
+
+
+def cpu_reference_step(sd, cfg, b):
+    """The reference's CPU implementation of the path: PyTorch-CPU oracle port of CIRIM.forward."""
+    import torch
+    from oracle import models as omodels
+
+    with torch.no_grad():
+        out = omodels.cirim_forward(sd, cfg, b["y"], b["sensitivity_maps"], b["mask"], None, b["target"])
+    return out[-1][-1]
+
+
+def run_reference(args):
+    import torch
+    from mridc_b200 import synth
+    import mridc_b200 as mb
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.cirim_cfg("GRU")
+    torch.manual_seed(1)
+    sd = {k: v.detach().clone() for k, v in mb.CIRIM(cfg).state_dict().items()}
+    b = build_inputs(1)
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, cfg, b)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        cpu_reference_step(sd, cfg, b)
+        done += 1
+        if time.perf_counter() - t0 > 240 and done < args.steps:
+            break  # bounded sample: keep the whole run within a few minutes
+    dt = time.perf_counter() - t0
+    val = done / dt
+    sample = "%d step(s) of 1 slice each (full CIRIM 5x8 GRU, 15x320x320), %d warm-up, torch-CPU %d threads" % (
+        done, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": "cirim_320x320x15coil_slices_per_sec", "value": val, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, 1),
+        "cpu_baseline": {"value": val, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(batch, n_gpus):
+    return {"workload": "CIRIM 5 cascades x 8 time steps, ConvGRU 64 filters (k5/k3d2/k3), SENSE, no_dc, keep_eta, "
+                        "fft non-centered/backward; 15-coil 320x320 knee-shaped slices, 4x equispaced 1-D mask "
+                        "(BASELINE.json configs[2])",
+            "slices_per_gpu_per_step": batch, "global_slices_per_step": batch * n_gpus,
+            "parallelism": "slice-sharded x%d, gather of reconstructions only" % n_gpus,
+            "l2": "per-step working set (y+S %.0f MB, hidden states %.0f MB) exceeds the 126 MB L2; no flush needed"
+                  % (batch * 2 * CHW8 / 1e6, batch * 4 * 64 * H * W * 4 / 1e6)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import mridc_b200 as mb
+    from mridc_b200 import _lib, _ops, sharding, synth
+
+    B = args.batch
+    cfg = synth.cirim_cfg("GRU")
+    torch.manual_seed(1)
+    model = mb.CIRIM(cfg).eval()
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
+    host = build_inputs(B, first_slice=rank * B)
+    pinned = {k: host[k].pin_memory() for k in ("y", "sensitivity_maps", "mask", "target")}
+    d = {k: v.to(dev) for k, v in pinned.items()}
+    n_global = B * world
+
+    def step_resident():
+        out = next(model(d["y"], d["sensitivity_maps"], d["mask"], None, d["target"]))
+        rec = out[-1][-1]
+        return sharding.gather_reconstructions(rec, n_global) if world > 1 else rec
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier_sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier_sync()
+    launches = _lib.launch_count()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end timing: host buffers, H2D + compute + D2H of the reconstruction every step ------
+    out_host = torch.empty((B, H, W), dtype=torch.complex64).pin_memory()
+
+    def step_e2e():
+        y = pinned["y"].to(dev, non_blocking=True)
+        S = pinned["sensitivity_maps"].to(dev, non_blocking=True)
+        m = pinned["mask"].to(dev, non_blocking=True)
+        out = next(model(y, S, m, None, d["target"]))
+        out_host.copy_(out[-1][-1], non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier_sync()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier_sync()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_val = n_global * args.steps / (ms2.item() / 1e3)
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("y", "sensitivity_maps", "mask"))
+    d2h = out_host.numel() * out_host.element_size()
+
+    # ---- per-kernel roofline passes (rank 0): CUDA events on the launching stream ---------------------
+    roof, roof_conv, share = None, None, None
+    if rank == 0:
+        peaks = load_peaks()
+        eta = d["y"].new_zeros((B, H, W, 2)).normal_()
+        ws = torch.empty((2, B, C, H, W, 2), device=dev)
+        outg = torch.empty((B, 4, H, W), device=dev)
+        mcan = _ops.canonical_mask(d["mask"], B, H, W)[0]
+        n_it = 40
+        for _ in range(5):
+            _ops.dc_rim_grad(eta, d["y"], d["sensitivity_maps"], mcan, 1.0, False, "backward", out=outg, ws=ws)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n_it):
+            _ops.dc_rim_grad(eta, d["y"], d["sensitivity_maps"], mcan, 1.0, False, "backward", out=outg, ws=ws)
+        e1.record()
+        torch.cuda.synchronize()
+        dc_ms = e0.elapsed_time(e1) / n_it
+        dc_bytes = B * DC_BYTES_PER_SLICE + mcan.numel() * mcan.element_size()
+        dc_gbs = dc_bytes / (dc_ms * 1e-3) / 1e9
+        roof_dc = {"bound": "hbm", "kernel": "fused DC gradient (expand_rowfft + col_dc + rowifft_reduce)",
+                   "achieved": dc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dc_gbs / peaks["hbm_gbs"],
+                   "frac_of_nominal_8000": dc_gbs / 8000.0, "traffic": None, "peak_src": peaks["src"],
+                   "ms_per_launch_group": dc_ms, "algorithmic_bytes": dc_bytes}
+        # conv stack of one time step (the compute-dominant kernels)
+        blk = model.cirim[0]
+        g4 = torch.randn((B, 4, H, W), device=dev)
+        hx = [torch.randn((B, 64, H, W), device=dev) * 0.1 for _ in range(2)]
+        etab = eta.clone()
+
+        def conv_stack():
+            x = g4
+            for h, layer in enumerate(blk.layers):
+                x = layer(x, hx[h])
+            return blk.final_layer[0](x, residual_nhwc=etab)
+
+        for _ in range(3):
+            conv_stack()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            conv_stack()
+        e1.record()
+        torch.cuda.synchronize()
+        cv_ms = e0.elapsed_time(e1) / 10
+        tf = B * CONV_FLOPS_PER_STEP / (cv_ms * 1e-3) / 1e12
+        roof_conv = {"bound": "tensor", "kernel": "ConvGRU stack of one time step (conv5x5, GRU1x1, conv3x3d2, GRU1x1, "
+                     "conv3x3 + eta update)", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "peak_src": peaks["src"],
+                     "ms_per_time_step": cv_ms, "note": "exact-fp32 CUDA-core path (FFMA); peak is the measured bf16 "
+                     "tensor figure, as the contract prescribes"}
+        step_ms = ms_total / args.steps
+        share = {"dc_share_of_step": 40 * dc_ms / step_ms, "conv_share_of_step": 40 * cv_ms / step_ms}
+        roof = roof_conv if cv_ms > dc_ms else roof_dc
+        roof = dict(roof)
+        extra = {"roofline_dc": roof_dc, "roofline_conv": roof_conv, "kernel_shares": share}
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        one = {k: host[k][:1] if host[k].shape[0] == B else host[k] for k in ("y", "sensitivity_maps", "mask", "target")}
+        t0 = time.perf_counter()
+        ref = cpu_reference_step(sd_cpu, cfg, one)
+        dt = time.perf_counter() - t0
+        ours = next(model(d["y"][:1], d["sensitivity_maps"][:1], d["mask"], None, d["target"][:1]))[-1][-1]
+        a = torch.view_as_real(ours.cpu()).double()
+        b = torch.view_as_real(ref).double()
+        cpu_base = {"value": 1.0 / dt, "unit": "slices/s", "cores": cores, "kind": "port",
+                    "sample": "1 slice of the same workload (full CIRIM 5x8), no warm-up, torch-CPU %d threads, %.1f s"
+                              % (cores, dt),
+                    "parity_rel_l2_vs_cuda": ((a - b).norm() / b.norm()).item()}
+    if rank == 0:
+        val = n_global * args.steps / (ms_total / 1e3)
+        line = {
+            "metric": "cirim_320x320x15coil_slices_per_sec", "value": val, "unit": "slices/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B, world), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "slices/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="slices per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,190 @@
+/*
+ * mridc_b200 -- C-ABI of the B200-native (sm_100a) unrolled-MRI-reconstruction hot path.
+ *
+ * The reference (wdika/mridc) is pure Python/PyTorch: it has no FFI seam of its own.  The entry points
+ * below are what a maintainer would bind (ctypes stub in INTEGRATION.md) behind the reference's Python
+ * API for this path.  Each entry cites the reference interface it replaces (paths relative to the
+ * upstream repo root, `mridc/collections/` abbreviated `mc/`).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (PyTorch),
+ *     contiguous, fp32 unless stated; complex tensors are interleaved (re,im) = "complex-last-2".
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation,
+ *     graph-capturable after one eager warm-up call (twiddle tables are created on first use per device
+ *     and FFT length, owned by the library, immutable afterwards).
+ *   - return 0 on success, negative MRB_E* otherwise; `mrb_last_error()` gives a thread-local message.
+ *   - norm:  0 = "backward"/"none", 1 = "ortho", 2 = "forward"   (mc/common/parts/fft.py:77-81,155-159)
+ *   - centered != 0: fftshift(F(ifftshift(x))) on both transforms (fft.py:74-84,152-162), any length.
+ *   - mask descriptor: `mask` points to [mask_b, mask_h, W] values of dtype `mask_dtype`
+ *     (0 = uint8/bool bytes, 1 = float32); mask_b in {1,B}, mask_h in {1,H} (broadcast when 1).
+ */
+#ifndef MRIDC_B200_H
+#define MRIDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRB_OK 0
+#define MRB_EINVAL (-1)   /* bad argument (shape, enum, null pointer) */
+#define MRB_EUNSUPPORTED (-2) /* valid but outside what the kernels cover (e.g. FFT length too large for smem) */
+#define MRB_ECUDA (-3)    /* CUDA runtime error; message holds cudaGetErrorString */
+
+#define MRB_NORM_BACKWARD 0
+#define MRB_NORM_ORTHO 1
+#define MRB_NORM_FORWARD 2
+
+#define MRB_MASK_U8 0
+#define MRB_MASK_F32 1
+
+#define MRB_PAD_ZERO 0
+#define MRB_PAD_REPLICATE 1
+
+#define MRB_ACT_NONE 0
+#define MRB_ACT_RELU 1
+#define MRB_ACT_LEAKY 2 /* slope passed separately */
+
+const char* mrb_last_error(void);
+int mrb_version(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset
+ * (bench.py's "gpu_launches"). */
+long long mrb_launch_count(void);
+void mrb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * L1 primitives -- mc/common/parts/fft.py, utils.py
+ * ------------------------------------------------------------------------------------------------- */
+
+/* 1-D complex FFT along the middle axis of a contiguous [outer, n, inner] complex64 tensor.
+ * Building block of fft2/ifft2 for arbitrary `spatial_dims` (fft.py:13-88, 91-166).
+ * in == out allowed. scale is applied to the output. in_rot/out_rot implement the centered variant:
+ * logical input index j is read from storage (j + in_rot) % n, logical output k is written to storage
+ * (k + out_rot) % n (in_rot = out_rot = n/2 for centered). */
+int mrb_fft1d_c2c(const void* in, void* out, long long outer, int n, long long inner, int inverse,
+                  int in_rot, int out_rot, float scale, void* stream);
+
+/* fft2 / ifft2 over the last two axes of [batch, H, W] complex64 (fft.py:13-88 / 91-166). */
+int mrb_fft2_c2c(const void* in, void* out, long long batch, int H, int W, int inverse, int centered,
+                 int norm, void* stream);
+
+/* roll along one axis of a contiguous [outer, n, inner] tensor of `elem_bytes`-byte elements
+ * (fft.py:169-202 roll_one_dim; bit-exact, any dtype incl. int64). out != in. */
+int mrb_roll(const void* in, void* out, long long outer, long long n, long long inner, int elem_bytes,
+             long long shift, void* stream);
+
+/* Strided element-wise complex ops with broadcasting (utils.py:96-118 complex_mul, conj_y != 0 multiplies by
+ * conj(y) as in utils.py:248).  ndim <= 6; strides in complex elements, 0 = broadcast; out contiguous. */
+int mrb_complex_mul(const void* x, const void* y, void* out, int ndim, const long long* shape,
+                    const long long* xstride, const long long* ystride, int conj_y, void* stream);
+/* utils.py:121-139 */
+int mrb_complex_conj(const void* x, void* out, long long n, void* stream);
+/* utils.py:142-157 (squared == 0) and :160-175 (squared != 0): [n,2] -> [n] */
+int mrb_complex_abs(const void* x, void* out, long long n, int squared, void* stream);
+/* utils.py:194-209 rss on a real view: x [outer, C, inner] fp32 -> out [outer, inner] = sqrt(sum_c x^2) */
+int mrb_rss(const void* x, void* out, long long outer, int C, long long inner, void* stream);
+/* utils.py:212-227 rss_complex: x [outer, C, inner] complex -> out [outer, inner] real */
+int mrb_rss_complex(const void* x, void* out, long long outer, int C, long long inner, void* stream);
+/* utils.py:230-248 sense(): sum_c x * conj(S): x,S [outer, C, inner] complex -> [outer, inner] complex */
+int mrb_sense_combine(const void* x, const void* S, void* out, long long outer, int C, long long inner,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused data-consistency operator
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Workspace bytes for the DC entry points below at (B, C, H, W): two complex64 [B,C,H,W] scratch images. */
+size_t mrb_dc_workspace_bytes(int B, int C, int H, int W);
+
+/* RIM log-likelihood gradient -- mc/reconstruction/models/rim/rim_utils.py:11-67.
+ *   eta [B,H,W,2], y,S [B,C,H,W,2], out [B,4,H,W] = (eta_re, eta_im, g_re, g_im),
+ *   g = sum_c conj(S) * ifft2(mask * (fft2(S*eta) - y)) * inv_sigma2  (mask VALUE multiplies: :54). */
+int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* mask, int mask_dtype,
+                    int mask_b, int mask_h, float inv_sigma2, void* out, int B, int C, int H, int W,
+                    int centered, int norm, void* ws, size_t ws_bytes, void* stream);
+
+/* sum_c ifft2(x) * conj(S) -- mc/reconstruction/models/varnet/vn_block.py:71-87 sens_reduce, also the
+ * zero-filled SENSE init of rim_block.py:195-211, zf.py:90-97, vn.py:131-139, unet.py:108-117.
+ *   x,S [B,C,H,W,2] -> out [B,H,W,2] */
+int mrb_sens_reduce(const void* x, const void* S, void* out, int B, int C, int H, int W, int centered,
+                    int norm, void* ws, size_t ws_bytes, void* stream);
+
+/* Soft data consistency -- vn_block.py:51-69 (sens_expand) + :109-119, and rim_block.py:256-267.
+ *   img [B,H,W,2]; S,base,pred,y,out [B,C,H,W,2];
+ *   E = fft2(S*img);  out = no_dc ? E : base - (mask != 0 ? pred - y : 0) * dc_weight - E
+ *   (mask TRUTHINESS selects: `torch.where(mask.bool(), ...)`, vn_block.py:110).
+ *   VarNet passes base = pred (:117); the RIM no_dc=False branch passes base = y (rim_block.py:258).
+ *   dc_weight: DEVICE pointer to one float (the learnable parameter; no host sync needed).
+ *   base/pred/y/mask/dc_weight may be null if no_dc. */
+int mrb_sens_expand_softdc(const void* img, const void* S, const void* base, const void* pred, const void* y,
+                           const void* mask, int mask_dtype, int mask_b, int mask_h, const void* dc_weight,
+                           int no_dc, void* out, int B, int C, int H, int W, int centered, int norm,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Convolutional / recurrent regulariser kernels (NCHW fp32)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* "same" 2-D convolution, odd kernel k, dilation dil, padding dil*(k-1)/2 of kind pad_mode.
+ *   ConvNonlinear (rim/conv_layers.py:36-123: replicate pad, bias, ReLU/LeakyReLU/none),
+ *   ConvGRU/MGU/IndRNN ih/hh convs (rim/rnn_cells.py:23-38: zero pad), U-Net 3x3 / 1x1 convs
+ *   (unet_base/unet_block.py:250-259,:185).
+ *   x [N,Cin,H,W] with batch stride x_bstride floats; w [Cout,Cin,k,k]; bias [Cout] or null;
+ *   out [N,Cout,H,W] with batch stride out_bstride floats.
+ *   Epilogue: v = acc + bias;  if (add) v += add_scale[co] * add[n,co,h,w]  (IndRNN: rnn_cells.py:391);
+ *             v = act(v) (leaky slope `slope`);
+ *   out_nhwc_residual != 0: out is [N,H,W,Cout] and v is ADDED to residual [N,H,W,Cout]
+ *   (rim_block.py:241-248: eta + grad.permute(0,2,3,1)). */
+int mrb_conv2d(const void* x, long long x_bstride, const void* w, const void* bias, void* out,
+               long long out_bstride, int N, int Cin, int Cout, int H, int W, int k, int dil, int pad_mode,
+               int act, float slope, const void* add, const void* add_scale, const void* residual,
+               int out_nhwc_residual, void* stream);
+
+/* Fused ConvGRU cell for kernel_size 1 (rim/rnn_cells.py:93-127; every shipped config uses k=1):
+ *   x [N,Cx,H,W], h [N,Ch,H,W] -> h_out [N,Ch,H,W]; w_ih [3Ch,Cx], b_ih [3Ch] or null, w_hh [3Ch,Ch]. */
+int mrb_gru_cell_1x1(const void* x, const void* h, const void* w_ih, const void* b_ih, const void* w_hh,
+                     void* h_out, int N, int Cx, int Ch, long long HW, void* stream);
+
+/* Gate arithmetic of ConvGRUCell (rnn_cells.py:121-125) on precomputed ih,hh [N,3Ch,HW]. */
+int mrb_gru_gates(const void* ih, const void* hh, const void* h, void* h_out, int N, int Ch, long long HW,
+                  void* stream);
+/* Gate arithmetic of ConvMGUCell (rnn_cells.py:257-261) on precomputed ih,hh [N,2Ch,HW]. */
+int mrb_mgu_gates(const void* ih, const void* hh, const void* h, void* h_out, int N, int Ch, long long HW,
+                  void* stream);
+
+/* Per-(n,c) InstanceNorm2d(affine=False, eps, biased var) followed by LeakyReLU(slope)
+ * (unet_block.py:251-253,:256-258,:294-295).  x [N,C,HW] batch stride x_bstride; out batch stride
+ * out_bstride (lets the caller write straight into a concat buffer, unet_block.py:223).
+ * stats: workspace of 2*N*C doubles. */
+int mrb_instnorm_lrelu(const void* x, long long x_bstride, void* out, long long out_bstride, int N, int C,
+                       long long HW, float eps, float slope, void* stats, void* stream);
+
+/* avg_pool2d(kernel 2, stride 2) (unet_block.py:204): x [NC,H,W] (plane stride via bstride/C) */
+int mrb_avgpool2(const void* x, long long x_bstride, void* out, long long out_bstride, int N, int C, int H,
+                 int W, void* stream);
+
+/* ConvTranspose2d(kernel 2, stride 2, bias False) (unet_block.py:293): x [N,Cin,H,W], w [Cin,Cout,2,2]
+ * -> out [N,Cout,2H,2W] */
+int mrb_conv_transpose2x2(const void* x, long long x_bstride, const void* w, void* out,
+                          long long out_bstride, int N, int Cin, int Cout, int H, int W, void* stream);
+
+/* Generic 2-D pad/crop copy: out[n,c,y,x] = in[n,c,map(y-off_y),map(x-off_x)], mode 0 zero fill outside,
+ * 1 replicate, 2 reflect (unet_block.py:93-111 pad/unpad, :216-222 reflect). */
+int mrb_pad2d(const void* x, long long x_bstride, void* out, long long out_bstride, int N, int C, int Hin,
+              int Win, int Hout, int Wout, int off_y, int off_x, int mode, void* stream);
+
+/* NormUnet.norm + complex_to_chan_dim (unet_block.py:55-60,:71-85): x [B,C,H,W,2] -> out [B,2C,H,W]
+ * normalised per (b, re/im group) with mean and UNBIASED std; mean_std out: [B,2,2] floats (mean,std);
+ * normalize == 0 only permutes.  stats: workspace of 4*B doubles. */
+int mrb_normunet_in(const void* x, void* out, void* mean_std, int B, int C, long long HW, int normalize,
+                    void* stats, void* stream);
+/* NormUnet.unnorm + chan_complex_to_last_dim (unet_block.py:62-69,:87-91): x [B,2C,HW] -> [B,C,HW,2] */
+int mrb_normunet_out(const void* x, const void* mean_std, void* out, int B, int C, long long HW,
+                     int normalize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRIDC_B200_H */

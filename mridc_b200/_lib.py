@@ -1,0 +1,111 @@
+"""ctypes binding of libmridc_b200.so (the C-ABI declared in include/mridc_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing, cannot be loaded, or a tensor is not a CUDA
+tensor, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmridc_b200.so")
+
+_vp, _ll, _i, _f, _sz = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_llp = ctypes.POINTER(ctypes.c_longlong)
+
+# name -> (restype, argtypes); must list every symbol of include/mridc_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "mrb_last_error": (ctypes.c_char_p, []),
+    "mrb_version": (_i, []),
+    "mrb_launch_count": (_ll, []),
+    "mrb_reset_launch_count": (None, []),
+    "mrb_fft1d_c2c": (_i, [_vp, _vp, _ll, _i, _ll, _i, _i, _i, _f, _vp]),
+    "mrb_fft2_c2c": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "mrb_roll": (_i, [_vp, _vp, _ll, _ll, _ll, _i, _ll, _vp]),
+    "mrb_complex_mul": (_i, [_vp, _vp, _vp, _i, _llp, _llp, _llp, _i, _vp]),
+    "mrb_complex_conj": (_i, [_vp, _vp, _ll, _vp]),
+    "mrb_complex_abs": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "mrb_rss": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
+    "mrb_rss_complex": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
+    "mrb_sense_combine": (_i, [_vp, _vp, _vp, _ll, _i, _ll, _vp]),
+    "mrb_dc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mrb_dc_rim_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "mrb_sens_reduce": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "mrb_sens_expand_softdc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i,
+                                    _vp, _sz, _vp]),
+    "mrb_conv2d": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i,
+                        _vp]),
+    "mrb_gru_cell_1x1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "mrb_gru_gates": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "mrb_mgu_gates": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "mrb_instnorm_lrelu": (_i, [_vp, _ll, _vp, _ll, _i, _i, _ll, _f, _f, _vp, _vp]),
+    "mrb_avgpool2": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "mrb_conv_transpose2x2": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "mrb_pad2d": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrb_normunet_in": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
+    "mrb_normunet_out": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "mridc_b200: CUDA library %s is missing. Build it with `python -m mridc_b200.build` "
+                "(there is no CPU fallback)." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().mrb_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError("mridc_b200: " + msg)
+        if rc == -2:
+            raise NotImplementedError("mridc_b200: " + msg)
+        raise RuntimeError("mridc_b200 (code %d): %s" % (rc, msg))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda(t, name="tensor", dtype=torch.float32):
+    """No CPU fallback: anything that is not a CUDA tensor of the expected dtype raises."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError(
+            "mridc_b200: %s is on %s; this package only runs on CUDA (sm_100a) -- there is no CPU fallback" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("mridc_b200: %s must be %s (got %s)" % (name, dtype, t.dtype))
+    return t
+
+
+def launch_count():
+    return int(load().mrb_launch_count())
+
+
+def reset_launch_count():
+    load().mrb_reset_launch_count()

@@ -1,0 +1,81 @@
+"""Build recipe for libmridc_b200.so (hand-written CUDA for sm_100a, C-ABI in include/mridc_b200.h).
+
+The library is built IN-TREE (mridc_b200/libmridc_b200.so) with nvcc so that it travels with the source
+snapshot to the GPU box; nvcc cross-compiles without a GPU.  `python -m mridc_b200.build` or
+`__graft_entry__.build()`.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libmridc_b200.so")
+STAMP = os.path.join(PKG_DIR, "csrc", ".build_stamp")
+SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libmridc_b200.so")
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root, _, files in sorted(os.walk(CSRC)):
+        for f in sorted(files):
+            if f.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, f), "rb") as fh:
+                    h.update(f.encode() + b"\0" + fh.read())
+    with open(os.path.join(PKG_DIR, "..", "include", "mridc_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into one shared library. Returns the library path."""
+    digest = _digest()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+        with open(STAMP) as fh:
+            if fh.read().strip() == digest:
+                return LIB_PATH
+    nvcc = _nvcc()
+    objdir = os.path.join(PKG_DIR, "csrc", "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed on %s:\n%s\n" % (src, out))
+        elif verbose or "warning" in out:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-lcuda"]
+    subprocess.check_call(cmd)
+    with open(STAMP, "w") as fh:
+        fh.write(digest)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,365 @@
+// Fused data-consistency operator (SENSE expand -> 2-D FFT -> mask/residual -> inverse FFT -> conj-coil reduce).
+//
+// Reference behaviour:
+//   RIM gradient     mridc/collections/reconstruction/models/rim/rim_utils.py:11-67
+//   sens_reduce      mridc/collections/reconstruction/models/varnet/vn_block.py:71-87
+//   sens_expand+DC   mridc/collections/reconstruction/models/varnet/vn_block.py:51-69, :109-119
+//
+// Three passes, intermediates T1/T2 ([B,C,H,W] complex64, caller workspace) stay L2-resident on B200:
+//   K1 expand_rowfft      CTA = (b, row h): all coils of the row in smem; p = S*eta, forward FFT along W.
+//   K2 col_dc / col_softdc CTA = (b, c, strip of 16 k_w): FFT along H, k-space epilogue, (inverse FFT along H).
+//   K3 rowifft_reduce     CTA = (b, row h): inverse FFT along W for all coils in smem, sum_c conj(S)*.
+// Centering is folded into index rotations on the loads/stores (valid for odd lengths too); the k-space in
+// the middle is never physically shifted.
+#include "fft.cuh"
+
+namespace mrb {
+
+int fft1d_launch(const float2* in, float2* out, long long outer, int n, long long inner, int inverse, int in_rot,
+                 int out_rot, float scale, cudaStream_t st);
+float norm_scale(int norm, int inverse, double npts);
+
+__device__ __forceinline__ int rot_add(int j, int rot, int n) {
+    int s = j + rot;
+    return s >= n ? s - n : s;
+}
+
+// K1: T1[b,c,h,kw] = FFT_W( S[b,c,h,(j+rw)%W] * img[b,h,(j+rw)%W] )   (un-normalised, un-centred along W)
+__global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float2* __restrict__ S,
+                                     float2* __restrict__ T1, int C, int H, int W, int cc, FftPlan p, int rw) {
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* Bf = A + (size_t)cc * p.ls;
+    float2* tw_s = Bf + (size_t)cc * p.ls;
+    load_twiddles(tw_s, p);
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float2* irow = img + ((long long)b * H + h) * W;
+    float2* St = fft_start_buf(p, A, Bf);
+    for (int c0 = 0; c0 < C; c0 += cc) {
+        const int nc = min(cc, C - c0);
+        if (c0 > 0) __syncthreads();
+        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
+            int c = t / W, j = t - c * W;
+            int src = rot_add(j, rw, W);
+            float2 e = irow[src];
+            float2 s = S[(((long long)b * C + c0 + c) * H + h) * W + src];
+            // rim_utils.py:47-48: re = e_re*s_re - e_im*s_im ; im = e_re*s_im + e_im*s_re
+            St[(size_t)c * p.ls + j] = make_float2(e.x * s.x - e.y * s.y, e.x * s.y + e.y * s.x);
+        }
+        block_fft<false>(A, Bf, nc, p, tw_s);
+        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
+            int c = t / W, k = t - c * W;
+            T1[(((long long)b * C + c0 + c) * H + h) * W + k] = A[(size_t)c * p.ls + k];
+        }
+    }
+}
+
+// K2 (RIM): per (b,c,strip): P = fscale * FFT_H(T1 rotated); r = mask*(P - y); T2 = IFFT_H(r) stored with the
+// output rotation along H.  T1's k_w axis is un-centred: centred storage column = (k_w + rw) % W.
+__global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __restrict__ y, float2* __restrict__ T2,
+                              MaskDesc mask, int C, int H, int W, int ti, FftPlan p, int rh, int rw, float fscale) {
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* Bf = A + (size_t)ti * p.ls;
+    float2* tw_s = Bf + (size_t)ti * p.ls;
+    load_twiddles(tw_s, p);
+    const int k0 = blockIdx.x * ti;
+    const int nl = min(ti, W - k0);
+    const int c = blockIdx.y, b = blockIdx.z;
+    const long long plane = ((long long)b * C + c) * H * W;
+    float2* St = fft_start_buf(p, A, Bf);
+    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
+        int j = t / nl, i = t - j * nl;
+        St[(size_t)i * p.ls + j] = T1[plane + (long long)rot_add(j, rh, H) * W + k0 + i];
+    }
+    block_fft<false>(A, Bf, nl, p, tw_s);
+    // k-space epilogue: result of forward FFT is in A; write the residual where the inverse wants its input.
+    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
+        int kh = t / nl, i = t - kh * nl;
+        int mh = rot_add(kh, rh, H), mw = rot_add(k0 + i, rw, W);
+        float2 P = cscale(A[(size_t)i * p.ls + kh], fscale);
+        float2 yv = y[plane + (long long)mh * W + mw];
+        float m = mask_value(mask, b, mh, mw);
+        // rim_utils.py:54: mask * (pred - masked_kspace)
+        float2 r = make_float2(m * (P.x - yv.x), m * (P.y - yv.y));
+        if (St == A) {
+            // in-place element update is safe: each (i,kh) is read and written by the same thread
+            A[(size_t)i * p.ls + kh] = r;
+        } else {
+            Bf[(size_t)i * p.ls + kh] = r;
+        }
+    }
+    block_fft<true>(A, Bf, nl, p, tw_s);
+    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
+        int d = t / nl, i = t - d * nl;  // d = storage row (image coordinates), n = logical output index
+        int n = d - rh;
+        if (n < 0) n += H;
+        T2[plane + (long long)d * W + k0 + i] = A[(size_t)i * p.ls + n];
+    }
+}
+
+// K2' (VarNet): out[b,c,mh,mw] = no_dc ? E : base - (mask!=0 ? pred - y : 0)*dcw - E,  E = fscale*FFT_H(T1 rot.)
+__global__ void col_softdc_kernel(const float2* __restrict__ T1, const float2* __restrict__ base,
+                                  const float2* __restrict__ pred,
+                                  const float2* __restrict__ y, float2* __restrict__ out, MaskDesc mask, int C, int H,
+                                  int W, int ti, FftPlan p, int rh, int rw, float fscale, const float* __restrict__ dcw_p,
+                                  int no_dc) {
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* Bf = A + (size_t)ti * p.ls;
+    float2* tw_s = Bf + (size_t)ti * p.ls;
+    load_twiddles(tw_s, p);
+    const int k0 = blockIdx.x * ti;
+    const int nl = min(ti, W - k0);
+    const int c = blockIdx.y, b = blockIdx.z;
+    const long long plane = ((long long)b * C + c) * H * W;
+    const float dcw = no_dc ? 0.f : *dcw_p;
+    float2* St = fft_start_buf(p, A, Bf);
+    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
+        int j = t / nl, i = t - j * nl;
+        St[(size_t)i * p.ls + j] = T1[plane + (long long)rot_add(j, rh, H) * W + k0 + i];
+    }
+    block_fft<false>(A, Bf, nl, p, tw_s);
+    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
+        int kh = t / nl, i = t - kh * nl;
+        int mh = rot_add(kh, rh, H), mw = rot_add(k0 + i, rw, W);
+        float2 E = cscale(A[(size_t)i * p.ls + kh], fscale);
+        long long o = plane + (long long)mh * W + mw;
+        if (no_dc) {
+            out[o] = E;
+        } else {
+            float2 bv = base[o];
+            float2 sd = make_float2(0.f, 0.f);
+            if (mask_value(mask, b, mh, mw) != 0.f) {  // vn_block.py:110 torch.where(mask.bool(), pred - ref, 0)
+                float2 pv = pred[o], yv = y[o];
+                sd = make_float2(pv.x - yv.x, pv.y - yv.y);
+            }
+            // vn_block.py:110,117: (pred - soft_dc*dc_weight) - eta
+            out[o] = make_float2((bv.x - sd.x * dcw) - E.x, (bv.y - sd.y * dcw) - E.y);
+        }
+    }
+}
+
+// K3: acc[b,h,w] = sum_c conj(S[b,c,h,w]) * IFFT_W(T2[b,c,h,:])  ; w = (n + rw) % W.
+// OUT_MODE 0: out [B,H,W] complex = acc*scale.   OUT_MODE 1 (RIM): out [B,4,H,W] = (eta_re, eta_im, acc*scale).
+template <int OUT_MODE>
+__global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float2* __restrict__ S,
+                                      const float2* __restrict__ eta, float* __restrict__ out, int C, int H, int W,
+                                      int cc, FftPlan p, int in_rw, int rw, float scale) {
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* Bf = A + (size_t)cc * p.ls;
+    float2* tw_s = Bf + (size_t)cc * p.ls;
+    load_twiddles(tw_s, p);
+    const int h = blockIdx.x, b = blockIdx.y;
+    float2* St = fft_start_buf(p, A, Bf);
+    // each thread owns output columns d = threadIdx.x + i*blockDim.x (registers hold the running coil sum)
+    constexpr int kMaxOwn = 8;
+    float2 acc[kMaxOwn];
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int c0 = 0; c0 < C; c0 += cc) {
+        const int nc = min(cc, C - c0);
+        if (c0 > 0) __syncthreads();
+        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
+            int c = t / W, j = t - c * W;
+            St[(size_t)c * p.ls + j] = T2[(((long long)b * C + c0 + c) * H + h) * W + rot_add(j, in_rw, W)];
+        }
+        block_fft<true>(A, Bf, nc, p, tw_s);
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) {
+            int d = threadIdx.x + i * blockDim.x;  // storage column
+            if (d < W) {
+                int n = d - rw;
+                if (n < 0) n += W;
+                float2 a = acc[i];
+                for (int c = 0; c < nc; ++c) {
+                    float2 v = A[(size_t)c * p.ls + n];
+                    float2 s = S[(((long long)b * C + c0 + c) * H + h) * W + d];
+                    // rim_utils.py:61-62: re += v_re*s_re + v_im*s_im ; im += v_im*s_re - v_re*s_im
+                    a.x += v.x * s.x + v.y * s.y;
+                    a.y += v.y * s.x - v.x * s.y;
+                }
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+        int d = threadIdx.x + i * blockDim.x;
+        if (d < W) {
+            if (OUT_MODE == 0) {
+                ((float2*)out)[((long long)b * H + h) * W + d] = cscale(acc[i], scale);
+            } else {
+                const long long HW = (long long)H * W;
+                float2 e = eta[((long long)b * H + h) * W + d];
+                float* o = out + (long long)b * 4 * HW + (long long)h * W + d;
+                o[0] = e.x;
+                o[HW] = e.y;
+                o[2 * HW] = acc[i].x * scale;
+                o[3 * HW] = acc[i].y * scale;
+            }
+        }
+    }
+}
+
+struct DcGeom {
+    FftPlan pw, ph;
+    int cc;       // coils per smem chunk in the row kernels
+    int ti;       // k_w strip width in the column kernels
+    int threads_row;
+    size_t smem_row, smem_col;
+};
+
+static int dc_geometry(int C, int H, int W, DcGeom* g) {
+    int rc = get_fft_plan(W, &g->pw);
+    if (rc) return rc;
+    rc = get_fft_plan(H, &g->ph);
+    if (rc) return rc;
+    const size_t max_smem = device_max_smem_optin();
+    const size_t row_budget = max_smem < 110 * 1024 ? max_smem : 110 * 1024;  // keep 2 CTAs / SM
+    int cc = C;
+    while (cc > 1 && fft_smem_bytes(g->pw, cc) > row_budget) cc = (cc + 1) / 2;
+    MRB_REQUIRE(fft_smem_bytes(g->pw, cc) <= max_smem, MRB_EUNSUPPORTED, "W=%d does not fit shared memory", W);
+    g->cc = cc;
+    g->smem_row = fft_smem_bytes(g->pw, cc);
+    int ti = 16;
+    while (ti > 1 && fft_smem_bytes(g->ph, ti) > row_budget) ti /= 2;
+    MRB_REQUIRE(fft_smem_bytes(g->ph, ti) <= max_smem, MRB_EUNSUPPORTED, "H=%d does not fit shared memory", H);
+    if (ti > W) ti = W;
+    g->ti = ti;
+    g->smem_col = fft_smem_bytes(g->ph, ti);
+    // row kernels: each thread owns <= 8 output columns
+    int tr = 256;
+    while (tr * 8 < W) tr *= 2;
+    MRB_REQUIRE(tr <= 1024, MRB_EUNSUPPORTED, "W=%d too large for the row-reduce kernel", W);
+    g->threads_row = tr;
+    return MRB_OK;
+}
+
+static int make_mask(const void* mask, int dtype, int mask_b, int mask_h, int B, int H, int W, MaskDesc* m) {
+    MRB_REQUIRE(mask != nullptr, MRB_EINVAL, "mask is null");
+    MRB_REQUIRE(dtype == MRB_MASK_U8 || dtype == MRB_MASK_F32, MRB_EINVAL, "bad mask dtype %d", dtype);
+    MRB_REQUIRE(mask_b == 1 || mask_b == B, MRB_EINVAL, "mask batch %d must be 1 or %d", mask_b, B);
+    MRB_REQUIRE(mask_h == 1 || mask_h == H, MRB_EINVAL, "mask height %d must be 1 or %d", mask_h, H);
+    m->ptr = mask;
+    m->dtype = dtype;
+    m->hstride = mask_h == 1 ? 0 : W;
+    m->bstride = mask_b == 1 ? 0 : mask_h * W;
+    return MRB_OK;
+}
+
+static int check_dims(int B, int C, int H, int W, int norm, const char* who) {
+    MRB_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "%s: bad shape B=%d C=%d H=%d W=%d", who, B, C, H, W);
+    MRB_REQUIRE(B <= 65535 && C <= 65535, MRB_EUNSUPPORTED, "%s: B and C must be <= 65535", who);
+    MRB_REQUIRE(norm >= 0 && norm <= 2, MRB_EINVAL, "%s: bad norm %d", who, norm);
+    return MRB_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel) {
+    MRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)device_max_smem_optin()));
+    return MRB_OK;
+}
+
+}  // namespace mrb
+
+using namespace mrb;
+
+extern "C" size_t mrb_dc_workspace_bytes(int B, int C, int H, int W) {
+    return (size_t)2 * (size_t)B * C * H * W * sizeof(float2);
+}
+
+extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* mask, int mask_dtype,
+                               int mask_b, int mask_h, float inv_sigma2, void* out, int B, int C, int H, int W,
+                               int centered, int norm, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_dims(B, C, H, W, norm, "mrb_dc_rim_grad");
+    if (rc) return rc;
+    MRB_REQUIRE(eta && y && S && out && ws, MRB_EINVAL, "mrb_dc_rim_grad: null pointer");
+    MRB_REQUIRE(ws_bytes >= mrb_dc_workspace_bytes(B, C, H, W), MRB_EINVAL, "mrb_dc_rim_grad: workspace too small");
+    MaskDesc m;
+    rc = make_mask(mask, mask_dtype, mask_b, mask_h, B, H, W, &m);
+    if (rc) return rc;
+    DcGeom g;
+    rc = dc_geometry(C, H, W, &g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* T1 = (float2*)ws;
+    float2* T2 = T1 + (size_t)B * C * H * W;
+    const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
+    const double npts = (double)H * W;
+    const float fs = norm_scale(norm, 0, npts), bs = norm_scale(norm, 1, npts);
+    if ((rc = set_smem(expand_rowfft_kernel))) return rc;
+    if ((rc = set_smem(col_dc_kernel))) return rc;
+    if ((rc = set_smem(rowifft_reduce_kernel<1>))) return rc;
+    expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1, C, H,
+                                                                        W, g.cc, g.pw, rw);
+    MRB_LAUNCHED();
+    col_dc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(T1, (const float2*)y, T2, m, C, H, W, g.ti,
+                                                                          g.ph, rh, rw, fs);
+    MRB_LAUNCHED();
+    rowifft_reduce_kernel<1><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+        T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_sens_reduce(const void* x, const void* S, void* out, int B, int C, int H, int W, int centered,
+                               int norm, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_dims(B, C, H, W, norm, "mrb_sens_reduce");
+    if (rc) return rc;
+    MRB_REQUIRE(x && S && out && ws, MRB_EINVAL, "mrb_sens_reduce: null pointer");
+    MRB_REQUIRE(ws_bytes >= mrb_dc_workspace_bytes(B, C, H, W) / 2, MRB_EINVAL, "mrb_sens_reduce: workspace too small");
+    DcGeom g;
+    rc = dc_geometry(C, H, W, &g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* T2 = (float2*)ws;
+    const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
+    const float bs = norm_scale(norm, 1, (double)H * W);
+    // inverse FFT along H (strided lines), rotations applied on both sides; W axis untouched (still centred)
+    rc = fft1d_launch((const float2*)x, T2, (long long)B * C, H, W, 1, rh, rh, 1.0f, st);
+    if (rc) return rc;
+    if ((rc = set_smem(rowifft_reduce_kernel<0>))) return rc;
+    rowifft_reduce_kernel<0><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(T2, (const float2*)S, nullptr, (float*)out,
+                                                                            C, H, W, g.cc, g.pw, rw, rw, bs);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_sens_expand_softdc(const void* img, const void* S, const void* base, const void* pred,
+                                      const void* y,
+                                      const void* mask, int mask_dtype, int mask_b, int mask_h,
+                                      const void* dc_weight, int no_dc, void* out, int B, int C, int H, int W, int centered, int norm,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_dims(B, C, H, W, norm, "mrb_sens_expand_softdc");
+    if (rc) return rc;
+    MRB_REQUIRE(img && S && out && ws, MRB_EINVAL, "mrb_sens_expand_softdc: null pointer");
+    MRB_REQUIRE(ws_bytes >= mrb_dc_workspace_bytes(B, C, H, W) / 2, MRB_EINVAL,
+                "mrb_sens_expand_softdc: workspace too small");
+    MaskDesc m;
+    memset(&m, 0, sizeof(m));
+    if (!no_dc) {
+        MRB_REQUIRE(base && pred && y && dc_weight, MRB_EINVAL,
+                    "mrb_sens_expand_softdc: base/pred/y/dc_weight required unless no_dc");
+        rc = make_mask(mask, mask_dtype, mask_b, mask_h, B, H, W, &m);
+        if (rc) return rc;
+    }
+    DcGeom g;
+    rc = dc_geometry(C, H, W, &g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float2* T1 = (float2*)ws;
+    const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
+    const float fs = norm_scale(norm, 0, (double)H * W);
+    if ((rc = set_smem(expand_rowfft_kernel))) return rc;
+    if ((rc = set_smem(col_softdc_kernel))) return rc;
+    expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)img, (const float2*)S, T1, C, H,
+                                                                        W, g.cc, g.pw, rw);
+    MRB_LAUNCHED();
+    col_softdc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(
+        T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.ti, g.ph, rh, rw, fs,
+        (const float*)dc_weight, no_dc);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}

@@ -1,0 +1,314 @@
+"""Drop-ins for the RIM building blocks of the reference (B200 kernels behind the same module API).
+
+  log_likelihood_gradient   mridc/collections/reconstruction/models/rim/rim_utils.py:11-67
+  ConvNonlinear / ConvRNNStack  .../rim/conv_layers.py:36-123 / :8-33
+  ConvGRUCell / ConvMGUCell / IndRNNCell  .../rim/rnn_cells.py:93-127 / :230-261 / :367-391
+  RIMBlock                  .../rim/rim_block.py:15-269
+
+Parameters live in the same sub-module / attribute names as the reference so that a reference
+``state_dict`` loads key-for-key (SURVEY.md section 8a "Weights"); the ``torch.nn`` layer objects are
+used only as parameter holders and for their initialisers -- the arithmetic is the sm_100a kernels.
+Inference only (no autograd through the kernels).
+"""
+from typing import Any, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _ops
+
+__all__ = ["log_likelihood_gradient", "ConvNonlinear", "ConvRNNStack", "ConvGRUCell", "ConvMGUCell", "IndRNNCell",
+           "RIMBlock"]
+
+
+def log_likelihood_gradient(eta: torch.Tensor, masked_kspace: torch.Tensor, sense: torch.Tensor, mask: torch.Tensor,
+                            sigma: float, fft_centered: bool, fft_normalization: str, spatial_dims: Sequence[int],
+                            coil_dim: int) -> torch.Tensor:
+    """rim_utils.py:11-67 as one fused data-consistency operator; returns [B, 4, H, W]."""
+    if coil_dim == 0:
+        coil_dim += 1  # rim_utils.py:41-42
+    if coil_dim != 1:
+        raise NotImplementedError("mridc_b200: fused RIM gradient expects coil_dim == 1 ([B, C, H, W, 2] data)")
+    _ops.check_spatial_dims(spatial_dims)
+    return _ops.dc_rim_grad(eta, masked_kspace, sense, mask, sigma, fft_centered, fft_normalization)
+
+
+def _pad_amount(dilation, kernel_size):
+    return (dilation * (kernel_size - 1)) // 2
+
+
+def _require_2d(conv_dim, who):
+    if conv_dim != 2:
+        raise NotImplementedError("mridc_b200: %s supports conv_dim == 2 only (got %s)" % (who, conv_dim))
+
+
+class ConvRNNStack(nn.Module):
+    """conv_layers.py:8-33."""
+
+    def __init__(self, convs, rnn):
+        super().__init__()
+        self.convs = convs
+        self.rnn = rnn
+
+    def forward(self, x, hidden):
+        return self.rnn(self.convs(x), hidden)
+
+
+class ConvNonlinear(nn.Module):
+    """conv_layers.py:36-123: ReplicationPad(dil*(k-1)//2) -> Conv(padding=0) -> ReLU / LeakyReLU / identity."""
+
+    def __init__(self, input_size, features, conv_dim, kernel_size, dilation, bias, nonlinear="relu"):
+        super().__init__()
+        _require_2d(conv_dim, "ConvNonlinear")
+        if kernel_size % 2 != 1:
+            raise NotImplementedError("mridc_b200: ConvNonlinear supports odd kernel sizes only")
+        self.input_size = input_size
+        self.features = features
+        self.kernel_size = kernel_size
+        self.dilation = dilation
+        self.bias = bias
+        self.conv_dim = conv_dim
+        if nonlinear is not None and nonlinear.upper() == "RELU":
+            self._act, self._slope = _ops.ACT_RELU, 0.0
+        elif nonlinear is not None and nonlinear.upper() == "LEAKYRELU":
+            self._act, self._slope = _ops.ACT_LEAKY, 0.01  # torch.nn.LeakyReLU() default slope
+        elif nonlinear is None:
+            self._act, self._slope = _ops.ACT_NONE, 0.0
+        else:
+            raise ValueError("Please specify a proper nonlinearity")
+        self.conv_layer = nn.Conv2d(in_channels=input_size, out_channels=features, kernel_size=kernel_size, padding=0,
+                                    dilation=dilation, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.kaiming_normal_(self.conv_layer.weight, nonlinearity="relu")
+        if self.conv_layer.bias is not None:
+            nn.init.zeros_(self.conv_layer.bias)
+
+    def check_forward_input(self, _input):
+        if _input.size(1) != self.input_size:
+            raise RuntimeError(f"input has inconsistent input_size: got {_input.size(1)}, expected {self.input_size}")
+
+    def forward(self, _input, residual_nhwc: Optional[torch.Tensor] = None):
+        self.check_forward_input(_input)
+        return _ops.conv2d(_input, self.conv_layer.weight, self.conv_layer.bias, self.kernel_size, self.dilation,
+                           _ops.PAD_REPLICATE, self._act, self._slope, residual=residual_nhwc)
+
+
+class _CellBase(nn.Module):
+    def check_forward_input(self, _input):
+        if _input.size(1) != self.input_size:
+            raise RuntimeError(f"input has inconsistent input_size: got {_input.size(1)}, expected {self.input_size}")
+
+    def check_forward_hidden(self, _input, hx, hidden_label=""):
+        if _input.size(0) != hx.size(0):
+            raise RuntimeError(
+                f"Input batch size {_input.size(0)} doesn't match hidden{hidden_label} batch size {hx.size(0)}")
+        if hx.size(1) != self.hidden_size:
+            raise RuntimeError(
+                f"hidden{hidden_label} has inconsistent hidden_size: got {hx.size(1)}, expected {self.hidden_size}")
+
+    @staticmethod
+    def orthotogonalize_weights(weights, chunks=1):
+        return torch.cat([nn.init.orthogonal_(w) for w in weights.chunk(chunks, 0)], 0)
+
+
+class ConvGRUCell(_CellBase):
+    """rnn_cells.py:8-127."""
+
+    def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
+        super().__init__()
+        _require_2d(conv_dim, "ConvGRUCell")
+        self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
+        self.kernel_size, self.dilation = kernel_size, dilation
+        pad = _pad_amount(dilation, kernel_size)
+        self.ih = nn.Conv2d(input_size, 3 * hidden_size, kernel_size, padding=pad, dilation=dilation, bias=bias)
+        self.hh = nn.Conv2d(hidden_size, 3 * hidden_size, kernel_size, padding=pad, dilation=dilation, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.ih.weight.data = self.orthotogonalize_weights(self.ih.weight.data)
+        self.hh.weight.data = self.orthotogonalize_weights(self.hh.weight.data)
+        if self.bias is True:
+            nn.init.zeros_(self.ih.bias)
+
+    def forward(self, _input, hx):
+        self.check_forward_input(_input)
+        self.check_forward_hidden(_input, hx)
+        lib = _lib.load()
+        _input, hx = _input.contiguous(), hx.contiguous()
+        N, _, H, W = _input.shape
+        out = torch.empty_like(hx)
+        if self.kernel_size == 1:
+            _lib.check(lib.mrb_gru_cell_1x1(_lib.ptr(_input), _lib.ptr(hx), _lib.ptr(self.ih.weight),
+                                            _lib.ptr(self.ih.bias), _lib.ptr(self.hh.weight), _lib.ptr(out), N,
+                                            self.input_size, self.hidden_size, H * W, _lib.stream_ptr()))
+            return out
+        ih = _ops.conv2d(_input, self.ih.weight, self.ih.bias, self.kernel_size, self.dilation, _ops.PAD_ZERO)
+        hh = _ops.conv2d(hx, self.hh.weight, None, self.kernel_size, self.dilation, _ops.PAD_ZERO)
+        _lib.check(lib.mrb_gru_gates(_lib.ptr(ih), _lib.ptr(hh), _lib.ptr(hx), _lib.ptr(out), N, self.hidden_size,
+                                     H * W, _lib.stream_ptr()))
+        return out
+
+
+class ConvMGUCell(_CellBase):
+    """rnn_cells.py:130-261."""
+
+    def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
+        super().__init__()
+        _require_2d(conv_dim, "ConvMGUCell")
+        self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
+        self.kernel_size, self.dilation = kernel_size, dilation
+        pad = _pad_amount(dilation, kernel_size)
+        self.ih = nn.Conv2d(input_size, 2 * hidden_size, kernel_size, padding=pad, dilation=dilation, bias=bias)
+        self.hh = nn.Conv2d(hidden_size, 2 * hidden_size, kernel_size, padding=pad, dilation=dilation, bias=False)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.ih.weight.data = self.orthotogonalize_weights(self.ih.weight.data)
+        self.hh.weight.data = self.orthotogonalize_weights(self.hh.weight.data)
+        nn.init.xavier_uniform_(self.ih.weight, nn.init.calculate_gain("relu"))
+        nn.init.xavier_uniform_(self.hh.weight)
+        if self.bias is True:
+            nn.init.zeros_(self.ih.bias)
+
+    def forward(self, _input, hx):
+        self.check_forward_input(_input)
+        self.check_forward_hidden(_input, hx)
+        _input, hx = _input.contiguous(), hx.contiguous()
+        N, _, H, W = _input.shape
+        ih = _ops.conv2d(_input, self.ih.weight, self.ih.bias, self.kernel_size, self.dilation, _ops.PAD_ZERO)
+        hh = _ops.conv2d(hx, self.hh.weight, None, self.kernel_size, self.dilation, _ops.PAD_ZERO)
+        out = torch.empty_like(hx)
+        _lib.check(_lib.load().mrb_mgu_gates(_lib.ptr(ih), _lib.ptr(hh), _lib.ptr(hx), _lib.ptr(out), N,
+                                             self.hidden_size, H * W, _lib.stream_ptr()))
+        return out
+
+
+class IndRNNCell(_CellBase):
+    """rnn_cells.py:264-391."""
+
+    def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
+        super().__init__()
+        _require_2d(conv_dim, "IndRNNCell")
+        self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
+        self.kernel_size, self.dilation = kernel_size, dilation
+        pad = _pad_amount(dilation, kernel_size)
+        self.ih = nn.Conv2d(input_size, hidden_size, kernel_size, padding=pad, dilation=dilation, bias=bias)
+        self.hh = nn.Parameter(
+            nn.init.normal_(torch.empty(1, hidden_size, 1, 1), std=1.0 / (hidden_size * (1 + kernel_size**2))))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.ih.weight.data = self.orthotogonalize_weights(self.ih.weight.data)
+        nn.init.normal_(self.ih.weight, std=1.0 / (self.hidden_size * (1 + self.kernel_size**2)))
+        if self.bias is True:
+            nn.init.zeros_(self.ih.bias)
+
+    def forward(self, _input, hx):
+        self.check_forward_input(_input)
+        self.check_forward_hidden(_input, hx)
+        # ReLU(ih(x) + hh * h) with the recurrent term and ReLU fused into the conv epilogue (rnn_cells.py:391)
+        return _ops.conv2d(_input, self.ih.weight, self.ih.bias, self.kernel_size, self.dilation, _ops.PAD_ZERO,
+                           _ops.ACT_RELU, 0.0, add=hx.contiguous(), add_scale=self.hh.reshape(-1))
+
+
+class RIMBlock(nn.Module):
+    """rim_block.py:15-269 (dimensionality 2)."""
+
+    def __init__(self, recurrent_layer=None, conv_filters=None, conv_kernels=None, conv_dilations=None,
+                 conv_bias=None, recurrent_filters=None, recurrent_kernels=None, recurrent_dilations=None,
+                 recurrent_bias=None, depth: int = 2, time_steps: int = 8, conv_dim: int = 2, no_dc: bool = False,
+                 fft_centered: bool = True, fft_normalization: str = "ortho",
+                 spatial_dims: Optional[Tuple[int, int]] = None, coil_dim: int = 1, dimensionality: int = 2,
+                 consecutive_slices: int = 1):
+        super().__init__()
+        if dimensionality != 2 or consecutive_slices > 1:
+            raise NotImplementedError("mridc_b200: RIMBlock supports dimensionality == 2, consecutive_slices == 1")
+        self.input_size = depth * 2
+        self.time_steps = time_steps
+        self.layers = nn.ModuleList()
+        conv_layer = None
+        for (
+            (conv_features, conv_k_size, conv_dilation, l_conv_bias, nonlinear),
+            (rnn_features, rnn_k_size, rnn_dilation, rnn_bias, rnn_type),
+        ) in zip(
+            zip(conv_filters, conv_kernels, conv_dilations, conv_bias, ["relu", "relu", None]),
+            zip(recurrent_filters, recurrent_kernels, recurrent_dilations, recurrent_bias,
+                [recurrent_layer, recurrent_layer, None]),
+        ):
+            conv_layer = None
+            if conv_features != 0:
+                conv_layer = ConvNonlinear(self.input_size, conv_features, conv_dim=conv_dim, kernel_size=conv_k_size,
+                                           dilation=conv_dilation, bias=l_conv_bias, nonlinear=nonlinear)
+                self.input_size = conv_features
+            if rnn_features != 0 and rnn_type is not None:
+                if rnn_type.upper() == "GRU":
+                    rnn_cls = ConvGRUCell
+                elif rnn_type.upper() == "MGU":
+                    rnn_cls = ConvMGUCell
+                elif rnn_type.upper() == "INDRNN":
+                    rnn_cls = IndRNNCell
+                else:
+                    raise ValueError("Please specify a proper recurrent layer type.")
+                rnn_layer = rnn_cls(self.input_size, rnn_features, conv_dim=conv_dim, kernel_size=rnn_k_size,
+                                    dilation=rnn_dilation, bias=rnn_bias)
+                self.input_size = rnn_features
+                self.layers.append(ConvRNNStack(conv_layer, rnn_layer))
+        self.final_layer = nn.Sequential(conv_layer)
+        self.recurrent_filters = recurrent_filters
+        self.fft_centered = fft_centered
+        self.fft_normalization = fft_normalization
+        self.spatial_dims = spatial_dims if spatial_dims is not None else [-2, -1]
+        self.coil_dim = coil_dim
+        self.no_dc = no_dc
+        if not self.no_dc:
+            self.dc_weight = nn.Parameter(torch.ones(1))
+            self.zero = torch.zeros(1, 1, 1, 1, 1)
+        self.dimensionality = dimensionality
+        self.consecutive_slices = consecutive_slices
+
+    @torch.no_grad()
+    def forward(self, pred: torch.Tensor, masked_kspace: torch.Tensor, sense: torch.Tensor, mask: torch.Tensor,
+                eta: torch.Tensor = None, hx: torch.Tensor = None, sigma: float = 1.0,
+                keep_eta: bool = False) -> Tuple[Any, Union[list, torch.Tensor, None]]:
+        _ops.check_spatial_dims(self.spatial_dims)
+        if self.coil_dim != 1:
+            raise NotImplementedError("mridc_b200: RIMBlock expects coil_dim == 1")
+        if isinstance(pred, list):
+            pred = pred[-1].detach()  # rim_block.py:185-186
+        masked_kspace = _lib.require_cuda(masked_kspace, "masked_kspace").contiguous()
+        sense = _lib.require_cuda(sense, "sense").contiguous()
+        B, C, H, W, _ = masked_kspace.shape
+        if hx is None:  # :188-193
+            hx = [masked_kspace.new_zeros((B, f, H, W)) for f in self.recurrent_filters if f != 0]
+        else:
+            hx = list(hx)
+        ws = torch.empty((2, B, C, H, W, 2), dtype=torch.float32, device=masked_kspace.device)
+        if eta is None or eta.ndim < 3:  # :195-211
+            eta = pred if keep_eta else _ops.sens_reduce(pred, sense, self.fft_centered, self.fft_normalization, ws=ws)
+        mcan = _ops.canonical_mask(mask, B, H, W)[0]  # canonicalise once for the whole time loop
+        etas = []
+        final = self.final_layer[0]
+        for _ in range(self.time_steps):  # :217-249
+            grad_eta = _ops.dc_rim_grad(eta, masked_kspace, sense, mcan, sigma, self.fft_centered,
+                                        self.fft_normalization, ws=ws)
+            for h, convrnn in enumerate(self.layers):
+                hx[h] = convrnn(grad_eta, hx[h])
+                grad_eta = hx[h]
+            # final conv (no bias/activation in the shipped configs) fused with eta + grad.permute(0,2,3,1)
+            eta = final(grad_eta, residual_nhwc=eta.contiguous())
+            etas.append(eta)
+        if self.no_dc:
+            return etas, hx  # :253-254
+        if mask.dtype != torch.bool:
+            # same failure mode as the reference's torch.where(mask, ...) (rim_block.py:256)
+            raise RuntimeError("where expected condition to be a boolean tensor, but got a tensor with dtype %s"
+                               % mask.dtype)
+        dcw = self.dc_weight.detach()
+        current_kspace = [
+            _ops.sens_expand_softdc(e, sense, masked_kspace, pred, masked_kspace, mcan, dcw, False, self.fft_centered,
+                                    self.fft_normalization, ws=ws)
+            for e in etas
+        ]  # :256-267: masked_kspace - soft_dc - fft2(S * e)
+        return current_kspace, hx

@@ -1,0 +1,207 @@
+"""Drop-ins for the U-Net regulariser of the reference (unet_base/unet_block.py:11-308) on B200 kernels.
+
+Sub-module names match the reference (``unet.down_sample_layers.N.layers.{0,4}.weight`` ...) so reference
+checkpoints load key-for-key; ``torch.nn`` layers only hold parameters / initialise them.  Convolutions run on
+the exact-fp32 CUDA-core kernel (the E2EVN fp32 noise floor is ~2.7e-5 against a 1e-4 tolerance, SURVEY
+section 7), InstanceNorm statistics in fp64.  Skip connections are written straight into the concat buffer
+(no ``torch.cat``).  Inference only (Dropout2d is the identity).
+"""
+import math
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _ops
+
+__all__ = ["NormUnet", "Unet", "ConvBlock", "TransposeConvBlock"]
+
+
+def _instnorm_lrelu(x, x_bs, out, out_bs, N, C, HW, slope=0.2, eps=1e-5):
+    stats = torch.empty((2 * N * C,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().mrb_instnorm_lrelu(_lib.ptr(x), x_bs, _lib.ptr(out), out_bs, N, C, HW, eps, slope,
+                                              _lib.ptr(stats), _lib.stream_ptr()))
+    return out
+
+
+class ConvBlock(nn.Module):
+    """unet_block.py:230-271: (3x3 conv, bias=False -> InstanceNorm2d -> LeakyReLU(0.2) -> Dropout2d) x 2."""
+
+    def __init__(self, in_chans: int, out_chans: int, drop_prob: float):
+        super().__init__()
+        self.in_chans, self.out_chans, self.drop_prob = in_chans, out_chans, drop_prob
+        self.layers = nn.Sequential(
+            nn.Conv2d(in_chans, out_chans, kernel_size=3, padding=1, bias=False),
+            nn.InstanceNorm2d(out_chans),
+            nn.LeakyReLU(negative_slope=0.2, inplace=True),
+            nn.Dropout2d(drop_prob),
+            nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False),
+            nn.InstanceNorm2d(out_chans),
+            nn.LeakyReLU(negative_slope=0.2, inplace=True),
+            nn.Dropout2d(drop_prob),
+        )
+
+    def run(self, x, x_bs, N, H, W, out=None, out_bs=None):
+        """x: buffer holding [N, in_chans, H, W] with batch stride x_bs.  Result goes to ``out`` (batch stride
+        out_bs) if given, else to a fresh contiguous tensor."""
+        if self.training and self.drop_prob > 0:
+            raise NotImplementedError("mridc_b200 is inference only (Dropout2d with p > 0 in training mode)")
+        C = self.out_chans
+        HW = H * W
+        t = _ops.conv2d(x, self.layers[0].weight, None, 3, 1, _ops.PAD_ZERO, x_bstride=x_bs, N=N,
+                        Cin=self.in_chans, H=H, W=W)
+        _instnorm_lrelu(t, C * HW, t, C * HW, N, C, HW)
+        u = _ops.conv2d(t, self.layers[4].weight, None, 3, 1, _ops.PAD_ZERO)
+        if out is None:
+            out, out_bs = u, C * HW
+        _instnorm_lrelu(u, C * HW, out, out_bs, N, C, HW)
+        return out
+
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        image = _lib.require_cuda(image, "image").contiguous()
+        N, C, H, W = image.shape
+        return self.run(image, C * H * W, N, H, W)
+
+
+class TransposeConvBlock(nn.Module):
+    """unet_block.py:274-308: ConvTranspose2d(k=2, s=2, bias=False) -> InstanceNorm2d -> LeakyReLU(0.2)."""
+
+    def __init__(self, in_chans: int, out_chans: int):
+        super().__init__()
+        self.in_chans, self.out_chans = in_chans, out_chans
+        self.layers = nn.Sequential(
+            nn.ConvTranspose2d(in_chans, out_chans, kernel_size=2, stride=2, bias=False),
+            nn.InstanceNorm2d(out_chans),
+            nn.LeakyReLU(negative_slope=0.2, inplace=True),
+        )
+
+    def run(self, x, N, H, W, out=None, out_bs=None):
+        C = self.out_chans
+        t = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().mrb_conv_transpose2x2(_lib.ptr(x), self.in_chans * H * W, _lib.ptr(self.layers[0].weight),
+                                                     _lib.ptr(t), C * 4 * H * W, N, self.in_chans, C, H, W,
+                                                     _lib.stream_ptr()))
+        if out is None:
+            out, out_bs = t, C * 4 * H * W
+        _instnorm_lrelu(t, C * 4 * H * W, out, out_bs, N, C, 4 * H * W)
+        return out
+
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        image = _lib.require_cuda(image, "image").contiguous()
+        N, _, H, W = image.shape
+        return self.run(image, N, H, W)
+
+
+class Unet(nn.Module):
+    """unet_block.py:139-227."""
+
+    def __init__(self, in_chans: int, out_chans: int, chans: int = 32, num_pool_layers: int = 4,
+                 drop_prob: float = 0.0):
+        super().__init__()
+        self.in_chans, self.out_chans, self.chans = in_chans, out_chans, chans
+        self.num_pool_layers, self.drop_prob = num_pool_layers, drop_prob
+        self.down_sample_layers = nn.ModuleList([ConvBlock(in_chans, chans, drop_prob)])
+        ch = chans
+        for _ in range(num_pool_layers - 1):
+            self.down_sample_layers.append(ConvBlock(ch, ch * 2, drop_prob))
+            ch *= 2
+        self.conv = ConvBlock(ch, ch * 2, drop_prob)
+        self.up_conv = nn.ModuleList()
+        self.up_transpose_conv = nn.ModuleList()
+        for _ in range(num_pool_layers - 1):
+            self.up_transpose_conv.append(TransposeConvBlock(ch * 2, ch))
+            self.up_conv.append(ConvBlock(ch * 2, ch, drop_prob))
+            ch //= 2
+        self.up_transpose_conv.append(TransposeConvBlock(ch * 2, ch))
+        self.up_conv.append(nn.Sequential(ConvBlock(ch * 2, ch, drop_prob),
+                                          nn.Conv2d(ch, self.out_chans, kernel_size=1, stride=1)))
+
+    @torch.no_grad()
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        image = _lib.require_cuda(image, "image").contiguous()
+        N, C, H, W = image.shape
+        dev = image.device
+        cats = []  # (concat buffer [N, 2*ch, h, w], ch, h, w): skip lives in channels [ch, 2ch)
+        cur, cur_bs, cur_c, h, w = image, C * H * W, C, H, W
+        for layer in self.down_sample_layers:
+            ch = layer.out_chans
+            cat = torch.empty((N, 2 * ch, h, w), dtype=torch.float32, device=dev)
+            skip = cat[:, ch:]  # view: batch stride 2*ch*h*w
+            layer.run(cur, cur_bs, N, h, w, out=skip, out_bs=2 * ch * h * w)
+            cats.append((cat, ch, h, w))
+            pooled = torch.empty((N, ch, h // 2, w // 2), dtype=torch.float32, device=dev)
+            _lib.check(lib.mrb_avgpool2(_lib.ptr(skip), 2 * ch * h * w, _lib.ptr(pooled), ch * (h // 2) * (w // 2), N,
+                                        ch, h, w, _lib.stream_ptr()))
+            cur, cur_bs, cur_c, h, w = pooled, ch * (h // 2) * (w // 2), ch, h // 2, w // 2
+        out = self.conv.run(cur, cur_bs, N, h, w)
+        for i, (tconv, conv) in enumerate(zip(self.up_transpose_conv, self.up_conv)):
+            cat, ch, sh, sw = cats.pop()
+            if (2 * h, 2 * w) == (sh, sw):
+                tconv.run(out, N, h, w, out=cat, out_bs=2 * ch * sh * sw)
+            else:
+                # odd skip size: reflect-pad right/bottom by one (unet_block.py:216-222)
+                up = tconv.run(out, N, h, w)
+                _lib.check(lib.mrb_pad2d(_lib.ptr(up), ch * 4 * h * w, _lib.ptr(cat), 2 * ch * sh * sw, N, ch, 2 * h,
+                                         2 * w, sh, sw, 0, 0, 2, _lib.stream_ptr()))
+            h, w = sh, sw
+            block = conv if isinstance(conv, ConvBlock) else conv[0]
+            out = block.run(cat, 2 * ch * h * w, N, h, w)
+            if not isinstance(conv, ConvBlock):
+                out = _ops.conv2d(out, conv[1].weight, conv[1].bias, 1, 1, _ops.PAD_ZERO)
+        return out
+
+
+class NormUnet(nn.Module):
+    """unet_block.py:11-136: complex -> channels, group-norm (2 groups, unbiased std), pad, U-Net, unpad, unnorm."""
+
+    def __init__(self, chans: int, num_pools: int, in_chans: int = 2, out_chans: int = 2, drop_prob: float = 0.0,
+                 padding_size: int = 15, normalize: bool = True, norm_groups: int = 2):
+        super().__init__()
+        self.unet = Unet(in_chans=in_chans, out_chans=out_chans, chans=chans, num_pool_layers=num_pools,
+                         drop_prob=drop_prob)
+        self.padding_size = padding_size
+        self.normalize = normalize
+        self.norm_groups = norm_groups
+
+    def pad_sizes(self, h, w):
+        w_mult = ((w - 1) | self.padding_size) + 1
+        h_mult = ((h - 1) | self.padding_size) + 1
+        w_pad = [math.floor((w_mult - w) / 2), math.ceil((w_mult - w) / 2)]
+        h_pad = [math.floor((h_mult - h) / 2), math.ceil((h_mult - h) / 2)]
+        return h_pad, w_pad, h_mult, w_mult
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        x = _lib.require_cuda(x, "x").contiguous()
+        if x.shape[-1] != 2 or x.dim() != 5:
+            raise NotImplementedError("mridc_b200: NormUnet expects complex input [B, C, H, W, 2]")
+        if self.norm_groups != 2:
+            raise NotImplementedError("mridc_b200: NormUnet supports norm_groups == 2")
+        B, C, H, W, _ = x.shape
+        dev = x.device
+        st = _lib.stream_ptr()
+        planar = torch.empty((B, 2 * C, H, W), dtype=torch.float32, device=dev)
+        mean_std = torch.empty((B, 2, 2), dtype=torch.float32, device=dev)
+        stats = torch.empty((4 * B,), dtype=torch.float64, device=dev)
+        _lib.check(lib.mrb_normunet_in(_lib.ptr(x), _lib.ptr(planar), _lib.ptr(mean_std), B, C, H * W,
+                                       int(bool(self.normalize)), _lib.ptr(stats), st))
+        h_pad, w_pad, h_mult, w_mult = self.pad_sizes(H, W)
+        if (h_mult, w_mult) != (H, W):
+            padded = torch.empty((B, 2 * C, h_mult, w_mult), dtype=torch.float32, device=dev)
+            _lib.check(lib.mrb_pad2d(_lib.ptr(planar), 2 * C * H * W, _lib.ptr(padded), 2 * C * h_mult * w_mult, B,
+                                     2 * C, H, W, h_mult, w_mult, h_pad[0], w_pad[0], 0, st))
+        else:
+            padded = planar
+        y = self.unet(padded)
+        Co = y.shape[1]
+        if (h_mult, w_mult) != (H, W):
+            un = torch.empty((B, Co, H, W), dtype=torch.float32, device=dev)
+            _lib.check(lib.mrb_pad2d(_lib.ptr(y), Co * h_mult * w_mult, _lib.ptr(un), Co * H * W, B, Co, h_mult, w_mult,
+                                     H, W, -h_pad[0], -w_pad[0], 0, st))
+            y = un
+        out = torch.empty((B, Co // 2, H, W, 2), dtype=torch.float32, device=dev)
+        _lib.check(lib.mrb_normunet_out(_lib.ptr(y), _lib.ptr(mean_std), _lib.ptr(out), B, Co // 2, H * W,
+                                        int(bool(self.normalize)), st))
+        return out

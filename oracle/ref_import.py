@@ -1,0 +1,83 @@
+"""Import the UNMODIFIED reference leaf modules from /root/reference (container only).
+
+Recipe: the reference's package ``__init__`` files pull in pytorch_lightning /
+omegaconf / hydra / h5py, none of which are installed.  We therefore (1) register stub ``omegaconf`` and
+``h5py`` modules, (2) pre-register empty namespace packages for the parent packages so their heavy
+``__init__.py`` never runs, (3) import only the leaf modules on the hot path.  Nothing is copied.
+Used by ``oracle/make_golden.py`` and by tests that are skipped when /root/reference is absent.
+"""
+import importlib
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("MRIDC_REFERENCE_ROOT", "/root/reference")
+
+_PKGS = [
+    "mridc",
+    "mridc.collections",
+    "mridc.collections.common",
+    "mridc.collections.common.parts",
+    "mridc.collections.common.data",
+    "mridc.collections.reconstruction",
+    "mridc.collections.reconstruction.data",
+    "mridc.collections.reconstruction.models",
+    "mridc.collections.reconstruction.models.rim",
+    "mridc.collections.reconstruction.models.varnet",
+    "mridc.collections.reconstruction.models.unet_base",
+]
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "mridc", "collections"))
+
+
+def _setup():
+    if "mridc" in sys.modules and getattr(sys.modules["mridc"], "__oracle_stub__", False):
+        return
+    sys.dont_write_bytecode = True  # never write __pycache__ into the read-only reference
+    here = os.path.dirname(os.path.abspath(__file__))
+    os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(here, "_ref", "numba"))
+    if "omegaconf" not in sys.modules:
+        oc = types.ModuleType("omegaconf")
+
+        class ListConfig(list):
+            pass
+
+        class DictConfig(dict):
+            pass
+
+        oc.ListConfig = ListConfig
+        oc.DictConfig = DictConfig
+        sys.modules["omegaconf"] = oc
+    if "h5py" not in sys.modules:
+        sys.modules["h5py"] = types.ModuleType("h5py")
+    for name in _PKGS:
+        mod = types.ModuleType(name)
+        mod.__path__ = [os.path.join(REF_ROOT, *name.split("."))]
+        mod.__oracle_stub__ = True
+        sys.modules[name] = mod
+
+
+def ref(name: str):
+    """Import e.g. ref('common.parts.fft') -> mridc.collections.common.parts.fft (reference code)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    _setup()
+    return importlib.import_module("mridc.collections." + name)
+
+
+class Ref:
+    """Lazy bundle of the hot-path leaf modules."""
+
+    def __init__(self):
+        self.fft = ref("common.parts.fft")
+        self.utils = ref("common.parts.utils")
+        self.subsample = ref("reconstruction.data.subsample")
+        self.subsample_nn = ref("common.data.subsample")
+        self.rim_utils = ref("reconstruction.models.rim.rim_utils")
+        self.rim_block = ref("reconstruction.models.rim.rim_block")
+        self.rnn_cells = ref("reconstruction.models.rim.rnn_cells")
+        self.conv_layers = ref("reconstruction.models.rim.conv_layers")
+        self.vn_block = ref("reconstruction.models.varnet.vn_block")
+        self.unet_block = ref("reconstruction.models.unet_base.unet_block")

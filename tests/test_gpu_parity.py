@@ -1,0 +1,422 @@
+"""GPU parity: the CUDA path (through the C-ABI) against (1) the committed reference vectors, (2) the CPU oracle
+on seeded inputs at sizes it finishes in seconds, (3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (fp32 path; north star: relative L2 <= 1e-4 on the reconstructed image, SSIM/PSNR to 4 decimals,
+masks / indices / crops bit-exact):
+  per-operator  rel-L2 <= 2e-6   (FFT, DC gradient, sens_reduce / expand, elementwise)
+  blocks        rel-L2 <= 1e-5   (RIM block 8 steps, NormUnet, VarNet block)
+  models        rel-L2 <= 1e-4   (CIRIM 5x8, E2EVN 12 cascades at 15x320x320)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import NORMS, mask_from_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+NRM3 = ["backward", "ortho", "forward"]
+LAYERS = ["GRU", "IndRNN", "MGU"]
+RIM_HP = dict(conv_filters=[16, 16, 2], conv_kernels=[5, 3, 3], conv_dilations=[1, 2, 1],
+              conv_bias=[True, True, False], recurrent_filters=[16, 16, 0], recurrent_kernels=[1, 1, 0],
+              recurrent_dilations=[1, 1, 0], recurrent_bias=[True, True, False], depth=2, time_steps=8, conv_dim=2,
+              spatial_dims=[-2, -1], coil_dim=1, dimensionality=2)
+
+
+def cu(a):
+    t = torch.from_numpy(a) if isinstance(a, np.ndarray) else a
+    return t.cuda()
+
+
+# ---------------------------------------------------------------------------------------------- L1
+def test_fft_golden(golden):
+    import mridc_b200 as mb
+
+    g = golden("prims")
+    worst = 0.0
+    for i in range(int(g["nfft"])):
+        cen, nrm, inv = g["fft%d_cfg" % i]
+        fn = mb.ifft2 if inv else mb.fft2
+        out = fn(cu(g["fft%d_x" % i]), centered=bool(cen), normalization=NORMS[nrm])
+        e = rel_l2(out, g["fft%d_out" % i])
+        worst = max(worst, e)
+        assert e < 2e-6, (i, e)
+    out = mb.fft2(cu(g["fftsd_x"]), centered=True, normalization="ortho", spatial_dims=[-3, -2])
+    assert rel_l2(out, g["fftsd_out"]) < 2e-6
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 13, 30, 49, 97, 128, 320, 640, 1000])
+def test_fft_lengths_vs_oracle(n):
+    import mridc_b200 as mb
+    from oracle import mri as omri
+
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(3, n, 5, 2, generator=g)
+    for cen in (False, True):
+        a = mb.fft2(x.cuda(), centered=cen, normalization="ortho", spatial_dims=[1, 2])
+        assert rel_l2(a, omri.fft2(x, cen, "ortho", [1, 2])) < 2e-6
+        a = mb.ifft2(x.cuda(), centered=cen, normalization="backward", spatial_dims=[-3, -2])
+        assert rel_l2(a, omri.ifft2(x, cen, "backward", [-3, -2])) < 2e-6
+
+
+def test_fft_complex_input_and_noncontiguous():
+    import mridc_b200 as mb
+    from oracle import mri as omri
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 6, 10, 2, generator=g)
+    xc = torch.view_as_complex(x)
+    assert rel_l2(mb.fft2(xc.cuda(), True, "ortho"), omri.fft2(xc, True, "ortho")) < 2e-6
+    xt = x.permute(1, 0, 2, 3)  # non-contiguous
+    assert rel_l2(mb.ifft2(xt.cuda(), False, "forward"), omri.ifft2(xt, False, "forward")) < 2e-6
+
+
+def test_shift_roll_bit_exact(golden):
+    import mridc_b200 as mb
+
+    g = golden("prims")
+    a = cu(g["roll_x"])
+    assert np.array_equal(mb.roll(a, [2, -3], [0, 2]).cpu().numpy(), g["roll_a"])
+    assert np.array_equal(mb.roll(a, [9], [1]).cpu().numpy(), g["roll_b"])
+    assert np.array_equal(mb.fftshift(a).cpu().numpy(), g["fftshift"])
+    assert np.array_equal(mb.ifftshift(a).cpu().numpy(), g["ifftshift"])
+    assert np.array_equal(mb.fftshift(a, [0, 1]).cpu().numpy(), g["fftshift_d"])
+    for dt in (torch.uint8, torch.int16, torch.float32, torch.float64, torch.complex128, torch.bool):
+        t = (torch.arange(5 * 7 * 3).reshape(5, 7, 3) % 2 == 0) if dt == torch.bool else \
+            torch.arange(5 * 7 * 3).reshape(5, 7, 3).to(dt)
+        assert torch.equal(mb.roll(t.cuda(), [3, 1], [1, 2]).cpu(), torch.roll(t, (3, 1), (1, 2)))
+    with pytest.raises(ValueError, match="len\\(shift\\) must match len\\(dim\\)"):
+        mb.roll(a, [1, 2], [0])
+
+
+def test_complex_utils_golden(golden):
+    import mridc_b200 as mb
+
+    g = golden("prims")
+    x, y, yb = cu(g["cx"]), cu(g["cy"]), cu(g["cyb"])
+    checks = {
+        "cmul": mb.complex_mul(x, y), "cmulb": mb.complex_mul(x, yb), "cconj": mb.complex_conj(x),
+        "cabs": mb.complex_abs(x), "cabssq": mb.complex_abs_sq(x), "rss1": mb.rss(x, 1), "rss0": mb.rss(x, 0),
+        "rssc1": mb.rss_complex(x, 1), "sense1": mb.sense(x, y, 1),
+        "cc_sense": mb.coil_combination(x, y, "SENSE", 1), "cc_rss": mb.coil_combination(x, y, "RSS", 1),
+    }
+    for k, v in checks.items():
+        assert v.shape == g[k].shape, k
+        assert rel_l2(v, g[k]) < 1e-6, k
+    assert np.array_equal(mb.complex_conj(x).cpu().numpy(), g["cconj"])  # pure sign flip: bit exact
+    with pytest.raises(ValueError, match="Output type not supported"):
+        mb.coil_combination(x, y, "sense", 1)
+    with pytest.raises(ValueError, match="separate complex dim"):
+        mb.complex_mul(x[..., :1], y)
+    with pytest.raises(ValueError, match="separate complex dim"):
+        mb.complex_abs(x[..., :1])
+    assert mb.check_stacked_complex(x).is_complex()
+
+
+def test_crops_bit_exact():
+    import mridc_b200 as mb
+
+    x = torch.arange(2 * 11 * 14).reshape(2, 11, 14).float().cuda()
+    assert torch.equal(mb.center_crop(x, (5, 6)), x[..., 3:8, 4:10])
+    xc = torch.arange(2 * 11 * 14 * 2).reshape(2, 11, 14, 2).float().cuda()
+    assert torch.equal(mb.complex_center_crop(xc, (4, 4)), xc[..., 3:7, 5:9, :])
+    a, b = mb.center_crop_to_smallest(x, x[..., :7, :9])
+    assert a.shape == b.shape == (2, 7, 9)
+    with pytest.raises(ValueError, match="Invalid shapes"):
+        mb.center_crop(x, (12, 3))
+
+
+# ---------------------------------------------------------------------------------------------- DC
+def test_dc_golden(golden):
+    import mridc_b200 as mb
+    from mridc_b200.varnet import VarNetBlock
+
+    g = golden("dc")
+    for i in range(int(g["ndc"])):
+        cen, nrm, sigma, md = g["dc%d_cfg" % i]
+        y, S, eta = cu(g["dc%d_y" % i]), cu(g["dc%d_S" % i]), cu(g["dc%d_eta" % i])
+        m = mask_from_golden(g["dc%d_mask" % i], md).cuda()
+        out = mb.log_likelihood_gradient(eta, y, S, m, float(sigma), bool(cen), NRM3[int(nrm)], [-2, -1], 1)
+        assert out.shape == g["dc%d_grad" % i].shape
+        assert rel_l2(out, g["dc%d_grad" % i]) < 2e-6, i
+        assert torch.equal(out[:, 0], eta[..., 0]) and torch.equal(out[:, 1], eta[..., 1])  # eta passthrough exact
+        vb = VarNetBlock(torch.nn.Identity(), bool(cen), NRM3[int(nrm)], [-2, -1], 1)
+        red = vb.sens_reduce(y, S)
+        assert red.shape == g["dc%d_red" % i].shape
+        assert rel_l2(red, g["dc%d_red" % i]) < 2e-6, i
+        assert rel_l2(vb.sens_expand(red, S), g["dc%d_exp" % i]) < 2e-6, i
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (1, 2, 5, 3), (3, 5, 33, 17), (2, 15, 64, 48), (1, 33, 40, 36)])
+def test_dc_shapes_vs_oracle(B, C, H, W):
+    import mridc_b200 as mb
+    from oracle import nets as onets
+
+    g = torch.Generator().manual_seed(B * 1000 + C * 100 + H)
+    y = torch.randn(B, C, H, W, 2, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g)
+    eta = torch.randn(B, H, W, 2, generator=g)
+    for mshape, dt in (((1, 1, 1, W, 1), torch.float32), ((B, 1, H, W, 1), torch.uint8), ((1, 1, H, W, 1), torch.bool)):
+        m = (torch.rand(*mshape, generator=g) < 0.5)
+        mt = m.to(dt)
+        for cen, nrm in ((True, "ortho"), (False, "backward")):
+            a = mb.log_likelihood_gradient(eta.cuda(), y.cuda(), S.cuda(), mt.cuda(), 0.7, cen, nrm, [-2, -1], 1)
+            b = onets.log_likelihood_gradient(eta, y, S, mt if dt != torch.bool else m.float(), 0.7, cen, nrm,
+                                              [-2, -1], 1)
+            assert rel_l2(a, b) < 2e-6
+
+
+def test_dc_float_valued_mask_multiplies():
+    """RIM multiplies by the mask VALUE (rim_utils.py:54); VarNet tests truthiness (vn_block.py:110)."""
+    import mridc_b200 as mb
+    from mridc_b200 import _ops
+    from oracle import nets as onets
+
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 2, 3, 12, 10
+    y, S = torch.randn(B, C, H, W, 2, generator=g), torch.randn(B, C, H, W, 2, generator=g)
+    eta = torch.randn(B, H, W, 2, generator=g)
+    m = torch.rand(1, 1, 1, W, 1, generator=g) * (torch.rand(1, 1, 1, W, 1, generator=g) < 0.6)
+    a = mb.log_likelihood_gradient(eta.cuda(), y.cuda(), S.cuda(), m.cuda(), 1.0, True, "ortho", [-2, -1], 1)
+    assert rel_l2(a, onets.log_likelihood_gradient(eta, y, S, m, 1.0, True, "ortho", [-2, -1], 1)) < 2e-6
+    pred = torch.randn(B, C, H, W, 2, generator=g)
+    dcw = torch.tensor([0.3])
+    out = _ops.sens_expand_softdc(eta.cuda(), S.cuda(), pred.cuda(), pred.cuda(), y.cuda(), m.cuda(), dcw.cuda(),
+                                  False, True, "ortho")
+    ref = pred - torch.where(m.bool(), pred - y, torch.zeros(1)) * dcw - onets.sens_expand(eta.unsqueeze(1), S, True,
+                                                                                           "ortho", [-2, -1])
+    assert rel_l2(out, ref) < 2e-6
+
+
+def test_dc_properties_full_size():
+    """BASELINE full size (15 x 320 x 320 and 16 x 640 x 320): adjointness <E x, k> == <x, E^H k>, round trip,
+    linearity of the gradient in (eta, y)."""
+    import mridc_b200 as mb
+    from mridc_b200 import _ops
+
+    for (C, H, W) in ((15, 320, 320), (16, 640, 320)):
+        g = torch.Generator(device="cuda").manual_seed(C)
+        S = torch.randn(1, C, H, W, 2, device="cuda", generator=g)
+        x = torch.randn(1, H, W, 2, device="cuda", generator=g)
+        k = torch.randn(1, C, H, W, 2, device="cuda", generator=g)
+        Ex = _ops.sens_expand_softdc(x, S, None, None, None, None, None, True, True, "ortho")
+        EHk = _ops.sens_reduce(k, S, True, "ortho")
+        lhs = torch.sum(torch.view_as_complex(Ex).conj() * torch.view_as_complex(k))
+        rhs = torch.sum(torch.view_as_complex(x).conj() * torch.view_as_complex(EHk))
+        assert abs(lhs - rhs).item() / abs(lhs).item() < 1e-5
+        # round trip of the standalone transforms
+        kk = mb.fft2(k, True, "ortho")
+        assert rel_l2(mb.ifft2(kk, True, "ortho"), k) < 2e-6
+        # Parseval (ortho)
+        assert abs(kk.double().pow(2).sum() - k.double().pow(2).sum()).item() / k.double().pow(2).sum().item() < 1e-6
+        # gradient is affine: g(eta, y) with mask of ones equals E^H(E eta - y)
+        ones = torch.ones(1, 1, 1, W, 1, device="cuda")
+        gr = mb.log_likelihood_gradient(x, k, S, ones, 1.0, True, "ortho", [-2, -1], 1)
+        direct = _ops.sens_reduce(Ex - k, S, True, "ortho")
+        assert rel_l2(gr[:, 2:].permute(0, 2, 3, 1), direct) < 5e-6
+        # zero mask -> zero gradient, bit exact
+        z = mb.log_likelihood_gradient(x, k, S, torch.zeros(1, 1, 1, W, 1, device="cuda"), 1.0, True, "ortho",
+                                       [-2, -1], 1)
+        assert torch.count_nonzero(z[:, 2:]) == 0
+
+
+def test_cpu_tensor_raises():
+    import mridc_b200 as mb
+
+    x = torch.randn(2, 4, 4, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.fft2(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.complex_mul(x, x)
+
+
+# ---------------------------------------------------------------------------------------------- blocks
+def _rim_block(hp, sd):
+    from mridc_b200.rim import RIMBlock
+
+    blk = RIMBlock(recurrent_layer=hp["recurrent_layer"], conv_filters=hp["conv_filters"],
+                   conv_kernels=hp["conv_kernels"], conv_dilations=hp["conv_dilations"], conv_bias=hp["conv_bias"],
+                   recurrent_filters=hp["recurrent_filters"], recurrent_kernels=hp["recurrent_kernels"],
+                   recurrent_dilations=hp["recurrent_dilations"], recurrent_bias=hp["recurrent_bias"], depth=2,
+                   time_steps=hp["time_steps"], conv_dim=2, no_dc=hp["no_dc"], fft_centered=hp["fft_centered"],
+                   fft_normalization=hp["fft_normalization"], spatial_dims=[-2, -1], coil_dim=1, dimensionality=2)
+    blk.load_state_dict(sd, strict=True)
+    return blk.cuda().eval()
+
+
+def test_rim_block_golden(golden):
+    g = golden("rim")
+    for i in range(int(g["nrim"])):
+        layer, rk, no_dc, cen, nrm, md = (int(v) for v in g["rim%d_cfg" % i])
+        hp = dict(RIM_HP, recurrent_layer=LAYERS[layer], no_dc=bool(no_dc), fft_centered=bool(cen),
+                  fft_normalization=NRM3[nrm], recurrent_kernels=[rk, rk, 0])
+        blk = _rim_block(hp, golden.weights(g, "rim%d_w_" % i))
+        y, S = cu(g["rim%d_y" % i]), cu(g["rim%d_S" % i])
+        m = mask_from_golden(g["rim%d_mask" % i], md).cuda()
+        etas, hx = blk(y.clone(), y, S, m, None, None, 1.0, False)
+        assert len(etas) == 8 and len(hx) == 2
+        assert rel_l2(etas[0], g["rim%d_first" % i]) < 1e-5, i
+        assert rel_l2(etas[-1], g["rim%d_last" % i]) < 1e-5, i
+        assert rel_l2(hx[0], g["rim%d_h0" % i]) < 1e-5, i
+        assert rel_l2(hx[1], g["rim%d_h1" % i]) < 1e-5, i
+
+
+def test_conv_layers_vs_oracle():
+    from mridc_b200.rim import ConvGRUCell, ConvMGUCell, ConvNonlinear, IndRNNCell
+    from oracle import nets as onets
+
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(4)
+    for cin, cout, k, dil, nl, H, W in ((4, 64, 5, 1, "relu", 37, 45), (64, 64, 3, 2, "relu", 20, 70),
+                                        (64, 2, 3, 1, None, 33, 33), (3, 7, 7, 1, "leakyrelu", 16, 19),
+                                        (5, 20, 3, 3, "relu", 24, 31), (9, 40, 1, 1, None, 10, 12)):
+        mod = ConvNonlinear(cin, cout, 2, k, dil, True, nl)
+        with torch.no_grad():
+            mod.conv_layer.bias.normal_()
+        x = torch.randn(2, cin, H, W, generator=g)
+        ref = onets.conv_nonlinear(x, mod.conv_layer.weight.detach(), mod.conv_layer.bias.detach(), k, dil, nl)
+        assert rel_l2(mod.cuda()(x.cuda()), ref) < 2e-6, (cin, cout, k, dil)
+    for cls, fn, key in ((ConvGRUCell, onets.conv_gru_cell, None), (ConvMGUCell, onets.conv_mgu_cell, None),
+                         (IndRNNCell, onets.indrnn_cell, "hh")):
+        for cx, ch, k, dil in ((64, 64, 1, 1), (16, 24, 3, 1), (8, 70, 1, 1), (6, 10, 3, 2)):
+            mod = cls(cx, ch, 2, k, dil, True)
+            with torch.no_grad():
+                mod.ih.bias.normal_()
+            x = torch.randn(2, cx, 19, 23, generator=g)
+            h = torch.randn(2, ch, 19, 23, generator=g)
+            hh = mod.hh.detach() if key else mod.hh.weight.detach()
+            ref = fn(x, h, mod.ih.weight.detach(), mod.ih.bias.detach(), hh, k, dil)
+            assert rel_l2(mod.cuda()(x.cuda(), h.cuda()), ref) < 2e-6, (cls.__name__, cx, ch, k)
+
+
+def test_unet_varnet_golden(golden):
+    from mridc_b200.unet import NormUnet
+    from mridc_b200.varnet import VarNetBlock
+
+    g = golden("unet_vn")
+    for i in range(int(g["nunet"])):
+        chans, pools, padsz = (int(v) for v in g["unet%d_cfg" % i])
+        nu = NormUnet(chans=chans, num_pools=pools, padding_size=padsz, normalize=True)
+        nu.load_state_dict(golden.weights(g, "unet%d_w_" % i), strict=True)
+        out = nu.cuda().eval()(cu(g["unet%d_x" % i]))
+        assert out.shape == g["unet%d_out" % i].shape
+        assert rel_l2(out, g["unet%d_out" % i]) < 1e-5, i
+    for j in range(int(g["nvn"])):
+        cen, nrm, no_dc = (int(v) for v in g["vn%d_cfg" % j])
+        vb = VarNetBlock(NormUnet(chans=4, num_pools=2, padding_size=11, normalize=True), bool(cen), NRM3[nrm],
+                         [-2, -1], 1, bool(no_dc))
+        vb.load_state_dict(golden.weights(g, "vn%d_w_" % j), strict=True)
+        vb = vb.cuda().eval()
+        out = vb(cu(g["vn%d_pred" % j]), cu(g["vn%d_y" % j]), cu(g["vn%d_S" % j]), cu(g["vn%d_mask" % j]))
+        assert rel_l2(out, g["vn%d_out" % j]) < 1e-5, j
+
+
+# ---------------------------------------------------------------------------------------------- models
+def test_models_golden(golden):
+    import mridc_b200 as mb
+
+    g = golden("models")
+    y, S, m = cu(g["in_y"]), cu(g["in_S"]), cu(g["in_mask"])
+    tgt = torch.view_as_complex(torch.from_numpy(g["in_target"])).cuda()
+    cfg = dict(RIM_HP, recurrent_layer="GRU", no_dc=True, fft_centered=True, fft_normalization="ortho",
+               num_cascades=2, keep_eta=True, coil_combination_method="SENSE", train_loss_fn="l1", val_loss_fn="l1")
+    model = mb.CIRIM(cfg)
+    sd = golden.weights(g, "cirim_w_")
+    sd["dc_weight"] = torch.ones(1)
+    model.load_state_dict(sd, strict=True)
+    gen = model.cuda().eval()(y, S, m, None, tgt)
+    out = next(gen)  # generator, like the reference (cirim.py:165)
+    ref = torch.view_as_complex(torch.from_numpy(g["cirim_out"]))
+    assert len(out) == 2 and len(out[0]) == 8
+    for c in range(2):
+        for t in range(8):
+            assert out[c][t].is_complex() and rel_l2(out[c][t], ref[c, t]) < 1e-5
+    vcfg = dict(num_cascades=3, channels=4, pooling_layers=2, padding_size=11, normalize=True, no_dc=False,
+                fft_centered=True, fft_normalization="ortho", spatial_dims=[-2, -1], coil_dim=1,
+                coil_combination_method="SENSE")
+    vn = mb.VarNet(vcfg)
+    vsd = golden.weights(g, "vn_w_")
+    vsd["dc_weight"] = torch.ones(1)
+    vn.load_state_dict(vsd, strict=True)
+    o = vn.cuda().eval()(y, S, m, None, tgt)
+    assert rel_l2(o, torch.view_as_complex(torch.from_numpy(g["vn_out"]))) < 1e-4
+    for meth in ("SENSE", "RSS"):
+        zf = mb.ZF(dict(coil_combination_method=meth.lower(), fft_centered=True, fft_normalization="ortho",
+                        spatial_dims=[-2, -1], coil_dim=1))
+        o = zf(y, S, m, tgt)
+        assert o.is_complex() and rel_l2(o, torch.view_as_complex(torch.from_numpy(g["zf_" + meth]))) < 2e-6
+    un = mb.UNet(dict(channels=4, pooling_layers=2, padding_size=11, normalize=True, fft_centered=True,
+                      fft_normalization="ortho", spatial_dims=[-2, -1], coil_dim=1, coil_combination_method="SENSE"))
+    un.load_state_dict(golden.weights(g, "unet_w_"), strict=True)
+    o = un.cuda().eval()(y, S, m, None, tgt)
+    assert rel_l2(o, torch.view_as_complex(torch.from_numpy(g["unet_out"]))) < 1e-5
+
+
+def _metrics4(pred, target):
+    from oracle import metrics as om
+
+    o = np.abs(pred)
+    t = np.abs(target)
+    o, t = o / o.max(), t / t.max()
+    R = o.max() - o.min()
+    return round(float(om.ssim(t, o, maxval=R)), 4), round(float(om.psnr(t, o, maxval=R)), 4)
+
+
+@pytest.mark.parametrize("centered,norm", [(False, "backward"), (True, "ortho")])
+def test_cirim_full_config_vs_oracle(centered, norm):
+    """Config 3: CIRIM 5 cascades x 8 steps, ConvGRU 64 filters, 15 x 320 x 320, 4x equispaced mask."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    cfg = synth.cirim_cfg("GRU", centered=centered, normalization=norm)
+    batch = synth.make_batch(1, 15, 320, 320, centered=centered, normalization=norm)
+    torch.manual_seed(1)
+    model = mb.CIRIM(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = omodels.cirim_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None,
+                                    batch["target"])
+    out = next(model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
+                            batch["target"].cuda()))
+    e = rel_l2(out[-1][-1], ref[-1][-1])
+    assert e <= 1e-4, e
+    assert _metrics4(out[-1][-1].cpu().numpy(), batch["target"].numpy()) == \
+        _metrics4(ref[-1][-1].numpy(), batch["target"].numpy())
+    assert rel_l2(out[0][0], ref[0][0]) <= 1e-5
+
+
+def test_varnet_full_config_vs_oracle():
+    """Config 2: E2EVN 12 cascades, 14 channels, 2 pools, 15 x 320 x 320, Gaussian-1D 4x mask."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    cfg = synth.varnet_cfg()
+    np.random.seed(123)
+    batch = synth.make_batch(1, 15, 320, 320, synth.Gaussian1DMask([0.7], [4]), seed=None)
+    torch.manual_seed(1)
+    model = mb.VarNet(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = omodels.varnet_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None,
+                                     batch["target"])
+    out = model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
+                       batch["target"].cuda())
+    e = rel_l2(out, ref)
+    assert e <= 1e-4, e
+    assert _metrics4(out.cpu().numpy(), batch["target"].numpy()) == _metrics4(ref.numpy(), batch["target"].numpy())
+
+
+def test_zf_config1_vs_oracle_and_crop():
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    cfg = synth.zf_cfg()
+    batch = synth.make_batch(2, 15, 320, 320)
+    tgt = batch["target"][..., 20:300, 10:310]  # exercises the centre crop
+    ref = omodels.zf_forward(cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], tgt)
+    out = mb.ZF(cfg)(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), tgt.cuda())
+    assert out.shape == ref.shape == (2, 280, 300)
+    assert rel_l2(out, ref) < 2e-6
