@@ -44,7 +44,16 @@ def _transform(data, centered, normalization, spatial_dims, inverse):
         data = ifftshift(data, dim=dims)
     norm = normalization if normalization.lower() != "none" else None
     fn = torch.fft.ifft2 if inverse else torch.fft.fft2
-    data = fn(data, dim=dims, norm=norm)
+    nd = data.dim()
+    pdims = [d % nd for d in dims]
+    if sorted(pdims) == list(range(nd - len(pdims), nd)):
+        data = fn(data, dim=dims, norm=norm)
+    else:
+        # Same transform, evaluated over trailing contiguous axes: torch 2.11's MKL path corrupts the heap for
+        # strided multi-dim C2C transforms over non-trailing dims (reproducer: ifft2 of a [3, n, 5] complex64
+        # tensor over dims (0, 1)); the reference itself pins torch 1.12.
+        last = list(range(nd - len(pdims), nd))
+        data = fn(data.movedim(pdims, last).contiguous(), dim=last, norm=norm).movedim(last, pdims)
     if centered:
         data = fftshift(data, dim=dims)
     return torch.view_as_real(data)
