@@ -99,11 +99,12 @@ int mrb_sense_combine(const void* x, const void* S, void* out, long long outer, 
 size_t mrb_dc_workspace_bytes(int B, int C, int H, int W);
 
 /* RIM log-likelihood gradient -- mc/reconstruction/models/rim/rim_utils.py:11-67.
- *   eta [B,H,W,2], y,S [B,C,H,W,2], out [B,4,H,W] = (eta_re, eta_im, g_re, g_im),
+ *   eta [B,H,W,2], y,S [B,C,H,W,2], out [B,4,H,W] = (eta_re, eta_im, g_re, g_im)  (the reference layout, :67),
+ *   or [B,H,W,4] when out_nhwc != 0 (channels-last feed of the tensor-core regulariser);
  *   g = sum_c conj(S) * ifft2(mask * (fft2(S*eta) - y)) * inv_sigma2  (mask VALUE multiplies: :54). */
 int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* mask, int mask_dtype,
-                    int mask_b, int mask_h, float inv_sigma2, void* out, int B, int C, int H, int W,
-                    int centered, int norm, void* ws, size_t ws_bytes, void* stream);
+                    int mask_b, int mask_h, float inv_sigma2, void* out, int out_nhwc, int B, int C, int H,
+                    int W, int centered, int norm, void* ws, size_t ws_bytes, void* stream);
 
 /* sum_c ifft2(x) * conj(S) -- mc/reconstruction/models/varnet/vn_block.py:71-87 sens_reduce, also the
  * zero-filled SENSE init of rim_block.py:195-211, zf.py:90-97, vn.py:131-139, unet.py:108-117.
@@ -183,6 +184,37 @@ int mrb_normunet_in(const void* x, void* out, void* mean_std, int B, int C, long
 /* NormUnet.unnorm + chan_complex_to_last_dim (unet_block.py:62-69,:87-91): x [B,2C,HW] -> [B,C,HW,2] */
 int mrb_normunet_out(const void* x, const void* mean_std, void* out, int B, int C, long long HW,
                      int normalize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM, error-compensated 3xTF32) RIM regulariser, channels-last fp32 activations.
+ * Same arithmetic as mrb_conv2d / mrb_gru_cell_1x1 to fp32 round-off; used by RIMBlock's time loop
+ * (rim_block.py:217-249) when the layer geometry matches (64 channels, GRU kernel size 1).
+ * Weights are packed once per parameter version into the UMMA shared-memory layout (hi/lo split).
+ * ------------------------------------------------------------------------------------------------- */
+/* profiling switches for the tensor-core kernel (bit 0: skip MMAs, 1: skip global loads, 2: skip epilogue);
+ * results are garbage when non-zero -- used only by tools/ to attribute time to the kernel's roles. */
+void mrb_tc_set_debug(int flags);
+/* floats needed by the pack: kind 0 = conv k x k (cin 64), 1 = GRU 1x1 (64 -> 64), 2 = conv 5x5 over 4 channels */
+size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k);
+/* w [cout, 64, k, k] (conv_layers.py:78-85) */
+int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int k, void* stream);
+/* w_ih, w_hh [3*ch, 64] (rnn_cells.py:23-38) */
+int mrb_tc_pack_gru(const void* w_ih, const void* w_hh, void* dst, int ch, int cx, void* stream);
+/* w [cout, 4, 5, 5] */
+int mrb_tc_pack_conv5x5x4(const void* w, void* dst, int cout, void* stream);
+/* ConvNonlinear k x k, dilation dil, replicate padding, 64 -> cout, NHWC in/out, bias, optional ReLU */
+int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W, int cout,
+                     int k, int dil, int relu, void* stream);
+/* ConvNonlinear 5x5 over the 4-channel RIM gradient [B,H,W,4] -> [B,H,W,cout] */
+int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
+                          int cout, int relu, void* stream);
+/* ConvGRUCell (kernel size 1): x, h, h_out [B,H,W,64]; b_ih [192] or null */
+int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, const void* b_ih, void* h_out, int B, int H,
+                    int W, int ch, void* stream);
+/* Final RIM conv (rim_block.py:239-248): k x k (odd), dilation dil, replicate padding, cin -> 2 channels, no bias,
+ * x [B,H,W,cin] channels-last, out [B,H,W,2] = eta + conv(x). */
+int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out, int B,
+                              int H, int W, int cin, int k, int dil, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ SIGNATURES = {
     "mrb_rss_complex": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
     "mrb_sense_combine": (_i, [_vp, _vp, _vp, _ll, _i, _ll, _vp]),
     "mrb_dc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "mrb_dc_rim_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "mrb_dc_rim_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mrb_sens_reduce": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mrb_sens_expand_softdc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i,
                                     _vp, _sz, _vp]),
@@ -46,6 +46,15 @@ SIGNATURES = {
     "mrb_pad2d": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_normunet_in": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
     "mrb_normunet_out": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
+    "mrb_tc_set_debug": (None, [_i]),
+    "mrb_tc_packed_floats": (_sz, [_i, _i, _i, _i]),
+    "mrb_tc_pack_conv": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mrb_tc_pack_gru": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mrb_tc_pack_conv5x5x4": (_i, [_vp, _vp, _i, _vp]),
+    "mrb_tc_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrb_tc_conv5x5x4_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mrb_tc_gru_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -75,8 +75,8 @@ def _check5(t, name):
     return t.contiguous()
 
 
-def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=None):
-    """rim_utils.py:11-67 -> [B, 4, H, W]."""
+def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=None, nhwc=False):
+    """rim_utils.py:11-67 -> [B, 4, H, W] (or channels-last [B, H, W, 4] when nhwc)."""
     y = _check5(y, "masked_kspace")
     S = _check5(S, "sense")
     B, C, H, W, _ = y.shape
@@ -86,12 +86,13 @@ def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=No
     eta = eta.contiguous()
     m, code, mb, mh = canonical_mask(mask, B, H, W)
     if out is None:
-        out = torch.empty((B, 4, H, W), dtype=torch.float32, device=y.device)
+        out = torch.empty((B, H, W, 4) if nhwc else (B, 4, H, W), dtype=torch.float32, device=y.device)
     if ws is None:
         ws = _ws(B, C, H, W, y.device)
     lib = _lib.load()
     _lib.check(lib.mrb_dc_rim_grad(_lib.ptr(eta), _lib.ptr(y), _lib.ptr(S), _lib.ptr(m), code, mb, mh,
-                                   1.0 / (float(sigma) ** 2.0), _lib.ptr(out), B, C, H, W, int(bool(centered)),
+                                   1.0 / (float(sigma) ** 2.0), _lib.ptr(out), int(bool(nhwc)), B, C, H, W,
+                                   int(bool(centered)),
                                    norm_code(normalization), _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr()))
     return out
 

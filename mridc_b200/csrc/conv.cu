@@ -309,9 +309,68 @@ __global__ void mgu_gates_kernel(const float* __restrict__ ih, const float* __re
     }
 }
 
+// Final RIM conv on channels-last input: cin -> 2 channels, replicate padding, fused eta update.
+// Thread = one pixel; weights (k*k*cin float2) broadcast from shared memory; the 256-byte channel vector of each
+// tap is read as float4 (neighbouring threads re-use it through L1).
+__global__ void __launch_bounds__(128) conv_c2_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ eta, float* __restrict__ out,
+                                                           int B, int H, int W, int cin, int k, int dil) {
+    extern __shared__ float2 w2[];  // [tap][ci] -> (w[0][ci][tap], w[1][ci][tap])
+    const int kk = k * k;
+    for (int t = threadIdx.x; t < kk * cin; t += blockDim.x) {
+        int ci = t % cin, tap = t / cin;
+        w2[t] = make_float2(w[(long long)ci * kk + tap], w[((long long)cin + ci) * kk + tap]);
+    }
+    __syncthreads();
+    const long long P = (long long)B * H * W;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int px = (int)(p % W);
+    const long long t1 = p / W;
+    const int py = (int)(t1 % H);
+    const int pb = (int)(t1 / H);
+    const int pad = dil * (k - 1) / 2;
+    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;  // two partial sums per output for ILP
+    for (int tap = 0; tap < kk; ++tap) {
+        const int yy = min(max(py + (tap / k) * dil - pad, 0), H - 1);
+        const int xx = min(max(px + (tap % k) * dil - pad, 0), W - 1);
+        const float4* xp = reinterpret_cast<const float4*>(x + (((long long)pb * H + yy) * W + xx) * cin);
+        const float4* wp = reinterpret_cast<const float4*>(w2 + (size_t)tap * cin);
+#pragma unroll 4
+        for (int c4 = 0; c4 < cin / 4; ++c4) {
+            const float4 v = xp[c4];
+            const float4 wa = wp[2 * c4], wb = wp[2 * c4 + 1];  // (w0[c],w1[c],w0[c+1],w1[c+1]), (c+2, c+3)
+            a0 = fmaf(v.x, wa.x, a0); a1 = fmaf(v.x, wa.y, a1);
+            c0 = fmaf(v.y, wa.z, c0); c1 = fmaf(v.y, wa.w, c1);
+            a0 = fmaf(v.z, wb.x, a0); a1 = fmaf(v.z, wb.y, a1);
+            c0 = fmaf(v.w, wb.z, c0); c1 = fmaf(v.w, wb.w, c1);
+        }
+    }
+    float o0 = a0 + c0, o1 = a1 + c1;
+    if (bias) { o0 += bias[0]; o1 += bias[1]; }
+    const float2 e = reinterpret_cast<const float2*>(eta)[p];
+    reinterpret_cast<float2*>(out)[p] = make_float2(e.x + o0, e.y + o1);
+}
+
 }  // namespace mrb
 
 using namespace mrb;
+
+extern "C" int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out,
+                                         int B, int H, int W, int cin, int k, int dil, void* stream) {
+    MRB_REQUIRE(x && w && eta && out, MRB_EINVAL, "mrb_conv_c2_nhwc_residual: null pointer");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && cin >= 4 && (cin % 4) == 0 && (k % 2) == 1 && dil >= 1, MRB_EINVAL,
+                "mrb_conv_c2_nhwc_residual: bad shape (cin must be a multiple of 4, k odd)");
+    size_t smem = (size_t)k * k * cin * sizeof(float2);
+    MRB_REQUIRE(smem <= 96 * 1024, MRB_EUNSUPPORTED, "mrb_conv_c2_nhwc_residual: weights too large");
+    MRB_CUDA(cudaFuncSetAttribute(conv_c2_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    const long long P = (long long)B * H * W;
+    conv_c2_nhwc_kernel<<<(unsigned)((P + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
+        (const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W, cin, k, dil);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
 
 extern "C" int mrb_conv2d(const void* x, long long x_bstride, const void* w, const void* bias, void* out,
                           long long out_bstride, int N, int Cin, int Cout, int H, int W, int k, int dil, int pad_mode,

@@ -142,6 +142,7 @@ __global__ void col_softdc_kernel(const float2* __restrict__ T1, const float2* _
 
 // K3: acc[b,h,w] = sum_c conj(S[b,c,h,w]) * IFFT_W(T2[b,c,h,:])  ; w = (n + rw) % W.
 // OUT_MODE 0: out [B,H,W] complex = acc*scale.   OUT_MODE 1 (RIM): out [B,4,H,W] = (eta_re, eta_im, acc*scale).
+// OUT_MODE 2 (RIM, channels-last for the tensor-core regulariser): out [B,H,W,4].
 template <int OUT_MODE>
 __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float2* __restrict__ S,
                                       const float2* __restrict__ eta, float* __restrict__ out, int C, int H, int W,
@@ -190,6 +191,10 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
         if (d < W) {
             if (OUT_MODE == 0) {
                 ((float2*)out)[((long long)b * H + h) * W + d] = cscale(acc[i], scale);
+            } else if (OUT_MODE == 2) {
+                float2 e = eta[((long long)b * H + h) * W + d];
+                reinterpret_cast<float4*>(out)[((long long)b * H + h) * W + d] =
+                    make_float4(e.x, e.y, acc[i].x * scale, acc[i].y * scale);
             } else {
                 const long long HW = (long long)H * W;
                 float2 e = eta[((long long)b * H + h) * W + d];
@@ -271,8 +276,8 @@ extern "C" size_t mrb_dc_workspace_bytes(int B, int C, int H, int W) {
 }
 
 extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* mask, int mask_dtype,
-                               int mask_b, int mask_h, float inv_sigma2, void* out, int B, int C, int H, int W,
-                               int centered, int norm, void* ws, size_t ws_bytes, void* stream) {
+                               int mask_b, int mask_h, float inv_sigma2, void* out, int out_nhwc, int B, int C, int H,
+                               int W, int centered, int norm, void* ws, size_t ws_bytes, void* stream) {
     int rc = check_dims(B, C, H, W, norm, "mrb_dc_rim_grad");
     if (rc) return rc;
     MRB_REQUIRE(eta && y && S && out && ws, MRB_EINVAL, "mrb_dc_rim_grad: null pointer");
@@ -292,14 +297,19 @@ extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, co
     if ((rc = set_smem(expand_rowfft_kernel))) return rc;
     if ((rc = set_smem(col_dc_kernel))) return rc;
     if ((rc = set_smem(rowifft_reduce_kernel<1>))) return rc;
+    if ((rc = set_smem(rowifft_reduce_kernel<2>))) return rc;
     expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1, C, H,
                                                                         W, g.cc, g.pw, rw);
     MRB_LAUNCHED();
     col_dc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(T1, (const float2*)y, T2, m, C, H, W, g.ti,
                                                                           g.ph, rh, rw, fs);
     MRB_LAUNCHED();
-    rowifft_reduce_kernel<1><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
-        T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
+    if (out_nhwc)
+        rowifft_reduce_kernel<2><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
+    else
+        rowifft_reduce_kernel<1><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
     MRB_LAUNCHED();
     return MRB_OK;
 }

@@ -267,6 +267,7 @@ class RIMBlock(nn.Module):
             self.zero = torch.zeros(1, 1, 1, 1, 1)
         self.dimensionality = dimensionality
         self.consecutive_slices = consecutive_slices
+        self._tc_engine = None  # built lazily on the first forward (tensor-core path, rim_tc.py)
 
     @torch.no_grad()
     def forward(self, pred: torch.Tensor, masked_kspace: torch.Tensor, sense: torch.Tensor, mask: torch.Tensor,
@@ -280,6 +281,7 @@ class RIMBlock(nn.Module):
         masked_kspace = _lib.require_cuda(masked_kspace, "masked_kspace").contiguous()
         sense = _lib.require_cuda(sense, "sense").contiguous()
         B, C, H, W, _ = masked_kspace.shape
+        hx_given = hx is not None
         if hx is None:  # :188-193
             hx = [masked_kspace.new_zeros((B, f, H, W)) for f in self.recurrent_filters if f != 0]
         else:
@@ -290,7 +292,15 @@ class RIMBlock(nn.Module):
         mcan = _ops.canonical_mask(mask, B, H, W)[0]  # canonicalise once for the whole time loop
         etas = []
         final = self.final_layer[0]
-        for _ in range(self.time_steps):  # :217-249
+        from .rim_tc import RimTcEngine
+
+        if self._tc_engine is None:
+            self._tc_engine = RimTcEngine(self) if RimTcEngine.supported(self) else False
+        use_tc = bool(self._tc_engine) and RimTcEngine.supported(self) and _lib.require_cuda(eta, "eta") is not None
+        if use_tc:
+            # tensor-core (tcgen05, 3xTF32) channels-last engine for the whole time loop
+            etas, hx = self._tc_engine.run(eta, masked_kspace, sense, mcan, sigma, hx if hx_given else None, ws)
+        for _ in range(0 if use_tc else self.time_steps):  # :217-249 (generic exact-fp32 kernels)
             grad_eta = _ops.dc_rim_grad(eta, masked_kspace, sense, mcan, sigma, self.fft_centered,
                                         self.fft_normalization, ws=ws)
             for h, convrnn in enumerate(self.layers):

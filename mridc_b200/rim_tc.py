@@ -1,0 +1,143 @@
+"""Tensor-core time-step engine for RIMBlock (channels-last activations, tcgen05 3xTF32 kernels of conv_tc.cu).
+
+Used by ``RIMBlock.forward`` when the block has the geometry of the shipped CIRIM/RIM configs
+(projects/reconstruction/model_zoo/conf/base_{cirim,rim}_run.yaml with recurrent_layer GRU): two
+ConvNonlinear(ReLU)+ConvGRUCell(kernel 1) stages with 64 channels and a final 64->2 ConvNonlinear.  Anything else
+runs on the generic exact-fp32 CUDA-core kernels.  Both paths are CUDA; neither is a CPU fallback.
+"""
+import os
+
+import torch
+
+from . import _lib, _ops
+
+
+def _enabled():
+    return os.environ.get("MRIDC_B200_DISABLE_TC", "0") != "1"
+
+
+class RimTcEngine:
+    def __init__(self, block):
+        self.block = block
+        self._key = None
+        self._packs = None
+
+    # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def supported(block) -> bool:
+        from .rim import ConvGRUCell, ConvNonlinear
+
+        if not _enabled() or len(block.layers) != 2:
+            return False
+        for i, st in enumerate(block.layers):
+            c, r = st.convs, st.rnn
+            if not isinstance(c, ConvNonlinear) or not isinstance(r, ConvGRUCell):
+                return False
+            if c._act != _ops.ACT_RELU or c.features != 64 or r.hidden_size != 64 or r.input_size != 64:
+                return False
+            if r.kernel_size != 1:
+                return False
+            if i == 0:
+                if not (c.input_size == 4 and c.kernel_size == 5 and c.dilation == 1):
+                    return False
+            else:
+                if c.input_size != 64 or c.kernel_size % 2 != 1 or 2 * c.kernel_size**2 > 20:
+                    return False
+        f = block.final_layer[0]
+        if not isinstance(f, ConvNonlinear) or f.features != 2 or f.input_size != 64 or f._act != _ops.ACT_NONE:
+            return False
+        if f.kernel_size % 2 != 1 or f.kernel_size**2 * 64 * 8 > 96 * 1024:
+            return False
+        return True
+
+    # ---------------------------------------------------------------------------------------------
+    def _params(self):
+        b = self.block
+        ps = []
+        for st in b.layers:
+            ps += [st.convs.conv_layer.weight, st.rnn.ih.weight, st.rnn.hh.weight]
+        return ps
+
+    def packs(self):
+        """Packed (hi/lo split, UMMA-swizzled) weights, rebuilt only when a parameter changes."""
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in self._params())
+        if key == self._key:
+            return self._packs
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        b = self.block
+        dev = b.layers[0].convs.conv_layer.weight.device
+        out = []
+        for i, stack in enumerate(b.layers):
+            c, r = stack.convs, stack.rnn
+            w = c.conv_layer.weight.detach().contiguous()
+            if i == 0:
+                pc = torch.empty(lib.mrb_tc_packed_floats(2, 64, 4, 5), dtype=torch.float32, device=dev)
+                _lib.check(lib.mrb_tc_pack_conv5x5x4(_lib.ptr(w), _lib.ptr(pc), 64, st))
+            else:
+                pc = torch.empty(lib.mrb_tc_packed_floats(0, 64, 64, c.kernel_size), dtype=torch.float32, device=dev)
+                _lib.check(lib.mrb_tc_pack_conv(_lib.ptr(w), _lib.ptr(pc), 64, 64, c.kernel_size, st))
+            pg = torch.empty(lib.mrb_tc_packed_floats(1, 64, 64, 1), dtype=torch.float32, device=dev)
+            wih = r.ih.weight.detach().contiguous()
+            whh = r.hh.weight.detach().contiguous()
+            _lib.check(lib.mrb_tc_pack_gru(_lib.ptr(wih), _lib.ptr(whh), _lib.ptr(pg), 64, 64, st))
+            out.append((pc, pg))
+        self._key, self._packs = key, out
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def conv_stack(self, g4, h, h_alt, xbuf, eta, packs=None):
+        """One time step of the regulariser (rim_block.py:233-248) on channels-last buffers: conv5x5 -> GRU ->
+        conv3x3(dil) -> GRU -> final conv + eta update.  h / h_alt are ping-pong lists, swapped in place."""
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        b = self.block
+        packs = self.packs() if packs is None else packs
+        B, H, W, _ = g4.shape
+        c0, c1 = b.layers[0].convs, b.layers[1].convs
+        r0, r1 = b.layers[0].rnn, b.layers[1].rnn
+        fin = b.final_layer[0]
+        _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias),
+                                             _lib.ptr(xbuf), B, H, W, 64, 1, st))
+        _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xbuf), _lib.ptr(h[0]), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias),
+                                       _lib.ptr(h_alt[0]), B, H, W, 64, st))
+        h[0], h_alt[0] = h_alt[0], h[0]
+        _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(h[0]), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias),
+                                        _lib.ptr(xbuf), B, H, W, 64, c1.kernel_size, c1.dilation, 1, st))
+        _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xbuf), _lib.ptr(h[1]), _lib.ptr(packs[1][1]), _lib.ptr(r1.ih.bias),
+                                       _lib.ptr(h_alt[1]), B, H, W, 64, st))
+        h[1], h_alt[1] = h_alt[1], h[1]
+        new_eta = torch.empty_like(eta)
+        _lib.check(lib.mrb_conv_c2_nhwc_residual(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight),
+                                                 _lib.ptr(fin.conv_layer.bias), _lib.ptr(eta), _lib.ptr(new_eta),
+                                                 B, H, W, 64, fin.kernel_size, fin.dilation, st))
+        return new_eta
+
+    # ---------------------------------------------------------------------------------------------
+    def run(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws):
+        """The time loop of rim_block.py:217-249.  eta [B,H,W,2]; hx: list of 2 NCHW-shaped tensors or None.
+        Returns (list of etas, [h0, h1]) with the hidden states NCHW-shaped (channels-last strides)."""
+        lib = _lib.load()
+        b = self.block
+        B, C, H, W, _ = masked_kspace.shape
+        dev = masked_kspace.device
+        packs = self.packs()
+        st = _lib.stream_ptr()
+
+        def nhwc_state(t):
+            if t is None:
+                return torch.zeros((B, H, W, 64), dtype=torch.float32, device=dev)
+            return t.permute(0, 2, 3, 1).contiguous()
+
+        h = [nhwc_state(hx[0] if hx is not None else None), nhwc_state(hx[1] if hx is not None else None)]
+        h_alt = [torch.empty_like(h[0]), torch.empty_like(h[1])]
+        xbuf = torch.empty((B, H, W, 64), dtype=torch.float32, device=dev)
+        g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        etas = []
+        eta = eta.contiguous()
+        for _ in range(b.time_steps):
+            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
+                             ws=ws, nhwc=True)
+            eta = self.conv_stack(g4, h, h_alt, xbuf, eta, packs)
+            etas.append(eta)
+        return etas, [h[0].permute(0, 3, 1, 2), h[1].permute(0, 3, 1, 2)]

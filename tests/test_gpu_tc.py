@@ -1,0 +1,140 @@
+"""GPU: tensor-core (tcgen05 / TMEM, 3xTF32) RIM regulariser kernels against the CPU oracle and the exact-fp32
+CUDA-core kernels.  Tolerance: rel-L2 <= 5e-6 per operator: the error-compensated 3xTF32 products are fp32-grade
+(~2^-23); what remains is the tensor core's truncating fp32 accumulation over the K chain (measured 1e-6 .. 3e-6
+at K = 576).  Plain TF32 would sit at ~5e-4; the end-to-end budget is 1e-4 with ~2x amplification."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(kind, w, w2=None, k=1):
+    from mridc_b200 import _lib
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    w = w.contiguous()
+    if kind == 2:
+        p = torch.empty(lib.mrb_tc_packed_floats(2, w.shape[0], 4, 5), device="cuda")
+        _lib.check(lib.mrb_tc_pack_conv5x5x4(_lib.ptr(w), _lib.ptr(p), w.shape[0], st))
+    elif kind == 0:
+        p = torch.empty(lib.mrb_tc_packed_floats(0, w.shape[0], 64, k), device="cuda")
+        _lib.check(lib.mrb_tc_pack_conv(_lib.ptr(w), _lib.ptr(p), w.shape[0], 64, k, st))
+    else:
+        p = torch.empty(lib.mrb_tc_packed_floats(1, 64, 64, 1), device="cuda")
+        _lib.check(lib.mrb_tc_pack_gru(_lib.ptr(w), _lib.ptr(w2), _lib.ptr(p), 64, 64, st))
+    return p
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (1, 320, 320)])
+def test_tc_ops_vs_oracle(B, H, W):
+    from mridc_b200 import _lib
+    from oracle import nets as onets
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(H)
+
+    def nhwc(t):
+        return t.permute(0, 2, 3, 1).contiguous().cuda()
+
+    # NB: every device tensor is bound to a name before its pointer is taken (a temporary would be returned to
+    # the caching allocator -- and possibly reused -- before the kernel is even launched).
+    # conv 5x5 over the 4-channel gradient
+    x4 = torch.randn(B, 4, H, W, generator=g)
+    w1 = torch.randn(64, 4, 5, 5, generator=g) * 0.2
+    b1 = torch.randn(64, generator=g)
+    ref = onets.conv_nonlinear(x4, w1, b1, 5, 1, "relu")
+    out = torch.empty(B, H, W, 64, device="cuda")
+    x4d, p1, b1d = nhwc(x4), _pack(2, w1.cuda()), b1.cuda()
+    _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(x4d), _lib.ptr(p1), _lib.ptr(b1d), _lib.ptr(out), B, H, W, 64, 1, st))
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
+    # conv 3x3 dilation 2 (and dilation 1), 64 -> 64
+    x = torch.randn(B, 64, H, W, generator=g)
+    xd = nhwc(x)
+    for dil, relu in ((2, 1), (1, 0)):
+        w2 = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+        b2 = torch.randn(64, generator=g)
+        ref = onets.conv_nonlinear(x, w2, b2, 3, dil, "relu" if relu else None)
+        p2, b2d = _pack(0, w2.cuda(), k=3), b2.cuda()
+        _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(xd), _lib.ptr(p2), _lib.ptr(b2d), _lib.ptr(out), B, H, W, 64, 3, dil,
+                                        relu, st))
+        assert rel_l2(out.permute(0, 3, 1, 2), ref) < 5e-6, dil
+    # ConvGRU cell, kernel size 1
+    h = torch.randn(B, 64, H, W, generator=g)
+    wih = torch.randn(192, 64, 1, 1, generator=g) * 0.1
+    whh = torch.randn(192, 64, 1, 1, generator=g) * 0.1
+    bih = torch.randn(192, generator=g)
+    ref = onets.conv_gru_cell(x, h, wih, bih, whh, 1, 1)
+    hd, pg, bihd = nhwc(h), _pack(1, wih.cuda(), whh.cuda()), bih.cuda()
+    _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pg), _lib.ptr(bihd), _lib.ptr(out), B, H, W, 64,
+                                   st))
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
+    # final conv 64 -> 2 with the eta update
+    w3 = torch.randn(2, 64, 3, 3, generator=g) * 0.05
+    eta = torch.randn(B, H, W, 2, generator=g)
+    ref = eta + onets.conv_nonlinear(x, w3, None, 3, 1, None).permute(0, 2, 3, 1)
+    o2 = torch.empty(B, H, W, 2, device="cuda")
+    w3d, etad = w3.cuda(), eta.cuda()
+    _lib.check(lib.mrb_conv_c2_nhwc_residual(_lib.ptr(xd), _lib.ptr(w3d), None, _lib.ptr(etad), _lib.ptr(o2), B, H, W,
+                                             64, 3, 1, st))
+    assert rel_l2(o2, ref) < 2e-6
+
+
+def test_dc_nhwc_layout_matches_nchw():
+    from mridc_b200 import _ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, C, H, W = 2, 5, 24, 20
+    y = torch.randn(B, C, H, W, 2, device="cuda", generator=g)
+    S = torch.randn(B, C, H, W, 2, device="cuda", generator=g)
+    eta = torch.randn(B, H, W, 2, device="cuda", generator=g)
+    m = (torch.rand(1, 1, 1, W, 1, device="cuda", generator=g) < 0.5).float()
+    a = _ops.dc_rim_grad(eta, y, S, m, 1.0, True, "ortho")
+    b = _ops.dc_rim_grad(eta, y, S, m, 1.0, True, "ortho", nhwc=True)
+    assert torch.equal(a, b.permute(0, 3, 1, 2))
+
+
+def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch):
+    """The shipped geometry (64 filters, GRU k=1): tensor-core engine == exact-fp32 kernels == oracle."""
+    from mridc_b200 import synth
+    from mridc_b200.rim import RIMBlock
+    from mridc_b200.rim_tc import RimTcEngine
+    from oracle import nets as onets
+
+    cfg = synth.cirim_cfg("GRU", centered=True, normalization="ortho")
+    kw = {k: cfg[k] for k in ("recurrent_layer", "conv_filters", "conv_kernels", "conv_dilations", "conv_bias",
+                              "recurrent_filters", "recurrent_kernels", "recurrent_dilations", "recurrent_bias",
+                              "depth", "time_steps", "conv_dim", "no_dc", "fft_centered", "fft_normalization",
+                              "spatial_dims", "coil_dim", "dimensionality")}
+    torch.manual_seed(3)
+    blk = RIMBlock(**kw).eval()
+    with torch.no_grad():
+        for st in blk.layers:
+            st.convs.conv_layer.bias.normal_(0, 0.1)
+            st.rnn.ih.bias.normal_(0, 0.1)
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    batch = synth.make_batch(2, 6, 48, 40, centered=True, normalization="ortho")
+    y, S, m = batch["y"], batch["sensitivity_maps"], batch["mask"]
+    with torch.no_grad():
+        ref, ref_h = onets.rim_block(sd, dict(cfg), y.clone(), y, S, m, None, None, 1.0, False)
+    blk = blk.cuda()
+    assert RimTcEngine.supported(blk)
+    etas, hx = blk(y.cuda(), y.cuda(), S.cuda(), m.cuda(), None, None, 1.0, False)
+    assert blk._tc_engine and len(etas) == 8
+    assert hx[0].shape == (2, 64, 48, 40)
+    for a, b in zip(etas, ref):
+        assert rel_l2(a, b) < 1e-5
+    assert rel_l2(hx[0], ref_h[0]) < 1e-5 and rel_l2(hx[1], ref_h[1]) < 1e-5
+    monkeypatch.setenv("MRIDC_B200_DISABLE_TC", "1")
+    etas32, hx32 = blk(y.cuda(), y.cuda(), S.cuda(), m.cuda(), None, None, 1.0, False)
+    assert rel_l2(etas[-1], etas32[-1]) < 1e-5 and rel_l2(hx[1], hx32[1]) < 1e-5
+    # continuing from given hidden states (NCHW in, as the reference API)
+    monkeypatch.delenv("MRIDC_B200_DISABLE_TC")
+    e2, h2 = blk(etas, y.cuda(), S.cuda(), m.cuda(), None, [t.contiguous() for t in hx32], 1.0, True)
+    with torch.no_grad():
+        r2, _ = onets.rim_block(sd, dict(cfg), ref, y, S, m, None, [t.clone() for t in ref_h], 1.0, True)
+    assert rel_l2(e2[-1], r2[-1]) < 2e-5
