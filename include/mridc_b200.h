@@ -194,6 +194,10 @@ int mrb_normunet_out(const void* x, const void* mean_std, void* out, int B, int 
 /* profiling switches for the tensor-core kernel (bit 0: skip MMAs, 1: skip global loads, 2: skip epilogue);
  * results are garbage when non-zero -- used only by tools/ to attribute time to the kernel's roles. */
 void mrb_tc_set_debug(int flags);
+/* device buffer of 148*16 uint64 cycle counters written by the kernel's roles (null = off; tools/ only) */
+void mrb_tc_set_prof(void* buf);
+/* tcgen05.mma issue/dependency micro-benchmark (tools/ only): out[0] = issue cycles, out[1] = cycles to completion */
+int mrb_tc_microbench(int N, int nacc, int iters, int a_in_tmem, void* out, void* stream);
 /* floats needed by the pack: kind 0 = conv k x k (cin 64), 1 = GRU 1x1 (64 -> 64), 2 = conv 5x5 over 4 channels */
 size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k);
 /* w [cout, 64, k, k] (conv_layers.py:78-85) */

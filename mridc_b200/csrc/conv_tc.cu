@@ -8,31 +8,37 @@
 //     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,    x_hi = rn_tf32(x), x_lo = rn_tf32(x - x_hi)
 // with fp32 accumulation in TMEM (split error and dropped term a_lo*b_lo are both ~2^-24 relative).
 //
-// Structure: one persistent CTA per SM.  Work item = (128-pixel tile, half of the output channels).  The
-// weights of the CTA's channel half (hi and lo, pre-packed in the UMMA K-major SWIZZLE_128B layout) stay
-// resident in shared memory for the whole kernel; activations stream through a ring of stages:
-//   loader warps (2 groups x 4, alternating segments) gather a [128 px x 32 ch] fp32 chunk per "segment"
-//                     (source tensor, tap offset with replicate clamp, channel chunk), split it into hi/lo and
-//                     store both in the swizzled layout (no TMA descriptor: the gather does the clamp that TMA's
-//                     zero fill cannot); the global loads of a group's next segment are in flight (registers)
-//                     while it converts and stores the current one;
-//   MMA warp (1 lane) issues 4 k-steps x 3 tcgen05.mma.kind::tf32 per segment into the TMEM accumulator and
-//                     tcgen05.commit's the stage back to the loaders / the accumulator to the epilogue;
-//   epilogue warps (8) tcgen05.ld the accumulator (one pixel per thread), apply bias + ReLU or the GRU gates,
-//                     and write NHWC.  Two TMEM accumulator buffers overlap the epilogue with the next tile.
+// Structure: one persistent CTA per SM.  Work item = (128-pixel tile, half of the output channels).
+//   * B operand = the weights of the CTA's channel half (hi and lo, pre-packed in the UMMA K-major SWIZZLE_128B
+//     layout): copied to shared memory once and resident for the whole kernel.
+//   * A operand = activations, held in TENSOR MEMORY (tcgen05.mma with A from TMEM): a ring of TMEM stages of
+//     64 columns (32 hi + 32 lo tf32 columns = one 32-channel K chunk for the 128 pixels/lanes).  Shared memory
+//     therefore carries no activation traffic for the MMAs, and the ring is deep (5-6 stages) although the
+//     resident weights fill most of shared memory -- the mbarrier round trip loader -> MMA -> commit -> loader
+//     measured at ~2k cycles needs that depth.
+//   loader warps (2 groups x 4, alternating segments): coalesced gather of a [128 px x 32 ch] fp32 chunk per
+//                     "segment" (source tensor, tap offset with replicate clamp, channel chunk) with the next
+//                     segment's loads in flight in registers; a per-warp 4 KB swizzled staging tile turns the
+//                     coalesced (4 rows x 128 B per instruction) view into row ownership (thread = pixel = TMEM
+//                     lane); split into hi/lo and tcgen05.st into the stage;
+//   MMA warp (1 lane) 4 k-steps x 3 tcgen05.mma.kind::tf32 per segment (A from TMEM, B descriptor in smem) and
+//                     tcgen05.commit of the stage back to the loaders / of the accumulator to the epilogue;
+//   epilogue warps (8) tcgen05.ld the accumulator (one pixel per thread, 2 warps per lane quadrant), apply
+//                     bias + ReLU or the GRU gates, and write NHWC.
 #include "common.cuh"
 
 namespace mrb {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int KC = 32;                        // channels per K chunk = one 128-byte swizzle row
-constexpr int CHUNK_BYTES = TILE_M * 128;     // A chunk (hi or lo): 16 KB
-constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;  // hi + lo
+constexpr int KC = 32;                        // channels per K chunk (32 tf32 columns of TMEM / one 128-byte B row)
+constexpr int A_STAGE_COLS = 2 * KC;          // hi + lo
 constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant (each takes half of the channels)
 constexpr int LOAD_GROUPS = 2, LOAD_WARPS = 4 * LOAD_GROUPS;  // loader groups alternate segments
 constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + 1) * 32;
 constexpr int MAX_SEGS = 20;
+constexpr int MAX_STAGES = 6;
+constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
 
 enum Mode { MODE_CONV_RELU = 0, MODE_GRU = 1, MODE_CONV_NOACT = 2 };
 
@@ -60,13 +66,17 @@ struct Params {
     int wchunk_rows;         // rows (N) of one resident weight chunk
     int n_wchunks;
     int acc_cols;            // TMEM columns of one accumulator buffer
-    int tmem_cols;           // allocation (power of two >= 2*acc_cols)
+    int acc_bufs;            // 1 or 2 accumulator buffers
+    int tmem_cols;           // allocation: 512
     int cout;                // output channels per pixel (both halves)
     int nhalf;               // output channels handled per item (cout / 2)
     int mode;
-    int stages;
+    int tb_depth;            // cp.async staging tiles per loader warp (2 or 3)
+    int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
     int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
+    unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py); null in production
     int debug;               // profiling switches (mrb_tc_set_debug): 1 skip MMAs, 2 skip global loads, 4 skip epilogue math
+    int stacked;             // 1: stacked-B issue (2 MMAs per k-step); requires small_off == n of every segment
     int small_off;           // != 0: the two cross terms (lo*hi, hi*lo) accumulate in columns dcol + small_off, so the
                              // long hi*hi chain sees 3x fewer (truncating) tensor-core accumulations; summed in the epilogue
     Segment seg[MAX_SEGS];
@@ -93,6 +103,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// polling wait with back-off: waiting warps must not steal issue slots from the single MMA-issuing thread
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try(bar, parity)) __nanosleep(ns);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -122,6 +149,93 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 tf32 columns starting at a_tmem
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// One segment = 4 k-steps x (lo*hi, hi*lo -> ds ; hi*hi -> d), issued from a single asm block: the issuing thread is
+// latency-bound (one dependent scalar instruction every few cycles, ~45 cycles minimum between MMAs measured with
+// tools/tc_microbench.py), so nothing but the MMAs themselves may sit between them.
+__device__ __forceinline__ void umma_segment_ts(uint32_t d, uint32_t ds, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
+                                                uint64_t dbl, uint32_t idesc, uint32_t acc_small0, uint32_t acc_big0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ps, pb, pt;\n\t"
+        ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
+        ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
+        "setp.ne.b32 ps, %7, 0;\n\t"
+        "setp.ne.b32 pb, %8, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
+        "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
+        "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
+        "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, ps;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %6, pb;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah1], bl1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah2], bl2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah3], bl3, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %6, pt;\n\t"
+        "}\n" ::"r"(d),
+        "r"(ds), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small0), "r"(acc_big0)
+        : "memory");
+}
+// Stacked-B variant (2 MMAs per k-step instead of 3): the packed weight chunk holds the hi rows immediately followed
+// by the lo rows, so ONE descriptor with N = 2n multiplies a_hi by [b_hi ; b_lo] -> columns [d, d+n) = a_hi*b_hi and
+// [d+n, d+2n) = a_hi*b_lo; the second MMA adds a_lo*b_hi (N = n) onto the cross-term columns [d+n, d+2n).
+__device__ __forceinline__ void umma_segment_ts_stacked(uint32_t d, uint32_t dsm, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
+                                                        uint32_t idesc2n, uint32_t idescn, uint32_t acc0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pa, pt;\n\t"
+        ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
+        ".reg .b64 bh1, bh2, bh3;\n\t"
+        "setp.ne.b32 pa, %7, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
+        "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
+        "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %5, pa;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
+        "}\n" ::"r"(d),
+        "r"(dsm), "r"(a_hi), "r"(a_lo), "l"(dbh), "r"(idesc2n), "r"(idescn), "r"(acc0)
+        : "memory");
+}
+struct SegIssue {  // per-segment operands of the MMA issuer, built once per CTA in shared memory
+    uint64_t dbh, dbl;
+    uint32_t idesc, dcol, first, idesc2n;
+};
+// registers -> TMEM: 16 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // TMEM -> registers: 8 consecutive columns of this thread's lane.  The wait is part of the same asm statement so
 // that no consumer of v[] can be scheduled before the asynchronous load has landed.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -159,24 +273,27 @@ __device__ __forceinline__ float tf32_rn(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+// gate non-linearities on the SFU (ex2.approx + rcp.approx, ~2 ulp): |error| ~1e-7 on outputs in [-1, 1]
+__device__ __forceinline__ float sigmoid_acc(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_acc(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // layout: [weights resident][stages][barriers]
+    // layout: [weights resident][loader staging tiles][barriers]
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int wbytes_chunk = P.wchunk_rows * 128;
     uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
-    uint8_t* st_s = w_s + (size_t)P.n_wchunks * 2 * wbytes_chunk;     // stages (1024-aligned: chunks are multiples of 1 KB)
-    uint64_t* bars = (uint64_t*)(st_s + (size_t)P.stages * STAGE_BYTES);
-    uint64_t* full = bars;                  // [stages]
-    uint64_t* empty = bars + P.stages;      // [stages]
-    uint64_t* acc_full = bars + 2 * P.stages;   // [2]
-    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint8_t* tb_s = w_s + (size_t)P.n_wchunks * 2 * wbytes_chunk;     // [LOAD_WARPS][32 rows x 128 B]
+    uint64_t* bars = (uint64_t*)(tb_s + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES);
+    uint64_t* full = bars;                          // [MAX_STAGES]
+    uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;             // [2]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    SegIssue* seg_tab = (SegIssue*)(acc_empty + 4);  // [MAX_SEGS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = blockIdx.x & 1;
@@ -185,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
-            mbar_init(&full[s], 128);  // one loader group fills a stage
+            mbar_init(&full[s], 128);  // one loader group (4 warps) fills a stage
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -193,6 +310,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             mbar_init(&acc_empty[b], EPI_WARPS * 32);
         }
         fence_barrier_init();
+    }
+    if ((int)threadIdx.x < P.nseg) {
+        const Segment sg = P.seg[threadIdx.x];
+        const uint32_t b_hi = smem_u32(w_s + (size_t)sg.wchunk * 2 * wbytes_chunk);
+        SegIssue si;
+        si.dbh = make_desc(b_hi);
+        si.dbl = make_desc(b_hi + wbytes_chunk);
+        si.idesc = make_idesc(TILE_M, sg.n);
+        si.dcol = (uint32_t)sg.dcol;
+        si.first = (uint32_t)sg.first;
+        si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
+        seg_tab[threadIdx.x] = si;
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
@@ -207,89 +336,150 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_col0 = (uint32_t)(P.acc_bufs * P.acc_cols);  // first TMEM column of the A ring
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + LOAD_WARPS) {
         // ============================== LOADERS ==============================
         const int lw = warp - EPI_WARPS;
         const int grp = lw >> 2;                     // loader group: handles segments grp, grp + 2, ...
-        const int lt = (lw & 3) * 32 + lane;         // 0..127 within the group
-        const int c16 = lt & 7;                      // 16-byte chunk within the 128-byte row
-        const int r0 = lt >> 3;                      // rows r0 + 16*i
+        const int quad = lw & 3;                     // == warp % 4: the TMEM lane quadrant this warp may write
+        const int c16 = lane & 7;                    // 16-byte chunk within the 128-byte row (coalesced view)
+        const int rl0 = lane >> 3;                   // rows rl0 + 4*i of the warp's 32 rows (coalesced view)
+        uint8_t* tbuf = tb_s + (size_t)lw * P.tb_depth * TBUF_BYTES;  // tb_depth staging tiles of this warp
+        const uint32_t W32 = (uint32_t)P.W, H32 = (uint32_t)P.H;
         int pb[8], py[8], px[8];
         bool pv[8];
         int coords_tile = -1;
+        bool uniform_rows = false;
 
-        auto issue_loads = [&](int tile, int sgi, float4(&v)[8]) {
+        // cp.async gather of one segment into staging tile `slot` (no registers held while in flight)
+        auto issue_loads = [&](int tile, int sgi, int slot) {
             if (tile != coords_tile) {
                 coords_tile = tile;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    long long p = (long long)tile * TILE_M + r0 + 16 * i;
+                    const long long p = (long long)tile * TILE_M + quad * 32 + rl0 + 4 * i;
                     pv[i] = p < P.P;
-                    long long q = pv[i] ? p : 0;
-                    px[i] = (int)(q % P.W);
-                    long long t = q / P.W;
-                    py[i] = (int)(t % P.H);
-                    pb[i] = (int)(t / P.H);
+                    const uint32_t q = pv[i] ? (uint32_t)p : 0u;  // P.P < 2^31 (checked on the host)
+                    const uint32_t t = q / W32;
+                    px[i] = (int)(q - t * W32);
+                    const uint32_t b = t / H32;
+                    py[i] = (int)(t - b * H32);
+                    pb[i] = (int)b;
                 }
+                uniform_rows = pv[7] && py[7] == py[0] && pb[7] == pb[0];
             }
             const Segment sg = P.seg[sgi];
             const float* src = P.src[sg.src];
             const int cs = P.cs[sg.src];
+            uint8_t* tb = tbuf + (size_t)slot * TBUF_BYTES;
+            if (!P.im2col && uniform_rows) {
+                // fast path: rows rl0 + 4*i are 4 pixels apart on one image row; only y may clamp (uniformly)
+                const int xlo = px[0] + sg.dx, xhi = px[0] + 28 + sg.dx;
+                if (xlo >= 0 && xhi < P.W) {
+                    const int yy = min(max(py[0] + sg.dy, 0), P.H - 1);
+                    const float* g = src + (((long long)pb[0] * P.H + yy) * P.W + xlo) * cs + sg.c0 + c16 * 4;
+                    const uint32_t nbytes = (P.debug & 2) ? 0u : 16u;
+                    const uint32_t sbase = smem_u32(tb);
+                    const long long gstep = 4ll * cs;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + swz(rl0 + 4 * i, c16)),
+                                     "l"(g + i * gstep), "r"(nbytes)
+                                     : "memory");
+                    return;
+                }
+            }
+            int dy = sg.dy, dx = sg.dx, coff = sg.c0 + c16 * 4;
+            bool tap_ok = true;
+            if (P.im2col) {
+                // chunk c16 of im2col row = tap t of the 5x5 window (4 channels = one float4)
+                const int t = sg.c0 * 8 + c16;
+                tap_ok = t < 25;
+                dy = t / 5 - 2; dx = t % 5 - 2; coff = 0;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pv[i] && !(P.debug & 2)) {
-                    if (P.im2col) {
-                        // chunk c16 of im2col row = tap t of the 5x5 window (4 channels = one float4)
-                        const int t = sg.c0 * 8 + c16;
-                        if (t < 25) {
-                            int yy = min(max(py[i] + t / 5 - 2, 0), P.H - 1);
-                            int xx = min(max(px[i] + t % 5 - 2, 0), P.W - 1);
-                            v[i] = __ldg(reinterpret_cast<const float4*>(src + (((long long)pb[i] * P.H + yy) * P.W + xx) * 4));
-                        }
-                    } else {
-                        int yy = min(max(py[i] + sg.dy, 0), P.H - 1);
-                        int xx = min(max(px[i] + sg.dx, 0), P.W - 1);
-                        v[i] = __ldg(reinterpret_cast<const float4*>(src + (((long long)pb[i] * P.H + yy) * P.W + xx) * cs +
-                                                                     sg.c0 + c16 * 4));
-                    }
-                }
+                const int r = rl0 + 4 * i;
+                const int yy = min(max(py[i] + dy, 0), P.H - 1);
+                const int xx = min(max(px[i] + dx, 0), P.W - 1);
+                const float* g = src + (((long long)pb[i] * P.H + yy) * P.W + xx) * cs + coff;
+                const uint32_t nbytes = (pv[i] && tap_ok && !(P.debug & 2)) ? 16u : 0u;  // 0 -> zero fill
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(tb + swz(r, c16))), "l"(g),
+                             "r"(nbytes)
+                             : "memory");
             }
         };
 
-        int it = 0, tile = first_tile, sgi = grp;
-        bool have = tile < P.n_tiles && sgi < P.nseg;
-        float4 vc[8], vn[8];
-        if (have) issue_loads(tile, sgi, vc);
-        while (have) {
-            int nsgi = sgi + LOAD_GROUPS, nit = it, ntile = tile;
-            if (nsgi >= P.nseg) { nsgi = grp; nit = it + 1; ntile = tile + tile_stride; }
-            const bool nhave = ntile < P.n_tiles;
-            if (nhave) issue_loads(ntile, nsgi, vn);  // in flight while the current chunk is converted and stored
-            const int sglob = it * P.nseg + sgi;
-            const int stage = sglob % P.stages;
-            const uint32_t phase = (uint32_t)(sglob / P.stages) & 1u;
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* a_hi = st_s + (size_t)stage * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + CHUNK_BYTES;
+        // this group's segment sequence (every LOAD_GROUPS-th global segment); all indices advance incrementally --
+        // the loader warps are instruction-issue bound, so no divisions in the per-segment path
+        const int spg = P.nseg / LOAD_GROUPS;
+        int n_items = 0;
+        for (int t = first_tile; t < P.n_tiles; t += tile_stride) ++n_items;
+        const int n_total = n_items * spg;
+        long long t_start = clock64(), t_wait = 0, t_st = 0, t_issue = 0, c0;
+        const int D = P.tb_depth;
+        // prefetch cursor
+        int pf_n = 0, pf_tile = first_tile, pf_sgi = grp, pf_slot = 0;
+        auto prefetch_next = [&]() {
+            if (pf_n < n_total) issue_loads(pf_tile, pf_sgi, pf_slot);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++pf_n;
+            pf_sgi += LOAD_GROUPS;
+            if (pf_sgi >= P.nseg) { pf_sgi = grp; pf_tile += tile_stride; }
+            if (++pf_slot == D) pf_slot = 0;
+        };
+        for (int n = 0; n < D - 1; ++n) prefetch_next();
+        // consume cursor: global segment index advances by LOAD_GROUPS (nseg is a multiple of it)
+        int slot = 0;
+        int stage = grp % P.stages;
+        uint32_t phase = (uint32_t)(grp / P.stages) & 1u;
+        for (int n = 0; n < n_total; ++n) {
+            c0 = clock64();
+            prefetch_next();
+            t_issue += clock64() - c0;
+            if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __syncwarp();
+            const uint8_t* tb = tbuf + (size_t)slot * TBUF_BYTES;
+            c0 = clock64();
+            mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+            t_wait += clock64() - c0;
+            tc_fence_after();
+            c0 = clock64();
+            // row ownership: thread = row `lane` of the warp's 32 rows = TMEM lane quad*32 + lane
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 16 * i;
-                float4 hi = make_float4(tf32_rn(vc[i].x), tf32_rn(vc[i].y), tf32_rn(vc[i].z), tf32_rn(vc[i].w));
-                float4 lo = make_float4(tf32_rn(vc[i].x - hi.x), tf32_rn(vc[i].y - hi.y), tf32_rn(vc[i].z - hi.z),
-                                        tf32_rn(vc[i].w - hi.w));
-                const uint32_t o = swz(r, c16);
+            for (int hf = 0; hf < 2; ++hf) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 a = *reinterpret_cast<const float4*>(tb + swz(lane, hf * 4 + c));
+                    // hi = rn_tf32(a) (exact tf32); lo = a - hi is exact in fp32 with |lo| <= 2^-12 |a|, and the tensor
+                    // core's own truncation of lo to tf32 costs <= 2^-23 |a|: no second conversion needed
+                    hi[4 * c + 0] = tf32_rn(a.x); lo[4 * c + 0] = a.x - hi[4 * c + 0];
+                    hi[4 * c + 1] = tf32_rn(a.y); lo[4 * c + 1] = a.y - hi[4 * c + 1];
+                    hi[4 * c + 2] = tf32_rn(a.z); lo[4 * c + 2] = a.z - hi[4 * c + 2];
+                    hi[4 * c + 3] = tf32_rn(a.w); lo[4 * c + 3] = a.w - hi[4 * c + 3];
+                }
                 if (!(P.debug & 8)) {
-                    *reinterpret_cast<float4*>(a_hi + o) = hi;
-                    *reinterpret_cast<float4*>(a_lo + o) = lo;
+                    tmem_st16(ta + hf * 16, hi);
+                    tmem_st16(ta + KC + hf * 16, lo);
                 }
             }
-            if (!(P.debug & 16)) fence_proxy_async();
+            tmem_st_wait();
+            tc_fence_before();
             mbar_arrive(&full[stage]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vc[i] = vn[i];
-            it = nit; tile = ntile; sgi = nsgi; have = nhave;
+            __syncwarp();  // every lane has read its row before the slot is refilled
+            t_st += clock64() - c0;
+            if (++slot == D) slot = 0;
+            stage += LOAD_GROUPS;
+            while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (P.prof && lane == 0 && lw == 0) {
+            unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+            o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_st; o[3] = t_issue;
         }
     } else if (warp == EPI_WARPS + LOAD_WARPS) {
         // ============================== MMA ISSUER ==============================
@@ -297,39 +487,45 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, c0;
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
-                const int buf = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int buf = it % P.acc_bufs;
+                const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
+                c0 = clock64();
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+                t_wacc += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + (uint32_t)(buf * P.acc_cols);
                 for (int sgi = 0; sgi < P.nseg; ++sgi) {
-                    const Segment sg = P.seg[sgi];
+                    const SegIssue si = seg_tab[sgi];
+                    c0 = clock64();
                     mbar_wait(&full[stage], phase);
+                    t_wfull += clock64() - c0;
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(st_s + (size_t)stage * STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + CHUNK_BYTES;
-                    const uint32_t b_hi = smem_u32(w_s + (size_t)sg.wchunk * 2 * wbytes_chunk);
-                    const uint32_t b_lo = b_hi + wbytes_chunk;
-                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo);
-                    const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-                    const uint32_t idesc = make_idesc(TILE_M, sg.n);
-                    const uint32_t d = d_base + (uint32_t)sg.dcol;
-                    const uint32_t ds = d + (uint32_t)P.small_off;
-                    const bool split = P.small_off != 0;
-#pragma unroll
-                    for (int k = 0; k < KC / 8; ++k) {
-                        if (P.debug & 1) break;
-                        const uint64_t ko = (uint64_t)(k * 2);  // 32 bytes per k-step, in 16-byte units
-                        const bool fresh = sg.first && k == 0;
-                        umma_tf32(ds, dal + ko, dbh + ko, idesc, fresh ? 0u : 1u);
-                        umma_tf32(ds, dah + ko, dbl + ko, idesc, 1u);
-                        umma_tf32(d, dah + ko, dbh + ko, idesc, (fresh && split) ? 0u : 1u);
+                    const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
+                    const uint32_t d = d_base + si.dcol;
+                    const uint32_t fresh = si.first;
+                    c0 = clock64();
+                    if (P.debug & 1) {
+                    } else if (P.stacked) {
+                        // the first stacked MMA of a fresh accumulator overwrites both [d, d+n) and [d+n, d+2n)
+                        umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc,
+                                                fresh ? 0u : 1u);
+                    } else {
+                        umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc,
+                                        fresh ? 0u : 1u, (fresh && P.small_off != 0) ? 0u : 1u);
                     }
+                    t_mma += clock64() - c0;
+                    c0 = clock64();
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    t_commit += clock64() - c0;
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);
+            }
+            if (P.prof) {
+                unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+                o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit;
             }
         }
     } else {
@@ -339,10 +535,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const int m = quad * 32 + lane;        // TMEM lane = pixel row of the tile
         const int j_lo = chalf * (P.nhalf / 2), j_hi = j_lo + P.nhalf / 2;
         int it = 0;
+        long long e_start = clock64(), e_wait = 0;
         for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
-            const int buf = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&acc_full[buf], acc_phase);
+            const int buf = it % P.acc_bufs;
+            const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
+            long long c0 = clock64();
+            mbar_wait_sleep(&acc_full[buf], acc_phase, 256);
+            e_wait += clock64() - c0;
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_cols);
             const long long p = (long long)tile * TILE_M + m;
@@ -377,7 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                             // rnn_cells.py:121-125
                             const float r = sigmoid_acc((xr[q] + br) + hr[q]);
                             const float z = sigmoid_acc((xz[q] + bz) + hz[q]);
-                            const float n = tanhf((xn[q] + bn) + r * hn[q]);
+                            const float n = tanh_acc((xn[q] + bn) + r * hn[q]);
                             o[q] = n * (1.f - z) + z * hp[q];
                         }
                         float4* op = reinterpret_cast<float4*>(P.out + p * Ch + ch0 + j);
@@ -410,6 +609,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
+        }
+        if (P.prof && threadIdx.x == 0) {
+            unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+            o[8] = clock64() - e_start; o[9] = e_wait;
         }
     }
     tc_fence_before();
@@ -471,16 +674,25 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 }
 
 static size_t smem_needed(const Params& P) {
-    return 1024 + (size_t)P.n_wchunks * 2 * P.wchunk_rows * 128 + (size_t)P.stages * STAGE_BYTES + 256;
+    return 1024 + (size_t)P.n_wchunks * 2 * P.wchunk_rows * 128 + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 +
+           MAX_SEGS * sizeof(SegIssue);
 }
 
 static int g_debug = 0;
+static unsigned long long* g_prof = nullptr;
 
 static int launch(Params& P, cudaStream_t st) {
     P.debug = g_debug;
+    P.prof = g_prof;
     const size_t max_smem = device_max_smem_optin();
-    P.stages = 4;
-    while (P.stages > 2 && smem_needed(P) > max_smem) --P.stages;
+    P.tmem_cols = 512;
+    P.stages = (512 - P.acc_bufs * P.acc_cols) / A_STAGE_COLS;
+    if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
+    MRB_REQUIRE(P.stages >= 2, MRB_EUNSUPPORTED, "tensor-core conv: accumulator leaves no room for the TMEM A ring");
+    MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
+    MRB_REQUIRE((P.nseg % LOAD_GROUPS) == 0, MRB_EUNSUPPORTED, "tensor-core conv: odd segment count");
+    P.tb_depth = 3;
+    if (smem_needed(P) > max_smem) P.tb_depth = 2;
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
     MRB_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     int sms = device_sm_count();
@@ -497,6 +709,7 @@ static int launch(Params& P, cudaStream_t st) {
 using namespace mrb;
 
 extern "C" void mrb_tc_set_debug(int flags) { tc::g_debug = flags; }
+extern "C" void mrb_tc_set_prof(void* buf) { tc::g_prof = (unsigned long long*)buf; }
 
 extern "C" size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k) {
     // kind 0: conv k x k (cin multiple of 32); 1: GRU 1x1 (cout = hidden, cin = 64 for both inputs); 2: conv 5x5 x 4ch
@@ -559,8 +772,8 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
     P.wchunk_rows = cout / 2; P.n_wchunks = k * k * 2;
     P.acc_cols = cout;  // hi*hi chain + cross-term chain
     P.small_off = cout / 2;
-    P.tmem_cols = 32;
-    while (P.tmem_cols < 2 * P.acc_cols) P.tmem_cols *= 2;
+    P.stacked = 1;
+    P.acc_bufs = (2 * cout <= 512 - 2 * tc::A_STAGE_COLS) ? 2 : 1;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.nseg = k * k * 2;
     const int pad = dil * (k - 1) / 2;
@@ -589,8 +802,8 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
     P.wchunk_rows = cout / 2; P.n_wchunks = 4;
     P.acc_cols = cout;
     P.small_off = cout / 2;
-    P.tmem_cols = 32;
-    while (P.tmem_cols < 2 * P.acc_cols) P.tmem_cols *= 2;
+    P.stacked = 1;
+    P.acc_bufs = (2 * cout <= 512 - 2 * tc::A_STAGE_COLS) ? 2 : 1;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.im2col = 1;
     P.nseg = 4;
@@ -617,7 +830,7 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
     P.cout = ch; P.nhalf = ch / 2;
     P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 4;
     P.acc_cols = 6 * (ch / 2);  // x-part (r,z,n) then h-part (r,z,n)
-    P.tmem_cols = 512;
+    P.acc_bufs = 1;             // 192 columns; the other 320 are the 5-stage TMEM A ring
     P.mode = tc::MODE_GRU;
     P.nseg = 4;
     for (int i = 0; i < 4; ++i) {

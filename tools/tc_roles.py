@@ -26,7 +26,19 @@ ops = {
  "gru": lambda: lib.mrb_tc_gru_nhwc(_lib.ptr(x), _lib.ptr(h), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias), _lib.ptr(out), B, H, W, 64, st),
  "conv3x3d2": lambda: lib.mrb_tc_conv_nhwc(_lib.ptr(x), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias), _lib.ptr(out), B, H, W, 64, 3, 2, 1, st),
 }
-for flags, name in ((0, "full"), (7, "barriers+sts+fence"), (7 + 8, "barriers+fence"), (7 + 16, "barriers+sts"), (7 + 24, "barriers")):
+for flags, name in ((0, "full"),):
     lib.mrb_tc_set_debug(flags)
     print("%-18s" % name, "  ".join("%s %7.1f us" % (k, t(f)) for k, f in ops.items()), flush=True)
 lib.mrb_tc_set_debug(0)
+prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+lib.mrb_tc_set_prof(_lib.ptr(prof))
+for dbg in (0, 8, 2, 4):
+  lib.mrb_tc_set_debug(dbg)
+  print("debug flags", dbg)
+  for k, f in ops.items():
+    prof.zero_(); f(); torch.cuda.synchronize()
+    p = prof.view(148, 16).double().mean(0).tolist()
+    if k != "conv3x3d2": continue
+    print("%-10s loader: total %7.0f wait_empty %7.0f store %7.0f issue %7.0f | mma: total %7.0f wait_full %7.0f wait_acc %7.0f issue %7.0f commit %7.0f | epi: total %7.0f wait %7.0f (cycles, mean over CTAs)" % (
+        k, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[10], p[8], p[9]))
+lib.mrb_tc_set_debug(0); lib.mrb_tc_set_prof(None)
