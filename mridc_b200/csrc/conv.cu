@@ -310,47 +310,74 @@ __global__ void mgu_gates_kernel(const float* __restrict__ ih, const float* __re
 }
 
 // Final RIM conv on channels-last input: cin -> 2 channels, replicate padding, fused eta update.
-// Thread = one pixel; weights (k*k*cin float2) broadcast from shared memory; the 256-byte channel vector of each
-// tap is read as float4 (neighbouring threads re-use it through L1).
+// CTA = 32 x 8 output pixels, 128 threads, each thread two pixels (y, y+4) x both outputs.  The input halo patch is
+// staged through shared memory in chunks of 16 channels (pixel stride padded to 20 floats: conflict-free LDS.128),
+// weights (k*k*cin float2) are broadcast from shared memory and shared by the thread's two pixels.
+constexpr int C2_TX = 32, C2_TY = 8, C2_CH = 16, C2_PSTR = 20;
 __global__ void __launch_bounds__(128) conv_c2_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias,
                                                            const float* __restrict__ eta, float* __restrict__ out,
                                                            int B, int H, int W, int cin, int k, int dil) {
-    extern __shared__ float2 w2[];  // [tap][ci] -> (w[0][ci][tap], w[1][ci][tap])
+    extern __shared__ float4 c2smem[];
     const int kk = k * k;
+    const int pad = dil * (k - 1) / 2;
+    const int PW = C2_TX + 2 * pad, PH = C2_TY + 2 * pad;
+    float2* w2 = reinterpret_cast<float2*>(c2smem);                        // [tap][ci] -> (w[0][ci][tap], w[1][ci][tap])
+    float* patch = reinterpret_cast<float*>(w2 + (size_t)kk * cin);        // [PH*PW][C2_PSTR]
     for (int t = threadIdx.x; t < kk * cin; t += blockDim.x) {
         int ci = t % cin, tap = t / cin;
         w2[t] = make_float2(w[(long long)ci * kk + tap], w[((long long)cin + ci) * kk + tap]);
     }
-    __syncthreads();
-    const long long P = (long long)B * H * W;
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const int px = (int)(p % W);
-    const long long t1 = p / W;
-    const int py = (int)(t1 % H);
-    const int pb = (int)(t1 / H);
-    const int pad = dil * (k - 1) / 2;
-    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;  // two partial sums per output for ILP
-    for (int tap = 0; tap < kk; ++tap) {
-        const int yy = min(max(py + (tap / k) * dil - pad, 0), H - 1);
-        const int xx = min(max(px + (tap % k) * dil - pad, 0), W - 1);
-        const float4* xp = reinterpret_cast<const float4*>(x + (((long long)pb * H + yy) * W + xx) * cin);
-        const float4* wp = reinterpret_cast<const float4*>(w2 + (size_t)tap * cin);
-#pragma unroll 4
-        for (int c4 = 0; c4 < cin / 4; ++c4) {
-            const float4 v = xp[c4];
-            const float4 wa = wp[2 * c4], wb = wp[2 * c4 + 1];  // (w0[c],w1[c],w0[c+1],w1[c+1]), (c+2, c+3)
-            a0 = fmaf(v.x, wa.x, a0); a1 = fmaf(v.x, wa.y, a1);
-            c0 = fmaf(v.y, wa.z, c0); c1 = fmaf(v.y, wa.w, c1);
-            a0 = fmaf(v.z, wb.x, a0); a1 = fmaf(v.z, wb.y, a1);
-            c0 = fmaf(v.w, wb.z, c0); c1 = fmaf(v.w, wb.w, c1);
+    const int tiles_x = (W + C2_TX - 1) / C2_TX;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * C2_TX, y0 = ty * C2_TY;
+    const int b = blockIdx.y;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // pixels (lx, ly) and (lx, ly + 4)
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    const float* xb = x + (long long)b * H * W * cin;
+    for (int c0 = 0; c0 < cin; c0 += C2_CH) {
+        __syncthreads();
+        // stage the patch chunk: one float4 per (pixel, quarter)
+        for (int t = threadIdx.x; t < PH * PW * 4; t += blockDim.x) {
+            const int q = t & 3, pp = t >> 2;
+            const int py = pp / PW, px = pp - py * PW;
+            const int gy = min(max(y0 - pad + py, 0), H - 1), gx = min(max(x0 - pad + px, 0), W - 1);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xb + ((long long)gy * W + gx) * cin + c0 + q * 4));
+            *reinterpret_cast<float4*>(patch + (size_t)pp * C2_PSTR + q * 4) = v;
+        }
+        __syncthreads();
+        for (int tap = 0; tap < kk; ++tap) {
+            const int dy = (tap / k) * dil, dx = (tap % k) * dil;
+            const float* p0 = patch + (size_t)((ly + dy) * PW + lx + dx) * C2_PSTR;
+            const float* p1 = p0 + (size_t)4 * PW * C2_PSTR;
+            const float4* wp = reinterpret_cast<const float4*>(w2 + (size_t)tap * cin + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 a = *reinterpret_cast<const float4*>(p0 + q * 4);
+                const float4 c = *reinterpret_cast<const float4*>(p1 + q * 4);
+                const float4 wa = wp[2 * q], wb = wp[2 * q + 1];  // (w0[c],w1[c],w0[c+1],w1[c+1]), (c+2, c+3)
+                acc[0][0] = fmaf(a.x, wa.x, acc[0][0]); acc[0][1] = fmaf(a.x, wa.y, acc[0][1]);
+                acc[0][0] = fmaf(a.y, wa.z, acc[0][0]); acc[0][1] = fmaf(a.y, wa.w, acc[0][1]);
+                acc[0][0] = fmaf(a.z, wb.x, acc[0][0]); acc[0][1] = fmaf(a.z, wb.y, acc[0][1]);
+                acc[0][0] = fmaf(a.w, wb.z, acc[0][0]); acc[0][1] = fmaf(a.w, wb.w, acc[0][1]);
+                acc[1][0] = fmaf(c.x, wa.x, acc[1][0]); acc[1][1] = fmaf(c.x, wa.y, acc[1][1]);
+                acc[1][0] = fmaf(c.y, wa.z, acc[1][0]); acc[1][1] = fmaf(c.y, wa.w, acc[1][1]);
+                acc[1][0] = fmaf(c.z, wb.x, acc[1][0]); acc[1][1] = fmaf(c.z, wb.y, acc[1][1]);
+                acc[1][0] = fmaf(c.w, wb.z, acc[1][0]); acc[1][1] = fmaf(c.w, wb.w, acc[1][1]);
+            }
         }
     }
-    float o0 = a0 + c0, o1 = a1 + c1;
-    if (bias) { o0 += bias[0]; o1 += bias[1]; }
-    const float2 e = reinterpret_cast<const float2*>(eta)[p];
-    reinterpret_cast<float2*>(out)[p] = make_float2(e.x + o0, e.y + o1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int oy = y0 + ly + 4 * i, ox = x0 + lx;
+        if (oy < H && ox < W) {
+            const long long p = ((long long)b * H + oy) * W + ox;
+            float o0 = acc[i][0], o1 = acc[i][1];
+            if (bias) { o0 += bias[0]; o1 += bias[1]; }
+            const float2 e = reinterpret_cast<const float2*>(eta)[p];
+            reinterpret_cast<float2*>(out)[p] = make_float2(e.x + o0, e.y + o1);
+        }
+    }
 }
 
 }  // namespace mrb
@@ -360,13 +387,15 @@ using namespace mrb;
 extern "C" int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out,
                                          int B, int H, int W, int cin, int k, int dil, void* stream) {
     MRB_REQUIRE(x && w && eta && out, MRB_EINVAL, "mrb_conv_c2_nhwc_residual: null pointer");
-    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && cin >= 4 && (cin % 4) == 0 && (k % 2) == 1 && dil >= 1, MRB_EINVAL,
-                "mrb_conv_c2_nhwc_residual: bad shape (cin must be a multiple of 4, k odd)");
-    size_t smem = (size_t)k * k * cin * sizeof(float2);
-    MRB_REQUIRE(smem <= 96 * 1024, MRB_EUNSUPPORTED, "mrb_conv_c2_nhwc_residual: weights too large");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && cin >= 16 && (cin % 16) == 0 && (k % 2) == 1 && dil >= 1 && B <= 65535,
+                MRB_EINVAL, "mrb_conv_c2_nhwc_residual: bad shape (cin must be a multiple of 16, k odd)");
+    const int pad = dil * (k - 1) / 2;
+    size_t smem = (size_t)k * k * cin * sizeof(float2) +
+                  (size_t)(C2_TX + 2 * pad) * (C2_TY + 2 * pad) * C2_PSTR * sizeof(float);
+    MRB_REQUIRE(smem <= 96 * 1024, MRB_EUNSUPPORTED, "mrb_conv_c2_nhwc_residual: kernel / dilation too large");
     MRB_CUDA(cudaFuncSetAttribute(conv_c2_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    const long long P = (long long)B * H * W;
-    conv_c2_nhwc_kernel<<<(unsigned)((P + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
+    dim3 grid((unsigned)(ceil_div(W, C2_TX) * ceil_div(H, C2_TY)), (unsigned)B);
+    conv_c2_nhwc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(
         (const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W, cin, k, dil);
     MRB_LAUNCHED();
     return MRB_OK;

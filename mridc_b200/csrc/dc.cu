@@ -11,6 +11,8 @@
 //   K3 rowifft_reduce     CTA = (b, row h): inverse FFT along W for all coils in smem, sum_c conj(S)*.
 // Centering is folded into index rotations on the loads/stores (valid for odd lengths too); the k-space in
 // the middle is never physically shifted.
+#include <stdlib.h>
+
 #include "fft.cuh"
 
 namespace mrb {
@@ -24,6 +26,10 @@ __device__ __forceinline__ int rot_add(int j, int rot, int n) {
     return s >= n ? s - n : s;
 }
 
+// Index arithmetic in these kernels is division-free (profiling showed the `t / W` style decompositions costing
+// more instructions than the butterflies): row kernels walk coils in the outer loop and columns across threads
+// (blockDim >= W when W <= 1024), column kernels split the thread index with shifts (strip width is a power of two).
+
 // K1: T1[b,c,h,kw] = FFT_W( S[b,c,h,(j+rw)%W] * img[b,h,(j+rw)%W] )   (un-normalised, un-centred along W)
 __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float2* __restrict__ S,
                                      float2* __restrict__ T1, int C, int H, int W, int cc, FftPlan p, int rw) {
@@ -34,31 +40,49 @@ __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float
     load_twiddles(tw_s, p);
     const int h = blockIdx.x, b = blockIdx.y;
     const float2* irow = img + ((long long)b * H + h) * W;
+    const long long cstride = (long long)H * W;
+    const float2* Srow = S + ((long long)b * C * H + h) * W;
+    float2* Trow = T1 + ((long long)b * C * H + h) * W;
     float2* St = fft_start_buf(p, A, Bf);
     for (int c0 = 0; c0 < C; c0 += cc) {
         const int nc = min(cc, C - c0);
         if (c0 > 0) __syncthreads();
-        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
-            int c = t / W, j = t - c * W;
-            int src = rot_add(j, rw, W);
-            float2 e = irow[src];
-            float2 s = S[(((long long)b * C + c0 + c) * H + h) * W + src];
-            // rim_utils.py:47-48: re = e_re*s_re - e_im*s_im ; im = e_re*s_im + e_im*s_re
-            St[(size_t)c * p.ls + j] = make_float2(e.x * s.x - e.y * s.y, e.x * s.y + e.y * s.x);
+        for (int j = threadIdx.x; j < W; j += blockDim.x) {
+            const int src = rot_add(j, rw, W);
+            const float2 e = __ldg(&irow[src]);
+            const float2* sp = Srow + (long long)c0 * cstride + src;
+            float2* dp = St + j;
+            int c = 0;
+            for (; c + 4 <= nc; c += 4) {  // 4 independent loads in flight
+                const float2 s0 = __ldg(sp + (long long)(c + 0) * cstride), s1 = __ldg(sp + (long long)(c + 1) * cstride);
+                const float2 s2 = __ldg(sp + (long long)(c + 2) * cstride), s3 = __ldg(sp + (long long)(c + 3) * cstride);
+                // rim_utils.py:47-48: re = e_re*s_re - e_im*s_im ; im = e_re*s_im + e_im*s_re
+                dp[(size_t)(c + 0) * p.ls] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);
+                dp[(size_t)(c + 1) * p.ls] = make_float2(e.x * s1.x - e.y * s1.y, e.x * s1.y + e.y * s1.x);
+                dp[(size_t)(c + 2) * p.ls] = make_float2(e.x * s2.x - e.y * s2.y, e.x * s2.y + e.y * s2.x);
+                dp[(size_t)(c + 3) * p.ls] = make_float2(e.x * s3.x - e.y * s3.y, e.x * s3.y + e.y * s3.x);
+            }
+            for (; c < nc; ++c) {
+                const float2 s0 = __ldg(sp + (long long)c * cstride);
+                dp[(size_t)c * p.ls] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);
+            }
         }
         block_fft<false>(A, Bf, nc, p, tw_s);
-        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
-            int c = t / W, k = t - c * W;
-            T1[(((long long)b * C + c0 + c) * H + h) * W + k] = A[(size_t)c * p.ls + k];
+        for (int k = threadIdx.x; k < W; k += blockDim.x) {
+            float2* tp = Trow + (long long)c0 * cstride + k;
+            const float2* ap = A + k;
+            for (int c = 0; c < nc; ++c) tp[(long long)c * cstride] = ap[(size_t)c * p.ls];
         }
     }
 }
 
+// column-strip helpers: strip of ti = 1 << tsh lines (k_w positions), thread -> (i = tid & (ti-1), row start tid >> tsh)
 // K2 (RIM): per (b,c,strip): P = fscale * FFT_H(T1 rotated); r = mask*(P - y); T2 = IFFT_H(r) stored with the
 // output rotation along H.  T1's k_w axis is un-centred: centred storage column = (k_w + rw) % W.
 __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __restrict__ y, float2* __restrict__ T2,
-                              MaskDesc mask, int C, int H, int W, int ti, FftPlan p, int rh, int rw, float fscale) {
+                              MaskDesc mask, int C, int H, int W, int tsh, FftPlan p, int rh, int rw, float fscale) {
     extern __shared__ float2 smem[];
+    const int ti = 1 << tsh;
     float2* A = smem;
     float2* Bf = A + (size_t)ti * p.ls;
     float2* tw_s = Bf + (size_t)ti * p.ls;
@@ -68,33 +92,45 @@ __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __res
     const int c = blockIdx.y, b = blockIdx.z;
     const long long plane = ((long long)b * C + c) * H * W;
     float2* St = fft_start_buf(p, A, Bf);
-    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
-        int j = t / nl, i = t - j * nl;
-        St[(size_t)i * p.ls + j] = T1[plane + (long long)rot_add(j, rh, H) * W + k0 + i];
+    const int i = threadIdx.x & (ti - 1), j0 = threadIdx.x >> tsh, jstep = blockDim.x >> tsh;
+    const bool act = i < nl;
+    const float2* tcol = T1 + plane + k0 + i;
+    if (act) {
+        int j = j0;
+        for (; j + 3 * jstep < H; j += 4 * jstep) {
+            const float2 v0 = tcol[(long long)rot_add(j, rh, H) * W], v1 = tcol[(long long)rot_add(j + jstep, rh, H) * W];
+            const float2 v2 = tcol[(long long)rot_add(j + 2 * jstep, rh, H) * W];
+            const float2 v3 = tcol[(long long)rot_add(j + 3 * jstep, rh, H) * W];
+            float2* d = St + (size_t)i * p.ls + j;
+            d[0] = v0; d[jstep] = v1; d[2 * jstep] = v2; d[3 * jstep] = v3;
+        }
+        for (; j < H; j += jstep) St[(size_t)i * p.ls + j] = tcol[(long long)rot_add(j, rh, H) * W];
     }
     block_fft<false>(A, Bf, nl, p, tw_s);
-    // k-space epilogue: result of forward FFT is in A; write the residual where the inverse wants its input.
-    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
-        int kh = t / nl, i = t - kh * nl;
-        int mh = rot_add(kh, rh, H), mw = rot_add(k0 + i, rw, W);
-        float2 P = cscale(A[(size_t)i * p.ls + kh], fscale);
-        float2 yv = y[plane + (long long)mh * W + mw];
-        float m = mask_value(mask, b, mh, mw);
-        // rim_utils.py:54: mask * (pred - masked_kspace)
-        float2 r = make_float2(m * (P.x - yv.x), m * (P.y - yv.y));
-        if (St == A) {
-            // in-place element update is safe: each (i,kh) is read and written by the same thread
-            A[(size_t)i * p.ls + kh] = r;
-        } else {
-            Bf[(size_t)i * p.ls + kh] = r;
+    // k-space epilogue: result of the forward FFT is in A; write the residual where the inverse wants its input.
+    if (act) {
+        const int mw = rot_add(k0 + i, rw, W);
+        for (int kh = j0; kh < H; kh += jstep) {
+            const int mh = rot_add(kh, rh, H);
+            const float m = mask_value(mask, b, mh, mw);
+            const float2 P = cscale(A[(size_t)i * p.ls + kh], fscale);
+            float2 r = make_float2(0.f, 0.f);
+            if (m != 0.f) {  // unsampled entries contribute exactly 0 whatever y holds: skip the read
+                const float2 yv = __ldg(&y[plane + (long long)mh * W + mw]);
+                r = make_float2(m * (P.x - yv.x), m * (P.y - yv.y));  // rim_utils.py:54: mask * (pred - masked_kspace)
+            }
+            // in-place update (St == A) is safe: each (i,kh) is read and written by the same thread
+            St[(size_t)i * p.ls + kh] = r;
         }
     }
     block_fft<true>(A, Bf, nl, p, tw_s);
-    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
-        int d = t / nl, i = t - d * nl;  // d = storage row (image coordinates), n = logical output index
-        int n = d - rh;
-        if (n < 0) n += H;
-        T2[plane + (long long)d * W + k0 + i] = A[(size_t)i * p.ls + n];
+    if (act) {
+        float2* ocol = T2 + plane + k0 + i;
+        for (int d = j0; d < H; d += jstep) {  // d = storage row (image coordinates), n = logical output index
+            int n = d - rh;
+            if (n < 0) n += H;
+            ocol[(long long)d * W] = A[(size_t)i * p.ls + n];
+        }
     }
 }
 
@@ -102,9 +138,10 @@ __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __res
 __global__ void col_softdc_kernel(const float2* __restrict__ T1, const float2* __restrict__ base,
                                   const float2* __restrict__ pred,
                                   const float2* __restrict__ y, float2* __restrict__ out, MaskDesc mask, int C, int H,
-                                  int W, int ti, FftPlan p, int rh, int rw, float fscale, const float* __restrict__ dcw_p,
+                                  int W, int tsh, FftPlan p, int rh, int rw, float fscale, const float* __restrict__ dcw_p,
                                   int no_dc) {
     extern __shared__ float2 smem[];
+    const int ti = 1 << tsh;
     float2* A = smem;
     float2* Bf = A + (size_t)ti * p.ls;
     float2* tw_s = Bf + (size_t)ti * p.ls;
@@ -115,27 +152,31 @@ __global__ void col_softdc_kernel(const float2* __restrict__ T1, const float2* _
     const long long plane = ((long long)b * C + c) * H * W;
     const float dcw = no_dc ? 0.f : *dcw_p;
     float2* St = fft_start_buf(p, A, Bf);
-    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
-        int j = t / nl, i = t - j * nl;
-        St[(size_t)i * p.ls + j] = T1[plane + (long long)rot_add(j, rh, H) * W + k0 + i];
+    const int i = threadIdx.x & (ti - 1), j0 = threadIdx.x >> tsh, jstep = blockDim.x >> tsh;
+    const bool act = i < nl;
+    if (act) {
+        const float2* tcol = T1 + plane + k0 + i;
+        for (int j = j0; j < H; j += jstep) St[(size_t)i * p.ls + j] = tcol[(long long)rot_add(j, rh, H) * W];
     }
     block_fft<false>(A, Bf, nl, p, tw_s);
-    for (int t = threadIdx.x; t < nl * H; t += blockDim.x) {
-        int kh = t / nl, i = t - kh * nl;
-        int mh = rot_add(kh, rh, H), mw = rot_add(k0 + i, rw, W);
-        float2 E = cscale(A[(size_t)i * p.ls + kh], fscale);
-        long long o = plane + (long long)mh * W + mw;
-        if (no_dc) {
-            out[o] = E;
-        } else {
-            float2 bv = base[o];
-            float2 sd = make_float2(0.f, 0.f);
-            if (mask_value(mask, b, mh, mw) != 0.f) {  // vn_block.py:110 torch.where(mask.bool(), pred - ref, 0)
-                float2 pv = pred[o], yv = y[o];
-                sd = make_float2(pv.x - yv.x, pv.y - yv.y);
+    if (act) {
+        const int mw = rot_add(k0 + i, rw, W);
+        for (int kh = j0; kh < H; kh += jstep) {
+            const int mh = rot_add(kh, rh, H);
+            const float2 E = cscale(A[(size_t)i * p.ls + kh], fscale);
+            const long long o = plane + (long long)mh * W + mw;
+            if (no_dc) {
+                out[o] = E;
+            } else {
+                const float2 bv = base[o];
+                float2 sd = make_float2(0.f, 0.f);
+                if (mask_value(mask, b, mh, mw) != 0.f) {  // vn_block.py:110 torch.where(mask.bool(), pred - ref, 0)
+                    const float2 pv = pred[o], yv = y[o];
+                    sd = make_float2(pv.x - yv.x, pv.y - yv.y);
+                }
+                // vn_block.py:110,117: (pred - soft_dc*dc_weight) - eta
+                out[o] = make_float2((bv.x - sd.x * dcw) - E.x, (bv.y - sd.y * dcw) - E.y);
             }
-            // vn_block.py:110,117: (pred - soft_dc*dc_weight) - eta
-            out[o] = make_float2((bv.x - sd.x * dcw) - E.x, (bv.y - sd.y * dcw) - E.y);
         }
     }
 }
@@ -153,33 +194,56 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
     float2* tw_s = Bf + (size_t)cc * p.ls;
     load_twiddles(tw_s, p);
     const int h = blockIdx.x, b = blockIdx.y;
+    const long long cstride = (long long)H * W;
+    const float2* Trow = T2 + ((long long)b * C * H + h) * W;
+    const float2* Srow = S + ((long long)b * C * H + h) * W;
     float2* St = fft_start_buf(p, A, Bf);
     // each thread owns output columns d = threadIdx.x + i*blockDim.x (registers hold the running coil sum)
-    constexpr int kMaxOwn = 8;
+    constexpr int kMaxOwn = 4;
     float2 acc[kMaxOwn];
 #pragma unroll
     for (int i = 0; i < kMaxOwn; ++i) acc[i] = make_float2(0.f, 0.f);
     for (int c0 = 0; c0 < C; c0 += cc) {
         const int nc = min(cc, C - c0);
         if (c0 > 0) __syncthreads();
-        for (int t = threadIdx.x; t < nc * W; t += blockDim.x) {
-            int c = t / W, j = t - c * W;
-            St[(size_t)c * p.ls + j] = T2[(((long long)b * C + c0 + c) * H + h) * W + rot_add(j, in_rw, W)];
+        for (int j = threadIdx.x; j < W; j += blockDim.x) {
+            const float2* tp = Trow + (long long)c0 * cstride + rot_add(j, in_rw, W);
+            float2* dp = St + j;
+            int c = 0;
+            for (; c + 4 <= nc; c += 4) {
+                const float2 v0 = tp[(long long)(c + 0) * cstride], v1 = tp[(long long)(c + 1) * cstride];
+                const float2 v2 = tp[(long long)(c + 2) * cstride], v3 = tp[(long long)(c + 3) * cstride];
+                dp[(size_t)(c + 0) * p.ls] = v0; dp[(size_t)(c + 1) * p.ls] = v1;
+                dp[(size_t)(c + 2) * p.ls] = v2; dp[(size_t)(c + 3) * p.ls] = v3;
+            }
+            for (; c < nc; ++c) dp[(size_t)c * p.ls] = tp[(long long)c * cstride];
         }
         block_fft<true>(A, Bf, nc, p, tw_s);
 #pragma unroll
         for (int i = 0; i < kMaxOwn; ++i) {
-            int d = threadIdx.x + i * blockDim.x;  // storage column
+            const int d = threadIdx.x + i * blockDim.x;  // storage column
             if (d < W) {
                 int n = d - rw;
                 if (n < 0) n += W;
                 float2 a = acc[i];
-                for (int c = 0; c < nc; ++c) {
-                    float2 v = A[(size_t)c * p.ls + n];
-                    float2 s = S[(((long long)b * C + c0 + c) * H + h) * W + d];
-                    // rim_utils.py:61-62: re += v_re*s_re + v_im*s_im ; im += v_im*s_re - v_re*s_im
-                    a.x += v.x * s.x + v.y * s.y;
-                    a.y += v.y * s.x - v.x * s.y;
+                const float2* sp = Srow + (long long)c0 * cstride + d;
+                const float2* ap = A + n;
+                int c = 0;
+                for (; c + 4 <= nc; c += 4) {
+                    const float2 s0 = __ldg(sp + (long long)(c + 0) * cstride), s1 = __ldg(sp + (long long)(c + 1) * cstride);
+                    const float2 s2 = __ldg(sp + (long long)(c + 2) * cstride), s3 = __ldg(sp + (long long)(c + 3) * cstride);
+                    const float2 v0 = ap[(size_t)(c + 0) * p.ls], v1 = ap[(size_t)(c + 1) * p.ls];
+                    const float2 v2 = ap[(size_t)(c + 2) * p.ls], v3 = ap[(size_t)(c + 3) * p.ls];
+                    // rim_utils.py:61-62: re += v_re*s_re + v_im*s_im ; im += v_im*s_re - v_re*s_im  (coil order kept)
+                    a.x += v0.x * s0.x + v0.y * s0.y; a.y += v0.y * s0.x - v0.x * s0.y;
+                    a.x += v1.x * s1.x + v1.y * s1.y; a.y += v1.y * s1.x - v1.x * s1.y;
+                    a.x += v2.x * s2.x + v2.y * s2.y; a.y += v2.y * s2.x - v2.x * s2.y;
+                    a.x += v3.x * s3.x + v3.y * s3.y; a.y += v3.y * s3.x - v3.x * s3.y;
+                }
+                for (; c < nc; ++c) {
+                    const float2 s0 = __ldg(sp + (long long)c * cstride);
+                    const float2 v0 = ap[(size_t)c * p.ls];
+                    a.x += v0.x * s0.x + v0.y * s0.y; a.y += v0.y * s0.x - v0.x * s0.y;
                 }
                 acc[i] = a;
             }
@@ -187,7 +251,7 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
     }
 #pragma unroll
     for (int i = 0; i < kMaxOwn; ++i) {
-        int d = threadIdx.x + i * blockDim.x;
+        const int d = threadIdx.x + i * blockDim.x;
         if (d < W) {
             if (OUT_MODE == 0) {
                 ((float2*)out)[((long long)b * H + h) * W + d] = cscale(acc[i], scale);
@@ -211,7 +275,8 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
 struct DcGeom {
     FftPlan pw, ph;
     int cc;       // coils per smem chunk in the row kernels
-    int ti;       // k_w strip width in the column kernels
+    int ti;       // k_w strip width in the column kernels (power of two)
+    int tsh;      // log2(ti)
     int threads_row;
     size_t smem_row, smem_col;
 };
@@ -222,7 +287,14 @@ static int dc_geometry(int C, int H, int W, DcGeom* g) {
     rc = get_fft_plan(H, &g->ph);
     if (rc) return rc;
     const size_t max_smem = device_max_smem_optin();
-    const size_t row_budget = max_smem < 110 * 1024 ? max_smem : 110 * 1024;  // keep 2 CTAs / SM
+    // shared-memory budget per CTA: small enough for ~5 resident CTAs per SM (the kernels are latency bound:
+    // more resident warps beat bigger tiles); MRB_DC_SMEM_KB overrides for experiments
+    static int budget_kb = [] {
+        const char* e = getenv("MRB_DC_SMEM_KB");
+        int v = e ? atoi(e) : 44;
+        return v < 8 ? 8 : v;
+    }();
+    const size_t row_budget = max_smem < (size_t)budget_kb * 1024 ? max_smem : (size_t)budget_kb * 1024;
     int cc = C;
     while (cc > 1 && fft_smem_bytes(g->pw, cc) > row_budget) cc = (cc + 1) / 2;
     MRB_REQUIRE(fft_smem_bytes(g->pw, cc) <= max_smem, MRB_EUNSUPPORTED, "W=%d does not fit shared memory", W);
@@ -231,13 +303,15 @@ static int dc_geometry(int C, int H, int W, DcGeom* g) {
     int ti = 16;
     while (ti > 1 && fft_smem_bytes(g->ph, ti) > row_budget) ti /= 2;
     MRB_REQUIRE(fft_smem_bytes(g->ph, ti) <= max_smem, MRB_EUNSUPPORTED, "H=%d does not fit shared memory", H);
-    if (ti > W) ti = W;
     g->ti = ti;
+    g->tsh = 0;
+    while ((1 << g->tsh) < ti) ++g->tsh;
     g->smem_col = fft_smem_bytes(g->ph, ti);
-    // row kernels: each thread owns <= 8 output columns
-    int tr = 256;
-    while (tr * 8 < W) tr *= 2;
-    MRB_REQUIRE(tr <= 1024, MRB_EUNSUPPORTED, "W=%d too large for the row-reduce kernel", W);
+    // row kernels: one thread per column when W <= 1024, else up to 4 columns per thread
+    int tr = ((W + 31) / 32) * 32;
+    if (tr > 1024) tr = 1024;
+    if (tr < 128) tr = 128;
+    MRB_REQUIRE(tr * 4 >= W, MRB_EUNSUPPORTED, "W=%d too large for the row-reduce kernel", W);
     g->threads_row = tr;
     return MRB_OK;
 }
@@ -301,7 +375,7 @@ extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, co
     expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1, C, H,
                                                                         W, g.cc, g.pw, rw);
     MRB_LAUNCHED();
-    col_dc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(T1, (const float2*)y, T2, m, C, H, W, g.ti,
+    col_dc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(T1, (const float2*)y, T2, m, C, H, W, g.tsh,
                                                                           g.ph, rh, rw, fs);
     MRB_LAUNCHED();
     if (out_nhwc)
@@ -368,7 +442,7 @@ extern "C" int mrb_sens_expand_softdc(const void* img, const void* S, const void
                                                                         W, g.cc, g.pw, rw);
     MRB_LAUNCHED();
     col_softdc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(
-        T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.ti, g.ph, rh, rw, fs,
+        T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.tsh, g.ph, rh, rw, fs,
         (const float*)dc_weight, no_dc);
     MRB_LAUNCHED();
     return MRB_OK;

@@ -46,6 +46,8 @@ int get_fft_plan(int n, FftPlan* out) {
     for (int v : f3) all.push_back(v);
     for (int v : f2) all.push_back(v);
     for (int v : f4) all.push_back(v);
+    if (n == 320) all = {5, 8, 8};   // fixed-plan fast paths of fft.cuh (3 stages: input buffer parity must match)
+    if (n == 640) all = {10, 8, 8};
     MRB_REQUIRE((int)all.size() <= kMaxStages, MRB_EUNSUPPORTED, "too many FFT stages for n=%d", n);
     p.nstages = (int)all.size();
     for (int i = 0; i < p.nstages; ++i) p.radix[i] = all[i];

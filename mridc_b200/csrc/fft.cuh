@@ -139,6 +139,87 @@ __device__ __forceinline__ void fft_stage_generic(const float2* __restrict__ src
     }
 }
 
+// ---- fixed-plan fast path (compile-time length and radices: 320 = 5*8*8, 640 = 10*8*8) --------------------------
+// All index arithmetic folds to constants, radix-8/10 butterflies stay in registers, three shared-memory passes.
+template <bool INV>
+__device__ __forceinline__ void bf8(float2* v) {
+    const float h = 0.70710678118654752440f;
+    float2 e0 = cadd(v[0], v[4]), e1 = cadd(v[1], v[5]), e2 = cadd(v[2], v[6]), e3 = cadd(v[3], v[7]);
+    float2 o0 = csub(v[0], v[4]), o1 = csub(v[1], v[5]), o2 = csub(v[2], v[6]), o3 = csub(v[3], v[7]);
+    // o[n] *= w8^n ; w8 = exp(-+ 2 pi i / 8)
+    o1 = INV ? make_float2(h * (o1.x - o1.y), h * (o1.x + o1.y)) : make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));
+    o2 = mul_mi<INV>(o2);
+    o3 = INV ? make_float2(-h * (o3.x + o3.y), h * (o3.x - o3.y)) : make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));
+    float2 e[4] = {e0, e1, e2, e3}, o[4] = {o0, o1, o2, o3};
+    butterfly<4, INV>(e);
+    butterfly<4, INV>(o);
+    v[0] = e[0]; v[2] = e[1]; v[4] = e[2]; v[6] = e[3];
+    v[1] = o[0]; v[3] = o[1]; v[5] = o[2]; v[7] = o[3];
+}
+
+template <bool INV>
+__device__ __forceinline__ void bf10(float2* v) {
+    float2 e[5] = {v[0], v[2], v[4], v[6], v[8]}, o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    butterfly<5, INV>(e);
+    butterfly<5, INV>(o);
+    // w10^k, k = 1..4 : exp(-+ 2 pi i k / 10)
+    const float c1 = 0.80901699437494742410f, s1 = 0.58778525229247312917f;
+    const float c2 = 0.30901699437494742410f, s2 = 0.95105651629515357212f;
+    const float2 w1 = make_float2(c1, INV ? s1 : -s1), w2 = make_float2(c2, INV ? s2 : -s2);
+    const float2 w3 = make_float2(-c2, INV ? s2 : -s2), w4 = make_float2(-c1, INV ? s1 : -s1);
+    o[1] = cmul(o[1], w1); o[2] = cmul(o[2], w2); o[3] = cmul(o[3], w3); o[4] = cmul(o[4], w4);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 5] = csub(e[k], o[k]);
+    }
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void bf_fixed(float2* v) {
+    if (R == 8) bf8<INV>(v);
+    else if (R == 10) bf10<INV>(v);
+    else butterfly<R, INV>(v);
+}
+
+template <int N, int R, int NS, bool INV>
+__device__ __forceinline__ void fft_stage_fixed(const float2* __restrict__ src, float2* __restrict__ dst, int nlines,
+                                                int ls, const float2* __restrict__ tw_s) {
+    constexpr int NB = N / R;
+    constexpr int TWMUL = N / (NS * R);
+    const int total = nlines * NB;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int line = t / NB;
+        const int j = t - line * NB;
+        const int k = (NS == 1) ? 0 : (j % NS);
+        const float2* s = src + line * ls;
+        float2* d = dst + line * ls;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = s[j + r * NB];
+        if (NS > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], twd<INV>(tw_s, r * k * TWMUL));
+        }
+        bf_fixed<R, INV>(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) d[base + r * NS] = v[r];
+    }
+}
+
+template <int N, int R1, int R2, int R3, bool INV>
+__device__ __forceinline__ void block_fft_fixed3(float2* A, float2* B, int nlines, int ls, const float2* tw_s) {
+    static_assert(R1 * R2 * R3 == N, "radices must multiply to N");
+    __syncthreads();
+    fft_stage_fixed<N, R1, 1, INV>(B, A, nlines, ls, tw_s);  // 3 stages: input in B, result in A
+    __syncthreads();
+    fft_stage_fixed<N, R2, R1, INV>(A, B, nlines, ls, tw_s);
+    __syncthreads();
+    fft_stage_fixed<N, R3, R1 * R2, INV>(B, A, nlines, ls, tw_s);
+    __syncthreads();
+}
+
 // Which buffer the caller must fill so that the result of block_fft lands in A.
 __device__ __forceinline__ float2* fft_start_buf(const FftPlan& p, float2* A, float2* B) {
     return (p.nstages & 1) ? B : A;
@@ -148,6 +229,8 @@ __device__ __forceinline__ float2* fft_start_buf(const FftPlan& p, float2* A, fl
 template <bool INV>
 __device__ __forceinline__ void block_fft(float2* A, float2* B, int nlines, const FftPlan& p,
                                           const float2* tw_s) {
+    if (p.n == 320) { block_fft_fixed3<320, 5, 8, 8, INV>(A, B, nlines, p.ls, tw_s); return; }
+    if (p.n == 640) { block_fft_fixed3<640, 10, 8, 8, INV>(A, B, nlines, p.ls, tw_s); return; }
     float2* src = fft_start_buf(p, A, B);
     float2* dst = (src == A) ? B : A;
     int Ns = 1;

@@ -46,7 +46,7 @@ class RimTcEngine:
         f = block.final_layer[0]
         if not isinstance(f, ConvNonlinear) or f.features != 2 or f.input_size != 64 or f._act != _ops.ACT_NONE:
             return False
-        if f.kernel_size % 2 != 1 or f.kernel_size**2 * 64 * 8 > 96 * 1024:
+        if f.kernel_size % 2 != 1 or f.kernel_size * f.dilation > 9:
             return False
         return True
 

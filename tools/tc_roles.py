@@ -42,3 +42,6 @@ for dbg in (0, 8, 2, 4):
     print("%-10s loader: total %7.0f wait_empty %7.0f store %7.0f issue %7.0f | mma: total %7.0f wait_full %7.0f wait_acc %7.0f issue %7.0f commit %7.0f | epi: total %7.0f wait %7.0f (cycles, mean over CTAs)" % (
         k, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[10], p[8], p[9]))
 lib.mrb_tc_set_debug(0); lib.mrb_tc_set_prof(None)
+w3 = blk.final_layer[0].conv_layer.weight
+eta = torch.randn(B, H, W, 2, device=dev); o2 = torch.empty_like(eta)
+print("conv_c2 %.1f us" % t(lambda: lib.mrb_conv_c2_nhwc_residual(_lib.ptr(x), _lib.ptr(w3), None, _lib.ptr(eta), _lib.ptr(o2), B, H, W, 64, 3, 1, st)))
