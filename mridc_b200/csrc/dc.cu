@@ -30,15 +30,53 @@ __device__ __forceinline__ int rot_add(int j, int rot, int n) {
 // more instructions than the butterflies): row kernels walk coils in the outer loop and columns across threads
 // (blockDim >= W when W <= 1024), column kernels split the thread index with shifts (strip width is a power of two).
 
+// Mask-aware pruning.  With a 1-D mask (one value per k_w column, the fastMRI case) every unsampled k-space column has
+// a zero residual, so only the sampled columns need the H-direction transforms and only they need to travel between
+// the passes.  Each CTA rebuilds the ascending list of active un-centred k_w indices (cols_s, count returned) from
+// the mask row with a ballot scan (W elements; cheaper than a separate launch plus a host-visible count).
+// For 2-D masks every column is treated as active (dense path through the same code).
+__device__ __forceinline__ int build_active_cols(const MaskDesc& mask, int b, int W, int rw, bool prune,
+                                                 unsigned short* cols_s, int* scratch) {
+    // scratch: [33] ints (warp totals + grand total)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int base = 0;
+    for (int k0 = 0; k0 < W; k0 += blockDim.x) {
+        const int kw = k0 + threadIdx.x;
+        bool f = false;
+        if (kw < W) f = prune ? (mask_value(mask, b, 0, rot_add(kw, rw, W)) != 0.f) : true;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        const int prefix = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) scratch[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) {
+            const int cnt = scratch[w];
+            if (w < wid) woff += cnt;
+            tot += cnt;
+        }
+        if (f) cols_s[base + woff + prefix] = (unsigned short)kw;
+        base += tot;
+        __syncthreads();
+    }
+    return base;
+}
+
 // K1: T1[b,c,h,kw] = FFT_W( S[b,c,h,(j+rw)%W] * img[b,h,(j+rw)%W] )   (un-normalised, un-centred along W)
+// COMPACT: only the active columns are stored, packed at the front of each T1 row (T1c[b,c,h,j] = X[cols[j]]).
+template <bool COMPACT>
 __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float2* __restrict__ S,
-                                     float2* __restrict__ T1, int C, int H, int W, int cc, FftPlan p, int rw) {
+                                     float2* __restrict__ T1, int C, int H, int W, int cc, FftPlan p, int rw,
+                                     MaskDesc mask, int prune) {
     extern __shared__ float2 smem[];
     float2* A = smem;
     float2* Bf = A + (size_t)cc * p.ls;
     float2* tw_s = Bf + (size_t)cc * p.ls;
+    unsigned short* cols_s = reinterpret_cast<unsigned short*>(tw_s + p.n);
+    __shared__ int scan_scratch[33];
     load_twiddles(tw_s, p);
     const int h = blockIdx.x, b = blockIdx.y;
+    int ns = W;
+    if (COMPACT) ns = build_active_cols(mask, b, W, rw, prune != 0, cols_s, scan_scratch);
     const float2* irow = img + ((long long)b * H + h) * W;
     const long long cstride = (long long)H * W;
     const float2* Srow = S + ((long long)b * C * H + h) * W;
@@ -68,9 +106,9 @@ __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float
             }
         }
         block_fft<false>(A, Bf, nc, p, tw_s);
-        for (int k = threadIdx.x; k < W; k += blockDim.x) {
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {
             float2* tp = Trow + (long long)c0 * cstride + k;
-            const float2* ap = A + k;
+            const float2* ap = A + (COMPACT ? (int)cols_s[k] : k);
             for (int c = 0; c < nc; ++c) tp[(long long)c * cstride] = ap[(size_t)c * p.ls];
         }
     }
@@ -79,17 +117,23 @@ __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float
 // column-strip helpers: strip of ti = 1 << tsh lines (k_w positions), thread -> (i = tid & (ti-1), row start tid >> tsh)
 // K2 (RIM): per (b,c,strip): P = fscale * FFT_H(T1 rotated); r = mask*(P - y); T2 = IFFT_H(r) stored with the
 // output rotation along H.  T1's k_w axis is un-centred: centred storage column = (k_w + rw) % W.
+// T1 / T2 hold compact rows: column j of the strip is the j-th active k_w (cols_s[j]); strips past the active count exit.
 __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __restrict__ y, float2* __restrict__ T2,
-                              MaskDesc mask, int C, int H, int W, int tsh, FftPlan p, int rh, int rw, float fscale) {
+                              MaskDesc mask, int C, int H, int W, int tsh, FftPlan p, int rh, int rw, float fscale,
+                              int prune) {
     extern __shared__ float2 smem[];
     const int ti = 1 << tsh;
     float2* A = smem;
     float2* Bf = A + (size_t)ti * p.ls;
     float2* tw_s = Bf + (size_t)ti * p.ls;
-    load_twiddles(tw_s, p);
-    const int k0 = blockIdx.x * ti;
-    const int nl = min(ti, W - k0);
+    unsigned short* cols_s = reinterpret_cast<unsigned short*>(tw_s + p.n);
+    __shared__ int scan_scratch[33];
     const int c = blockIdx.y, b = blockIdx.z;
+    const int ns = build_active_cols(mask, b, W, rw, prune != 0, cols_s, scan_scratch);
+    const int k0 = blockIdx.x * ti;
+    if (k0 >= ns) return;  // uniform per CTA
+    load_twiddles(tw_s, p);
+    const int nl = min(ti, ns - k0);
     const long long plane = ((long long)b * C + c) * H * W;
     float2* St = fft_start_buf(p, A, Bf);
     const int i = threadIdx.x & (ti - 1), j0 = threadIdx.x >> tsh, jstep = blockDim.x >> tsh;
@@ -109,7 +153,7 @@ __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __res
     block_fft<false>(A, Bf, nl, p, tw_s);
     // k-space epilogue: result of the forward FFT is in A; write the residual where the inverse wants its input.
     if (act) {
-        const int mw = rot_add(k0 + i, rw, W);
+        const int mw = rot_add((int)cols_s[k0 + i], rw, W);
         for (int kh = j0; kh < H; kh += jstep) {
             const int mh = rot_add(kh, rh, H);
             const float m = mask_value(mask, b, mh, mw);
@@ -184,16 +228,21 @@ __global__ void col_softdc_kernel(const float2* __restrict__ T1, const float2* _
 // K3: acc[b,h,w] = sum_c conj(S[b,c,h,w]) * IFFT_W(T2[b,c,h,:])  ; w = (n + rw) % W.
 // OUT_MODE 0: out [B,H,W] complex = acc*scale.   OUT_MODE 1 (RIM): out [B,4,H,W] = (eta_re, eta_im, acc*scale).
 // OUT_MODE 2 (RIM, channels-last for the tensor-core regulariser): out [B,H,W,4].
-template <int OUT_MODE>
+// COMPACT: T2 rows hold only the active columns (packed); they are scattered into zero-filled lines.
+template <int OUT_MODE, bool COMPACT>
 __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float2* __restrict__ S,
                                       const float2* __restrict__ eta, float* __restrict__ out, int C, int H, int W,
-                                      int cc, FftPlan p, int in_rw, int rw, float scale) {
+                                      int cc, FftPlan p, int in_rw, int rw, float scale, MaskDesc mask, int prune) {
     extern __shared__ float2 smem[];
     float2* A = smem;
     float2* Bf = A + (size_t)cc * p.ls;
     float2* tw_s = Bf + (size_t)cc * p.ls;
+    unsigned short* cols_s = reinterpret_cast<unsigned short*>(tw_s + p.n);
+    __shared__ int scan_scratch[33];
     load_twiddles(tw_s, p);
     const int h = blockIdx.x, b = blockIdx.y;
+    int ns = W;
+    if (COMPACT) ns = build_active_cols(mask, b, W, rw, prune != 0, cols_s, scan_scratch);
     const long long cstride = (long long)H * W;
     const float2* Trow = T2 + ((long long)b * C * H + h) * W;
     const float2* Srow = S + ((long long)b * C * H + h) * W;
@@ -206,9 +255,14 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
     for (int c0 = 0; c0 < C; c0 += cc) {
         const int nc = min(cc, C - c0);
         if (c0 > 0) __syncthreads();
-        for (int j = threadIdx.x; j < W; j += blockDim.x) {
-            const float2* tp = Trow + (long long)c0 * cstride + rot_add(j, in_rw, W);
-            float2* dp = St + j;
+        if (COMPACT && ns < W) {
+            for (int j = threadIdx.x; j < W; j += blockDim.x)
+                for (int c = 0; c < nc; ++c) St[(size_t)c * p.ls + j] = make_float2(0.f, 0.f);
+            __syncthreads();
+        }
+        for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+            const float2* tp = Trow + (long long)c0 * cstride + (COMPACT ? j : rot_add(j, in_rw, W));
+            float2* dp = St + (COMPACT ? (int)cols_s[j] : j);
             int c = 0;
             for (; c + 4 <= nc; c += 4) {
                 const float2 v0 = tp[(long long)(c + 0) * cstride], v1 = tp[(long long)(c + 1) * cstride];
@@ -296,17 +350,18 @@ static int dc_geometry(int C, int H, int W, DcGeom* g) {
     }();
     const size_t row_budget = max_smem < (size_t)budget_kb * 1024 ? max_smem : (size_t)budget_kb * 1024;
     int cc = C;
+    MRB_REQUIRE(W <= 65535 && H <= 65535, MRB_EUNSUPPORTED, "H and W must be <= 65535");
     while (cc > 1 && fft_smem_bytes(g->pw, cc) > row_budget) cc = (cc + 1) / 2;
     MRB_REQUIRE(fft_smem_bytes(g->pw, cc) <= max_smem, MRB_EUNSUPPORTED, "W=%d does not fit shared memory", W);
     g->cc = cc;
-    g->smem_row = fft_smem_bytes(g->pw, cc);
+    g->smem_row = fft_smem_bytes(g->pw, cc) + (size_t)W * sizeof(unsigned short) + 16;
     int ti = 16;
     while (ti > 1 && fft_smem_bytes(g->ph, ti) > row_budget) ti /= 2;
     MRB_REQUIRE(fft_smem_bytes(g->ph, ti) <= max_smem, MRB_EUNSUPPORTED, "H=%d does not fit shared memory", H);
     g->ti = ti;
     g->tsh = 0;
     while ((1 << g->tsh) < ti) ++g->tsh;
-    g->smem_col = fft_smem_bytes(g->ph, ti);
+    g->smem_col = fft_smem_bytes(g->ph, ti) + (size_t)W * sizeof(unsigned short) + 16;
     // row kernels: one thread per column when W <= 1024, else up to 4 columns per thread
     int tr = ((W + 31) / 32) * 32;
     if (tr > 1024) tr = 1024;
@@ -337,7 +392,8 @@ static int check_dims(int B, int C, int H, int W, int norm, const char* who) {
 
 template <typename K>
 static int set_smem(K kernel) {
-    MRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)device_max_smem_optin()));
+    // static shared memory (scan scratch) counts against the same limit
+    MRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)device_max_smem_optin() - 1024));
     return MRB_OK;
 }
 
@@ -368,22 +424,23 @@ extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, co
     const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
     const double npts = (double)H * W;
     const float fs = norm_scale(norm, 0, npts), bs = norm_scale(norm, 1, npts);
-    if ((rc = set_smem(expand_rowfft_kernel))) return rc;
+    if ((rc = set_smem(expand_rowfft_kernel<true>))) return rc;
     if ((rc = set_smem(col_dc_kernel))) return rc;
-    if ((rc = set_smem(rowifft_reduce_kernel<1>))) return rc;
-    if ((rc = set_smem(rowifft_reduce_kernel<2>))) return rc;
-    expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1, C, H,
-                                                                        W, g.cc, g.pw, rw);
+    if ((rc = set_smem(rowifft_reduce_kernel<1, true>))) return rc;
+    if ((rc = set_smem(rowifft_reduce_kernel<2, true>))) return rc;
+    const int prune = (mask_h == 1) ? 1 : 0;  // 1-D masks: only sampled k_w columns are transformed along H
+    expand_rowfft_kernel<true><<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1,
+                                                                              C, H, W, g.cc, g.pw, rw, m, prune);
     MRB_LAUNCHED();
     col_dc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(T1, (const float2*)y, T2, m, C, H, W, g.tsh,
-                                                                          g.ph, rh, rw, fs);
+                                                                          g.ph, rh, rw, fs, prune);
     MRB_LAUNCHED();
     if (out_nhwc)
-        rowifft_reduce_kernel<2><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
-            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
+        rowifft_reduce_kernel<2, true><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2, m, prune);
     else
-        rowifft_reduce_kernel<1><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
-            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2);
+        rowifft_reduce_kernel<1, true><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+            T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2, m, prune);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -404,9 +461,11 @@ extern "C" int mrb_sens_reduce(const void* x, const void* S, void* out, int B, i
     // inverse FFT along H (strided lines), rotations applied on both sides; W axis untouched (still centred)
     rc = fft1d_launch((const float2*)x, T2, (long long)B * C, H, W, 1, rh, rh, 1.0f, st);
     if (rc) return rc;
-    if ((rc = set_smem(rowifft_reduce_kernel<0>))) return rc;
-    rowifft_reduce_kernel<0><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(T2, (const float2*)S, nullptr, (float*)out,
-                                                                            C, H, W, g.cc, g.pw, rw, rw, bs);
+    if ((rc = set_smem(rowifft_reduce_kernel<0, false>))) return rc;
+    MaskDesc nomask;
+    memset(&nomask, 0, sizeof(nomask));
+    rowifft_reduce_kernel<0, false><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
+        T2, (const float2*)S, nullptr, (float*)out, C, H, W, g.cc, g.pw, rw, rw, bs, nomask, 0);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -436,10 +495,10 @@ extern "C" int mrb_sens_expand_softdc(const void* img, const void* S, const void
     float2* T1 = (float2*)ws;
     const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
     const float fs = norm_scale(norm, 0, (double)H * W);
-    if ((rc = set_smem(expand_rowfft_kernel))) return rc;
+    if ((rc = set_smem(expand_rowfft_kernel<false>))) return rc;
     if ((rc = set_smem(col_softdc_kernel))) return rc;
-    expand_rowfft_kernel<<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)img, (const float2*)S, T1, C, H,
-                                                                        W, g.cc, g.pw, rw);
+    expand_rowfft_kernel<false><<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)img, (const float2*)S, T1,
+                                                                               C, H, W, g.cc, g.pw, rw, m, 0);
     MRB_LAUNCHED();
     col_softdc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(
         T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.tsh, g.ph, rh, rw, fs,
