@@ -76,6 +76,9 @@ struct Params {
     int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
     unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py); null in production
     int debug;               // profiling switches (mrb_tc_set_debug): 1 skip MMAs, 2 skip global loads, 4 skip epilogue math
+    int ngroups;             // conv: number of independent accumulator groups (each [hi*hi | cross], 2*nhalf columns);
+                             // the tensor core's fp32 accumulation truncates, so its error grows linearly with the
+                             // chain length -- short chains summed in the epilogue (RN fp32) keep it at fp32 level
     int stacked;             // 1: stacked-B issue (2 MMAs per k-step); requires small_off == n of every segment
     int small_off;           // != 0: the two cross terms (lo*hi, hi*lo) accumulate in columns dcol + small_off, so the
                              // long hi*hi chain sees 3x fewer (truncating) tensor-core accumulations; summed in the epilogue
@@ -593,6 +596,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                         tmem_ld8(t0 + P.small_off + j, a2);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) a[q] += a2[q];
+                        for (int g = 1; g < P.ngroups; ++g) {
+                            float b1[8], b2[8];
+                            tmem_ld8(t0 + g * 2 * P.nhalf + j, b1);
+                            tmem_ld8(t0 + g * 2 * P.nhalf + P.small_off + j, b2);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) a[q] += b1[q] + b2[q];
+                        }
                     }
                     if (valid) {
                         float o[8];
@@ -770,10 +780,13 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
     P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
     P.cout = cout; P.nhalf = cout / 2;
     P.wchunk_rows = cout / 2; P.n_wchunks = k * k * 2;
-    P.acc_cols = cout;  // hi*hi chain + cross-term chain
+    // one accumulator group per kernel row (k taps = 2k K-chunks = 8k k-steps per chain)
+    P.ngroups = k;
+    P.acc_cols = k * cout;  // per group: hi*hi chain + cross-term chain
     P.small_off = cout / 2;
     P.stacked = 1;
-    P.acc_bufs = (2 * cout <= 512 - 2 * tc::A_STAGE_COLS) ? 2 : 1;
+    P.acc_bufs = (2 * P.acc_cols <= 512 - 3 * tc::A_STAGE_COLS) ? 2 : 1;
+    MRB_REQUIRE(P.acc_cols <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.nseg = k * k * 2;
     const int pad = dil * (k - 1) / 2;
@@ -781,8 +794,9 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
         for (int kc = 0; kc < 2; ++kc) {
             tc::Segment& s = P.seg[t * 2 + kc];
             s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
-            s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = 0; s.n = (short)(cout / 2);
-            s.first = (t == 0 && kc == 0);
+            s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = (short)((t / k) * cout);
+            s.n = (short)(cout / 2);
+            s.first = ((t % k) == 0 && kc == 0);
         }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -800,6 +814,7 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
     P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
     P.cout = cout; P.nhalf = cout / 2;
     P.wchunk_rows = cout / 2; P.n_wchunks = 4;
+    P.ngroups = 1;
     P.acc_cols = cout;
     P.small_off = cout / 2;
     P.stacked = 1;

@@ -11,6 +11,20 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 
 
+def _diag(out_nchw, ref, tol, what):
+    """rel-L2 check that reports where the error sits (pixels / channels) when it fails."""
+    e = rel_l2(out_nchw, ref)
+    if e >= tol:
+        o = torch.as_tensor(out_nchw).detach().cpu().float()
+        d = (o - ref).abs()
+        idx = (d > 10 * tol * ref.abs().max()).nonzero()
+        W = ref.shape[-1]
+        msg = "%s: rel-L2 %.3e >= %.1e; %d bad elems; chans %s; pixels %s" % (
+            what, e, tol, idx.shape[0], sorted(set(int(i[1]) for i in idx))[:64],
+            sorted(set(int(i[2]) * W + int(i[3]) for i in idx))[:64])
+        raise AssertionError(msg)
+
+
 def _pack(kind, w, w2=None, k=1):
     from mridc_b200 import _lib
 
@@ -51,7 +65,7 @@ def test_tc_ops_vs_oracle(B, H, W):
     out = torch.empty(B, H, W, 64, device="cuda")
     x4d, p1, b1d = nhwc(x4), _pack(2, w1.cuda()), b1.cuda()
     _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(x4d), _lib.ptr(p1), _lib.ptr(b1d), _lib.ptr(out), B, H, W, 64, 1, st))
-    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
+    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "conv5x5x4")
     # conv 3x3 dilation 2 (and dilation 1), 64 -> 64
     x = torch.randn(B, 64, H, W, generator=g)
     xd = nhwc(x)
@@ -62,7 +76,7 @@ def test_tc_ops_vs_oracle(B, H, W):
         p2, b2d = _pack(0, w2.cuda(), k=3), b2.cuda()
         _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(xd), _lib.ptr(p2), _lib.ptr(b2d), _lib.ptr(out), B, H, W, 64, 3, dil,
                                         relu, st))
-        assert rel_l2(out.permute(0, 3, 1, 2), ref) < 5e-6, dil
+        _diag(out.permute(0, 3, 1, 2), ref, 5e-6, "conv3x3 dil %d" % dil)
     # ConvGRU cell, kernel size 1
     h = torch.randn(B, 64, H, W, generator=g)
     wih = torch.randn(192, 64, 1, 1, generator=g) * 0.1
@@ -72,7 +86,7 @@ def test_tc_ops_vs_oracle(B, H, W):
     hd, pg, bihd = nhwc(h), _pack(1, wih.cuda(), whh.cuda()), bih.cuda()
     _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pg), _lib.ptr(bihd), _lib.ptr(out), B, H, W, 64,
                                    st))
-    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 2e-6
+    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "gru")
     # final conv 64 -> 2 with the eta update
     w3 = torch.randn(2, 64, 3, 3, generator=g) * 0.05
     eta = torch.randn(B, H, W, 2, generator=g)
@@ -138,3 +152,34 @@ def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch):
     with torch.no_grad():
         r2, _ = onets.rim_block(sd, dict(cfg), ref, y, S, m, None, [t.clone() for t in ref_h], 1.0, True)
     assert rel_l2(e2[-1], r2[-1]) < 2e-5
+
+
+def test_tc_kernels_are_deterministic():
+    """Race detector: the warp-specialised pipeline must give bit-identical results run to run."""
+    from mridc_b200 import _lib
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, W = 2, 96, 112
+    x = torch.randn(B, H, W, 64, device="cuda", generator=g)
+    h = torch.randn(B, H, W, 64, device="cuda", generator=g)
+    g4 = torch.randn(B, H, W, 4, device="cuda", generator=g)
+    w1 = torch.randn(64, 4, 5, 5, device="cuda", generator=g) * 0.2
+    w2 = torch.randn(64, 64, 3, 3, device="cuda", generator=g) * 0.05
+    wih = torch.randn(192, 64, device="cuda", generator=g) * 0.1
+    whh = torch.randn(192, 64, device="cuda", generator=g) * 0.1
+    b = torch.randn(192, device="cuda", generator=g)
+    p1, p2, pg = _pack(2, w1), _pack(0, w2, k=3), _pack(1, wih, whh)
+    outs = [[], [], []]
+    for _ in range(12):
+        o1, o2, o3 = (torch.empty(B, H, W, 64, device="cuda") for _ in range(3))
+        _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(g4), _lib.ptr(p1), _lib.ptr(b), _lib.ptr(o1), B, H, W, 64, 1, st))
+        _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(x), _lib.ptr(p2), _lib.ptr(b), _lib.ptr(o2), B, H, W, 64, 3, 2, 1, st))
+        _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pg), _lib.ptr(b), _lib.ptr(o3), B, H, W, 64, st))
+        for lst, o in zip(outs, (o1, o2, o3)):
+            lst.append(o)
+    torch.cuda.synchronize()
+    for lst in outs:
+        for o in lst[1:]:
+            assert torch.equal(o, lst[0])
