@@ -35,7 +35,9 @@ constexpr int KC = 32;                        // channels per K chunk (32 tf32 c
 constexpr int A_STAGE_COLS = 2 * KC;          // hi + lo
 constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant (each takes half of the channels)
 constexpr int LOAD_GROUPS = 2, LOAD_WARPS = 4 * LOAD_GROUPS;  // loader groups alternate segments
-constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + 1) * 32;
+constexpr int MMA_WARPS = 2;                  // two issuing lanes (alternate segments): one thread cannot feed the pipe
+constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + MMA_WARPS + 1) * 32;  // + weight-streaming warp
+constexpr int B_STAGES = 6;                   // streamed-weights ring (stream_b)
 constexpr int MAX_SEGS = 20;
 constexpr int MAX_STAGES = 6;
 constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
@@ -69,8 +71,11 @@ struct Params {
     int acc_bufs;            // 1 or 2 accumulator buffers
     int tmem_cols;           // allocation: 512
     int cout;                // output channels per pixel (both halves)
-    int nhalf;               // output channels handled per item (cout / 2)
+    int n_split;             // 1 or 2: CTAs per pixel tile (each takes cout / n_split output channels)
+    int nhalf;               // output channels handled per item (cout / n_split)
     int mode;
+    int stream_b;            // 1: weights are not resident; each loader group streams the B chunk of its segment
+                             // (hi rows | lo rows, wchunk_rows*256 B) into its own ring of tb_depth slots
     int tb_depth;            // cp.async staging tiles per loader warp (2 or 3)
     int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
     int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
@@ -79,6 +84,7 @@ struct Params {
     int ngroups;             // conv: number of independent accumulator groups (each [hi*hi | cross], 2*nhalf columns);
                              // the tensor core's fp32 accumulation truncates, so its error grows linearly with the
                              // chain length -- short chains summed in the epilogue (RN fp32) keep it at fp32 level
+    int n_issuers;           // 1 or 2 MMA-issuing lanes (2: segments alternate; each issuer owns its accumulator group)
     int stacked;             // 1: stacked-B issue (2 MMAs per k-step); requires small_off == n of every segment
     int small_off;           // != 0: the two cross terms (lo*hi, hi*lo) accumulate in columns dcol + small_off, so the
                              // long hi*hi chain sees 3x fewer (truncating) tensor-core accumulations; summed in the epilogue
@@ -252,6 +258,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// four 8-column loads with a single wait (GRU epilogue: hh_n, r, z, ih_n blocks)
+__device__ __forceinline__ void tmem_ld8x4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, float* v0, float* v1, float* v2,
+                                           float* v3) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%33];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%34];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%35];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v0[i] = __uint_as_float(r[i]);
+        v1[i] = __uint_as_float(r[8 + i]);
+        v2[i] = __uint_as_float(r[16 + i]);
+        v3[i] = __uint_as_float(r[24 + i]);
+    }
+}
 __device__ __forceinline__ void tmem_ld_wait() {}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
@@ -289,19 +319,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int wbytes_chunk = P.wchunk_rows * 128;
     uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
-    uint8_t* tb_s = w_s + (size_t)P.n_wchunks * 2 * wbytes_chunk;     // [LOAD_WARPS][32 rows x 128 B]
-    uint64_t* bars = (uint64_t*)(tb_s + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES);
+    uint8_t* tb_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [LOAD_WARPS][depth][32 rows x 128 B]
+    uint8_t* bst_s = tb_s + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES;  // [B_STAGES][2*wbytes_chunk] if stream_b
+    uint64_t* bars = (uint64_t*)(bst_s + (P.stream_b ? (size_t)B_STAGES * 2 * wbytes_chunk : 0));
     uint64_t* full = bars;                          // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
     uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [2]
     uint64_t* acc_empty = acc_full + 2;             // [2]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-    SegIssue* seg_tab = (SegIssue*)(acc_empty + 4);  // [MAX_SEGS]
+    uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
+    uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
+    SegIssue* seg_tab = (SegIssue*)(b_empty + B_STAGES);  // [MAX_SEGS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int half = blockIdx.x & 1;
-    const int first_tile = blockIdx.x >> 1;
-    const int tile_stride = gridDim.x >> 1;
+    const int half = blockIdx.x % P.n_split;
+    const int first_tile = blockIdx.x / P.n_split;
+    const int tile_stride = gridDim.x / P.n_split;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
@@ -309,8 +342,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_full[b], P.n_issuers);
             mbar_init(&acc_empty[b], EPI_WARPS * 32);
+        }
+        for (int b = 0; b < B_STAGES; ++b) {
+            mbar_init(&b_full[b], 1);   // the producer's arrive.expect_tx; the bulk copy completes the transaction bytes
+            mbar_init(&b_empty[b], 1);  // tcgen05.commit of the MMAs that read the slot
         }
         fence_barrier_init();
     }
@@ -328,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
-    {
+    if (!P.stream_b) {
         const float4* g = reinterpret_cast<const float4*>(P.wpack) + (size_t)half * P.n_wchunks * 2 * wbytes_chunk / 16;
         float4* s = reinterpret_cast<float4*>(w_s);
         const int n16 = P.n_wchunks * 2 * wbytes_chunk / 16;
@@ -340,6 +377,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_col0 = (uint32_t)(P.acc_bufs * P.acc_cols);  // first TMEM column of the A ring
+    {
+        // Accumulate-only protocol: every accumulator column starts at zero and the epilogue re-zeroes what it has read.
+        if (warp < EPI_WARPS) {
+            const float z16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            const int ncol = P.acc_bufs * P.acc_cols, hc = ncol / 2;  // multiple of 32
+            for (int j = (warp >> 2) * hc; j < ((warp >> 2) + 1) * hc; j += 16) tmem_st16(tq + (uint32_t)j, z16);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + LOAD_WARPS) {
         // ============================== LOADERS ==============================
@@ -355,6 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         int coords_tile = -1;
         bool uniform_rows = false;
 
+        const int gt = (lw & 3) * 32 + lane;  // thread index within the loader group (0..127)
         // cp.async gather of one segment into staging tile `slot` (no registers held while in flight)
         auto issue_loads = [&](int tile, int sgi, int slot) {
             if (tile != coords_tile) {
@@ -484,51 +535,89 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
             o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_st; o[3] = t_issue;
         }
-    } else if (warp == EPI_WARPS + LOAD_WARPS) {
-        // ============================== MMA ISSUER ==============================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+    } else if (warp >= EPI_WARPS + LOAD_WARPS && warp < EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
+        // ============================== MMA ISSUERS ==============================
+        // Issuer mi handles segments mi, mi + 2, ... of every tile (the same split as the loader groups).  All MMAs
+        // accumulate (the epilogue leaves the accumulators zeroed), so the two issue streams need no mutual ordering.
+        const int mi = warp - (EPI_WARPS + LOAD_WARPS);
+        if (lane == 0 && mi < P.n_issuers) {
+            const int NI = P.n_issuers;
+            const bool prof = P.prof != nullptr;
+            int stage = mi % P.stages;
+            uint32_t phase = (uint32_t)(mi / P.stages) & 1u;
+            int bs = mi % B_STAGES;
+            uint32_t bphase = (uint32_t)(mi / B_STAGES) & 1u;
             int it = 0;
-            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, c0;
+            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, c0 = 0;
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
                 const int buf = it % P.acc_bufs;
                 const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
-                c0 = clock64();
+                if (prof) c0 = clock64();
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
-                t_wacc += clock64() - c0;
+                if (prof) t_wacc += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + (uint32_t)(buf * P.acc_cols);
-                for (int sgi = 0; sgi < P.nseg; ++sgi) {
-                    const SegIssue si = seg_tab[sgi];
-                    c0 = clock64();
+                for (int sgi = mi; sgi < P.nseg; sgi += NI) {
+                    SegIssue si = seg_tab[sgi];
+                    if (P.stream_b) {
+                        const uint32_t b_hi = smem_u32(bst_s + (size_t)bs * 2 * wbytes_chunk);
+                        si.dbh = make_desc(b_hi);
+                        si.dbl = make_desc(b_hi + wbytes_chunk);
+                        if (prof) c0 = clock64();
+                        mbar_wait(&b_full[bs], bphase);
+                        if (prof) t_wb += clock64() - c0;
+                    }
+                    if (prof) c0 = clock64();
                     mbar_wait(&full[stage], phase);
-                    t_wfull += clock64() - c0;
+                    if (prof) t_wfull += clock64() - c0;
                     tc_fence_after();
                     const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
                     const uint32_t d = d_base + si.dcol;
-                    const uint32_t fresh = si.first;
-                    c0 = clock64();
+                    if (prof) c0 = clock64();
                     if (P.debug & 1) {
                     } else if (P.stacked) {
-                        // the first stacked MMA of a fresh accumulator overwrites both [d, d+n) and [d+n, d+2n)
-                        umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc,
-                                                fresh ? 0u : 1u);
+                        umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc, 1u);
                     } else {
-                        umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc,
-                                        fresh ? 0u : 1u, (fresh && P.small_off != 0) ? 0u : 1u);
+                        umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc, 1u, 1u);
                     }
-                    t_mma += clock64() - c0;
-                    c0 = clock64();
+                    if (prof) { t_mma += clock64() - c0; c0 = clock64(); }
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
-                    t_commit += clock64() - c0;
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    if (P.stream_b) {
+                        umma_commit(&b_empty[bs]);
+                        bs += NI;
+                        while (bs >= B_STAGES) { bs -= B_STAGES; bphase ^= 1u; }
+                    }
+                    if (prof) t_commit += clock64() - c0;
+                    stage += NI;
+                    while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
                 }
                 umma_commit(&acc_full[buf]);
             }
-            if (P.prof) {
+            if (prof && mi == 0) {
                 unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
-                o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit;
+                o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb;
+            }
+        }
+    } else if (warp == EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
+        // ============================== WEIGHT STREAMER (stream_b) ==============================
+        // one lane, one bulk copy (cp.async.bulk, 2*wbytes_chunk contiguous bytes: hi rows | lo rows) per segment
+        if (P.stream_b && lane == 0) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            const uint32_t bytes = (uint32_t)(2 * wbytes_chunk);
+            for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
+                for (int sgi = 0; sgi < P.nseg; ++sgi) {
+                    mbar_wait_sleep(&b_empty[bs], bphase ^ 1, 64);
+                    const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(P.wpack) + (size_t)P.seg[sgi].wchunk * bytes;
+                    const uint32_t bar = smem_u32(&b_full[bs]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                            smem_u32(bst_s + (size_t)bs * bytes)),
+                        "l"(gsrc), "r"(bytes), "r"(bar)
+                        : "memory");
+                    if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+                }
             }
         }
     } else {
@@ -554,19 +643,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             } else if (P.mode == MODE_GRU) {
                 const int nh = P.nhalf;  // hidden channels of this half
                 for (int j = j_lo; j < j_hi; j += 8) {
-                    float xr[8], xz[8], xn[8], hr[8], hz[8], hn[8];
-                    tmem_ld8(t0 + j, xr);
-                    tmem_ld8(t0 + nh + j, xz);
-                    tmem_ld8(t0 + 2 * nh + j, xn);
-                    tmem_ld8(t0 + 3 * nh + j, hr);
-                    tmem_ld8(t0 + 4 * nh + j, hz);
-                    tmem_ld8(t0 + 5 * nh + j, hn);
-                    tmem_ld_wait();
+                    float ar[8], az[8], xn[8], hn[8];
+                    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+                    if (valid) {  // issue the global loads first: their latency overlaps the TMEM loads
+                        const float4* hpp = reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j);
+                        h0 = __ldg(hpp);
+                        h1 = __ldg(hpp + 1);
+                    }
+                    tmem_ld8x4(t0 + j, t0 + nh + j, t0 + 2 * nh + j, t0 + 3 * nh + j, hn, ar, az, xn);
                     if (valid) {
                         const int Ch = P.cout;
                         float hp[8];
-                        const float4* hpp = reinterpret_cast<const float4*>(P.hprev + p * Ch + ch0 + j);
-                        float4 h0 = hpp[0], h1 = hpp[1];
                         hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w;
                         hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
                         float o[8];
@@ -576,9 +663,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                             const float br = P.bias ? P.bias[c] : 0.f;
                             const float bz = P.bias ? P.bias[Ch + c] : 0.f;
                             const float bn = P.bias ? P.bias[2 * Ch + c] : 0.f;
-                            // rnn_cells.py:121-125
-                            const float r = sigmoid_acc((xr[q] + br) + hr[q]);
-                            const float z = sigmoid_acc((xz[q] + bz) + hz[q]);
+                            // rnn_cells.py:121-125 (ih + hh of the r and z gates were summed by the tensor core)
+                            const float r = sigmoid_acc(ar[q] + br);
+                            const float z = sigmoid_acc(az[q] + bz);
                             const float n = tanh_acc((xn[q] + bn) + r * hn[q]);
                             o[q] = n * (1.f - z) + z * hp[q];
                         }
@@ -617,6 +704,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     }
                 }
             }
+            if (!(P.debug & 4)) {
+                // leave the columns this thread has read zeroed for the next tile that accumulates into the buffer
+                const float z16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const int nblk = P.acc_cols / P.nhalf;
+                for (int blk = 0; blk < nblk; ++blk)
+                    for (int j = j_lo; j < j_hi; j += 16) tmem_st16(t0 + (uint32_t)(blk * P.nhalf + j), z16);
+                tmem_st_wait();
+            }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
         }
@@ -641,13 +736,14 @@ struct PackDesc {
     const float* w2;
     int mode;             // 0 conv taps (chunk = tap*2 + kchunk), 1 GRU (chunks 0,1 = ih ; 2,3 = hh), 2 im2col 5x5x4
     int cout, cin, ksz;   // conv geometry
-    int nhalf;            // output channels per half
+    int nhalf;            // output channels per split part
     int rows;             // rows per chunk
     int n_chunks;
+    int n_split;
 };
 
 __global__ void pack_weights_kernel(PackDesc D, float* dst) {
-    const int total = 2 * D.n_chunks * D.rows * KC;
+    const int total = D.n_split * D.n_chunks * D.rows * KC;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         int k = t % KC;
         int r = (t / KC) % D.rows;
@@ -659,11 +755,14 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
             const int co = half * D.nhalf + r, ci = kc * KC + k;
             if (co < D.cout && ci < D.cin) v = D.w[((long long)co * D.cin + ci) * D.ksz * D.ksz + tap];
         } else if (D.mode == 1) {
-            // rows: [r gate (nhalf) ; z gate ; n gate] of this half
+            // chunks 0,1: w_hh with rows [n ; r ; z] of this half (accumulator columns [0, 3*nhalf));
+            // chunks 2,3: w_ih with rows [r ; z ; n] (columns [nhalf, 4*nhalf)): the r and z columns are shared
             const int Ch = D.cout;
-            const int g = r / D.nhalf, j = r % D.nhalf;
+            const int blk = r / D.nhalf, j = r % D.nhalf;
+            const bool is_hh = ch < 2;
+            const int g = is_hh ? ((blk + 2) % 3) : blk;  // hh order n,r,z -> gate index 2,0,1
             const int row = g * Ch + half * D.nhalf + j;
-            const float* w = (ch < 2) ? D.w : D.w2;
+            const float* w = is_hh ? D.w2 : D.w;
             const int ci = (ch & 1) * KC + k;
             v = w[(long long)row * D.cin + ci];
         } else {
@@ -684,8 +783,9 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 }
 
 static size_t smem_needed(const Params& P) {
-    return 1024 + (size_t)P.n_wchunks * 2 * P.wchunk_rows * 128 + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 +
-           MAX_SEGS * sizeof(SegIssue);
+    const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
+    const size_t wres = P.stream_b ? (size_t)B_STAGES * chunk2 : (size_t)P.n_wchunks * chunk2;
+    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + MAX_SEGS * sizeof(SegIssue);
 }
 
 static int g_debug = 0;
@@ -706,8 +806,8 @@ static int launch(Params& P, cudaStream_t st) {
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
     MRB_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     int sms = device_sm_count();
-    int grid = sms & ~1;  // pairs of CTAs (one per channel half)
-    if (grid > 2 * P.n_tiles) grid = 2 * P.n_tiles;
+    int grid = (sms / P.n_split) * P.n_split;  // groups of n_split CTAs share a pixel tile
+    if (grid > P.n_split * P.n_tiles) grid = P.n_split * P.n_tiles;
     tc_kernel<<<grid, THREADS, smem_needed(P), st>>>(P);
     MRB_LAUNCHED();
     return MRB_OK;
@@ -723,16 +823,16 @@ extern "C" void mrb_tc_set_prof(void* buf) { tc::g_prof = (unsigned long long*)b
 
 extern "C" size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k) {
     // kind 0: conv k x k (cin multiple of 32); 1: GRU 1x1 (cout = hidden, cin = 64 for both inputs); 2: conv 5x5 x 4ch
-    if (kind == 0) return (size_t)2 * (k * k * (cin / 32)) * 2 * (cout / 2) * 32;
+    if (kind == 0) return (size_t)(k * k * (cin / 32)) * 2 * cout * 32;
     if (kind == 1) return (size_t)2 * 4 * 2 * (3 * cout / 2) * 32;
-    return (size_t)2 * 4 * 2 * (cout / 2) * 32;
+    return (size_t)4 * 2 * cout * 32;
 }
 
 extern "C" int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int k, void* stream) {
     MRB_REQUIRE(w && dst, MRB_EINVAL, "mrb_tc_pack_conv: null pointer");
-    MRB_REQUIRE(cin == 64 && (cout % 32) == 0 && cout >= 32 && cout <= 256 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS,
+    MRB_REQUIRE(cin == 64 && (cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS,
                 MRB_EUNSUPPORTED, "mrb_tc_pack_conv: need cin == 64, cout multiple of 32, k*k*2 <= %d", tc::MAX_SEGS);
-    tc::PackDesc D{(const float*)w, nullptr, 0, cout, cin, k, cout / 2, cout / 2, k * k * 2};
+    tc::PackDesc D{(const float*)w, nullptr, 0, cout, cin, k, cout, cout, k * k * 2, 1};
     tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
@@ -741,7 +841,7 @@ extern "C" int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int
 extern "C" int mrb_tc_pack_gru(const void* w_ih, const void* w_hh, void* dst, int ch, int cx, void* stream) {
     MRB_REQUIRE(w_ih && w_hh && dst, MRB_EINVAL, "mrb_tc_pack_gru: null pointer");
     MRB_REQUIRE(ch == 64 && cx == 64, MRB_EUNSUPPORTED, "mrb_tc_pack_gru: tensor-core GRU needs 64 input and hidden channels");
-    tc::PackDesc D{(const float*)w_ih, (const float*)w_hh, 1, ch, cx, 1, ch / 2, 3 * ch / 2, 4};
+    tc::PackDesc D{(const float*)w_ih, (const float*)w_hh, 1, ch, cx, 1, ch / 2, 3 * ch / 2, 4, 2};
     tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
@@ -749,8 +849,8 @@ extern "C" int mrb_tc_pack_gru(const void* w_ih, const void* w_hh, void* dst, in
 
 extern "C" int mrb_tc_pack_conv5x5x4(const void* w, void* dst, int cout, void* stream) {
     MRB_REQUIRE(w && dst, MRB_EINVAL, "mrb_tc_pack_conv5x5x4: null pointer");
-    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 256, MRB_EUNSUPPORTED, "mrb_tc_pack_conv5x5x4: bad cout");
-    tc::PackDesc D{(const float*)w, nullptr, 2, cout, 4, 5, cout / 2, cout / 2, 4};
+    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128, MRB_EUNSUPPORTED, "mrb_tc_pack_conv5x5x4: bad cout");
+    tc::PackDesc D{(const float*)w, nullptr, 2, cout, 4, 5, cout, cout, 4, 1};  // not split: N = cout per CTA
     tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
@@ -770,7 +870,7 @@ static int tc_common(tc::Params& P, int B, int H, int W) {
 extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
                                 int cout, int k, int dil, int relu, void* stream) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv_nhwc: null pointer");
-    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 256 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS && dil >= 1,
+    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS && dil >= 1,
                 MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: unsupported geometry");
     tc::Params P;
     memset(&P, 0, sizeof(P));
@@ -778,15 +878,23 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = nullptr; P.cs[1] = 0;
     P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
-    P.cout = cout; P.nhalf = cout / 2;
-    P.wchunk_rows = cout / 2; P.n_wchunks = k * k * 2;
-    // one accumulator group per kernel row (k taps = 2k K-chunks = 8k k-steps per chain)
-    P.ngroups = k;
-    P.acc_cols = k * cout;  // per group: hi*hi chain + cross-term chain
-    P.small_off = cout / 2;
+    // All output channels in one CTA (stacked MMAs of N = 2*cout and cout: half the MMA instructions of a channel
+    // split, which is what bounds this kernel); the k*k*2 weight chunks (2*cout*128 B each) do not fit shared memory
+    // next to the staging tiles, so each loader group streams the chunk of its segment from L2.
+    P.n_split = 1;
+    P.stream_b = 1;
+    P.cout = cout; P.nhalf = cout;
+    P.wchunk_rows = cout; P.n_wchunks = k * k * 2;
+    // accumulator groups (short accumulation chains, see Params::ngroups): as many as TMEM allows next to a 4-stage A ring
+    // two accumulator groups, one per MMA issuer (= K-chunk parity): fixed accumulation order inside a group
+    // (bit-reproducible), half-length chains (see Params::ngroups); the epilogue adds the groups
+    P.ngroups = 2;
+    P.n_issuers = 2;
+    MRB_REQUIRE(P.ngroups * 2 * cout <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");
+    P.acc_cols = P.ngroups * 2 * cout;  // per group: hi*hi chain + cross-term chain
+    P.small_off = cout;
     P.stacked = 1;
-    P.acc_bufs = (2 * P.acc_cols <= 512 - 3 * tc::A_STAGE_COLS) ? 2 : 1;
-    MRB_REQUIRE(P.acc_cols <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");
+    P.acc_bufs = 1;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.nseg = k * k * 2;
     const int pad = dil * (k - 1) / 2;
@@ -794,9 +902,9 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
         for (int kc = 0; kc < 2; ++kc) {
             tc::Segment& s = P.seg[t * 2 + kc];
             s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
-            s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = (short)((t / k) * cout);
-            s.n = (short)(cout / 2);
-            s.first = ((t % k) == 0 && kc == 0);
+            s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = (short)(kc * 2 * cout);
+            s.n = (short)cout;
+            s.first = 0;
         }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -805,27 +913,30 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
 extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
                                      int cout, int relu, void* stream) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv5x5x4_nhwc: null pointer");
-    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 256, MRB_EUNSUPPORTED, "mrb_tc_conv5x5x4_nhwc: bad cout");
+    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128, MRB_EUNSUPPORTED, "mrb_tc_conv5x5x4_nhwc: bad cout");
     tc::Params P;
     memset(&P, 0, sizeof(P));
     int rc = tc_common(P, B, H, W);
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 4;
     P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
-    P.cout = cout; P.nhalf = cout / 2;
-    P.wchunk_rows = cout / 2; P.n_wchunks = 4;
+    P.n_split = 1;  // all output channels in one CTA: weights (4 chunks x 2 x cout x 128 B) stay resident
+    P.cout = cout; P.nhalf = cout;
+    P.wchunk_rows = cout; P.n_wchunks = 4;
     P.ngroups = 1;
-    P.acc_cols = cout;
-    P.small_off = cout / 2;
+    P.n_issuers = 1;
+    P.acc_cols = 2 * cout;
+    P.small_off = cout;
     P.stacked = 1;
-    P.acc_bufs = (2 * cout <= 512 - 2 * tc::A_STAGE_COLS) ? 2 : 1;
+    P.acc_bufs = 2;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.im2col = 1;
     P.nseg = 4;
     for (int c = 0; c < 4; ++c) {
         tc::Segment& s = P.seg[c];
-        s.src = 0; s.dy = 0; s.dx = 0; s.c0 = (short)c; s.wchunk = (short)c; s.dcol = 0; s.n = (short)(cout / 2);
-        s.first = (c == 0);
+        s.src = 0; s.dy = 0; s.dx = 0; s.c0 = (short)c; s.wchunk = (short)c; s.dcol = 0;
+        s.n = (short)cout;
+        s.first = 0;
     }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -842,16 +953,25 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = (const float*)h; P.cs[1] = 64;
     P.wpack = (const float*)wpack; P.bias = (const float*)b_ih; P.hprev = (const float*)h; P.out = (float*)h_out;
+    P.n_split = 2;
     P.cout = ch; P.nhalf = ch / 2;
     P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 4;
-    P.acc_cols = 6 * (ch / 2);  // x-part (r,z,n) then h-part (r,z,n)
-    P.acc_bufs = 1;             // 192 columns; the other 320 are the 5-stage TMEM A ring
+    // accumulator columns (nh = ch/2): [0,nh) = hh_n, [nh,2nh) = r, [2nh,3nh) = z (hh + ih summed by the tensor core),
+    // [3nh,4nh) = ih_n.  h-part first (N = 3nh at column 0, overwrite), then x-part (N = 3nh at column nh, accumulate):
+    // the ih_n columns are therefore kept zeroed between items by the epilogue.
+    // One issuer, two accumulator buffers: the gate epilogue (SFU heavy) overlaps the next tile's MMAs; measured
+    // faster than two issuers with a single 2-set buffer (the N = 96 MMAs are execution bound anyway).
+    P.ngroups = 1;
+    P.n_issuers = 1;
+    P.acc_cols = 4 * (ch / 2);
+    P.acc_bufs = 2;
     P.mode = tc::MODE_GRU;
     P.nseg = 4;
     for (int i = 0; i < 4; ++i) {
         tc::Segment& s = P.seg[i];
-        s.src = (short)(i >> 1); s.dy = 0; s.dx = 0; s.c0 = (short)((i & 1) * 32); s.wchunk = (short)i;
-        s.dcol = (short)((i >> 1) * 3 * (ch / 2)); s.n = (short)(3 * ch / 2); s.first = ((i & 1) == 0);
+        const int is_x = i >> 1;
+        s.src = (short)(is_x ? 0 : 1); s.dy = 0; s.dx = 0; s.c0 = (short)((i & 1) * 32); s.wchunk = (short)i;
+        s.dcol = (short)(is_x ? ch / 2 : 0); s.n = (short)(3 * ch / 2); s.first = 0;
     }
     return tc::launch(P, (cudaStream_t)stream);
 }

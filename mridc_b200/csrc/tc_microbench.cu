@@ -34,6 +34,49 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(int N, int nacc, int iters, 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tb = slot;
+    if (a_in_tmem == 5) {
+        // two issuing threads (lane 0 of warps 0 and 1), disjoint accumulators: is the ~45-cycle floor per thread or per pipe?
+        __shared__ uint64_t bar5[2];
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar5[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar5[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && threadIdx.x < 64) {
+            const int w = threadIdx.x >> 5;
+            const uint64_t bdesc = make_desc(smem_u32(smem + 16384));
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a_t = tb + 480;
+            const uint32_t d0 = tb + (uint32_t)(w * 2 * N), d1 = d0 + (uint32_t)N;
+            long long t0 = clock64();
+            for (int i = 0; i < iters; i += 8) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %4, p;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %3, %4, p;\n\t}\n" ::"r"(d0),
+                    "r"(d1), "r"(a_t), "l"(bdesc), "r"(idesc)
+                    : "memory");
+            }
+            long long t1 = clock64();
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar5[w])) : "memory");
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(ok)
+                             : "r"(smem_u32(&bar5[w]))
+                             : "memory");
+            }
+            long long t2 = clock64();
+            if (w == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        }
+    } else
     if (threadIdx.x == 0) {
         const uint64_t adesc = make_desc(smem_u32(smem));
         const uint64_t bdesc = make_desc(smem_u32(smem + 16384));
