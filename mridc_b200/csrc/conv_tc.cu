@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
     uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
     SegIssue* seg_tab = (SegIssue*)(b_empty + B_STAGES);  // [MAX_SEGS]
+    float* bias_s = (float*)(seg_tab + MAX_SEGS);          // [3 * 256]: bias staged once per CTA (epilogue reads it per tile)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = blockIdx.x % P.n_split;
@@ -362,6 +363,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         si.first = (uint32_t)sg.first;
         si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
         seg_tab[threadIdx.x] = si;
+    }
+    {
+        const int nb = (P.mode == MODE_GRU) ? 3 * P.cout : P.cout;
+        for (int i = threadIdx.x; i < nb; i += THREADS) bias_s[i] = P.bias ? P.bias[i] : 0.f;
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const int buf = it % P.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
             long long c0 = clock64();
-            mbar_wait_sleep(&acc_full[buf], acc_phase, 256);
+            mbar_wait_sleep(&acc_full[buf], acc_phase, 64);
             e_wait += clock64() - c0;
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_cols);
@@ -660,9 +665,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int c = ch0 + j + q;
-                            const float br = P.bias ? P.bias[c] : 0.f;
-                            const float bz = P.bias ? P.bias[Ch + c] : 0.f;
-                            const float bn = P.bias ? P.bias[2 * Ch + c] : 0.f;
+                            const float br = bias_s[c], bz = bias_s[Ch + c], bn = bias_s[2 * Ch + c];
                             // rnn_cells.py:121-125 (ih + hh of the r and z gates were summed by the tensor core)
                             const float r = sigmoid_acc(ar[q] + br);
                             const float z = sigmoid_acc(az[q] + bz);
@@ -676,26 +679,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                 }
             } else {
                 for (int j = j_lo; j < j_hi; j += 8) {
-                    float a[8];
-                    tmem_ld8(t0 + j, a);
-                    if (P.small_off) {
-                        float a2[8];
-                        tmem_ld8(t0 + P.small_off + j, a2);
+                    float a[8], a2[8], b1[8], b2[8];
+                    if (P.ngroups == 2) {
+                        // [main g0 | cross g0 | main g1 | cross g1]: four loads, one wait
+                        tmem_ld8x4(t0 + j, t0 + P.small_off + j, t0 + 2 * P.nhalf + j, t0 + 2 * P.nhalf + P.small_off + j, a, a2, b1,
+                                   b2);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) a[q] += a2[q];
-                        for (int g = 1; g < P.ngroups; ++g) {
-                            float b1[8], b2[8];
-                            tmem_ld8(t0 + g * 2 * P.nhalf + j, b1);
-                            tmem_ld8(t0 + g * 2 * P.nhalf + P.small_off + j, b2);
+                        for (int q = 0; q < 8; ++q) a[q] = (a[q] + a2[q]) + (b1[q] + b2[q]);
+                    } else {
+                        tmem_ld8(t0 + j, a);
+                        if (P.small_off) {
+                            tmem_ld8(t0 + P.small_off + j, a2);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) a[q] += b1[q] + b2[q];
+                            for (int q = 0; q < 8; ++q) a[q] += a2[q];
+                            for (int g = 1; g < P.ngroups; ++g) {
+                                tmem_ld8(t0 + g * 2 * P.nhalf + j, b1);
+                                tmem_ld8(t0 + g * 2 * P.nhalf + P.small_off + j, b2);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) a[q] += b1[q] + b2[q];
+                            }
                         }
                     }
                     if (valid) {
                         float o[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float v = a[q] + (P.bias ? P.bias[ch0 + j + q] : 0.f);
+                            float v = a[q] + bias_s[ch0 + j + q];
                             o[q] = (P.mode == MODE_CONV_RELU) ? fmaxf(v, 0.f) : v;
                         }
                         float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
@@ -785,7 +794,8 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)B_STAGES * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + MAX_SEGS * sizeof(SegIssue);
+    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + MAX_SEGS * sizeof(SegIssue) +
+           3 * 256 * sizeof(float);
 }
 
 static int g_debug = 0;
