@@ -44,3 +44,10 @@ lib.mrb_tc_set_debug(0); lib.mrb_tc_set_prof(None)
 w3 = blk.final_layer[0].conv_layer.weight
 eta = torch.randn(B, H, W, 2, device=dev); o2 = torch.empty_like(eta)
 print("conv_c2 %.1f us" % t(lambda: lib.mrb_conv_c2_nhwc_residual(_lib.ptr(x), _lib.ptr(w3), None, _lib.ptr(eta), _lib.ptr(o2), B, H, W, 64, 3, 1, st)))
+lib.mrb_tc_set_prof(_lib.ptr(prof))
+for k, f in ops.items():
+    prof.zero_(); f(); torch.cuda.synchronize()
+    pv = prof.view(148, 16).double()
+    tot = pv[:, 8]  # epilogue total per CTA (runs to the end of the kernel)
+    print("%-10s per-CTA epilogue-total cycles: min %.0f mean %.0f max %.0f  (max/mean %.2f)" % (k, tot.min(), tot.mean(), tot.max(), tot.max() / tot.mean()))
+lib.mrb_tc_set_prof(None)
