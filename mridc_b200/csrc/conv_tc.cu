@@ -37,7 +37,7 @@ constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant 
 constexpr int LOAD_GROUPS = 2, LOAD_WARPS = 4 * LOAD_GROUPS;  // loader groups alternate segments
 constexpr int MMA_WARPS = 2;                  // two issuing lanes (alternate segments): one thread cannot feed the pipe
 constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + MMA_WARPS + 1) * 32;  // + weight-streaming warp
-constexpr int B_STAGES = 6;                   // streamed-weights ring (stream_b)
+constexpr int B_STAGES = 6;                   // max depth of the streamed-weights ring (Params::b_stages)
 constexpr int MAX_SEGS = 20;
 constexpr int MAX_STAGES = 6;
 constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
@@ -76,6 +76,7 @@ struct Params {
     int mode;
     int stream_b;            // 1: weights are not resident; each loader group streams the B chunk of its segment
                              // (hi rows | lo rows, wchunk_rows*256 B) into its own ring of tb_depth slots
+    int b_stages;            // depth of the streamed-weights ring (<= B_STAGES)
     int tb_depth;            // cp.async staging tiles per loader warp (2 or 3)
     int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
     int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
     uint8_t* tb_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [LOAD_WARPS][depth][32 rows x 128 B]
     uint8_t* bst_s = tb_s + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES;  // [B_STAGES][2*wbytes_chunk] if stream_b
-    uint64_t* bars = (uint64_t*)(bst_s + (P.stream_b ? (size_t)B_STAGES * 2 * wbytes_chunk : 0));
+    uint64_t* bars = (uint64_t*)(bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0));
     uint64_t* full = bars;                          // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
     uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [2]
@@ -550,8 +551,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const bool prof = P.prof != nullptr;
             int stage = mi % P.stages;
             uint32_t phase = (uint32_t)(mi / P.stages) & 1u;
-            int bs = mi % B_STAGES;
-            uint32_t bphase = (uint32_t)(mi / B_STAGES) & 1u;
+            int bs = mi % P.b_stages;
+            uint32_t bphase = (uint32_t)(mi / P.b_stages) & 1u;
             int it = 0;
             long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, c0 = 0;
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
@@ -590,7 +591,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     if (P.stream_b) {
                         umma_commit(&b_empty[bs]);
                         bs += NI;
-                        while (bs >= B_STAGES) { bs -= B_STAGES; bphase ^= 1u; }
+                        while (bs >= P.b_stages) { bs -= P.b_stages; bphase ^= 1u; }
                     }
                     if (prof) t_commit += clock64() - c0;
                     stage += NI;
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                             smem_u32(bst_s + (size_t)bs * bytes)),
                         "l"(gsrc), "r"(bytes), "r"(bar)
                         : "memory");
-                    if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+                    if (++bs == P.b_stages) { bs = 0; bphase ^= 1; }
                 }
             }
         }
@@ -636,14 +637,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
             const int buf = it % P.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
-            long long c0 = clock64();
-            mbar_wait_sleep(&acc_full[buf], acc_phase, 64);
-            e_wait += clock64() - c0;
-            tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_cols);
             const long long p = (long long)tile * TILE_M + m;
             const bool valid = p < P.P;
             const int ch0 = half * P.nhalf;
+            long long c0 = clock64();
+            mbar_wait_sleep(&acc_full[buf], acc_phase, 64);
+            e_wait += clock64() - c0;
+            tc_fence_after();
             if (P.debug & 4) {
             } else if (P.mode == MODE_GRU) {
                 const int nh = P.nhalf;  // hidden channels of this half
@@ -793,7 +794,7 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
-    const size_t wres = P.stream_b ? (size_t)B_STAGES * chunk2 : (size_t)P.n_wchunks * chunk2;
+    const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
     return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + MAX_SEGS * sizeof(SegIssue) +
            3 * 256 * sizeof(float);
 }
@@ -811,6 +812,7 @@ static int launch(Params& P, cudaStream_t st) {
     MRB_REQUIRE(P.stages >= 2, MRB_EUNSUPPORTED, "tensor-core conv: accumulator leaves no room for the TMEM A ring");
     MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
     MRB_REQUIRE((P.nseg % LOAD_GROUPS) == 0, MRB_EUNSUPPORTED, "tensor-core conv: odd segment count");
+    if (P.b_stages == 0) P.b_stages = B_STAGES;
     P.tb_depth = 3;
     if (smem_needed(P) > max_smem) P.tb_depth = 2;
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
@@ -963,14 +965,15 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = (const float*)h; P.cs[1] = 64;
     P.wpack = (const float*)wpack; P.bias = (const float*)b_ih; P.hprev = (const float*)h; P.out = (float*)h_out;
+    // Channel split (two CTAs per pixel tile, N = 96 MMAs), weights resident, two 128-column accumulator buffers.
+    // The alternative -- all 192 gate rows in one CTA with streamed weights (N = 192, execution-bound MMAs) -- was
+    // measured equal (221 vs 188-219 us at B=4): 256 accumulator columns leave no room for a second buffer, and the gate
+    // epilogue (TMEM read 64 B/clk + 6 SFU ops per output) then serialises with the MMAs.
     P.n_split = 2;
     P.cout = ch; P.nhalf = ch / 2;
     P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 4;
     // accumulator columns (nh = ch/2): [0,nh) = hh_n, [nh,2nh) = r, [2nh,3nh) = z (hh + ih summed by the tensor core),
-    // [3nh,4nh) = ih_n.  h-part first (N = 3nh at column 0, overwrite), then x-part (N = 3nh at column nh, accumulate):
-    // the ih_n columns are therefore kept zeroed between items by the epilogue.
-    // One issuer, two accumulator buffers: the gate epilogue (SFU heavy) overlaps the next tile's MMAs; measured
-    // faster than two issuers with a single 2-set buffer (the N = 96 MMAs are execution bound anyway).
+    // [3nh,4nh) = ih_n.  h-part: N = 3nh at column 0; x-part: N = 3nh at column nh (accumulate-only protocol).
     P.ngroups = 1;
     P.n_issuers = 1;
     P.acc_cols = 4 * (ch / 2);
