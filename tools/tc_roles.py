@@ -32,7 +32,7 @@ for flags, name in ((0, "full"),):
 lib.mrb_tc_set_debug(0)
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 lib.mrb_tc_set_prof(_lib.ptr(prof))
-for dbg in (0,):
+for dbg in (0, 4, 8, 12, 2):
   lib.mrb_tc_set_debug(dbg)
   print("debug flags", dbg)
   for k, f in ops.items():
