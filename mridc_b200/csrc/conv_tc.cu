@@ -51,7 +51,7 @@ struct Segment {
     short wchunk;  // resident weight chunk index
     short dcol;    // accumulator column offset
     short n;       // MMA N for this segment
-    short first;   // 1: overwrite the accumulator columns (first contribution)
+    short first;   // 1: first contribution to its accumulator columns (overwrite); 2: GRU x-part (see umma_first_split)
 };
 
 struct Params {
@@ -128,8 +128,20 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// long waits (loaders on a free stage, epilogue on a finished tile): try_wait with a suspend-time hint parks the warp in
+// hardware until the phase completes (or the hint expires) instead of spinning through issue slots
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-    while (!mbar_try(bar, parity)) __nanosleep(ns);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -144,9 +156,17 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// The MMA-issuing warps run warp-uniform code and elect one lane per tcgen05 instruction (elect.sync picks the same
+// lane for the same full mask): with every operand provably uniform the MMAs issue straight from uniform registers.
+// Issued from a single-lane branch instead, each MMA costs a 12-instruction R2UR "waterfall" (~45 cycles measured).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = 128, K = 8
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -173,11 +193,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // One segment = 4 k-steps x (lo*hi, hi*lo -> ds ; hi*hi -> d), issued from a single asm block: the issuing thread is
 // latency-bound (one dependent scalar instruction every few cycles, ~45 cycles minimum between MMAs measured with
 // tools/tc_microbench.py), so nothing but the MMAs themselves may sit between them.
+// skip_first != 0: the first MMA (lo*hi of k-step 0) has been issued separately by umma_first_split().
 __device__ __forceinline__ void umma_segment_ts(uint32_t d, uint32_t ds, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
-                                                uint64_t dbl, uint32_t idesc, uint32_t acc_small0, uint32_t acc_big0) {
+                                                uint64_t dbl, uint32_t idesc, uint32_t acc_small0, uint32_t acc_big0,
+                                                uint32_t skip_first) {
     asm volatile(
         "{\n\t"
-        ".reg .pred ps, pb, pt;\n\t"
+        ".reg .pred ps, pb, pt, pe, pf;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.b32 pf, %9, 0;\n\t"
+        "and.pred pf, pf, pe;\n\t"
         ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
         ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
         "setp.ne.b32 ps, %7, 0;\n\t"
@@ -187,20 +212,38 @@ __device__ __forceinline__ void umma_segment_ts(uint32_t d, uint32_t ds, uint32_
         "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
         "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
         "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, ps;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %6, pb;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah1], bl1, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah2], bl2, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah3], bl3, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %6, pt;\n\t"
+        "@pf tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, ps;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %6, pb;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah1], bl1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah2], bl2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah3], bl3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %6, pt;\n\t"
         "}\n" ::"r"(d),
-        "r"(ds), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small0), "r"(acc_big0)
+        "r"(ds), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small0), "r"(acc_big0), "r"(skip_first)
+        : "memory");
+}
+// First MMA of a segment whose accumulator columns are partly shared with an earlier segment (GRU x-part: the r and z
+// columns already hold the h-part, the n columns are fresh): rows [0, n_acc) of the B chunk accumulate, rows
+// [n_acc, n_acc + n_new) overwrite.  Replaces the epilogue's re-zeroing of the accumulators.
+__device__ __forceinline__ void umma_first_split(uint32_t ds, uint32_t a, uint64_t db, uint32_t idesc_acc, uint32_t idesc_new,
+                                                 uint32_t n_acc) {
+    const uint64_t db2 = db + (uint64_t)((n_acc * 128u) >> 4);  // n_acc is a multiple of 8: whole 1024-byte row groups
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pt, pz;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 pz, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %4, %6, pz;\n\t"
+        "}\n" ::"r"(ds),
+        "r"(ds + n_acc), "r"(a), "l"(db), "l"(db2), "r"(idesc_acc), "r"(idesc_new)
         : "memory");
 }
 // Stacked-B variant (2 MMAs per k-step instead of 3): the packed weight chunk holds the hi rows immediately followed
@@ -210,7 +253,8 @@ __device__ __forceinline__ void umma_segment_ts_stacked(uint32_t d, uint32_t dsm
                                                         uint32_t idesc2n, uint32_t idescn, uint32_t acc0) {
     asm volatile(
         "{\n\t"
-        ".reg .pred pa, pt;\n\t"
+        ".reg .pred pa, pt, pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
         ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
         ".reg .b64 bh1, bh2, bh3;\n\t"
         "setp.ne.b32 pa, %7, 0;\n\t"
@@ -218,21 +262,24 @@ __device__ __forceinline__ void umma_segment_ts_stacked(uint32_t d, uint32_t dsm
         "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
         "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
         "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %5, pa;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %5, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %5, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %5, pt;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %5, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
         "}\n" ::"r"(d),
         "r"(dsm), "r"(a_hi), "r"(a_lo), "l"(dbh), "r"(idesc2n), "r"(idescn), "r"(acc0)
         : "memory");
 }
-struct SegIssue {  // per-segment operands of the MMA issuer, built once per CTA in shared memory
+// lane-0 broadcast: tells the compiler that a value is warp-uniform (see umma_commit)
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni64(uint64_t v) { return ((uint64_t)uni((uint32_t)(v >> 32)) << 32) | uni((uint32_t)v); }
+struct SegIssue {  // per-segment operands of the MMA issuer
     uint64_t dbh, dbl;
-    uint32_t idesc, dcol, first, idesc2n;
+    uint32_t idesc, first, idesc2n;
 };
 // registers -> TMEM: 16 consecutive columns of this thread's lane
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
@@ -300,20 +347,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits zero).  Used for both split terms so that the
-// tensor core's own operand truncation is a no-op: a = hi + lo + O(2^-24 |a|).
-__device__ __forceinline__ float tf32_rn(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+// round-to-nearest (ties away, like cvt.rna) fp32 -> tf32 (10-bit mantissa, low 13 bits zero).  Used for both split
+// terms so that the tensor core's own operand truncation is a no-op: a = hi + lo + O(2^-24 |a|).
+// Two integer instructions; cvt.rna.tf32.f32 itself compiles to four on sm_100a (add, |x| >= inf test, select, mask)
+// and the loaders are instruction-issue bound.  Inf / NaN pass through unchanged (the mask clears the added bit).
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// explicit shared-space 128-bit load (a generic pointer would compile to LD.E)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
 }
-// gate non-linearities on the SFU (ex2.approx + rcp.approx, ~2 ulp): |error| ~1e-7 on outputs in [-1, 1]
-__device__ __forceinline__ float sigmoid_acc(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
-__device__ __forceinline__ float tanh_acc(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
+// gate non-linearities on the SFU: one ex2.approx and one rcp.approx each (~2 ulp, |error| ~1e-7 on outputs in
+// [-1, 1]); the raw PTX forms skip the range fix-ups of __expf / __fdividef (saturation is already exact: ex2 -> 0 or
+// +inf, rcp(inf) = 0)
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// sigmoid(a + b) with bs = -log2(e) * b folded on the host side of the epilogue (bias table)
+__device__ __forceinline__ float sigmoid_fused(float a, float bs) { return rcp_approx(1.f + ex2_approx(fmaf(a, -kLog2e, bs))); }
+__device__ __forceinline__ float tanh_acc(float v) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(v * (2.f * kLog2e))), 1.f); }
+
+// (x0, x1) - (y0, y1) as one packed fp32x2 instruction (same IEEE result as two scalar subtractions)
+__device__ __forceinline__ void sub2(float x0, float x1, float y0, float y1, float& r0, float& r1) {
+    unsigned long long x, y, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
 
 // byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+template <bool GRU>
 __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // layout: [weights resident][loader staging tiles][barriers]
@@ -330,10 +405,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
     uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
     uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
-    SegIssue* seg_tab = (SegIssue*)(b_empty + B_STAGES);  // [MAX_SEGS]
-    float* bias_s = (float*)(seg_tab + MAX_SEGS);          // [3 * 256]: bias staged once per CTA (epilogue reads it per tile)
+    float* bias_s = (float*)(b_empty + B_STAGES);  // [3 * 256]: bias staged once per CTA (epilogue reads it per tile)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform for the compiler (role branches and the MMA issuers' operands
+    // then live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int half = blockIdx.x % P.n_split;
     const int first_tile = blockIdx.x / P.n_split;
     const int tile_stride = gridDim.x / P.n_split;
@@ -353,29 +429,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         }
         fence_barrier_init();
     }
-    if ((int)threadIdx.x < P.nseg) {
-        const Segment sg = P.seg[threadIdx.x];
-        const uint32_t b_hi = smem_u32(w_s + (size_t)sg.wchunk * 2 * wbytes_chunk);
-        SegIssue si;
-        si.dbh = make_desc(b_hi);
-        si.dbl = make_desc(b_hi + wbytes_chunk);
-        si.idesc = make_idesc(TILE_M, sg.n);
-        si.dcol = (uint32_t)sg.dcol;
-        si.first = (uint32_t)sg.first;
-        si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
-        seg_tab[threadIdx.x] = si;
-    }
     {
-        const int nb = (P.mode == MODE_GRU) ? 3 * P.cout : P.cout;
-        for (int i = threadIdx.x; i < nb; i += THREADS) bias_s[i] = P.bias ? P.bias[i] : 0.f;
+        // GRU: the r and z biases are pre-scaled by -log2(e) for sigmoid_fused()
+        const int nb = GRU ? 3 * P.cout : P.cout;
+        for (int i = threadIdx.x; i < nb; i += THREADS) {
+            const float b = P.bias ? P.bias[i] : 0.f;
+            bias_s[i] = (GRU && i < 2 * P.cout) ? -kLog2e * b : b;
+        }
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
     if (!P.stream_b) {
         const float4* g = reinterpret_cast<const float4*>(P.wpack) + (size_t)half * P.n_wchunks * 2 * wbytes_chunk / 16;
-        float4* s = reinterpret_cast<float4*>(w_s);
+        const uint32_t s = smem_u32(w_s);
         const int n16 = P.n_wchunks * 2 * wbytes_chunk / 16;
-        for (int i = threadIdx.x; i < n16; i += THREADS) s[i] = g[i];
+        for (int i = threadIdx.x; i < n16; i += THREADS) {
+            const float4 v = __ldg(g + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s + 16u * (uint32_t)i), "f"(v.x), "f"(v.y), "f"(v.z),
+                         "f"(v.w)
+                         : "memory");
+        }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -383,20 +456,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_col0 = (uint32_t)(P.acc_bufs * P.acc_cols);  // first TMEM column of the A ring
-    {
-        // Accumulate-only protocol: every accumulator column starts at zero and the epilogue re-zeroes what it has read.
-        if (warp < EPI_WARPS) {
-            const float z16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const uint32_t tq = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-            const int ncol = P.acc_bufs * P.acc_cols, hc = ncol / 2;  // multiple of 32
-            for (int j = (warp >> 2) * hc; j < ((warp >> 2) + 1) * hc; j += 16) tmem_st16(tq + (uint32_t)j, z16);
-            tmem_st_wait();
-        }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    }
-
     if (warp >= EPI_WARPS && warp < EPI_WARPS + LOAD_WARPS) {
         // ============================== LOADERS ==============================
         const int lw = warp - EPI_WARPS;
@@ -411,28 +470,58 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         int coords_tile = -1;
         bool uniform_rows = false;
 
-        const int gt = (lw & 3) * 32 + lane;  // thread index within the loader group (0..127)
         // cp.async gather of one segment into staging tile `slot` (no registers held while in flight)
         auto issue_loads = [&](int tile, int sgi, int slot) {
-            if (tile != coords_tile) {
-                coords_tile = tile;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const long long p = (long long)tile * TILE_M + quad * 32 + rl0 + 4 * i;
-                    pv[i] = p < P.P;
-                    const uint32_t q = pv[i] ? (uint32_t)p : 0u;  // P.P < 2^31 (checked on the host)
-                    const uint32_t t = q / W32;
-                    px[i] = (int)(q - t * W32);
-                    const uint32_t b = t / H32;
-                    py[i] = (int)(t - b * H32);
-                    pb[i] = (int)b;
-                }
-                uniform_rows = pv[7] && py[7] == py[0] && pb[7] == pb[0];
-            }
             const Segment sg = P.seg[sgi];
             const float* src = P.src[sg.src];
             const int cs = P.cs[sg.src];
             uint8_t* tb = tbuf + (size_t)slot * TBUF_BYTES;
+            if (!P.im2col && sg.dy == 0 && sg.dx == 0) {
+                // centre tap / 1x1 kernel: pixel p is row p of the [P, cs] matrix -- no (b, y, x) decomposition, no clamp
+                const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
+                const float* g = src + p0 * cs + sg.c0 + c16 * 4;
+                const uint32_t sbase = smem_u32(tb);
+                const long long gstep = 4ll * cs;
+                const bool on = !(P.debug & 2);
+                if ((long long)(tile + 1) * TILE_M <= P.P) {  // whole tile inside the image stack: no per-row predicate
+                    const uint32_t nbytes = on ? 16u : 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + swz(rl0 + 4 * i, c16)),
+                                     "l"(g + i * gstep), "r"(nbytes)
+                                     : "memory");
+                    return;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = p0 + 4 * i < P.P;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + swz(rl0 + 4 * i, c16)),
+                                 "l"(ok ? g + i * gstep : src), "r"((ok && on) ? 16u : 0u)
+                                 : "memory");
+                }
+                return;
+            }
+            if (tile != coords_tile) {
+                coords_tile = tile;
+                // one division pair per tile; rows rl0 + 4*i follow by carry (x -> y -> b)
+                const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
+                const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;  // P.P < 2^31 (checked on the host)
+                const uint32_t t = q / W32;
+                int x = (int)(q - t * W32);
+                const uint32_t b0 = t / H32;
+                int y = (int)(t - b0 * H32), b = (int)b0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    pv[i] = p0 + 4 * i < P.P;
+                    px[i] = pv[i] ? x : 0; py[i] = pv[i] ? y : 0; pb[i] = pv[i] ? b : 0;
+                    x += 4;
+                    while (x >= P.W) {
+                        x -= P.W;
+                        if (++y == P.H) { y = 0; ++b; }
+                    }
+                }
+                uniform_rows = pv[7] && py[7] == py[0] && pb[7] == pb[0];
+            }
             if (!P.im2col && uniform_rows) {
                 // fast path: rows rl0 + 4*i are 4 pixels apart on one image row; only y may clamp (uniformly)
                 const int xlo = px[0] + sg.dx, xhi = px[0] + 28 + sg.dx;
@@ -477,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         int n_items = 0;
         for (int t = first_tile; t < P.n_tiles; t += tile_stride) ++n_items;
         const int n_total = n_items * spg;
-        long long t_start = clock64(), t_wait = 0, t_st = 0, t_issue = 0, c0;
+        long long t_start = clock64(), t_wait = 0, t_st = 0, t_issue = 0, t_stw = 0, c0;
         const int D = P.tb_depth;
         // prefetch cursor
         int pf_n = 0, pf_tile = first_tile, pf_sgi = grp, pf_slot = 0;
@@ -501,7 +590,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 2;" ::: "memory");
             __syncwarp();
-            const uint8_t* tb = tbuf + (size_t)slot * TBUF_BYTES;
+            const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * TBUF_BYTES);
             c0 = clock64();
             mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
             t_wait += clock64() - c0;
@@ -514,24 +603,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                 float hi[16], lo[16];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 a = *reinterpret_cast<const float4*>(tb + swz(lane, hf * 4 + c));
+                    const float4 a = lds128(tb + swz(lane, hf * 4 + c));
                     // hi = rn_tf32(a) (exact tf32); lo = a - hi is exact in fp32 with |lo| <= 2^-12 |a|, and the tensor
-                    // core's own truncation of lo to tf32 costs <= 2^-23 |a|: no second conversion needed
-                    hi[4 * c + 0] = tf32_rn(a.x); lo[4 * c + 0] = a.x - hi[4 * c + 0];
-                    hi[4 * c + 1] = tf32_rn(a.y); lo[4 * c + 1] = a.y - hi[4 * c + 1];
-                    hi[4 * c + 2] = tf32_rn(a.z); lo[4 * c + 2] = a.z - hi[4 * c + 2];
-                    hi[4 * c + 3] = tf32_rn(a.w); lo[4 * c + 3] = a.w - hi[4 * c + 3];
+                    // core's own truncation of lo to tf32 costs <= 2^-23 |a|: no second conversion needed.
+                    // The subtractions are packed (sub.f32x2): the loaders are instruction-issue bound.
+                    hi[4 * c + 0] = tf32_rn(a.x); hi[4 * c + 1] = tf32_rn(a.y);
+                    hi[4 * c + 2] = tf32_rn(a.z); hi[4 * c + 3] = tf32_rn(a.w);
+                    sub2(a.x, a.y, hi[4 * c + 0], hi[4 * c + 1], lo[4 * c + 0], lo[4 * c + 1]);
+                    sub2(a.z, a.w, hi[4 * c + 2], hi[4 * c + 3], lo[4 * c + 2], lo[4 * c + 3]);
                 }
                 if (!(P.debug & 8)) {
                     tmem_st16(ta + hf * 16, hi);
                     tmem_st16(ta + KC + hf * 16, lo);
                 }
             }
+            const long long c2 = clock64();
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&full[stage]);
             __syncwarp();  // every lane has read its row before the slot is refilled
             t_st += clock64() - c0;
+            t_stw += clock64() - c2;
             if (++slot == D) slot = 0;
             stage += LOAD_GROUPS;
             while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
@@ -539,14 +631,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (P.prof && lane == 0 && lw == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
-            o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_st; o[3] = t_issue;
+            o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_st; o[3] = t_issue; o[13] = t_stw;
         }
     } else if (warp >= EPI_WARPS + LOAD_WARPS && warp < EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
         // ============================== MMA ISSUERS ==============================
         // Issuer mi handles segments mi, mi + 2, ... of every tile (the same split as the loader groups).  All MMAs
-        // accumulate (the epilogue leaves the accumulators zeroed), so the two issue streams need no mutual ordering.
+        // of one issuer go to its own accumulator group, so the two issue streams need no mutual ordering.
         const int mi = warp - (EPI_WARPS + LOAD_WARPS);
-        if (lane == 0 && mi < P.n_issuers) {
+        if (mi < P.n_issuers) {  // whole warp, warp-uniform control flow (see umma_commit)
             const int NI = P.n_issuers;
             const bool prof = P.prof != nullptr;
             int stage = mi % P.stages;
@@ -554,21 +646,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             int bs = mi % P.b_stages;
             uint32_t bphase = (uint32_t)(mi / P.b_stages) & 1u;
             int it = 0;
-            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, c0 = 0;
+            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, t_prep = 0, c0 = 0, c1 = 0;
+            int buf = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t tmem_u = uni(tmem_base);
+            const uint32_t w_u32 = smem_u32(w_s), bst_u32 = smem_u32(bst_s);
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
-                const int buf = it % P.acc_bufs;
-                const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
                 if (prof) c0 = clock64();
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
                 if (prof) t_wacc += clock64() - c0;
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)(buf * P.acc_cols);
+                const uint32_t d_base = tmem_u + (uint32_t)(buf * P.acc_cols);
                 for (int sgi = mi; sgi < P.nseg; sgi += NI) {
-                    SegIssue si = seg_tab[sgi];
+                    if (prof) c1 = clock64();
+                    // every MMA operand is derived from kernel parameters and uniform loop state (no shared-memory
+                    // table, no shuffles): it stays in uniform registers, and it is ready before the waits return
+                    const Segment sg = P.seg[sgi];
+                    const uint32_t b_hi = P.stream_b ? bst_u32 + (uint32_t)(bs * 2 * wbytes_chunk)
+                                                     : w_u32 + (uint32_t)(sg.wchunk * 2 * wbytes_chunk);
+                    SegIssue si;
+                    si.dbh = make_desc(b_hi);
+                    si.dbl = make_desc(b_hi + wbytes_chunk);
+                    si.idesc = make_idesc(TILE_M, sg.n);
+                    si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
+                    si.first = (uint32_t)sg.first;
+                    const uint32_t a_hi = tmem_u + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
+                    const uint32_t d = d_base + (uint32_t)sg.dcol;
                     if (P.stream_b) {
-                        const uint32_t b_hi = smem_u32(bst_s + (size_t)bs * 2 * wbytes_chunk);
-                        si.dbh = make_desc(b_hi);
-                        si.dbl = make_desc(b_hi + wbytes_chunk);
                         if (prof) c0 = clock64();
                         mbar_wait(&b_full[bs], bphase);
                         if (prof) t_wb += clock64() - c0;
@@ -577,14 +681,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     mbar_wait(&full[stage], phase);
                     if (prof) t_wfull += clock64() - c0;
                     tc_fence_after();
-                    const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
-                    const uint32_t d = d_base + si.dcol;
-                    if (prof) c0 = clock64();
+                    if (prof) { c0 = clock64(); t_prep += c0 - c1; }
                     if (P.debug & 1) {
                     } else if (P.stacked) {
-                        umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc, 1u);
+                        // si.first: first segment of its accumulator group -> the N = 2n MMA of k-step 0 overwrites
+                        // [main | cross]; everything after it accumulates (MMAs of one thread execute in order)
+                        umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc,
+                                                si.first ? 0u : 1u);
+                    } else if (si.first == 2) {
+                        // GRU x-part, first chunk: r/z columns accumulate onto the h-part, the i_n columns start here
+                        umma_first_split(d, a_hi + KC, si.dbh, make_idesc(TILE_M, 2 * P.nhalf), make_idesc(TILE_M, P.nhalf),
+                                         (uint32_t)(2 * P.nhalf));
+                        umma_segment_ts(d, d, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc, 1u, 1u, 1u);
                     } else {
-                        umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc, 1u, 1u);
+                        umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc,
+                                        si.first ? 0u : 1u, 1u, 0u);
                     }
                     if (prof) { t_mma += clock64() - c0; c0 = clock64(); }
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
@@ -598,10 +709,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
                 }
                 umma_commit(&acc_full[buf]);
+                if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
             }
-            if (prof && mi == 0) {
+            if (prof && mi == 0 && lane == 0) {
                 unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
-                o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb;
+                o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb; o[12] = t_prep;
             }
         }
     } else if (warp == EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
@@ -633,10 +745,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const int m = quad * 32 + lane;        // TMEM lane = pixel row of the tile
         const int j_lo = chalf * (P.nhalf / 2), j_hi = j_lo + P.nhalf / 2;
         int it = 0;
+        const uint32_t bias_u32 = smem_u32(bias_s);
         long long e_start = clock64(), e_wait = 0;
+        int buf = 0;
+        uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
-            const int buf = it % P.acc_bufs;
-            const uint32_t acc_phase = (uint32_t)(it / P.acc_bufs) & 1u;
             const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * P.acc_cols);
             const long long p = (long long)tile * TILE_M + m;
             const bool valid = p < P.P;
@@ -646,32 +759,38 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             e_wait += clock64() - c0;
             tc_fence_after();
             if (P.debug & 4) {
-            } else if (P.mode == MODE_GRU) {
+            } else if (GRU) {
                 const int nh = P.nhalf;  // hidden channels of this half
+                const int Ch = P.cout;
                 for (int j = j_lo; j < j_hi; j += 8) {
                     float ar[8], az[8], xn[8], hn[8];
                     float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
                     if (valid) {  // issue the global loads first: their latency overlaps the TMEM loads
-                        const float4* hpp = reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j);
+                        const float4* hpp = reinterpret_cast<const float4*>(P.hprev + p * Ch + ch0 + j);
                         h0 = __ldg(hpp);
                         h1 = __ldg(hpp + 1);
                     }
                     tmem_ld8x4(t0 + j, t0 + nh + j, t0 + 2 * nh + j, t0 + 3 * nh + j, hn, ar, az, xn);
                     if (valid) {
-                        const int Ch = P.cout;
-                        float hp[8];
-                        hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w;
-                        hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
+                        const float hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                         float o[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int c = ch0 + j + q;
-                            const float br = bias_s[c], bz = bias_s[Ch + c], bn = bias_s[2 * Ch + c];
-                            // rnn_cells.py:121-125 (ih + hh of the r and z gates were summed by the tensor core)
-                            const float r = sigmoid_acc(ar[q] + br);
-                            const float z = sigmoid_acc(az[q] + bz);
-                            const float n = tanh_acc((xn[q] + bn) + r * hn[q]);
-                            o[q] = n * (1.f - z) + z * hp[q];
+                        for (int q4 = 0; q4 < 8; q4 += 4) {
+                            const int c = ch0 + j + q4;  // multiple of 4: 128-bit reads of the bias table
+                            const float4 br4 = lds128(bias_u32 + 4u * (uint32_t)c);
+                            const float4 bz4 = lds128(bias_u32 + 4u * (uint32_t)(Ch + c));
+                            const float4 bn4 = lds128(bias_u32 + 4u * (uint32_t)(2 * Ch + c));
+                            const float br[4] = {br4.x, br4.y, br4.z, br4.w}, bz[4] = {bz4.x, bz4.y, bz4.z, bz4.w};
+                            const float bn[4] = {bn4.x, bn4.y, bn4.z, bn4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int q = q4 + u;
+                                // rnn_cells.py:121-125 (ih + hh of the r and z gates were summed by the tensor core)
+                                const float r = sigmoid_fused(ar[q], br[u]);
+                                const float z = sigmoid_fused(az[q], bz[u]);
+                                const float n = tanh_acc(fmaf(r, hn[q], xn[q] + bn[u]));
+                                o[q] = fmaf(z, hp[q], n * (1.f - z));
+                            }
                         }
                         float4* op = reinterpret_cast<float4*>(P.out + p * Ch + ch0 + j);
                         op[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -703,10 +822,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     }
                     if (valid) {
                         float o[8];
+                        const float4 bi0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j));
+                        const float4 bi1 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j + 4));
+                        const float bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+                        const bool relu = P.mode == MODE_CONV_RELU;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float v = a[q] + bias_s[ch0 + j + q];
-                            o[q] = (P.mode == MODE_CONV_RELU) ? fmaxf(v, 0.f) : v;
+                            const float v = a[q] + bi[q];
+                            o[q] = relu ? fmaxf(v, 0.f) : v;
                         }
                         float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
                         op[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -714,16 +837,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     }
                 }
             }
-            if (!(P.debug & 4)) {
-                // leave the columns this thread has read zeroed for the next tile that accumulates into the buffer
-                const float z16[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const int nblk = P.acc_cols / P.nhalf;
-                for (int blk = 0; blk < nblk; ++blk)
-                    for (int j = j_lo; j < j_hi; j += 16) tmem_st16(t0 + (uint32_t)(blk * P.nhalf + j), z16);
-                tmem_st_wait();
-            }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
+            if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
         }
         if (P.prof && threadIdx.x == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
@@ -795,8 +911,7 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + MAX_SEGS * sizeof(SegIssue) +
-           3 * 256 * sizeof(float);
+    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float);
 }
 
 static int g_debug = 0;
@@ -816,11 +931,13 @@ static int launch(Params& P, cudaStream_t st) {
     P.tb_depth = 3;
     if (smem_needed(P) > max_smem) P.tb_depth = 2;
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
-    MRB_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    MRB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    MRB_CUDA(cudaFuncSetAttribute(tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     int sms = device_sm_count();
     int grid = (sms / P.n_split) * P.n_split;  // groups of n_split CTAs share a pixel tile
     if (grid > P.n_split * P.n_tiles) grid = P.n_split * P.n_tiles;
-    tc_kernel<<<grid, THREADS, smem_needed(P), st>>>(P);
+    if (P.mode == MODE_GRU) tc_kernel<true><<<grid, THREADS, smem_needed(P), st>>>(P);
+    else tc_kernel<false><<<grid, THREADS, smem_needed(P), st>>>(P);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -916,7 +1033,7 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
             s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
             s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = (short)(kc * 2 * cout);
             s.n = (short)cout;
-            s.first = 0;
+            s.first = (short)(t == 0);  // one accumulator group per K-chunk parity = per issuer
         }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -948,7 +1065,7 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
         tc::Segment& s = P.seg[c];
         s.src = 0; s.dy = 0; s.dx = 0; s.c0 = (short)c; s.wchunk = (short)c; s.dcol = 0;
         s.n = (short)cout;
-        s.first = 0;
+        s.first = (short)(c == 0);
     }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -973,7 +1090,8 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
     P.cout = ch; P.nhalf = ch / 2;
     P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 4;
     // accumulator columns (nh = ch/2): [0,nh) = hh_n, [nh,2nh) = r, [2nh,3nh) = z (hh + ih summed by the tensor core),
-    // [3nh,4nh) = ih_n.  h-part: N = 3nh at column 0; x-part: N = 3nh at column nh (accumulate-only protocol).
+    // [3nh,4nh) = ih_n.  h-part: N = 3nh at column 0; x-part: N = 3nh at column nh.  The first h chunk overwrites its
+    // columns, the first x chunk accumulates onto r/z and overwrites ih_n (Segment::first = 2).
     P.ngroups = 1;
     P.n_issuers = 1;
     P.acc_cols = 4 * (ch / 2);
@@ -984,7 +1102,8 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
         tc::Segment& s = P.seg[i];
         const int is_x = i >> 1;
         s.src = (short)(is_x ? 0 : 1); s.dy = 0; s.dx = 0; s.c0 = (short)((i & 1) * 32); s.wchunk = (short)i;
-        s.dcol = (short)(is_x ? ch / 2 : 0); s.n = (short)(3 * ch / 2); s.first = 0;
+        s.dcol = (short)(is_x ? ch / 2 : 0); s.n = (short)(3 * ch / 2);
+        s.first = (short)(i == 0 ? 1 : (i == 2 ? 2 : 0));
     }
     return tc::launch(P, (cudaStream_t)stream);
 }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(int N, int nacc, int iters, 
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a_t = tb + 480;  // A operand columns (garbage values, timing only)
         long long t0 = clock64();
-        if (a_in_tmem >= 3) {
+        if (a_in_tmem == 3 || a_in_tmem == 4) {
             // like mode 2 but with a tcgen05.commit (mode 3), or commit + fence::after (mode 4), after every 12 MMAs
             __shared__ uint64_t bar2;
             if (true) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
@@ -108,9 +108,10 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(int N, int nacc, int iters, 
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
                 if (a_in_tmem == 4) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-        } else if (a_in_tmem == 2) {
-            // tight issue loop: 8 unrolled MMAs per iteration, predicate hoisted, 2 accumulators
-            const uint32_t d0 = tb, d1 = tb + (uint32_t)N;
+        } else if (a_in_tmem == 2 || a_in_tmem == 6) {
+            // tight issue loop: 8 unrolled MMAs per iteration, predicate hoisted; mode 2 alternates between two
+            // accumulators, mode 6 chains every MMA onto the same accumulator columns (dependent accumulation)
+            const uint32_t d0 = tb, d1 = a_in_tmem == 6 ? tb : tb + (uint32_t)N;
             for (int i = 0; i < iters; i += 8) {
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\t"

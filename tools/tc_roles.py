@@ -32,14 +32,14 @@ for flags, name in ((0, "full"),):
 lib.mrb_tc_set_debug(0)
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 lib.mrb_tc_set_prof(_lib.ptr(prof))
-for dbg in (0, 4, 8, 12, 2):
+for dbg in (0,):
   lib.mrb_tc_set_debug(dbg)
   print("debug flags", dbg)
   for k, f in ops.items():
     prof.zero_(); f(); torch.cuda.synchronize()
     p = prof.view(148, 16).double().mean(0).tolist()
-    print("%-10s loader: total %7.0f wait_empty %7.0f store %7.0f issue %7.0f | mma: total %7.0f wait_full %7.0f wait_acc %7.0f issue %7.0f commit %7.0f wait_b %7.0f | epi: total %7.0f wait %7.0f (cycles, mean over CTAs)" % (
-        k, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[10], p[11], p[8], p[9]))
+    print("%-10s loader: total %7.0f wait_empty %7.0f store %7.0f (st-wait+arrive %7.0f) issue %7.0f | mma: total %7.0f wait_full %7.0f wait_acc %7.0f issue %7.0f commit %7.0f wait_b %7.0f seg-top..issue %7.0f | epi: total %7.0f wait %7.0f (cycles, mean over CTAs)" % (
+        k, p[0], p[1], p[2], p[13], p[3], p[4], p[5], p[6], p[7], p[10], p[11], p[12], p[8], p[9]))
 lib.mrb_tc_set_debug(0); lib.mrb_tc_set_prof(None)
 w3 = blk.final_layer[0].conv_layer.weight
 eta = torch.randn(B, H, W, 2, device=dev); o2 = torch.empty_like(eta)
