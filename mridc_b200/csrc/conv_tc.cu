@@ -41,6 +41,7 @@ constexpr int B_STAGES = 6;                   // max depth of the streamed-weigh
 constexpr int MAX_SEGS = 20;
 constexpr int MAX_STAGES = 6;
 constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
+constexpr int HALO_ROWS = 40;                 // halo mode: 32 pixels + 2*pad on each side of up to two image-row pieces
 
 enum Mode { MODE_CONV_RELU = 0, MODE_GRU = 1, MODE_CONV_NOACT = 2 };
 
@@ -78,6 +79,9 @@ struct Params {
                              // (hi rows | lo rows, wchunk_rows*256 B) into its own ring of tb_depth slots
     int b_stages;            // depth of the streamed-weights ring (<= B_STAGES)
     int tb_depth;            // cp.async staging tiles per loader warp (2 or 3)
+    int tb_bytes;            // bytes of one staging tile (32 rows, or HALO_ROWS rows in halo mode)
+    int halo;                // 1: k x k conv, one gather per (tile, kernel row) feeds the k taps of that row (see loaders)
+    int ksz, dil;            // conv geometry (halo mode)
     int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
     int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
     unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py); null in production
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     const int wbytes_chunk = P.wchunk_rows * 128;
     uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
     uint8_t* tb_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [LOAD_WARPS][depth][32 rows x 128 B]
-    uint8_t* bst_s = tb_s + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES;  // [B_STAGES][2*wbytes_chunk] if stream_b
+    uint8_t* bst_s = tb_s + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes;  // [B_STAGES][2*wbytes_chunk] if stream_b
     uint64_t* bars = (uint64_t*)(bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0));
     uint64_t* full = bars;                          // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const int quad = lw & 3;                     // == warp % 4: the TMEM lane quadrant this warp may write
         const int c16 = lane & 7;                    // 16-byte chunk within the 128-byte row (coalesced view)
         const int rl0 = lane >> 3;                   // rows rl0 + 4*i of the warp's 32 rows (coalesced view)
-        uint8_t* tbuf = tb_s + (size_t)lw * P.tb_depth * TBUF_BYTES;  // tb_depth staging tiles of this warp
+        uint8_t* tbuf = tb_s + (size_t)lw * P.tb_depth * P.tb_bytes;  // tb_depth staging tiles of this warp
         const uint32_t W32 = (uint32_t)P.W, H32 = (uint32_t)P.H;
         int pb[8], py[8], px[8];
         bool pv[8];
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const Segment sg = P.seg[sgi];
             const float* src = P.src[sg.src];
             const int cs = P.cs[sg.src];
-            uint8_t* tb = tbuf + (size_t)slot * TBUF_BYTES;
+            uint8_t* tb = tbuf + (size_t)slot * P.tb_bytes;
             if (!P.im2col && sg.dy == 0 && sg.dx == 0) {
                 // centre tap / 1x1 kernel: pixel p is row p of the [P, cs] matrix -- no (b, y, x) decomposition, no clamp
                 const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
@@ -592,32 +596,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             if (pf_sgi >= P.nseg) { pf_sgi = grp; pf_tile += tile_stride; }
             if (++pf_slot == D) pf_slot = 0;
         };
-        for (int n = 0; n < D - 1; ++n) prefetch_next();
-        // consume cursor: global segment index advances by LOAD_GROUPS (nseg is a multiple of it)
-        int slot = 0;
-        int stage = grp % P.stages;
-        uint32_t phase = (uint32_t)(grp / P.stages) & 1u;
-        for (int n = 0; n < n_total; ++n) {
-            c0 = clock64();
-            prefetch_next();
-            t_issue += clock64() - c0;
-            if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 2;" ::: "memory");
-            __syncwarp();
-            const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * TBUF_BYTES);
-            c0 = clock64();
-            mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
-            t_wait += clock64() - c0;
-            tc_fence_after();
-            c0 = clock64();
-            // row ownership: thread = row `lane` of the warp's 32 rows = TMEM lane quad*32 + lane
+        // staging row `row` of tile tb -> hi/lo split -> TMEM stage (thread = pixel = TMEM lane quad*32 + lane)
+        auto store_stage = [&](uint32_t tb, int row, int stage) {
             const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 float hi[16], lo[16];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 a = lds128(tb + swz(lane, hf * 4 + c));
+                    const float4 a = lds128(tb + swz(row, hf * 4 + c));
                     // hi = rn_tf32(a) (exact tf32); lo = a - hi is exact in fp32 with |lo| <= 2^-12 |a|, and the tensor
                     // core's own truncation of lo to tf32 costs <= 2^-23 |a|: no second conversion needed.
                     // The subtractions are packed (sub.f32x2): the loaders are instruction-issue bound.
@@ -631,6 +618,127 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     tmem_st16(ta + KC + hf * 16, lo);
                 }
             }
+        };
+        int stage = grp % P.stages;
+        uint32_t phase = (uint32_t)(grp / P.stages) & 1u;
+        if (P.halo) {
+            // ---- halo mode (k x k conv, group = K chunk) ----
+            // The k taps of one kernel row read the same image row shifted by dil pixels.  One gather per (tile, kernel
+            // row) brings the warp's 32 pixels plus pad = dil*(k-1)/2 pixels on each side (replicate clamp applied to the
+            // source column) into a staging tile; tap kx then reads staging row lane + kx*dil.  A warp's 32 pixels may
+            // straddle two image rows: the second piece gets its own 2*pad halo (rows shifted by another 2*pad).
+            // Cuts the gathers (issue slots and L2 traffic) by k.
+            const int k = P.ksz, dil = P.dil, pad = dil * (k - 1) / 2;
+            const int cs = P.cs[0];
+            const float* src = P.src[0];
+            const int n_units = n_items * k;
+            // per-tile geometry of this lane's staging rows s = rl0 + 4*i
+            int xoff[HALO_ROWS / 4];
+            unsigned selB = 0, rowok = 0;
+            int nA = 32;
+            long long rowA = 0, rowB = 0;  // (b*H + y) of the two pieces (before the tap's dy)
+            int yA = 0, yB = 0;
+            auto tile_geometry = [&](int tile) {
+                const long long p0 = (long long)tile * TILE_M + quad * 32;
+                selB = 0; rowok = 0;
+                if (p0 >= P.P) return;
+                const uint32_t q = (uint32_t)p0;
+                const uint32_t t = q / W32;
+                const int x0 = (int)(q - t * W32);
+                const uint32_t b0 = t / H32;
+                yA = (int)(t - b0 * H32);
+                rowA = (long long)b0 * P.H;
+                nA = min(32, P.W - x0);
+                const bool hasB = nA < 32 && p0 + nA < P.P;
+                yB = yA + 1;
+                rowB = rowA;
+                if (yB == P.H) { yB = 0; rowB += P.H; }
+                const int nrows = 32 + 2 * pad + (nA < 32 ? 2 * pad : 0);
+#pragma unroll
+                for (int i = 0; i < HALO_ROWS / 4; ++i) {
+                    const int sr = rl0 + 4 * i;
+                    const bool inB = sr >= nA + 2 * pad;
+                    const int vx = inB ? sr - nA - 3 * pad : x0 - pad + sr;
+                    xoff[i] = min(max(vx, 0), P.W - 1) * cs;
+                    if (inB) selB |= 1u << i;
+                    if (sr < nrows && (!inB || hasB)) rowok |= 1u << i;
+                }
+            };
+            int geo_tile = -1;
+            auto issue_halo = [&](int tile, int ky, int slot) {
+                if (tile != geo_tile) { geo_tile = tile; tile_geometry(tile); }
+                const int dy = ky * dil - pad;
+                const float* gA = src + (rowA + min(max(yA + dy, 0), P.H - 1)) * P.W * cs + grp * KC + c16 * 4;
+                const float* gB = src + (rowB + min(max(yB + dy, 0), P.H - 1)) * P.W * cs + grp * KC + c16 * 4;
+                const uint32_t sbase = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const bool on = !(P.debug & 2);
+#pragma unroll
+                for (int i = 0; i < HALO_ROWS / 4; ++i) {
+                    const bool ok = (rowok >> i) & 1u;
+                    const float* g = (((selB >> i) & 1u) ? gB : gA) + xoff[i];
+                    cp_async16(sbase + swz(rl0 + 4 * i, c16), ok ? (const void*)g : (const void*)src, (ok && on) ? 16u : 0u, cg);
+                }
+            };
+            int pf_u = 0, pf_tile = first_tile, pf_ky = 0, pf_slot = 0;
+            auto prefetch_unit = [&]() {
+                if (pf_u < n_units) issue_halo(pf_tile, pf_ky, pf_slot);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                ++pf_u;
+                if (++pf_ky == k) { pf_ky = 0; pf_tile += tile_stride; }
+                pf_slot ^= 1;
+            };
+            prefetch_unit();
+            int slot = 0, ky = 0, tile = first_tile;
+            int nA_cur = 32;
+            for (int u = 0; u < n_units; ++u) {
+                if (ky == 0) {  // nA of the tile being consumed (the prefetch cursor may already be on the next tile)
+                    const long long p0 = (long long)tile * TILE_M + quad * 32;
+                    const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
+                    nA_cur = min(32, P.W - (int)(q % W32));
+                }
+                c0 = clock64();
+                prefetch_unit();
+                t_issue += clock64() - c0;
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const int row0 = lane + (lane >= nA_cur ? 2 * pad : 0);
+                for (int kx = 0; kx < k; ++kx) {
+                    c0 = clock64();
+                    mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+                    t_wait += clock64() - c0;
+                    tc_fence_after();
+                    c0 = clock64();
+                    store_stage(tb, row0 + kx * dil, stage);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&full[stage]);
+                    t_st += clock64() - c0;
+                    stage += LOAD_GROUPS;
+                    while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+                }
+                __syncwarp();  // every lane has read its rows before the slot is refilled
+                slot ^= 1;
+                if (++ky == k) { ky = 0; tile += tile_stride; }
+            }
+        } else {
+        for (int n = 0; n < D - 1; ++n) prefetch_next();
+        // consume cursor: global segment index advances by LOAD_GROUPS (nseg is a multiple of it)
+        int slot = 0;
+        for (int n = 0; n < n_total; ++n) {
+            c0 = clock64();
+            prefetch_next();
+            t_issue += clock64() - c0;
+            if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 2;" ::: "memory");
+            __syncwarp();
+            const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+            c0 = clock64();
+            mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+            t_wait += clock64() - c0;
+            tc_fence_after();
+            c0 = clock64();
+            store_stage(tb, lane, stage);
             const long long c2 = clock64();
             tmem_st_wait();
             tc_fence_before();
@@ -641,6 +749,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             if (++slot == D) slot = 0;
             stage += LOAD_GROUPS;
             while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+        }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (P.prof && lane == 0 && lw == 0) {
@@ -954,7 +1063,7 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * TBUF_BYTES + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float);
+    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float);
 }
 
 static int g_debug = 0;
@@ -971,7 +1080,8 @@ static int launch(Params& P, cudaStream_t st) {
     MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
     MRB_REQUIRE((P.nseg % LOAD_GROUPS) == 0, MRB_EUNSUPPORTED, "tensor-core conv: odd segment count");
     if (P.b_stages == 0) P.b_stages = B_STAGES;
-    P.tb_depth = 3;
+    P.tb_bytes = P.halo ? HALO_ROWS * 128 : TBUF_BYTES;
+    P.tb_depth = P.halo ? 2 : 3;  // halo mode: one staging tile feeds k segments, current + next is enough
     if (smem_needed(P) > max_smem) P.tb_depth = 2;
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
     MRB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -1070,6 +1180,9 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.nseg = k * k * 2;
     const int pad = dil * (k - 1) / 2;
+    P.ksz = k; P.dil = dil;
+    // halo gathers need the two-piece staging layout to hold (4*pad extra rows) and a warp's 32 pixels on <= 2 image rows
+    P.halo = (4 * pad <= tc::HALO_ROWS - 32 && W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 1 : 0;
     for (int t = 0; t < k * k; ++t)
         for (int kc = 0; kc < 2; ++kc) {
             tc::Segment& s = P.seg[t * 2 + kc];

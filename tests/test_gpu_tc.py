@@ -43,7 +43,7 @@ def _pack(kind, w, w2=None, k=1):
     return p
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (1, 320, 320)])
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (3, 33, 32), (2, 5, 100), (1, 320, 320)])
 def test_tc_ops_vs_oracle(B, H, W):
     from mridc_b200 import _lib
     from oracle import nets as onets
