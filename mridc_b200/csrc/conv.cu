@@ -9,6 +9,8 @@
 // thread an 8-pixel x TN-channel register tile; input halo patch and weight slab of CK input channels staged in
 // shared memory per K step; the (k-1)*dil+8 wide input window of a row is loaded once and slid across the taps.
 // This is the exact-fp32 path (U-Net, generic shapes); see conv_tc.cu for the tensor-core RIM path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mrb {
@@ -380,6 +382,131 @@ __global__ void __launch_bounds__(128) conv_c2_nhwc_kernel(const float* __restri
     }
 }
 
+// Fast path of the same operator for the shipped geometry (k = 3, dilation 1): CTA = 32 x 16 output pixels, 128 threads,
+// each thread FOUR vertically adjacent pixels x both outputs.
+//   * the 18 x 34 halo patch travels in chunks of F_CH channels through a cp.async.cg double buffer (pixel stride padded
+//     by 4 floats: conflict-free LDS.128), so the global latency of chunk c+1 hides behind the arithmetic of chunk c;
+//   * the three kernel rows reuse the six patch rows a thread holds in registers (2x fewer shared-memory reads than
+//     one pixel per thread);
+//   * arithmetic is packed fp32x2 (fma.rn.f32x2): a pair = two input channels of one output, summed at the end.
+constexpr int F_TX = 32, F_PW = F_TX + 2;
+__device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float b0, float b1) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
+template <int ROWS, int F_CH>
+__global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ eta,
+                                                         float* __restrict__ out, int B, int H, int W, int cin) {
+    constexpr int F_TY = 4 * ROWS, F_PH = F_TY + 2, F_PS = F_CH + 4, NQ = F_CH / 4;
+    extern __shared__ float4 c2smem[];
+    float4* wq = c2smem;                                                   // [tap][cin/4][out] -> 4 input channels
+    float* patch = reinterpret_cast<float*>(wq + (size_t)9 * (cin / 4) * 2);  // [2][F_PH*F_PW][F_PS]
+    for (int t = threadIdx.x; t < 9 * (cin / 4) * 2; t += blockDim.x) {
+        const int o = t & 1, cq = (t >> 1) % (cin / 4), tap = (t >> 1) / (cin / 4);
+        const float* wp = w + ((long long)o * cin + cq * 4) * 9 + tap;
+        wq[t] = make_float4(wp[0], wp[9], wp[18], wp[27]);
+    }
+    const int tiles_x = (W + F_TX - 1) / F_TX;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * F_TX, y0 = ty * F_TY;
+    const int b = blockIdx.y;
+    const int lx = threadIdx.x & 31, yg = threadIdx.x >> 5;  // pixels (lx, ROWS*yg + i), i = 0..ROWS-1
+    const float* xb = x + (long long)b * H * W * cin;
+    const uint32_t patch_u32 = (uint32_t)__cvta_generic_to_shared(patch);
+    // staging list of this thread: float4 t = tid + 128*i of the [F_PH*F_PW pixels][2 quads] chunk; the clamped source
+    // offsets are the same for every chunk (computed once), the shared-memory offset is linear in i
+    constexpr int kStage = (F_PH * F_PW * NQ + 127) / 128;
+    int goff[kStage];
+#pragma unroll
+    for (int i = 0; i < kStage; ++i) {
+        const int t = threadIdx.x + 128 * i;
+        const int q = t % NQ, pp = t / NQ;
+        const int py = pp / F_PW, px = pp - py * F_PW;
+        const int gy = min(max(y0 - 1 + py, 0), H - 1), gx = min(max(x0 - 1 + px, 0), W - 1);
+        goff[i] = t < F_PH * F_PW * NQ ? (gy * W + gx) * cin + q * 4 : -1;  // H*W*cin < 2^31 (checked on the host)
+    }
+    const uint32_t soff0 = (uint32_t)(((threadIdx.x / NQ) * F_PS + (threadIdx.x % NQ) * 4) * 4);
+    auto stage = [&](int chunk, int buf) {
+        const uint32_t dst = patch_u32 + (uint32_t)(buf * F_PH * F_PW * F_PS * 4) + soff0;
+        const float* g = xb + chunk * F_CH;
+#pragma unroll
+        for (int i = 0; i < kStage; ++i)
+            if (goff[i] >= 0)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)((128 / NQ) * F_PS * 4 * i)), "l"(g + goff[i])
+                             : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float2 acc[ROWS][2];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+    const int nchunks = cin / F_CH;
+    stage(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            stage(c + 1, (c + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // chunk c visible to every thread (and the weights, first time round)
+        const float* pb = patch + (size_t)(c & 1) * F_PH * F_PW * F_PS;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float4 xr[ROWS + 2];
+#pragma unroll
+                for (int r = 0; r < ROWS + 2; ++r)
+                    xr[r] = *reinterpret_cast<const float4*>(pb + (size_t)((ROWS * yg + r) * F_PW + lx + dx) * F_PS + q * 4);
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const float4* wp = wq + (size_t)((dy * 3 + dx) * (cin / 4) + c * NQ + q) * 2;
+                    const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+                    for (int i = 0; i < ROWS; ++i) {
+                        const float4 v = xr[i + dy];
+                        ffma2(acc[i][0], v.x, v.y, w0.x, w0.y);
+                        ffma2(acc[i][0], v.z, v.w, w0.z, w0.w);
+                        ffma2(acc[i][1], v.x, v.y, w1.x, w1.y);
+                        ffma2(acc[i][1], v.z, v.w, w1.z, w1.w);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone done with buffer c&1 before chunk c+2 overwrites it
+    }
+    const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const int oy = y0 + ROWS * yg + i, ox = x0 + lx;
+        if (oy < H && ox < W) {
+            const long long p = ((long long)b * H + oy) * W + ox;
+            const float2 e = reinterpret_cast<const float2*>(eta)[p];
+            reinterpret_cast<float2*>(out)[p] =
+                make_float2(e.x + ((acc[i][0].x + acc[i][0].y) + b0), e.y + ((acc[i][1].x + acc[i][1].y) + b1));
+        }
+    }
+}
+
+template <int ROWS, int F_CH>
+static int launch_c2_k3(const float* x, const float* w, const float* bias, const float* eta, float* out, int B, int H, int W,
+                        int cin, cudaStream_t st) {
+    constexpr int F_TY = 4 * ROWS, F_PH = F_TY + 2, F_PS = F_CH + 4;
+    const size_t smem3 = (size_t)9 * (cin / 4) * 2 * sizeof(float4) + (size_t)2 * F_PH * F_PW * F_PS * sizeof(float);
+    MRB_REQUIRE(smem3 <= 200 * 1024 && (long long)H * W * cin < 2147483647LL, MRB_EUNSUPPORTED,
+                "mrb_conv_c2_nhwc_residual: image or channel count too large");
+    MRB_CUDA(cudaFuncSetAttribute(conv_c2_k3_kernel<ROWS, F_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid3((unsigned)(ceil_div(W, F_TX) * ceil_div(H, F_TY)), (unsigned)B);
+    conv_c2_k3_kernel<ROWS, F_CH><<<grid3, 128, smem3, st>>>(x, w, bias, eta, out, B, H, W, cin);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
 }  // namespace mrb
 
 using namespace mrb;
@@ -389,6 +516,12 @@ extern "C" int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const voi
     MRB_REQUIRE(x && w && eta && out, MRB_EINVAL, "mrb_conv_c2_nhwc_residual: null pointer");
     MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && cin >= 16 && (cin % 16) == 0 && (k % 2) == 1 && dil >= 1 && B <= 65535,
                 MRB_EINVAL, "mrb_conv_c2_nhwc_residual: bad shape (cin must be a multiple of 16, k odd)");
+    if (k == 3 && dil == 1 && (cin % 32) == 0 && !getenv("MRB_C2_GENERIC")) {
+        // 4 rows per thread, 16-channel chunks (98 KB, two CTAs per SM): 48.5 us at B=4 vs 53.8 (8-channel chunks, three
+        // CTAs), 57-59 (2 rows per thread) and 87 for the generic kernel below
+        return launch_c2_k3<4, 16>((const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W,
+                                   cin, (cudaStream_t)stream);
+    }
     const int pad = dil * (k - 1) / 2;
     size_t smem = (size_t)k * k * cin * sizeof(float2) +
                   (size_t)(C2_TX + 2 * pad) * (C2_TY + 2 * pad) * C2_PSTR * sizeof(float);

@@ -21,6 +21,13 @@ int fft1d_launch(const float2* in, float2* out, long long outer, int n, long lon
                  int out_rot, float scale, cudaStream_t st);
 float norm_scale(int norm, int inverse, double npts);
 
+// Streamed operands (sensitivity maps, the T1/T2 intermediates): read through L2 only.  The L1 path costs issue slots
+// on B200 without any reuse to win (same finding as the tensor-core loaders' cp.async.cg).
+#ifndef MRB_DC_LDG
+#define LDSTREAM(p) __ldcg(p)
+#else
+#define LDSTREAM(p) __ldg(p)
+#endif
 __device__ __forceinline__ int rot_add(int j, int rot, int n) {
     int s = j + rot;
     return s >= n ? s - n : s;
@@ -92,8 +99,8 @@ __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float
             float2* dp = St + j;
             int c = 0;
             for (; c + 4 <= nc; c += 4) {  // 4 independent loads in flight
-                const float2 s0 = __ldg(sp + (long long)(c + 0) * cstride), s1 = __ldg(sp + (long long)(c + 1) * cstride);
-                const float2 s2 = __ldg(sp + (long long)(c + 2) * cstride), s3 = __ldg(sp + (long long)(c + 3) * cstride);
+                const float2 s0 = LDSTREAM(sp + (long long)(c + 0) * cstride), s1 = LDSTREAM(sp + (long long)(c + 1) * cstride);
+                const float2 s2 = LDSTREAM(sp + (long long)(c + 2) * cstride), s3 = LDSTREAM(sp + (long long)(c + 3) * cstride);
                 // rim_utils.py:47-48: re = e_re*s_re - e_im*s_im ; im = e_re*s_im + e_im*s_re
                 dp[(size_t)(c + 0) * p.ls] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);
                 dp[(size_t)(c + 1) * p.ls] = make_float2(e.x * s1.x - e.y * s1.y, e.x * s1.y + e.y * s1.x);
@@ -101,7 +108,7 @@ __global__ void expand_rowfft_kernel(const float2* __restrict__ img, const float
                 dp[(size_t)(c + 3) * p.ls] = make_float2(e.x * s3.x - e.y * s3.y, e.x * s3.y + e.y * s3.x);
             }
             for (; c < nc; ++c) {
-                const float2 s0 = __ldg(sp + (long long)c * cstride);
+                const float2 s0 = LDSTREAM(sp + (long long)c * cstride);
                 dp[(size_t)c * p.ls] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);
             }
         }
@@ -142,13 +149,13 @@ __global__ void col_dc_kernel(const float2* __restrict__ T1, const float2* __res
     if (act) {
         int j = j0;
         for (; j + 3 * jstep < H; j += 4 * jstep) {
-            const float2 v0 = tcol[(long long)rot_add(j, rh, H) * W], v1 = tcol[(long long)rot_add(j + jstep, rh, H) * W];
-            const float2 v2 = tcol[(long long)rot_add(j + 2 * jstep, rh, H) * W];
-            const float2 v3 = tcol[(long long)rot_add(j + 3 * jstep, rh, H) * W];
+            const float2 v0 = LDSTREAM(tcol + (long long)rot_add(j, rh, H) * W), v1 = LDSTREAM(tcol + (long long)rot_add(j + jstep, rh, H) * W);
+            const float2 v2 = LDSTREAM(tcol + (long long)rot_add(j + 2 * jstep, rh, H) * W);
+            const float2 v3 = LDSTREAM(tcol + (long long)rot_add(j + 3 * jstep, rh, H) * W);
             float2* d = St + (size_t)i * p.ls + j;
             d[0] = v0; d[jstep] = v1; d[2 * jstep] = v2; d[3 * jstep] = v3;
         }
-        for (; j < H; j += jstep) St[(size_t)i * p.ls + j] = tcol[(long long)rot_add(j, rh, H) * W];
+        for (; j < H; j += jstep) St[(size_t)i * p.ls + j] = LDSTREAM(tcol + (long long)rot_add(j, rh, H) * W);
     }
     block_fft<false>(A, Bf, nl, p, tw_s);
     // k-space epilogue: result of the forward FFT is in A; write the residual where the inverse wants its input.
@@ -265,12 +272,12 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
             float2* dp = St + (COMPACT ? (int)cols_s[j] : j);
             int c = 0;
             for (; c + 4 <= nc; c += 4) {
-                const float2 v0 = tp[(long long)(c + 0) * cstride], v1 = tp[(long long)(c + 1) * cstride];
-                const float2 v2 = tp[(long long)(c + 2) * cstride], v3 = tp[(long long)(c + 3) * cstride];
+                const float2 v0 = LDSTREAM(tp + (long long)(c + 0) * cstride), v1 = LDSTREAM(tp + (long long)(c + 1) * cstride);
+                const float2 v2 = LDSTREAM(tp + (long long)(c + 2) * cstride), v3 = LDSTREAM(tp + (long long)(c + 3) * cstride);
                 dp[(size_t)(c + 0) * p.ls] = v0; dp[(size_t)(c + 1) * p.ls] = v1;
                 dp[(size_t)(c + 2) * p.ls] = v2; dp[(size_t)(c + 3) * p.ls] = v3;
             }
-            for (; c < nc; ++c) dp[(size_t)c * p.ls] = tp[(long long)c * cstride];
+            for (; c < nc; ++c) dp[(size_t)c * p.ls] = LDSTREAM(tp + (long long)c * cstride);
         }
         block_fft<true>(A, Bf, nc, p, tw_s);
 #pragma unroll
@@ -284,8 +291,8 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
                 const float2* ap = A + n;
                 int c = 0;
                 for (; c + 4 <= nc; c += 4) {
-                    const float2 s0 = __ldg(sp + (long long)(c + 0) * cstride), s1 = __ldg(sp + (long long)(c + 1) * cstride);
-                    const float2 s2 = __ldg(sp + (long long)(c + 2) * cstride), s3 = __ldg(sp + (long long)(c + 3) * cstride);
+                    const float2 s0 = LDSTREAM(sp + (long long)(c + 0) * cstride), s1 = LDSTREAM(sp + (long long)(c + 1) * cstride);
+                    const float2 s2 = LDSTREAM(sp + (long long)(c + 2) * cstride), s3 = LDSTREAM(sp + (long long)(c + 3) * cstride);
                     const float2 v0 = ap[(size_t)(c + 0) * p.ls], v1 = ap[(size_t)(c + 1) * p.ls];
                     const float2 v2 = ap[(size_t)(c + 2) * p.ls], v3 = ap[(size_t)(c + 3) * p.ls];
                     // rim_utils.py:61-62: re += v_re*s_re + v_im*s_im ; im += v_im*s_re - v_re*s_im  (coil order kept)
@@ -295,7 +302,7 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
                     a.x += v3.x * s3.x + v3.y * s3.y; a.y += v3.y * s3.x - v3.x * s3.y;
                 }
                 for (; c < nc; ++c) {
-                    const float2 s0 = __ldg(sp + (long long)c * cstride);
+                    const float2 s0 = LDSTREAM(sp + (long long)c * cstride);
                     const float2 v0 = ap[(size_t)c * p.ls];
                     a.x += v0.x * s0.x + v0.y * s0.y; a.y += v0.y * s0.x - v0.x * s0.y;
                 }
