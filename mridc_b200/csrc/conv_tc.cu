@@ -83,7 +83,8 @@ struct Params {
     int halo;                // 1: k x k conv, one gather per (tile, kernel row) feeds the k taps of that row (see loaders)
     int ksz, dil;            // conv geometry (halo mode)
     int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
-    int im2col;              // 1: source 0 is [B,H,W,4] and chunk c0 gathers taps 8*c0 .. 8*c0+7 of a 5x5 window
+    int im2col;              // != 0: source 0 is [B,H,W,4] and chunk c0 holds taps 8*c0 .. 8*c0+7 of a 5x5 window
+                             // (1: gathered tap by tap from global memory, 2: from a halo patch in shared memory)
     unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py); null in production
     int debug;               // profiling switches (mrb_tc_set_debug): 1 skip MMAs, 2 skip global loads, 4 skip epilogue math
     int ngroups;             // conv: number of independent accumulator groups (each [hi*hi | cross], 2*nhalf columns);
@@ -721,6 +722,117 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                 slot ^= 1;
                 if (++ky == k) { ky = 0; tile += tile_stride; }
             }
+        } else if (P.im2col == 2) {
+            // ---- 5x5 x 4-channel im2col from a halo patch ----
+            // One gather per tile brings the warp's 32 pixels (+2 on each side, two-piece layout as above) of the five
+            // image rows y-2..y+2 into a [5][HALO_ROWS] x 16 B patch; the four K chunks (8 taps each) are then assembled
+            // from shared memory: tap (ky, kx) of pixel `lane` is patch[ky][row0 + kx].  Replaces 32 scattered 16-byte
+            // gathers per pixel and tile by ~6.
+            const float* src = P.src[0];
+            constexpr int PAD = 2, NE = (5 * HALO_ROWS + 31) / 32;  // patch elements per lane
+            int eoff[NE];      // clamped source column (in floats) of patch element e = lane + 32*i
+            unsigned eB = 0, eok = 0;
+            int nA = 32, yA = 0, yB = 0;
+            long long rowA = 0, rowB = 0;
+            auto tile_geometry = [&](int tile) {
+                const long long p0 = (long long)tile * TILE_M + quad * 32;
+                eB = 0; eok = 0;
+                if (p0 >= P.P) return;
+                const uint32_t q = (uint32_t)p0;
+                const uint32_t t = q / W32;
+                const int x0 = (int)(q - t * W32);
+                const uint32_t b0 = t / H32;
+                yA = (int)(t - b0 * H32);
+                rowA = (long long)b0 * P.H;
+                nA = min(32, P.W - x0);
+                const bool hasB = nA < 32 && p0 + nA < P.P;
+                yB = yA + 1;
+                rowB = rowA;
+                if (yB == P.H) { yB = 0; rowB += P.H; }
+                const int nrows = 32 + 2 * PAD + (nA < 32 ? 2 * PAD : 0);
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const int e = lane + 32 * i;
+                    const int sr = e % HALO_ROWS;
+                    const bool inB = sr >= nA + 2 * PAD;
+                    const int vx = inB ? sr - nA - 3 * PAD : x0 - PAD + sr;
+                    eoff[i] = min(max(vx, 0), P.W - 1) * 4;
+                    if (inB) eB |= 1u << i;
+                    if (e < 5 * HALO_ROWS && sr < nrows && (!inB || hasB)) eok |= 1u << i;
+                }
+            };
+            auto issue_patch = [&](int tile, int slot) {
+                tile_geometry(tile);
+                const uint32_t sbase = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const bool on = !(P.debug & 2);
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const int e = lane + 32 * i;
+                    const int ky = e / HALO_ROWS;
+                    const bool ok = (eok >> i) & 1u;
+                    const bool inB = (eB >> i) & 1u;
+                    const int yy = min(max((inB ? yB : yA) + ky - PAD, 0), P.H - 1);
+                    const float* g = src + ((inB ? rowB : rowA) + yy) * P.W * 4 + eoff[i];
+                    cp_async16(sbase + 16u * (uint32_t)e, ok ? (const void*)g : (const void*)src, (ok && on) ? 16u : 0u, cg);
+                }
+            };
+            int pf_t = 0, pf_tile = first_tile, pf_slot = 0;
+            auto prefetch_patch = [&]() {
+                if (pf_t < n_items) issue_patch(pf_tile, pf_slot);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                ++pf_t;
+                pf_tile += tile_stride;
+                pf_slot ^= 1;
+            };
+            prefetch_patch();
+            int slot = 0, tile = first_tile;
+            for (int it = 0; it < n_items; ++it, tile += tile_stride) {
+                const long long p0 = (long long)tile * TILE_M + quad * 32;
+                const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
+                const int nA_cur = min(32, P.W - (int)(q % W32));
+                c0 = clock64();
+                prefetch_patch();
+                t_issue += clock64() - c0;
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const int row0 = lane + (lane >= nA_cur ? 2 * PAD : 0);
+                for (int sgi = grp; sgi < P.nseg; sgi += LOAD_GROUPS) {
+                    c0 = clock64();
+                    mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+                    t_wait += clock64() - c0;
+                    tc_fence_after();
+                    c0 = clock64();
+                    const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int t = sgi * 8 + hf * 4 + c;       // tap index (K chunk sgi holds taps 8*sgi .. 8*sgi+7)
+                            const int ky = (t * 13) >> 6, kx = t - 5 * ky;  // t / 5, t % 5 for t < 32
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (t < 25) a = lds128(tb + 16u * (uint32_t)(ky * HALO_ROWS + row0 + kx));
+                            hi[4 * c + 0] = tf32_rn(a.x); hi[4 * c + 1] = tf32_rn(a.y);
+                            hi[4 * c + 2] = tf32_rn(a.z); hi[4 * c + 3] = tf32_rn(a.w);
+                            sub2(a.x, a.y, hi[4 * c + 0], hi[4 * c + 1], lo[4 * c + 0], lo[4 * c + 1]);
+                            sub2(a.z, a.w, hi[4 * c + 2], hi[4 * c + 3], lo[4 * c + 2], lo[4 * c + 3]);
+                        }
+                        if (!(P.debug & 8)) {
+                            tmem_st16(ta + hf * 16, hi);
+                            tmem_st16(ta + KC + hf * 16, lo);
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&full[stage]);
+                    t_st += clock64() - c0;
+                    stage += LOAD_GROUPS;
+                    while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+                }
+                __syncwarp();  // every lane has read its taps before the slot is refilled
+                slot ^= 1;
+            }
         } else {
         for (int n = 0; n < D - 1; ++n) prefetch_next();
         // consume cursor: global segment index advances by LOAD_GROUPS (nseg is a multiple of it)
@@ -1215,7 +1327,7 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
     P.stacked = 1;
     P.acc_bufs = 2;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
-    P.im2col = 1;
+    P.im2col = (W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 2 : 1;  // 2: taps assembled from a shared-memory halo patch
     P.nseg = 4;
     for (int c = 0; c < 4; ++c) {
         tc::Segment& s = P.seg[c];
