@@ -16,5 +16,6 @@ from .rim import (  # noqa: F401
 from .unet import NormUnet, Unet, ConvBlock, TransposeConvBlock  # noqa: F401
 from .varnet import VarNetBlock  # noqa: F401
 from .models import CIRIM, VarNet, UNet, ZF  # noqa: F401
+from .pipeline import HostPrefetcher  # noqa: F401
 
 __version__ = "0.1.0"

@@ -428,3 +428,16 @@ def test_zf_config1_vs_oracle_and_crop():
     out = mb.ZF(cfg)(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), tgt.cuda())
     assert out.shape == ref.shape == (2, 280, 300)
     assert rel_l2(out, ref) < 2e-6
+
+
+@pytest.mark.gpu
+def test_host_prefetcher_streams_batches_in_order():
+    import mridc_b200 as mb
+
+    host = [{"y": torch.full((4, 8), float(i)).pin_memory(), "tag": i} for i in range(5)]
+    seen = []
+    for bt in mb.HostPrefetcher(iter(host), "cuda:0"):
+        assert bt["y"].is_cuda
+        seen.append((bt["tag"], float((bt["y"] * 2).sum().item())))
+    assert seen == [(i, 64.0 * i) for i in range(5)]
+    assert list(mb.HostPrefetcher(iter([]), "cuda:0")) == []

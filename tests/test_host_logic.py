@@ -152,3 +152,11 @@ def test_synth_batch_shapes_and_determinism():
     m = b1["mask"].bool().reshape(-1)
     assert torch.count_nonzero(b1["y"][..., ~m, :]) == 0 and torch.count_nonzero(b1["y"][..., m, :]) > 0
     assert not torch.equal(b1["y"][0], b1["y"][1])
+
+
+def test_host_prefetcher_rejects_cpu_device():
+    import pytest
+    import mridc_b200 as mb
+
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        mb.HostPrefetcher([], "cpu")
