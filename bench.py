@@ -253,21 +253,41 @@ def run_ours(args):
         outg = torch.empty((B, 4, H, W), device=dev)
         mcan = _ops.canonical_mask(d["mask"], B, H, W)[0]
         n_it = 40
-        for _ in range(5):
+        # the product path: hybrid-space row form (1-D mask), hybrid k-space prepared once per slice batch
+        yhyb = _ops.dc_hybrid_prepare(d["y"], mcan, False, ws=ws[0])
+        outg4 = torch.empty((B, H, W, 4), device=dev)
+
+        def dc_call():
+            _ops.dc_rim_grad(eta, d["y"], d["sensitivity_maps"], mcan, 1.0, False, "backward", out=outg4, nhwc=True,
+                             y_hybrid=yhyb)
+
+        def dc_call_3pass():
             _ops.dc_rim_grad(eta, d["y"], d["sensitivity_maps"], mcan, 1.0, False, "backward", out=outg, ws=ws)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(n_it):
-            _ops.dc_rim_grad(eta, d["y"], d["sensitivity_maps"], mcan, 1.0, False, "backward", out=outg, ws=ws)
-        e1.record()
-        torch.cuda.synchronize()
-        dc_ms = e0.elapsed_time(e1) / n_it
+
+        def time_it(fn):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_it):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n_it
+
+        dc_ms = time_it(dc_call)
+        dc3_ms = time_it(dc_call_3pass)
         dc_bytes = B * DC_BYTES_PER_SLICE + mcan.numel() * mcan.element_size()
         dc_gbs = dc_bytes / (dc_ms * 1e-3) / 1e9
-        roof_dc = {"bound": "hbm", "kernel": "fused DC gradient (expand_rowfft + col_dc + rowifft_reduce)",
+        roof_dc = {"bound": "hbm",
+                   "kernel": "DC gradient, hybrid-space row form (row_dc_kernel: S*eta -> FFT_W -> mask*(. - yh) -> IFFT_W "
+                             "-> sum_c conj(S)*.; the H transforms cancel for 1-D masks, yh prepared once per batch)",
                    "achieved": dc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dc_gbs / peaks["hbm_gbs"],
                    "frac_of_nominal_8000": dc_gbs / 8000.0, "traffic": None, "peak_src": peaks["src"],
-                   "ms_per_launch_group": dc_ms, "algorithmic_bytes": dc_bytes}
+                   "ms_per_launch_group": dc_ms, "algorithmic_bytes": dc_bytes,
+                   "general_three_pass_ms": dc3_ms, "general_three_pass_gbs": dc_bytes / (dc3_ms * 1e-3) / 1e9,
+                   "note": "algorithmic bytes = SURVEY 8(d) contract figure (S and y once, eta in, 4-channel out); the row "
+                           "form actually reads S once and only the sampled columns of yh"}
         # conv stack of one time step (the compute-dominant kernels), tensor-core channels-last engine
         blk = model.cirim[0]
         eng = blk._tc_engine

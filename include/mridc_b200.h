@@ -106,6 +106,18 @@ int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* m
                     int mask_b, int mask_h, float inv_sigma2, void* out, int out_nhwc, int B, int C, int H,
                     int W, int centered, int norm, void* ws, size_t ws_bytes, void* stream);
 
+/* Hybrid-space form of the same gradient for 1-D (column) masks, mask [mask_b, 1, W].  When the mask does not depend
+ * on k_h the H-direction transforms of fft2 / ifft2 in rim_utils.py:50-58 cancel:
+ *     ifft2(M * (fft2(x) - y)) = bs*H * V_W[ M * (fs * U_W x - yh) ],   yh = (1/H) * V_H y   (U/V: centred DFTs)
+ * mrb_dc_hybrid_prepare computes yh once per slice batch (y is constant over the unrolled network): [B,C,H,W,2] buffer
+ * whose rows hold the sampled columns packed at the front; ws as for mrb_sens_reduce (one [B,C,H,W] complex image).
+ * mrb_dc_rim_grad_hybrid is then one kernel of row transforms per evaluation (same outputs as mrb_dc_rim_grad). */
+int mrb_dc_hybrid_prepare(const void* y, const void* mask, int mask_dtype, int mask_b, void* yh, int B, int C,
+                          int H, int W, int centered, void* ws, size_t ws_bytes, void* stream);
+int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const void* S, const void* mask, int mask_dtype,
+                           int mask_b, float inv_sigma2, void* out, int out_nhwc, int B, int C, int H, int W,
+                           int centered, int norm, void* stream);
+
 /* sum_c ifft2(x) * conj(S) -- mc/reconstruction/models/varnet/vn_block.py:71-87 sens_reduce, also the
  * zero-filled SENSE init of rim_block.py:195-211, zf.py:90-97, vn.py:131-139, unet.py:108-117.
  *   x,S [B,C,H,W,2] -> out [B,H,W,2] */

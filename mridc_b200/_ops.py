@@ -75,8 +75,26 @@ def _check5(t, name):
     return t.contiguous()
 
 
-def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=None, nhwc=False):
-    """rim_utils.py:11-67 -> [B, 4, H, W] (or channels-last [B, H, W, 4] when nhwc)."""
+def dc_hybrid_prepare(y, mask, centered, ws=None):
+    """Hybrid-space k-space for 1-D (column) masks: (1/H) * centred inverse DFT of y along H, sampled columns packed at the
+    front of each row.  Prepared once per slice batch; feeds ``dc_rim_grad(..., y_hybrid=...)`` (see mridc_b200.h).
+    Returns None when the mask depends on k_h (the general three-pass operator applies)."""
+    y = _check5(y, "masked_kspace")
+    B, C, H, W, _ = y.shape
+    m, code, mb, mh = canonical_mask(mask, B, H, W)
+    if mh != 1:
+        return None
+    if ws is None:
+        ws = _ws(B, C, H, W, y.device, halves=1)
+    yh = torch.empty_like(y)
+    _lib.check(_lib.load().mrb_dc_hybrid_prepare(_lib.ptr(y), _lib.ptr(m), code, mb, _lib.ptr(yh), B, C, H, W,
+                                                 int(bool(centered)), _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr()))
+    return yh
+
+
+def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=None, nhwc=False, y_hybrid=None):
+    """rim_utils.py:11-67 -> [B, 4, H, W] (or channels-last [B, H, W, 4] when nhwc).
+    y_hybrid: result of dc_hybrid_prepare(y, mask, centered) -> single-kernel row form (1-D masks only)."""
     y = _check5(y, "masked_kspace")
     S = _check5(S, "sense")
     B, C, H, W, _ = y.shape
@@ -87,9 +105,16 @@ def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=No
     m, code, mb, mh = canonical_mask(mask, B, H, W)
     if out is None:
         out = torch.empty((B, H, W, 4) if nhwc else (B, 4, H, W), dtype=torch.float32, device=y.device)
+    lib = _lib.load()
+    if y_hybrid is not None:
+        if mh != 1 or y_hybrid.shape != y.shape:
+            raise ValueError("y_hybrid needs a 1-D column mask and the shape of masked_kspace")
+        _lib.check(lib.mrb_dc_rim_grad_hybrid(_lib.ptr(eta), _lib.ptr(y_hybrid), _lib.ptr(S), _lib.ptr(m), code, mb,
+                                              1.0 / (float(sigma) ** 2.0), _lib.ptr(out), int(bool(nhwc)), B, C, H, W,
+                                              int(bool(centered)), norm_code(normalization), _lib.stream_ptr()))
+        return out
     if ws is None:
         ws = _ws(B, C, H, W, y.device)
-    lib = _lib.load()
     _lib.check(lib.mrb_dc_rim_grad(_lib.ptr(eta), _lib.ptr(y), _lib.ptr(S), _lib.ptr(m), code, mb, mh,
                                    1.0 / (float(sigma) ** 2.0), _lib.ptr(out), int(bool(nhwc)), B, C, H, W,
                                    int(bool(centered)),

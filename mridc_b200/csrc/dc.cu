@@ -333,6 +333,157 @@ __global__ void rowifft_reduce_kernel(const float2* __restrict__ T2, const float
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hybrid-space form of the RIM gradient for 1-D (column) masks.
+//
+// With a mask that does not depend on k_h, the H-direction transforms of fft2 and ifft2 (rim_utils.py:50-58) cancel:
+//     ifft2( M(k_w) * (fft2(x) - y) ) = bs*H * V_W[ M * (fs * U_W x - yh) ],      yh = (1/H) * V_H y
+// (U/V unnormalised centred forward/inverse DFTs along one axis, fs/bs the normalisation factors of the 2-D pair).
+// yh depends only on the measured k-space, which is constant over the whole unrolled network: it is prepared once
+// per slice batch (mrb_dc_hybrid_prepare, sampled columns only, packed) and every gradient evaluation becomes ONE
+// kernel of row transforms: no column pass, no T1/T2 intermediates, and S is read from HBM once instead of twice.
+// ---------------------------------------------------------------------------------------------------------------
+
+// yh[b,c,h,j] = tmp[b,c,h,(cols[j] + rw) % W]: pack the sampled columns of the H-transformed k-space
+__global__ void compact_hybrid_kernel(const float2* __restrict__ tmp, float2* __restrict__ yh, MaskDesc mask, int C, int H,
+                                      int W, int rw, int rows_per_cta) {
+    extern __shared__ float2 smem[];
+    unsigned short* cols_s = reinterpret_cast<unsigned short*>(smem);
+    __shared__ int scan_scratch[33];
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int ns = build_active_cols(mask, b, W, rw, true, cols_s, scan_scratch);
+    const long long plane = ((long long)b * C + c) * H * W;
+    const int h0 = blockIdx.x * rows_per_cta, h1 = min(H, h0 + rows_per_cta);
+    for (int h = h0; h < h1; ++h)
+        for (int j = threadIdx.x; j < ns; j += blockDim.x)
+            yh[plane + (long long)h * W + j] = LDSTREAM(tmp + plane + (long long)h * W + rot_add((int)cols_s[j], rw, W));
+}
+
+#ifndef MRB_ROWDC_REGS
+#define MRB_ROWDC_REGS 64  // 3 CTAs of 320 threads per SM
+#endif
+// One CTA per (b, image row h), all coils in shared memory (chunks of cc):
+//   p = S*eta -> forward FFT along W -> r = m*(fs*P - yh) on the sampled columns, 0 elsewhere -> inverse FFT along W
+//   -> acc += conj(S) * .   Thread t owns storage column t in both the load and the reduce step, so its S values stay
+//   in registers (KEEP_S: blockDim >= W and cc <= 8); out modes as in rowifft_reduce_kernel.
+template <int OUT_MODE, bool KEEP_S>
+__global__ void __maxnreg__(MRB_ROWDC_REGS) row_dc_kernel(const float2* __restrict__ eta, const float2* __restrict__ S, const float2* __restrict__ yh,
+                              float* __restrict__ out, int C, int H, int W, int cc, FftPlan p, int rw, float fscale,
+                              float oscale, MaskDesc mask) {
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* Bf = A + (size_t)cc * p.ls;
+    float2* tw_s = Bf + (size_t)cc * p.ls;
+    unsigned short* cols_s = reinterpret_cast<unsigned short*>(tw_s + p.n);
+    unsigned short* pos_s = cols_s + W;  // un-centred k_w -> index in the packed column list, 0xffff = not sampled
+    __shared__ int scan_scratch[33];
+    load_twiddles(tw_s, p);
+    const int h = blockIdx.x, b = blockIdx.y;
+    for (int k = threadIdx.x; k < W; k += blockDim.x) pos_s[k] = 0xffff;
+    const int ns = build_active_cols(mask, b, W, rw, true, cols_s, scan_scratch);  // ends with a barrier
+    for (int j = threadIdx.x; j < ns; j += blockDim.x) pos_s[cols_s[j]] = (unsigned short)j;
+    const long long cstride = (long long)H * W;
+    const long long rowoff = ((long long)b * C * H + h) * W;
+    const float2* Srow = S + rowoff;
+    const float2* Yrow = yh + rowoff;
+    const float2* erow = eta + ((long long)b * H + h) * W;
+    float2* St = fft_start_buf(p, A, Bf);
+    constexpr int kMaxOwn = 4, kKeep = 8;
+    float2 acc[kMaxOwn];
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int c0 = 0; c0 < C; c0 += cc) {
+        const int nc = min(cc, C - c0);
+        __syncthreads();  // pos_s ready (first chunk) / previous chunk's reduce done with the buffers
+        float2 sreg[kKeep];
+        // ---- expand: storage column d -> FFT input index j = d - rw ----
+        for (int d = threadIdx.x; d < W; d += blockDim.x) {
+            int j = d - rw;
+            if (j < 0) j += W;
+            const float2 e = __ldg(&erow[d]);
+            const float2* sp = Srow + (long long)c0 * cstride + d;
+            float2* dp = St + j;
+            if (KEEP_S) {
+#pragma unroll
+                for (int c = 0; c < kKeep; ++c)
+                    if (c < nc) sreg[c] = LDSTREAM(sp + (long long)c * cstride);
+#pragma unroll
+                for (int c = 0; c < kKeep; ++c)
+                    if (c < nc)  // rim_utils.py:47-48
+                        dp[(size_t)c * p.ls] = make_float2(e.x * sreg[c].x - e.y * sreg[c].y, e.x * sreg[c].y + e.y * sreg[c].x);
+            } else {
+                for (int c = 0; c < nc; ++c) {
+                    const float2 s0 = LDSTREAM(sp + (long long)c * cstride);
+                    dp[(size_t)c * p.ls] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);
+                }
+            }
+        }
+        block_fft<false>(A, Bf, nc, p, tw_s);
+        // ---- k-space residual (in place when St == A; every (c,k) is read and written by the same thread) ----
+        for (int k = threadIdx.x; k < W; k += blockDim.x) {
+            const int j = pos_s[k];
+            if (j == 0xffff) {
+                for (int c = 0; c < nc; ++c) St[(size_t)c * p.ls + k] = make_float2(0.f, 0.f);
+            } else {
+                const float m = mask_value(mask, b, 0, rot_add(k, rw, W));
+                const float2* yp = Yrow + (long long)c0 * cstride + j;
+                for (int c = 0; c < nc; ++c) {
+                    const float2 P = cscale(A[(size_t)c * p.ls + k], fscale);
+                    const float2 yv = LDSTREAM(yp + (long long)c * cstride);
+                    St[(size_t)c * p.ls + k] = make_float2(m * (P.x - yv.x), m * (P.y - yv.y));  // rim_utils.py:54
+                }
+            }
+        }
+        block_fft<true>(A, Bf, nc, p, tw_s);
+        // ---- reduce: acc[d] += conj(S[c][d]) * A[c][d - rw]  (coil order kept, rim_utils.py:61-62) ----
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) {
+            const int d = threadIdx.x + i * blockDim.x;
+            if (d < W) {
+                int n = d - rw;
+                if (n < 0) n += W;
+                float2 a = acc[i];
+                const float2* ap = A + n;
+                if (KEEP_S) {
+#pragma unroll
+                    for (int c = 0; c < kKeep; ++c)
+                        if (c < nc) {
+                            const float2 v0 = ap[(size_t)c * p.ls], s0 = sreg[c];
+                            a.x += v0.x * s0.x + v0.y * s0.y; a.y += v0.y * s0.x - v0.x * s0.y;
+                        }
+                } else {
+                    const float2* sp = Srow + (long long)c0 * cstride + d;
+                    for (int c = 0; c < nc; ++c) {
+                        const float2 s0 = LDSTREAM(sp + (long long)c * cstride);
+                        const float2 v0 = ap[(size_t)c * p.ls];
+                        a.x += v0.x * s0.x + v0.y * s0.y; a.y += v0.y * s0.x - v0.x * s0.y;
+                    }
+                }
+                acc[i] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+        const int d = threadIdx.x + i * blockDim.x;
+        if (d < W) {
+            const float2 e = erow[d];
+            if (OUT_MODE == 2) {
+                reinterpret_cast<float4*>(out)[((long long)b * H + h) * W + d] =
+                    make_float4(e.x, e.y, acc[i].x * oscale, acc[i].y * oscale);
+            } else {
+                const long long HW = (long long)H * W;
+                float* o = out + (long long)b * 4 * HW + (long long)h * W + d;
+                o[0] = e.x;
+                o[HW] = e.y;
+                o[2 * HW] = acc[i].x * oscale;
+                o[3 * HW] = acc[i].y * oscale;
+            }
+        }
+    }
+}
+
 struct DcGeom {
     FftPlan pw, ph;
     int cc;       // coils per smem chunk in the row kernels
@@ -448,6 +599,64 @@ extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, co
     else
         rowifft_reduce_kernel<1, true><<<dim3(H, B), g.threads_row, g.smem_row, st>>>(
             T2, (const float2*)S, (const float2*)eta, (float*)out, C, H, W, g.cc, g.pw, 0, rw, bs * inv_sigma2, m, prune);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_dc_hybrid_prepare(const void* y, const void* mask, int mask_dtype, int mask_b, void* yh, int B, int C,
+                                     int H, int W, int centered, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_dims(B, C, H, W, 0, "mrb_dc_hybrid_prepare");
+    if (rc) return rc;
+    MRB_REQUIRE(y && yh && ws, MRB_EINVAL, "mrb_dc_hybrid_prepare: null pointer");
+    MRB_REQUIRE(ws_bytes >= mrb_dc_workspace_bytes(B, C, H, W) / 2, MRB_EINVAL, "mrb_dc_hybrid_prepare: workspace too small");
+    MRB_REQUIRE(W <= 65535, MRB_EUNSUPPORTED, "mrb_dc_hybrid_prepare: W must be <= 65535");
+    MaskDesc m;
+    rc = make_mask(mask, mask_dtype, mask_b, 1, B, H, W, &m);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
+    // (1/H) * centred inverse DFT along H of the whole k-space (once per slice batch), then pack the sampled columns
+    rc = fft1d_launch((const float2*)y, (float2*)ws, (long long)B * C, H, W, 1, rh, rh, 1.0f / (float)H, st);
+    if (rc) return rc;
+    const int rows_per_cta = 16;
+    compact_hybrid_kernel<<<dim3(ceil_div(H, rows_per_cta), C, B), 256, (size_t)W * sizeof(unsigned short) + 16, st>>>(
+        (const float2*)ws, (float2*)yh, m, C, H, W, rw, rows_per_cta);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const void* S, const void* mask, int mask_dtype,
+                                      int mask_b, float inv_sigma2, void* out, int out_nhwc, int B, int C, int H, int W,
+                                      int centered, int norm, void* stream) {
+    int rc = check_dims(B, C, H, W, norm, "mrb_dc_rim_grad_hybrid");
+    if (rc) return rc;
+    MRB_REQUIRE(eta && yh && S && out, MRB_EINVAL, "mrb_dc_rim_grad_hybrid: null pointer");
+    MaskDesc m;
+    rc = make_mask(mask, mask_dtype, mask_b, 1, B, H, W, &m);
+    if (rc) return rc;
+    DcGeom g;
+    rc = dc_geometry(C, H, W, &g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rw = centered ? W / 2 : 0;
+    const double npts = (double)H * W;
+    const float fs = norm_scale(norm, 0, npts);
+    const float os = norm_scale(norm, 1, npts) * (float)H * inv_sigma2;
+    const size_t smem = g.smem_row + (size_t)W * sizeof(unsigned short);
+    const bool keep = g.threads_row >= W && g.cc <= 8;
+#define MRB_ROW_DC(MODE, KEEP)                                                                                        \
+    do {                                                                                                              \
+        if ((rc = set_smem(row_dc_kernel<MODE, KEEP>))) return rc;                                                    \
+        row_dc_kernel<MODE, KEEP><<<dim3(H, B), g.threads_row, smem, st>>>((const float2*)eta, (const float2*)S,      \
+                                                                           (const float2*)yh, (float*)out, C, H, W,    \
+                                                                           g.cc, g.pw, rw, fs, os, m);                 \
+    } while (0)
+    if (out_nhwc) {
+        if (keep) MRB_ROW_DC(2, true); else MRB_ROW_DC(2, false);
+    } else {
+        if (keep) MRB_ROW_DC(1, true); else MRB_ROW_DC(1, false);
+    }
+#undef MRB_ROW_DC
     MRB_LAUNCHED();
     return MRB_OK;
 }

@@ -12,6 +12,8 @@ Inference only (no autograd through the kernels).
 """
 from typing import Any, Optional, Sequence, Tuple, Union
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -290,6 +292,8 @@ class RIMBlock(nn.Module):
         if eta is None or eta.ndim < 3:  # :195-211
             eta = pred if keep_eta else _ops.sens_reduce(pred, sense, self.fft_centered, self.fft_normalization, ws=ws)
         mcan = _ops.canonical_mask(mask, B, H, W)[0]  # canonicalise once for the whole time loop
+        # 1-D column masks: hybrid-space k-space once per forward -> single-kernel gradient in the time loop
+        yhyb = None if os.environ.get("MRIDC_B200_DC_3PASS") else _ops.dc_hybrid_prepare(masked_kspace, mcan, self.fft_centered, ws=ws[0])
         etas = []
         final = self.final_layer[0]
         from .rim_tc import RimTcEngine
@@ -299,10 +303,10 @@ class RIMBlock(nn.Module):
         use_tc = bool(self._tc_engine) and RimTcEngine.supported(self) and _lib.require_cuda(eta, "eta") is not None
         if use_tc:
             # tensor-core (tcgen05, 3xTF32) channels-last engine for the whole time loop
-            etas, hx = self._tc_engine.run(eta, masked_kspace, sense, mcan, sigma, hx if hx_given else None, ws)
+            etas, hx = self._tc_engine.run(eta, masked_kspace, sense, mcan, sigma, hx if hx_given else None, ws, yhyb)
         for _ in range(0 if use_tc else self.time_steps):  # :217-249 (generic exact-fp32 kernels)
             grad_eta = _ops.dc_rim_grad(eta, masked_kspace, sense, mcan, sigma, self.fft_centered,
-                                        self.fft_normalization, ws=ws)
+                                        self.fft_normalization, ws=ws, y_hybrid=yhyb)
             for h, convrnn in enumerate(self.layers):
                 hx[h] = convrnn(grad_eta, hx[h])
                 grad_eta = hx[h]

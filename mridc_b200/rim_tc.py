@@ -114,7 +114,7 @@ class RimTcEngine:
         return new_eta
 
     # ---------------------------------------------------------------------------------------------
-    def run(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws):
+    def run(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid=None):
         """The time loop of rim_block.py:217-249.  eta [B,H,W,2]; hx: list of 2 NCHW-shaped tensors or None.
         Returns (list of etas, [h0, h1]) with the hidden states NCHW-shaped (channels-last strides)."""
         lib = _lib.load()
@@ -137,7 +137,7 @@ class RimTcEngine:
         eta = eta.contiguous()
         for _ in range(b.time_steps):
             _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
-                             ws=ws, nhwc=True)
+                             ws=ws, nhwc=True, y_hybrid=y_hybrid)
             eta = self.conv_stack(g4, h, h_alt, xbuf, eta, packs)
             etas.append(eta)
         return etas, [h[0].permute(0, 3, 1, 2), h[1].permute(0, 3, 1, 2)]

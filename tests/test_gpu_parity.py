@@ -441,3 +441,40 @@ def test_host_prefetcher_streams_batches_in_order():
         seen.append((bt["tag"], float((bt["y"] * 2).sum().item())))
     assert seen == [(i, 64.0 * i) for i in range(5)]
     assert list(mb.HostPrefetcher(iter([]), "cuda:0")) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (1, 2, 5, 3), (3, 5, 33, 17), (2, 15, 64, 48), (1, 9, 40, 36), (1, 4, 320, 320)])
+def test_dc_hybrid_row_form_vs_oracle_and_three_pass(B, C, H, W):
+    """1-D masks: the single-kernel hybrid-space gradient (H transforms cancelled analytically) equals the reference
+    formula and the general three-pass operator; masks that depend on k_h are refused."""
+    from mridc_b200 import _ops
+    from oracle import nets as onets
+
+    g = torch.Generator().manual_seed(B * 1000 + C * 100 + H + 7)
+    y = torch.randn(B, C, H, W, 2, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g)
+    eta = torch.randn(B, H, W, 2, generator=g)
+    masks = [
+        (torch.rand(1, 1, 1, W, 1, generator=g) < 0.3).to(torch.uint8),
+        (torch.rand(B, 1, 1, W, 1, generator=g) < 0.5).float(),                     # per-slice column masks
+        torch.rand(1, 1, 1, W, 1, generator=g) * (torch.rand(1, 1, 1, W, 1, generator=g) < 0.6),  # mask VALUE multiplies
+        torch.zeros(1, 1, 1, W, 1),                                                  # nothing sampled
+    ]
+    for m in masks:
+        y_m = y * (m != 0)
+        for cen, nrm in ((True, "ortho"), (False, "backward"), (True, "forward")):
+            yh = _ops.dc_hybrid_prepare(y_m.cuda(), m.cuda(), cen)
+            assert yh is not None
+            for nhwc in (False, True):
+                a = _ops.dc_rim_grad(eta.cuda(), y_m.cuda(), S.cuda(), m.cuda(), 0.7, cen, nrm, nhwc=nhwc, y_hybrid=yh)
+                if nhwc:
+                    a = a.permute(0, 3, 1, 2)
+                ref = onets.log_likelihood_gradient(eta, y_m, S, m.float(), 0.7, cen, nrm, [-2, -1], 1)
+                assert rel_l2(a, ref) < 2e-6
+                three = _ops.dc_rim_grad(eta.cuda(), y_m.cuda(), S.cuda(), m.cuda(), 0.7, cen, nrm)
+                assert rel_l2(a, three) < 2e-6
+                assert torch.equal(a[:, :2].cpu(), eta.permute(0, 3, 1, 2))
+    m2d = (torch.rand(1, 1, H, W, 1, generator=g) < 0.5).to(torch.uint8)
+    if H > 1:
+        assert _ops.dc_hybrid_prepare(y.cuda(), m2d.cuda(), True) is None

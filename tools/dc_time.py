@@ -13,7 +13,7 @@ def t(fn, n=50):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-for B in (1, 4):
+for B in (1, 4, 8):
     y = torch.randn(B, C, H, W, 2, device=dev); S = torch.randn(B, C, H, W, 2, device=dev)
     eta = torch.randn(B, H, W, 2, device=dev)
     mask = (torch.rand(1, 1, 1, W, 1, device=dev) < 0.25).to(torch.uint8)
@@ -21,7 +21,12 @@ for B in (1, 4):
     bytes_alg = B * (2 * C * H * W * 8 + 3 * H * W * 8) + W
     for cen, nrm in ((False, "backward"), (True, "ortho")):
         us = t(lambda: _ops.dc_rim_grad(eta, y, S, mask, 1.0, cen, nrm, out=out, ws=ws, nhwc=True))
-        print("B=%d centered=%s rim_grad %7.1f us  -> %6.0f GB/s algorithmic" % (B, cen, us, bytes_alg / us / 1e3))
+        print("B=%d centered=%s rim_grad (3-pass) %7.1f us  -> %6.0f GB/s algorithmic" % (B, cen, us, bytes_alg / us / 1e3))
+        yh = _ops.dc_hybrid_prepare(y, mask, cen)
+        us = t(lambda: _ops.dc_rim_grad(eta, y, S, mask, 1.0, cen, nrm, out=out, nhwc=True, y_hybrid=yh))
+        print("B=%d centered=%s rim_grad (hybrid) %7.1f us  -> %6.0f GB/s algorithmic" % (B, cen, us, bytes_alg / us / 1e3))
+        us = t(lambda: _ops.dc_hybrid_prepare(y, mask, cen, ws=ws[0]))
+        print("B=%d centered=%s hybrid prepare   %7.1f us (once per slice batch)" % (B, cen, us))
     us = t(lambda: _ops.sens_reduce(y, S, False, "backward", ws=ws))
     print("B=%d sens_reduce %7.1f us" % (B, us))
     us = t(lambda: _ops.sens_expand_softdc(eta, S, None, None, None, None, None, True, False, "backward", ws=ws))
