@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # reference arm: the CPU oracle port
 
 A "step" = one pass of the hot path (CIRIM.forward: 5 cascades x 8 time steps, ConvGRU, SENSE) over one batch of
-`--batch` (default 8) synthetic 15-coil 320x320 slices per GPU, followed by the gather of the reconstructions.  One process
+`--batch` (default 16) synthetic 15-coil 320x320 slices per GPU, followed by the gather of the reconstructions.  One process
 per GPU (torchrun for N > 1), slices sharded across ranks, no data-path collective, weak scaling.
 Prints ONE JSON line on rank 0.
 """
@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="slices per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="slices per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -14,9 +14,9 @@ __all__ = ["HostPrefetcher"]
 class HostPrefetcher:
     """Iterate over dictionaries of (pinned) host tensors, yielding the same dictionaries on ``device``.
 
-    One batch is always in flight on a private copy stream; the consumer's stream waits on the upload's event, and the
-    device tensors are tied to the consumer's stream (``record_stream``) so the caching allocator cannot recycle them
-    while kernels still read them.  Non-tensor values are passed through untouched.
+    One batch is always in flight on a private copy stream; the consumer's stream waits on the upload's event.  The
+    device tensors are two persistent buffer sets that alternate, so a yielded batch is valid until the iterator is
+    advanced TWICE (clone what must live longer).  Non-tensor values are passed through untouched.
     """
 
     def __init__(self, batches: Iterable[Dict[str, object]], device):
@@ -25,29 +25,47 @@ class HostPrefetcher:
         if self.device.type != "cuda":
             raise RuntimeError("HostPrefetcher: device must be a CUDA device (there is no CPU path)")
 
-    def _upload(self, batch, stream):
+    def _upload(self, batch, stream, slot):
+        bufs = self._bufs[slot]
         with torch.cuda.stream(stream):
-            dev = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            if self._done[slot] is not None:
+                stream.wait_event(self._done[slot])  # the consumer has finished with the batch that lived in this slot
+            dev = {}
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    dst = bufs.get(k)
+                    if dst is None or dst.shape != v.shape or dst.dtype != v.dtype:
+                        dst = bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    dst.copy_(v, non_blocking=True)
+                    dev[k] = dst
+                else:
+                    dev[k] = v
             ev = torch.cuda.Event()
             ev.record(stream)
         return dev, ev
 
     def __iter__(self) -> Iterator[Dict[str, object]]:
+        # two persistent sets of device buffers (no allocator traffic in steady state): batch i lives in slot i % 2 and
+        # is overwritten by batch i + 2 only after the consumer's work on batch i has been enqueued and has finished
         stream = torch.cuda.Stream(self.device)
+        self._bufs = [{}, {}]
+        self._done = [None, None]
         it = iter(self.batches)
         try:
-            pending = self._upload(next(it), stream)
+            pending = self._upload(next(it), stream, 0)
         except StopIteration:
             return
+        i = 0
         while pending is not None:
             cur, ev = pending
             consumer = torch.cuda.current_stream(self.device)
             consumer.wait_event(ev)
-            for v in cur.values():
-                if isinstance(v, torch.Tensor):
-                    v.record_stream(consumer)
             try:
-                pending = self._upload(next(it), stream)
+                pending = self._upload(next(it), stream, (i + 1) % 2)
             except StopIteration:
                 pending = None
             yield cur
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            self._done[i % 2] = done
+            i += 1
