@@ -274,7 +274,9 @@ class RIMBlock(nn.Module):
     @torch.no_grad()
     def forward(self, pred: torch.Tensor, masked_kspace: torch.Tensor, sense: torch.Tensor, mask: torch.Tensor,
                 eta: torch.Tensor = None, hx: torch.Tensor = None, sigma: float = 1.0,
-                keep_eta: bool = False) -> Tuple[Any, Union[list, torch.Tensor, None]]:
+                keep_eta: bool = False, y_hybrid: Optional[dict] = None) -> Tuple[Any, Union[list, torch.Tensor, None]]:
+        """rim_block.py:134-269.  ``y_hybrid`` (not in the reference signature): a dict the caller keeps across cascades so
+        that the hybrid-space k-space of ``masked_kspace`` (dc_hybrid_prepare) is computed once per slice batch."""
         _ops.check_spatial_dims(self.spatial_dims)
         if self.coil_dim != 1:
             raise NotImplementedError("mridc_b200: RIMBlock expects coil_dim == 1")
@@ -293,7 +295,16 @@ class RIMBlock(nn.Module):
             eta = pred if keep_eta else _ops.sens_reduce(pred, sense, self.fft_centered, self.fft_normalization, ws=ws)
         mcan = _ops.canonical_mask(mask, B, H, W)[0]  # canonicalise once for the whole time loop
         # 1-D column masks: hybrid-space k-space once per forward -> single-kernel gradient in the time loop
-        yhyb = None if os.environ.get("MRIDC_B200_DC_3PASS") else _ops.dc_hybrid_prepare(masked_kspace, mcan, self.fft_centered, ws=ws[0])
+        yhyb = None
+        if not os.environ.get("MRIDC_B200_DC_3PASS"):
+            key = (masked_kspace.data_ptr(), masked_kspace._version, mcan.data_ptr(), mcan._version, bool(self.fft_centered))
+            if y_hybrid is not None and y_hybrid.get("key") == key:
+                yhyb = y_hybrid["yh"]
+            else:
+                yhyb = _ops.dc_hybrid_prepare(masked_kspace, mcan, self.fft_centered, ws=ws[0])
+                if y_hybrid is not None:
+                    # keep the tensors alive with the entry: a recycled allocation can then never alias the key
+                    y_hybrid.update(key=key, yh=yhyb, y=masked_kspace, mask=mcan)
         etas = []
         final = self.final_layer[0]
         from .rim_tc import RimTcEngine

@@ -25,9 +25,11 @@ g4 = torch.randn(B, H, W, 4, device=dev)
 hx = [torch.randn(B, H, W, 64, device=dev) * 0.1 for _ in range(2)]
 hx_alt = [torch.empty_like(t) for t in hx]
 xbuf = torch.empty(B, H, W, 64, device=dev)
+yhyb = _ops.dc_hybrid_prepare(y, mask, False, ws=ws[0])
+g4o = torch.empty(B, H, W, 4, device=dev)
 for _ in range(reps):
     if what in ("all", "dc"):
-        _ops.dc_rim_grad(eta, y, S, mask, 1.0, False, "backward", ws=ws)
+        _ops.dc_rim_grad(eta, y, S, mask, 1.0, False, "backward", out=g4o, nhwc=True, y_hybrid=yhyb)
     if what in ("all", "conv"):
         eng.conv_stack(g4, hx, hx_alt, xbuf, eta)
     if what in ("all", "vn"):
