@@ -41,6 +41,8 @@ constexpr int B_STAGES = 6;                   // max depth of the streamed-weigh
 constexpr int MAX_SEGS = 20;
 constexpr int MAX_STAGES = 6;
 constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
+constexpr int EPI_ROW_BYTES = 80;             // 64 B of payload per pixel, padded: conflict-free for both access patterns
+constexpr int EPI_TILE_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int HALO_ROWS = 40;                 // halo mode: 32 pixels + 2*pad on each side of up to two image-row pieces
 
 enum Mode { MODE_CONV_RELU = 0, MODE_GRU = 1, MODE_CONV_NOACT = 2 };
@@ -357,6 +359,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // Two integer instructions; cvt.rna.tf32.f32 itself compiles to four on sm_100a (add, |x| >= inf test, select, mask)
 // and the loaders are instruction-issue bound.  Inf / NaN pass through unchanged (the mask clears the added bit).
 __device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // 16-byte global -> shared async copy (src_bytes 0 = zero fill); bypass_l1: .cg (streamed once) vs .ca (re-read by taps)
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, uint32_t src_bytes, bool bypass_l1) {
     if (bypass_l1)
@@ -418,6 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
     uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
     float* bias_s = (float*)(b_empty + B_STAGES);  // [3 * 256]: bias staged once per CTA (epilogue reads it per tile)
+    uint8_t* epi_s = (uint8_t*)(bias_s + 3 * 256); // GRU: [EPI_WARPS][2][32 px][EPI_ROW_BYTES] per-warp exchange tiles
 
     // warp index through a shuffle: provably warp-uniform for the compiler (role branches and the MMA issuers' operands
     // then live in uniform registers)
@@ -981,6 +987,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const int j_lo = chalf * (P.nhalf / 2), j_hi = j_lo + P.nhalf / 2;
         int it = 0;
         const uint32_t bias_u32 = smem_u32(bias_s);
+        const uint32_t et0 = smem_u32(epi_s) + (uint32_t)(warp * 2 * EPI_TILE_BYTES);  // this warp's two exchange tiles
+        // h_prev of a tile (independent of the MMAs): asynchronous coalesced copy into an exchange tile, issued one tile
+        // ahead so that its latency never shows
+        auto fetch_hprev = [&](int tile, uint32_t dst) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int prow = (lane >> 2) + 8 * k;
+                const long long pp = (long long)tile * TILE_M + quad * 32 + prow;
+                const bool ok = tile < P.n_tiles && pp < P.P;
+                cp_async16(dst + (uint32_t)(prow * EPI_ROW_BYTES + (lane & 3) * 16),
+                           ok ? (const void*)(P.hprev + pp * P.cout + half * P.nhalf + j_lo + (lane & 3) * 4) : (const void*)P.out,
+                           ok ? 16u : 0u, true);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (GRU && !(P.debug & 4)) fetch_hprev(first_tile, et0);
         long long e_start = clock64(), e_wait = 0;
         int buf = 0;
         uint32_t acc_phase = 0;
@@ -990,26 +1012,39 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const bool valid = p < P.P;
             const int ch0 = half * P.nhalf;
             bool released = false;
+            const uint32_t et = et0 + (uint32_t)((it & 1) * EPI_TILE_BYTES);
+            if (GRU && !(P.debug & 4)) {
+                fetch_hprev(tile + tile_stride, et0 + (uint32_t)(((it + 1) & 1) * EPI_TILE_BYTES));  // next tile, other buffer
+                asm volatile("cp.async.wait_group 1;" ::: "memory");                                 // this tile's has landed
+                __syncwarp();
+            }
             long long c0 = clock64();
             mbar_wait_sleep(&acc_full[buf], acc_phase, 64);
             e_wait += clock64() - c0;
             tc_fence_after();
             if (P.debug & 4) {
             } else if (GRU) {
+                // nhalf == 32: this warp owns 16 channels (64 B) of its 32 pixels.  Thread = pixel is what TMEM dictates,
+                // but as a global access pattern it touches 32 different 128-byte lines per instruction (the L1 data
+                // pipe was the busiest unit of the kernel, 64 %).  h_prev and the new state therefore go through a
+                // per-warp exchange tile: global side = 4 lanes per pixel x 16 B (8 lines per instruction).
                 const int nh = P.nhalf;  // hidden channels of this half
                 const int Ch = P.cout;
-                for (int j = j_lo; j < j_hi; j += 8) {
+                float o[16];
+                {
                     float ar[8], az[8], xn[8], hn[8];
-                    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
-                    if (valid) {  // issue the global loads first: their latency overlaps the TMEM loads
-                        const float4* hpp = reinterpret_cast<const float4*>(P.hprev + p * Ch + ch0 + j);
-                        h0 = __ldg(hpp);
-                        h1 = __ldg(hpp + 1);
-                    }
-                    tmem_ld8x4(t0 + j, t0 + nh + j, t0 + 2 * nh + j, t0 + 3 * nh + j, hn, ar, az, xn);
-                    if (valid) {
+#pragma unroll
+                    for (int jb = 0; jb < 2; ++jb) {
+                        const int j = j_lo + 8 * jb;
+                        tmem_ld8x4(t0 + j, t0 + nh + j, t0 + 2 * nh + j, t0 + 3 * nh + j, hn, ar, az, xn);
+                        if (jb == 1) {  // both halves of this thread's accumulator columns are in registers
+                            tc_fence_before();
+                            mbar_arrive(&acc_empty[buf]);
+                            released = true;
+                        }
+                        const float4 h0 = lds128(et + (uint32_t)(lane * EPI_ROW_BYTES + jb * 32));
+                        const float4 h1 = lds128(et + (uint32_t)(lane * EPI_ROW_BYTES + jb * 32 + 16));
                         const float hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                        float o[8];
 #pragma unroll
                         for (int q4 = 0; q4 < 8; q4 += 4) {
                             const int c = ch0 + j + q4;  // multiple of 4: 128-bit reads of the bias table
@@ -1025,14 +1060,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                                 const float r = sigmoid_fused(ar[q], br[u]);
                                 const float z = sigmoid_fused(az[q], bz[u]);
                                 const float n = tanh_acc(fmaf(r, hn[q], xn[q] + bn[u]));
-                                o[q] = fmaf(z, hp[q], n * (1.f - z));
+                                o[jb * 8 + q] = fmaf(z, hp[q], n * (1.f - z));
                             }
                         }
-                        float4* op = reinterpret_cast<float4*>(P.out + p * Ch + ch0 + j);
-                        op[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        op[1] = make_float4(o[4], o[5], o[6], o[7]);
                     }
                 }
+                __syncwarp();  // every lane has read its h_prev row: the tile can take the results
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    sts128(et + (uint32_t)(lane * EPI_ROW_BYTES + i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int prow = (lane >> 2) + 8 * k;
+                    const long long pp = (long long)tile * TILE_M + quad * 32 + prow;
+                    if (pp < P.P)
+                        *reinterpret_cast<float4*>(P.out + pp * Ch + ch0 + j_lo + (lane & 3) * 4) =
+                            lds128(et + (uint32_t)(prow * EPI_ROW_BYTES + (lane & 3) * 16));
+                }
+                __syncwarp();  // stores have read the tile before the next h_prev block lands in it
             } else if (P.ngroups == 2 && P.nhalf == 64 && P.acc_bufs == 1) {
                 // single accumulator buffer (3x3 conv): sum the four accumulator regions into registers first and hand
                 // the buffer back to the MMA issuers BEFORE the bias / ReLU / global stores
@@ -1175,7 +1221,8 @@ __global__ void pack_weights_kernel(PackDesc D, float* dst) {
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float);
+    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float) +
+           (P.mode == MODE_GRU ? (size_t)EPI_WARPS * 2 * EPI_TILE_BYTES : 0);
 }
 
 static int g_debug = 0;
