@@ -990,15 +990,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const uint32_t et0 = smem_u32(epi_s) + (uint32_t)(warp * 2 * EPI_TILE_BYTES);  // this warp's two exchange tiles
         // h_prev of a tile (independent of the MMAs): asynchronous coalesced copy into an exchange tile, issued one tile
         // ahead so that its latency never shows
+        // global side of the exchange: lane -> pixel (lane >> 2) + 8*k of the warp's 32, 16-byte piece lane & 3
+        const long long xoff = ((long long)(quad * 32 + (lane >> 2))) * P.cout + half * P.nhalf + j_lo + (lane & 3) * 4;
+        const uint32_t xs = (uint32_t)((lane >> 2) * EPI_ROW_BYTES + (lane & 3) * 16);
         auto fetch_hprev = [&](int tile, uint32_t dst) {
+            const float* g = P.hprev + (long long)tile * TILE_M * P.cout + xoff;
+            if (tile < P.n_tiles && (long long)(tile + 1) * TILE_M <= P.P) {  // whole tile inside: no per-row predicate
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int prow = (lane >> 2) + 8 * k;
-                const long long pp = (long long)tile * TILE_M + quad * 32 + prow;
-                const bool ok = tile < P.n_tiles && pp < P.P;
-                cp_async16(dst + (uint32_t)(prow * EPI_ROW_BYTES + (lane & 3) * 16),
-                           ok ? (const void*)(P.hprev + pp * P.cout + half * P.nhalf + j_lo + (lane & 3) * 4) : (const void*)P.out,
-                           ok ? 16u : 0u, true);
+                for (int k = 0; k < 4; ++k) cp_async16(dst + xs + (uint32_t)(8 * k * EPI_ROW_BYTES), g + 8 * k * P.cout, 16u, true);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long pp = (long long)tile * TILE_M + quad * 32 + (lane >> 2) + 8 * k;
+                    const bool ok = tile < P.n_tiles && pp < P.P;
+                    cp_async16(dst + xs + (uint32_t)(8 * k * EPI_ROW_BYTES), ok ? (const void*)(g + 8 * k * P.cout) : (const void*)P.out,
+                               ok ? 16u : 0u, true);
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -1070,13 +1077,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                 for (int i = 0; i < 4; ++i)
                     sts128(et + (uint32_t)(lane * EPI_ROW_BYTES + i * 16), make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
                 __syncwarp();
+                {
+                    float* g = P.out + (long long)tile * TILE_M * Ch + xoff;
+                    if ((long long)(tile + 1) * TILE_M <= P.P) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int prow = (lane >> 2) + 8 * k;
-                    const long long pp = (long long)tile * TILE_M + quad * 32 + prow;
-                    if (pp < P.P)
-                        *reinterpret_cast<float4*>(P.out + pp * Ch + ch0 + j_lo + (lane & 3) * 4) =
-                            lds128(et + (uint32_t)(prow * EPI_ROW_BYTES + (lane & 3) * 16));
+                        for (int k = 0; k < 4; ++k)
+                            *reinterpret_cast<float4*>(g + 8 * k * Ch) = lds128(et + xs + (uint32_t)(8 * k * EPI_ROW_BYTES));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if ((long long)tile * TILE_M + quad * 32 + (lane >> 2) + 8 * k < P.P)
+                                *reinterpret_cast<float4*>(g + 8 * k * Ch) = lds128(et + xs + (uint32_t)(8 * k * EPI_ROW_BYTES));
+                    }
                 }
                 __syncwarp();  // stores have read the tile before the next h_prev block lands in it
             } else if (P.ngroups == 2 && P.nhalf == 64 && P.acc_bufs == 1) {
