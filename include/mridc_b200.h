@@ -232,6 +232,35 @@ int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, const void*
 int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out, int B,
                               int H, int W, int cin, int k, int dil, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Quantitative MRI (qRIM / qCIRIM, BASELINE.json configs[4]): pointwise kernels around the fused DC operator.
+ * The data-consistency part of analytical_log_likelihood_gradient
+ * (mridc/collections/quantitative/models/qrim/utils.py:166-295) is mrb_dc_rim_grad with the echoes folded into the
+ * batch: eta = mrb_megre_signal(maps), then mrb_megre_grad turns its per-echo output into the map gradient.
+ * maps are [B, HW] fp32; gamma4 (host pointer, may be null = ones) multiplies (R2*, S0, B0, phi) first
+ * (qrim_block.py:196-199); tes: n_echoes echo times (host doubles); scaling: SignalForwardModel.scaling (1e-3).
+ * ------------------------------------------------------------------------------------------------- */
+/* SignalForwardModel.__call__ (qrim/utils.py:36-155): -> out [B, E, HW] complex64 (NaN -> 0); no_phase != 0 selects
+ * MEGRENoPhaseSignalModel (b0 / phi unused). */
+int mrb_megre_signal(const void* r2star, const void* s0, const void* b0, const void* phi, const float* gamma4,
+                     const double* tes, int n_echoes, double scaling, int B, long long HW, int no_phase, void* out,
+                     void* stream);
+/* qrim/utils.py:236-295: d [B*E, 4, HW] = mrb_dc_rim_grad output for the B*E signal images (channels 2,3 = the
+ * coil-combined residual) -> out[b, 0..3, HW] = (R2*_re, S0_re, R2*_im, S0_im) gradient, mean over echoes, divided by
+ * `divisor` (qrim_block.py:222: 100), NaN -> 0 when zero_nan (:223); out has out_channels (>= 4) channels per sample. */
+int mrb_megre_grad(const void* d, const void* r2star, const void* s0, const void* b0, const void* phi,
+                   const float* gamma4, const double* tes, int n_echoes, double scaling, int B, long long HW,
+                   float divisor, int zero_nan, void* out, int out_channels, void* stream);
+/* qrim_block.py:232-236: eta <- eta + delta with channel 0 (R2*) clamped at >= 0; eta = channels
+ * [eta_offset, eta_offset + 4) of a [B, eta_channels, HW] buffer (updated in place), delta / out [B, 4, HW]. */
+int mrb_qrim_eta_update(void* eta, int eta_channels, int eta_offset, const void* delta, void* out, int B,
+                        long long HW, void* stream);
+/* RescaleByMax.reverse (qrim/utils.py:25-28): out[b] = x[b] * scales[b], or |x[b]| * scales[b] when take_abs
+ * (qcirim.py:287-289 applies it to torch.abs(pred)); the reference indexes its 4 regularisation factors by BATCH
+ * index, so B <= 4.  scales: host pointer, B floats. */
+int mrb_scale_batch(const void* x, void* out, int B, long long per_batch, const float* scales, int take_abs,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,10 @@ from .rim import (  # noqa: F401
 )
 from .unet import NormUnet, Unet, ConvBlock, TransposeConvBlock  # noqa: F401
 from .varnet import VarNetBlock  # noqa: F401
-from .models import CIRIM, VarNet, UNet, ZF  # noqa: F401
+from .qrim import (  # noqa: F401
+    RescaleByMax, SignalForwardModel, expand_op, analytical_log_likelihood_gradient, qRIMBlock,
+)
+from .models import CIRIM, VarNet, UNet, ZF, qCIRIM  # noqa: F401
 from .pipeline import HostPrefetcher  # noqa: F401
 
 __version__ = "0.1.0"

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libmridc_b200.so")
 
 _vp, _ll, _i, _f, _sz = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 _llp = ctypes.POINTER(ctypes.c_longlong)
+_fp, _dp, _d = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), ctypes.c_double
 
 # name -> (restype, argtypes); must list every symbol of include/mridc_b200.h (tests/test_abi.py checks)
 SIGNATURES = {
@@ -59,6 +60,10 @@ SIGNATURES = {
     "mrb_tc_conv5x5x4_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrb_tc_gru_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrb_megre_signal": (_i, [_vp, _vp, _vp, _vp, _fp, _dp, _i, _d, _i, _ll, _i, _vp, _vp]),
+    "mrb_megre_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _fp, _dp, _i, _d, _i, _ll, _f, _i, _vp, _i, _vp]),
+    "mrb_qrim_eta_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _ll, _vp]),
+    "mrb_scale_batch": (_i, [_vp, _vp, _i, _ll, _fp, _i, _vp]),
 }
 
 _lib = None

@@ -9,19 +9,21 @@ of scope -- ``trainer`` is accepted and ignored
   VarNet  mridc/collections/reconstruction/models/vn.py:22-142
   UNet    mridc/collections/reconstruction/models/unet.py:21-121
   ZF      mridc/collections/reconstruction/models/zf.py:20-100
+  qCIRIM  mridc/collections/quantitative/models/qcirim.py:21-341 (quantitative module; BASELINE.json configs[4])
 """
 import math
-from typing import Any, Generator, Mapping, Union
+from typing import Any, Generator, List, Mapping, Union
 
 import torch
 import torch.nn as nn
 
 from . import _lib, _ops, utils
+from .qrim import RescaleByMax, SignalForwardModel, qRIMBlock
 from .rim import RIMBlock
 from .unet import NormUnet
 from .varnet import VarNetBlock
 
-__all__ = ["CIRIM", "VarNet", "UNet", "ZF"]
+__all__ = ["CIRIM", "VarNet", "UNet", "ZF", "qCIRIM"]
 
 
 def _cfg_dict(cfg) -> dict:
@@ -228,3 +230,89 @@ class ZF(_BaseModel):
         pred = utils.check_stacked_complex(pred)
         _, pred = utils.center_crop_to_smallest(target, pred)
         return pred
+
+
+class qCIRIM(_BaseModel):
+    """quantitative Cascades of Independently Recurrent Inference Machines, qcirim.py:21 -- the quantitative module
+    (R2*, S0, B0, phi mapping from multi-echo k-space).  ``use_reconstruction_module`` (a CIRIM per echo followed by a
+    least-squares re-fit of the maps, qcirim.py:185-245) is not on the BASELINE configs[4] path and raises."""
+
+    def __init__(self, cfg, trainer=None):
+        super().__init__(cfg, trainer)
+        c = self._cfg
+        dimensionality = c.get("quantitative_module_dimensionality")
+        if dimensionality != 2:
+            raise ValueError(f"Only 2D is currently supported for qMRI models.Found {dimensionality}")  # qcirim.py:45-49
+        if not c.get("quantitative_module_no_dc"):
+            raise ValueError("qCIRIM does not support explicit DC component.")  # :51-53
+        self.fft_centered = c.get("fft_centered")
+        self.fft_normalization = c.get("fft_normalization")
+        self.spatial_dims = _listify(c.get("spatial_dims"))
+        self.coil_dim = c.get("coil_dim")
+        self.coil_combination_method = c.get("coil_combination_method")
+        self.shift_B0_input = c.get("shift_B0_input")
+        self.cirim = nn.ModuleList([])
+        self.use_reconstruction_module = c.get("use_reconstruction_module")
+        if self.use_reconstruction_module:
+            raise NotImplementedError(
+                "mridc_b200: qCIRIM with use_reconstruction_module=True is out of scope (SURVEY 8f rank 2)")
+        self.qcirim = nn.ModuleList([
+            qRIMBlock(
+                recurrent_layer=c.get("quantitative_module_recurrent_layer"),
+                conv_filters=_listify(c.get("quantitative_module_conv_filters")),
+                conv_kernels=_listify(c.get("quantitative_module_conv_kernels")),
+                conv_dilations=_listify(c.get("quantitative_module_conv_dilations")),
+                conv_bias=_listify(c.get("quantitative_module_conv_bias")),
+                recurrent_filters=_listify(c.get("quantitative_module_recurrent_filters")),
+                recurrent_kernels=_listify(c.get("quantitative_module_recurrent_kernels")),
+                recurrent_dilations=_listify(c.get("quantitative_module_recurrent_dilations")),
+                recurrent_bias=_listify(c.get("quantitative_module_recurrent_bias")),
+                depth=c.get("quantitative_module_depth"),
+                time_steps=c.get("quantitative_module_time_steps"),
+                conv_dim=c.get("quantitative_module_conv_dim"),
+                no_dc=c.get("quantitative_module_no_dc"),
+                linear_forward_model=SignalForwardModel(
+                    sequence=c.get("quantitative_module_signal_forward_model_sequence")),
+                fft_centered=self.fft_centered,
+                fft_normalization=self.fft_normalization,
+                spatial_dims=self.spatial_dims,
+                coil_dim=self.coil_dim,
+                coil_combination_method=self.coil_combination_method,
+                dimensionality=dimensionality,
+            )
+            for _ in range(c.get("quantitative_module_num_cascades"))
+        ])
+        self.accumulate_estimates = c.get("quantitative_module_accumulate_estimates")
+        self.gamma = torch.tensor(_listify(c.get("quantitative_module_gamma_regularization_factors")))  # :141
+        self.preprocessor = RescaleByMax
+
+    @torch.no_grad()
+    def forward(self, R2star_map_init: torch.Tensor, S0_map_init: torch.Tensor, B0_map_init: torch.Tensor,
+                phi_map_init: torch.Tensor, TEs: List, y: torch.Tensor, sensitivity_maps: torch.Tensor,
+                mask_brain: torch.Tensor, sampling_mask: torch.Tensor) -> Union[Generator, torch.Tensor]:
+        """qcirim.py:145-312 -- yields [pred, R2star, S0, B0, phi] where pred is an empty tensor (no reconstruction
+        module) and every map entry is list[num_cascades] of list[time_steps] of [B, H, W]."""
+        _lib.require_cuda(y, "y")
+        g = [float(self.gamma[k]) for k in range(4)]
+        # :247-250 (x / gamma: a true division, the block multiplies the factor back in, qrim_block.py:196-199)
+        maps = [_lib.require_cuda(m, n) / g[k] for k, (m, n) in enumerate(
+            ((R2star_map_init, "R2star_map_init"), (S0_map_init, "S0_map_init"), (B0_map_init, "B0_map_init"),
+             (phi_map_init, "phi_map_init")))]
+        prediction = y  # :252 clones; nothing below writes to y
+        eta = None
+        hx = None
+        cascades = [[], [], [], []]
+        for i, cascade in enumerate(self.qcirim):
+            prediction, hx = cascade(prediction, y, maps[0], maps[1], maps[2], maps[3], TEs, sensitivity_maps,
+                                     sampling_mask, eta, hx, self.gamma, keep_eta=i != 0)
+            maps = [prediction[-1][:, k] for k in range(4)]  # :279-284
+            steps = [self.process_intermediate_pred(pred, None, None, False, _abs=True) for pred in prediction]
+            for k in range(4):
+                cascades[k].append([s[k] for s in steps])
+        yield [torch.empty([]), cascades[0], cascades[1], cascades[2], cascades[3]]
+
+    def process_intermediate_pred(self, pred, sensitivity_maps, target, do_coil_combination=False, _abs=False):
+        """qcirim.py:314-341: RescaleByMax.reverse(pred, gamma) split into the four maps.  ``_abs`` folds the caller's
+        ``torch.abs(pred)`` (:300) into the same kernel."""
+        x = self.preprocessor.reverse(pred, self.gamma, _take_abs=_abs)
+        return x[:, 0, ...], x[:, 1, ...], x[:, 2, ...], x[:, 3, ...]

@@ -225,3 +225,99 @@ def unet_cfg(channels=64, pooling_layers=2, padding_size=11, centered=False, nor
 def zf_cfg(method="SENSE", centered=False, normalization="backward"):
     return dict(coil_combination_method=method, use_sens_net=False, fft_centered=centered,
                 fft_normalization=normalization, spatial_dims=[-2, -1], coil_dim=1)
+
+
+# --------------------------------------------------------------------------------------------------
+# quantitative (BASELINE.json configs[4]: qCIRIM R2* mapping, 32-coil multi-echo 7T-shaped slices)
+# --------------------------------------------------------------------------------------------------
+QMRI_SHAPE = (232, 288)  # AHEAD-like in-plane matrix (non-power-of-2: 232 = 8*29, 288 = 32*9)
+QMRI_TES = [3.0, 11.5, 20.0, 28.5]  # ms, base_qcirim_run.yaml / qrim/utils.py:64
+QMRI_GAMMA = [150.0, 150.0, 1000.0, 150.0]  # base_qcirim_run.yaml:91-95
+
+
+def qcirim_cfg(num_cascades=1, filters=128, recurrent_layer="IndRNN", time_steps=8, centered=False,
+               normalization="backward", sequence="MEGRE"):
+    """Flat cfg with the quantitative-module keys of projects/quantitative/model_zoo/conf/base_qcirim_run.yaml:7-121."""
+    return dict(
+        use_reconstruction_module=False, quantitative_module_recurrent_layer=recurrent_layer,
+        quantitative_module_conv_filters=[filters, filters, 4], quantitative_module_conv_kernels=[5, 3, 3],
+        quantitative_module_conv_dilations=[1, 2, 1], quantitative_module_conv_bias=[True, True, False],
+        quantitative_module_recurrent_filters=[filters, filters, 0], quantitative_module_recurrent_kernels=[1, 1, 0],
+        quantitative_module_recurrent_dilations=[1, 1, 0], quantitative_module_recurrent_bias=[True, True, False],
+        quantitative_module_depth=2, quantitative_module_time_steps=time_steps, quantitative_module_conv_dim=2,
+        quantitative_module_num_cascades=num_cascades, quantitative_module_no_dc=True,
+        quantitative_module_keep_eta=True, quantitative_module_accumulate_estimates=True,
+        quantitative_module_signal_forward_model_sequence=sequence, quantitative_module_dimensionality=2,
+        quantitative_module_gamma_regularization_factors=list(QMRI_GAMMA), shift_B0_input=False, dimensionality=2,
+        coil_combination_method="SENSE", use_sens_net=False, fft_centered=centered, fft_normalization=normalization,
+        spatial_dims=[-2, -1], coil_dim=2)
+
+
+def cached_poisson_mask():
+    """The 12x Poisson-disc mask of configs[4], generated once by the reference's Poisson2DMaskFunc (its numba RNG is
+    unseeded, subsample.py:584-600) and committed bit-packed (oracle/make_golden.py::gen_poisson) -> [H, W] float32."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                        "poisson_mask.npz")
+    d = np.load(path)
+    H, W = (int(v) for v in d["shape"])
+    return np.unpackbits(d["bits"])[: H * W].reshape(H, W).astype(np.float32)
+
+
+def make_qmri_batch(B: int, C: int = 32, H: Optional[int] = None, W: Optional[int] = None, mask: np.ndarray = None,
+                    tes: Sequence[float] = tuple(QMRI_TES), centered: bool = False, normalization: str = "backward",
+                    first_slice: int = 0):
+    """Synthetic multi-echo GRE slices -> dict of CPU torch tensors: y [B,E,C,H,W,2] (undersampled MEGRE k-space),
+    sensitivity_maps [B,C,H,W,2], sampling_mask [B,1,H,W,1] float32, mask_brain [B,1,H,W,1], the ground-truth maps
+    R2star / S0 / B0 / phi [B,H,W] and their *_init versions (a smoothed / biased guess, standing in for the
+    reference's least-squares initial fit), TEs (list of ms)."""
+    import torch
+
+    if H is None or W is None:
+        H, W = QMRI_SHAPE
+    if mask is None:
+        mask = cached_poisson_mask()
+        if mask.shape != (H, W):
+            raise ValueError("the cached Poisson mask is %s; pass mask= for %s" % (mask.shape, (H, W)))
+        if not centered:
+            # the pattern is drawn with its calibration disc at the array centre; a non-centred FFT has DC at [0, 0]
+            # (utils.apply_mask's `shift` option, common/parts/utils.py:335-336)
+            mask = np.fft.ifftshift(mask)
+    S = coil_maps(C, H, W)
+    S = S / np.max(np.abs(S))
+    u = np.linspace(-1, 1, H)[:, None]
+    v = np.linspace(-1, 1, W)[None, :]
+    maps, inits, ys = [], [], []
+    for b in range(B):
+        x = phantom(H, W, first_slice + b)
+        mag = np.abs(x) / np.max(np.abs(x))
+        brain = (mag > 0.05).astype(np.float64)
+        r2 = brain * (25.0 + 30.0 * mag + 10.0 * np.sin(5 * u) * np.cos(4 * v))       # 1/s
+        b0 = brain * (40.0 * u * v + 15.0 * np.sin(3 * v))                              # rad/s-scaled field map
+        s0 = mag * np.cos(np.angle(x))                                                  # Re S0
+        ph = mag * np.sin(np.angle(x))                                                  # Im S0
+        sig = np.stack([(s0 + 1j * ph) * np.exp(-te * 1e-3 * r2) * np.exp(-1j * b0 * 1e-3 * te) for te in tes])
+        k = _fft2c(sig[:, None] * S[None], centered, normalization)                     # [E, C, H, W]
+        ys.append(k * mask[None, None])
+        maps.append((r2, s0, b0, ph))
+        rng = np.random.RandomState(4321 + first_slice + b)
+        inits.append(tuple(m * (1.0 + 0.1 * rng.standard_normal()) + 0.02 * np.abs(m).max() * rng.standard_normal(m.shape)
+                           for m in (r2, s0, b0, ph)))
+
+    def c2r(a):
+        a = np.asarray(a)
+        return torch.from_numpy(np.stack((a.real, a.imag), -1).astype(np.float32))
+
+    def f32(a):
+        return torch.from_numpy(np.asarray(a).astype(np.float32))
+
+    m5 = np.broadcast_to(mask.reshape(1, 1, H, W, 1), (B, 1, H, W, 1)).astype(np.float32).copy()
+    out = {
+        "y": c2r(np.stack(ys)), "sensitivity_maps": c2r(np.broadcast_to(S[None], (B, C, H, W)).copy()),
+        "sampling_mask": torch.from_numpy(m5), "mask_brain": torch.ones(B, 1, H, W, 1), "TEs": [float(t) for t in tes],
+    }
+    for i, name in enumerate(("R2star_map", "S0_map", "B0_map", "phi_map")):
+        out[name] = f32(np.stack([m[i] for m in maps]))
+        out[name + "_init"] = f32(np.stack([m[i] for m in inits]))
+    return out

@@ -17,6 +17,7 @@ from . import metrics as ometrics  # noqa: F401
 from . import models as omodels
 from . import mri as omri
 from . import nets as onets
+from . import qnets as oqnets
 from .ref_import import Ref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -343,16 +344,180 @@ def gen_models(R):
     print("models.npz: %d arrays" % len(out))
 
 
+QRIM_HP = dict(conv_filters=[16, 16, 4], conv_kernels=[5, 3, 3], conv_dilations=[1, 2, 1], conv_bias=[True, True, False],
+               recurrent_filters=[16, 16, 0], recurrent_kernels=[1, 1, 0], recurrent_dilations=[1, 1, 0],
+               recurrent_bias=[True, True, False], time_steps=8, spatial_dims=[-2, -1], coil_dim=2,
+               coil_combination_method="SENSE")
+QGAMMA = [150.0, 150.0, 1000.0, 150.0]
+
+
+def qmri_inputs(B, E, C, H, W, seed, mask_kind):
+    """Seeded qMRI-shaped inputs: maps in physical ranges (R2* ~ 0..100 1/s, B0 ~ +-60 Hz-ish), k-space of the MEGRE
+    signal of slightly different maps (so the residual is neither zero nor huge), mask 1-D / 2-D / per-batch 2-D."""
+    g = torch.Generator().manual_seed(seed)
+    r2 = torch.rand(B, H, W, generator=g) * 90 + 5
+    s0 = torch.randn(B, H, W, generator=g)
+    b0 = torch.randn(B, H, W, generator=g) * 40
+    ph = torch.randn(B, H, W, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g) * 0.5
+    tes = [3.0, 11.5, 20.0, 28.5][:E] if E <= 4 else [3.0 + 4.25 * e for e in range(E)]
+    sig = oqnets.megre_signal(r2 * 1.1, s0 + 0.2, b0 * 0.9, ph - 0.1, tes)
+    k = omri.fft2(omri.complex_mul(sig.unsqueeze(2), S.unsqueeze(1)), False, "backward", [-2, -1])
+    k = k + 0.05 * torch.randn(k.shape, generator=g)
+    if mask_kind == "1d":
+        m = (torch.rand(B, 1, 1, W, 1, generator=g) < 0.4).float()
+        m[..., W // 2, :] = 1
+    elif mask_kind == "2d":
+        # one pattern for the whole batch; the reference indexes sampling_mask[idx], so it still carries the batch dim
+        m = (torch.rand(1, 1, H, W, 1, generator=g) < 0.35).float().expand(B, 1, H, W, 1).contiguous()
+    else:
+        m = (torch.rand(B, 1, H, W, 1, generator=g) < 0.35).float()
+    y = k * m.unsqueeze(1)
+    return r2, s0, b0, ph, tes, y, S, m
+
+
+def gen_qmri(R):
+    """qRIM / qCIRIM: signal model, analytic gradient, qRIMBlock, model-level forward."""
+    out = {}
+    # --- signal model + analytic gradient, one sample (qrim/utils.py) ---
+    i = 0
+    for (E, C, H, W, mk, cen, nrm, seq) in [(4, 3, 12, 10, "1d", False, "backward", "MEGRE"),
+                                            (4, 5, 9, 14, "2d", True, "ortho", "MEGRE"),
+                                            (3, 2, 16, 6, "2d", False, "forward", "MEGRE"),
+                                            (2, 3, 8, 8, "1d", True, "backward", "MEGRE_no_phase")]:
+        r2, s0, b0, ph, tes, y, S, m = qmri_inputs(1, E, C, H, W, 700 + i, mk)
+        fm = R.qrim_utils.SignalForwardModel(sequence=seq)
+        sig = fm(r2, s0, b0, ph, tes)
+        o_sig = oqnets.megre_signal(r2, s0, b0, ph, tes, no_phase=seq.lower() == "megre_no_phase")
+        _close(o_sig, sig, "qmri signal", rtol=0, atol=0)
+        g = R.qrim_utils.analytical_log_likelihood_gradient(fm, r2[0], s0[0], b0[0], ph[0], tes, S[0], y[0], m[0], cen,
+                                                            nrm, [-2, -1], 2)
+        o_g = oqnets.analytical_log_likelihood_gradient(r2[0], s0[0], b0[0], ph[0], tes, S[0], y[0], m[0], cen, nrm,
+                                                        [-2, -1], 2, no_phase=seq.lower() == "megre_no_phase")
+        _close(o_g, g, "qmri gradient", rtol=1e-6, atol=1e-6 * g.abs().max().item())
+        out.update({"grad%d_%s" % (i, k): v for k, v in _np(dict(
+            r2=r2, s0=s0, b0=b0, ph=ph, tes=np.asarray(tes), y=y, S=S, mask=m, signal=sig, grad=g)).items()})
+        out["grad%d_cfg" % i] = np.asarray([int(cen), ["backward", "ortho", "forward"].index(nrm),
+                                            int(seq.lower() == "megre_no_phase")])
+        i += 1
+    out["ngrad"] = np.asarray(i)
+    # --- qRIMBlock (qrim/qrim_block.py) ---
+    i = 0
+    for (layer, B, mk, cen, nrm) in [("IndRNN", 2, "1d", False, "backward"), ("GRU", 1, "2d", True, "ortho"),
+                                     ("MGU", 2, "2db", False, "ortho")]:
+        hp = dict(QRIM_HP, recurrent_layer=layer, fft_centered=cen, fft_normalization=nrm, sequence="MEGRE")
+        torch.manual_seed(40 + i)
+        blk = R.qrim_block.qRIMBlock(
+            recurrent_layer=layer, conv_filters=hp["conv_filters"], conv_kernels=hp["conv_kernels"],
+            conv_dilations=hp["conv_dilations"], conv_bias=hp["conv_bias"], recurrent_filters=hp["recurrent_filters"],
+            recurrent_kernels=hp["recurrent_kernels"], recurrent_dilations=hp["recurrent_dilations"],
+            recurrent_bias=hp["recurrent_bias"], depth=2, time_steps=hp["time_steps"], conv_dim=2, no_dc=True,
+            linear_forward_model=R.qrim_utils.SignalForwardModel(sequence="MEGRE"), fft_centered=cen,
+            fft_normalization=nrm, spatial_dims=[-2, -1], coil_dim=2, coil_combination_method="SENSE",
+            dimensionality=2).eval()
+        sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+        r2, s0, b0, ph, tes, y, S, m = qmri_inputs(B, 4, 3, 14, 12, 800 + i, mk)
+        gamma = torch.tensor(QGAMMA)
+        maps = [r2 / gamma[0], s0 / gamma[1], b0 / gamma[2], ph / gamma[3]]
+        with torch.no_grad():
+            etas, _ = blk(y.clone(), y, maps[0], maps[1], maps[2], maps[3], tes, S, m, None, None, gamma, False)
+            o_etas, _ = oqnets.qrim_block(sd, hp, y, maps[0], maps[1], maps[2], maps[3], tes, S, m, None, None, gamma)
+        for a, b in zip(o_etas, etas):
+            _close(a, b, "qrim %s step" % layer, rtol=1e-5, atol=1e-6)
+        out.update({"blk%d_%s" % (i, k): v for k, v in _np(dict(
+            r2=maps[0], s0=maps[1], b0=maps[2], ph=maps[3], tes=np.asarray(tes), y=y, S=S, mask=m, first=etas[0],
+            last=etas[-1])).items()})
+        out.update({"blk%d_w_%s" % (i, k): v.numpy() for k, v in sd.items()})
+        out["blk%d_cfg" % i] = np.asarray([["GRU", "IndRNN", "MGU"].index(layer), int(cen),
+                                           ["backward", "ortho", "forward"].index(nrm)])
+        i += 1
+    out["nblk"] = np.asarray(i)
+    # --- model level: qCIRIM.forward glue (qcirim.py:247-341) restated around the REFERENCE blocks ---
+    cfg = oqnets_cfg(num_cascades=2)
+    torch.manual_seed(77)
+    blocks = [R.qrim_block.qRIMBlock(
+        recurrent_layer=cfg["quantitative_module_recurrent_layer"], conv_filters=cfg["quantitative_module_conv_filters"],
+        conv_kernels=cfg["quantitative_module_conv_kernels"], conv_dilations=cfg["quantitative_module_conv_dilations"],
+        conv_bias=cfg["quantitative_module_conv_bias"], recurrent_filters=cfg["quantitative_module_recurrent_filters"],
+        recurrent_kernels=cfg["quantitative_module_recurrent_kernels"],
+        recurrent_dilations=cfg["quantitative_module_recurrent_dilations"],
+        recurrent_bias=cfg["quantitative_module_recurrent_bias"], depth=2,
+        time_steps=cfg["quantitative_module_time_steps"], conv_dim=2, no_dc=True,
+        linear_forward_model=R.qrim_utils.SignalForwardModel(sequence="MEGRE"), fft_centered=cfg["fft_centered"],
+        fft_normalization=cfg["fft_normalization"], spatial_dims=[-2, -1], coil_dim=2, coil_combination_method="SENSE",
+        dimensionality=2).eval() for _ in range(2)]
+    sd = {}
+    for ci, b in enumerate(blocks):
+        sd.update({"qcirim.%d.%s" % (ci, k): v.detach().clone() for k, v in b.state_dict().items()})
+    r2, s0, b0, ph, tes, y, S, m = qmri_inputs(2, 4, 4, 16, 12, 900, "2d")
+    gamma = torch.tensor(QGAMMA)
+    with torch.no_grad():
+        # reference blocks driven by the reference's forward glue, transcribed line by line (qcirim.py:247-312)
+        mp = [r2 / gamma[0], s0 / gamma[1], b0 / gamma[2], ph / gamma[3]]
+        prediction = y.clone()
+        ref_maps = [[], [], [], []]
+        for ci, cascade in enumerate(blocks):
+            prediction, _ = cascade(prediction, y, mp[0], mp[1], mp[2], mp[3], tes, S, m, None, None, gamma,
+                                    keep_eta=ci != 0)
+            mp = [prediction[-1][:, k] for k in range(4)]
+            steps = [R.qrim_utils.RescaleByMax.reverse(torch.abs(p), gamma) for p in prediction]
+            for k in range(4):
+                ref_maps[k].append([s[:, k, ...] for s in steps])
+        o = oqnets.qcirim_forward(sd, cfg, r2, s0, b0, ph, tes, y, S, torch.ones_like(m), m)
+    for k in range(4):
+        for ci in range(2):
+            for a, b in zip(o[1 + k][ci], ref_maps[k][ci]):
+                _close(a, b, "qcirim map %d" % k, rtol=1e-5, atol=1e-5)
+    out.update({"model_%s" % k: v for k, v in _np(dict(
+        r2=r2, s0=s0, b0=b0, ph=ph, tes=np.asarray(tes), y=y, S=S, mask=m,
+        r2_last=ref_maps[0][-1][-1], s0_last=ref_maps[1][-1][-1], b0_last=ref_maps[2][-1][-1],
+        ph_last=ref_maps[3][-1][-1], r2_first=ref_maps[0][0][0])).items()})
+    out.update({"model_w_%s" % k: v.numpy() for k, v in sd.items()})
+    np.savez_compressed(os.path.join(GOLDEN, "qmri.npz"), **out)
+    print("qmri.npz: %d arrays" % len(out))
+
+
+def oqnets_cfg(num_cascades=1, filters=16, layer="IndRNN", centered=False, normalization="backward"):
+    """Flat qCIRIM cfg with the keys of projects/quantitative/model_zoo/conf/base_qcirim_run.yaml:7-121."""
+    return dict(
+        use_reconstruction_module=False, quantitative_module_recurrent_layer=layer,
+        quantitative_module_conv_filters=[filters, filters, 4], quantitative_module_conv_kernels=[5, 3, 3],
+        quantitative_module_conv_dilations=[1, 2, 1], quantitative_module_conv_bias=[True, True, False],
+        quantitative_module_recurrent_filters=[filters, filters, 0], quantitative_module_recurrent_kernels=[1, 1, 0],
+        quantitative_module_recurrent_dilations=[1, 1, 0], quantitative_module_recurrent_bias=[True, True, False],
+        quantitative_module_depth=2, quantitative_module_time_steps=8, quantitative_module_conv_dim=2,
+        quantitative_module_num_cascades=num_cascades, quantitative_module_no_dc=True,
+        quantitative_module_keep_eta=True, quantitative_module_accumulate_estimates=True,
+        quantitative_module_signal_forward_model_sequence="MEGRE", quantitative_module_dimensionality=2,
+        quantitative_module_gamma_regularization_factors=list(QGAMMA), shift_B0_input=False, dimensionality=2,
+        coil_combination_method="SENSE", use_sens_net=False, fft_centered=centered, fft_normalization=normalization,
+        spatial_dims=[-2, -1], coil_dim=2)
+
+
+def gen_poisson(R):
+    """BASELINE.json configs[4]: 12x Poisson-disc 2-D mask.  The reference draws it from numba's unseeded generator
+    (subsample.py:584-600), so it is generated ONCE here with the reference function and cached bit-packed; both
+    implementations are always fed this tensor."""
+    H, W = 232, 288
+    np.random.seed(123)
+    mf = R.subsample.Poisson2DMaskFunc([0.7], [12])
+    m, acc = mf((1, H, W, 2), seed=123)
+    m = m.numpy().reshape(H, W)
+    assert set(np.unique(m)) <= {0.0, 1.0}
+    np.savez_compressed(os.path.join(GOLDEN, "poisson_mask.npz"), shape=np.asarray([H, W]), acc=np.asarray(acc),
+                        bits=np.packbits(m.astype(np.uint8)))
+    print("poisson_mask.npz: %dx%d, acceleration %s, sampled fraction %.4f" % (H, W, acc, m.mean()))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
     R = Ref()
-    gen_masks(R)
-    gen_prims(R)
-    gen_dc(R)
-    gen_rim(R)
-    gen_unet(R)
-    gen_models(R)
+    only = set(sys.argv[1:])  # e.g. `python -m oracle.make_golden qmri` regenerates one fixture file
+    for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("unet", gen_unet),
+                     ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson)):
+        if not only or name in only:
+            fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print("golden fixtures total %.1f KB" % (tot / 1024))
 

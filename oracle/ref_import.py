@@ -25,6 +25,9 @@ _PKGS = [
     "mridc.collections.reconstruction.models.rim",
     "mridc.collections.reconstruction.models.varnet",
     "mridc.collections.reconstruction.models.unet_base",
+    "mridc.collections.quantitative",
+    "mridc.collections.quantitative.models",
+    "mridc.collections.quantitative.models.qrim",
 ]
 
 
@@ -81,3 +84,5 @@ class Ref:
         self.conv_layers = ref("reconstruction.models.rim.conv_layers")
         self.vn_block = ref("reconstruction.models.varnet.vn_block")
         self.unet_block = ref("reconstruction.models.unet_base.unet_block")
+        self.qrim_utils = ref("quantitative.models.qrim.utils")
+        self.qrim_block = ref("quantitative.models.qrim.qrim_block")

@@ -160,3 +160,39 @@ def test_host_prefetcher_rejects_cpu_device():
 
     with pytest.raises(RuntimeError, match="CUDA device"):
         mb.HostPrefetcher([], "cpu")
+
+
+def test_qcirim_ctor_errors():
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+
+    with pytest.raises(ValueError, match="Only 2D is currently supported"):
+        mb.qCIRIM(dict(synth.qcirim_cfg(filters=8), quantitative_module_dimensionality=3))
+    with pytest.raises(ValueError, match="does not support explicit DC"):
+        mb.qCIRIM(dict(synth.qcirim_cfg(filters=8), quantitative_module_no_dc=False))
+    with pytest.raises(NotImplementedError):
+        mb.qCIRIM(dict(synth.qcirim_cfg(filters=8), use_reconstruction_module=True))
+    # no CPU fallback on the quantitative path either
+    m = torch.zeros(1, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.SignalForwardModel("MEGRE")(m, m, m, m)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.RescaleByMax.reverse(torch.zeros(1, 4, 4, 4), torch.ones(4))
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_qrim_initialisers_reproduce_reference_weights():
+    import mridc_b200 as mb
+
+    R = ref_import.Ref()
+    kw = dict(conv_filters=[8, 8, 4], conv_kernels=[5, 3, 3], conv_dilations=[1, 2, 1], conv_bias=[True, True, False],
+              recurrent_filters=[8, 8, 0], recurrent_kernels=[1, 1, 0], recurrent_dilations=[1, 1, 0],
+              recurrent_bias=[True, True, False], depth=2, time_steps=8, conv_dim=2, no_dc=True, coil_dim=2)
+    for layer in ("GRU", "MGU", "IndRNN"):
+        torch.manual_seed(3)
+        a = R.qrim_block.qRIMBlock(recurrent_layer=layer, **kw).state_dict()
+        torch.manual_seed(3)
+        b = mb.qRIMBlock(recurrent_layer=layer, **kw).state_dict()
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (layer, k)
