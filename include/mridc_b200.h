@@ -90,6 +90,9 @@ int mrb_rss_complex(const void* x, void* out, long long outer, int C, long long 
 /* utils.py:230-248 sense(): sum_c x * conj(S): x,S [outer, C, inner] complex -> [outer, inner] complex */
 int mrb_sense_combine(const void* x, const void* S, void* out, long long outer, int C, long long inner,
                       void* stream);
+/* BaseSensitivityModel.divide_root_sum_of_squares (reconstruction/models/base.py:826-840):
+ * x [outer, C, inner] complex64 -> out = x / sqrt(sum_c |x_c|^2) (same shape, distinct buffer) */
+int mrb_divide_rss(const void* x, void* out, long long outer, int C, long long inner, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused data-consistency operator

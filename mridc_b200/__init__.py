@@ -15,6 +15,7 @@ from .rim import (  # noqa: F401
 )
 from .unet import NormUnet, Unet, ConvBlock, TransposeConvBlock  # noqa: F401
 from .varnet import VarNetBlock  # noqa: F401
+from .sensitivity import BaseSensitivityModel  # noqa: F401
 from .qrim import (  # noqa: F401
     RescaleByMax, SignalForwardModel, expand_op, analytical_log_likelihood_gradient, qRIMBlock,
 )

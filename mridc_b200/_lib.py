@@ -31,6 +31,7 @@ SIGNATURES = {
     "mrb_rss": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
     "mrb_rss_complex": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
     "mrb_sense_combine": (_i, [_vp, _vp, _vp, _ll, _i, _ll, _vp]),
+    "mrb_divide_rss": (_i, [_vp, _vp, _ll, _i, _ll, _vp]),
     "mrb_dc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mrb_dc_rim_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mrb_dc_hybrid_prepare": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

@@ -125,6 +125,28 @@ __global__ void coil_reduce_kernel(const void* __restrict__ xv, const void* __re
     }
 }
 
+// BaseSensitivityModel.divide_root_sum_of_squares (reconstruction/models/base.py:826-840): x [outer, C, inner] complex
+// -> x / sqrt(sum_c |x_c|^2); the second read of x hits L1/L2
+__global__ void divide_rss_kernel(const float2* __restrict__ x, float2* __restrict__ out, long long outer, int C,
+                                  long long inner) {
+    const long long total = outer * inner;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long o = t / inner, i = t - o * inner;
+        const long long base = o * C * inner + i;
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float2 v = x[base + c * inner];
+            acc += v.x * v.x + v.y * v.y;
+        }
+        const float r = sqrtf(acc);
+        for (int c = 0; c < C; ++c) {
+            const float2 v = x[base + c * inner];
+            out[base + c * inner] = make_float2(__fdiv_rn(v.x, r), __fdiv_rn(v.y, r));
+        }
+    }
+}
+
 static inline unsigned grid_for(long long total, int threads) {
     long long b = (total + threads - 1) / threads;
     long long cap = (long long)device_sm_count() * 16;
@@ -186,6 +208,16 @@ static int coil_reduce(const void* x, const void* S, void* out, long long outer,
     MRB_REQUIRE(outer >= 0 && inner >= 0 && C >= 0, MRB_EINVAL, "%s: negative extent", who);
     if (outer * inner == 0) return MRB_OK;
     coil_reduce_kernel<MODE><<<grid_for(outer * inner, 256), 256, 0, (cudaStream_t)stream>>>(x, S, out, outer, C, inner);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_divide_rss(const void* x, void* out, long long outer, int C, long long inner, void* stream) {
+    MRB_REQUIRE(x && out, MRB_EINVAL, "mrb_divide_rss: null pointer");
+    MRB_REQUIRE(outer >= 0 && inner >= 0 && C >= 0, MRB_EINVAL, "mrb_divide_rss: negative extent");
+    if (outer * inner * C == 0) return MRB_OK;
+    divide_rss_kernel<<<grid_for(outer * inner, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)x, (float2*)out, outer,
+                                                                                       C, inner);
     MRB_LAUNCHED();
     return MRB_OK;
 }

@@ -20,6 +20,7 @@ import torch.nn as nn
 from . import _lib, _ops, utils
 from .qrim import RescaleByMax, SignalForwardModel, qRIMBlock
 from .rim import RIMBlock
+from .sensitivity import BaseSensitivityModel
 from .unet import NormUnet
 from .varnet import VarNetBlock
 
@@ -46,8 +47,17 @@ class _BaseModel(nn.Module):
         super().__init__()
         self._cfg = _cfg_dict(cfg)
         self.trainer = trainer
-        if self._cfg.get("use_sens_net"):
-            raise NotImplementedError("mridc_b200: use_sens_net (BaseSensitivityModel) is a 'next' row (SURVEY 8f)")
+        # base.py:81-94: the sensitivity network is built by the base class, i.e. BEFORE the cascades (same RNG order).
+        # As in the reference it is applied by the caller of ``forward`` (``sensitivity_maps = model.sens_net(kspace,
+        # mask)``, base.py:234-235 / :300-301 / :392-393), not inside it.
+        self.use_sens_net = self._cfg.get("use_sens_net")
+        if self.use_sens_net:
+            c = self._cfg
+            self.sens_net = BaseSensitivityModel(
+                c.get("sens_chans"), c.get("sens_pools"), fft_centered=c.get("fft_centered"),
+                fft_normalization=c.get("fft_normalization"), spatial_dims=_listify(c.get("spatial_dims")),
+                coil_dim=c.get("coil_dim"), mask_type=c.get("sens_mask_type"), normalize=c.get("sens_normalize"),
+                mask_center=c.get("sens_mask_center"))
 
     @property
     def cfg(self):

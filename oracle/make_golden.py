@@ -509,13 +509,68 @@ def gen_poisson(R):
     print("poisson_mask.npz: %dx%d, acceleration %s, sampled fraction %.4f" % (H, W, acc, m.mean()))
 
 
+def _ref_sens_model(R):
+    """BaseSensitivityModel lives in reconstruction/models/base.py, whose module imports need Lightning: run the class
+    definition alone (oracle/ref_import.py::ref_class_from_source) against the imported reference leaf modules."""
+    from abc import ABC
+    from typing import Optional, Sequence, Tuple
+
+    from .ref_import import ref_class_from_source
+
+    ns = dict(nn=torch.nn, torch=torch, ABC=ABC, Optional=Optional, Sequence=Sequence, Tuple=Tuple, utils=R.utils,
+              fft=R.fft, unet_block=R.unet_block)
+    return ref_class_from_source("mridc/collections/reconstruction/models/base.py", "BaseSensitivityModel", ns)
+
+
+def gen_sens(R):
+    """Sensitivity-estimation network, reference class executed from its own source."""
+    Sens = _ref_sens_model(R)
+    out = {}
+    i = 0
+    for (B, C, H, W, chans, pools, mtype, cen, nrm, normalize, mcenter, nlf) in [
+            (2, 3, 20, 24, 4, 2, "2D", True, "ortho", True, True, None),
+            (1, 4, 18, 30, 4, 3, "1D", False, "backward", True, True, None),
+            (1, 2, 16, 16, 4, 2, "1D", True, "ortho", True, True, 6),
+            (1, 3, 17, 21, 4, 2, "2D", False, "backward", False, False, None)]:
+        torch.manual_seed(60 + i)
+        net = Sens(chans, pools, fft_centered=cen, fft_normalization=nrm, spatial_dims=[-2, -1], coil_dim=1,
+                   mask_type=mtype, normalize=normalize, mask_center=mcenter).eval()
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        g = torch.Generator().manual_seed(600 + i)
+        y = torch.randn(B, C, H, W, 2, generator=g)
+        # per-sample column masks with a fully sampled centre band of different widths
+        m = (torch.rand(B, 1, 1, W, 1, generator=g) < 0.3).float()
+        for b in range(B):
+            half = 2 + b
+            m[b, 0, 0, W // 2 - half: W // 2 + half, 0] = 1
+            m[b, 0, 0, W // 2 - half - 1, 0] = 0
+            m[b, 0, 0, W // 2 + half, 0] = 0
+        y = y * m
+        with torch.no_grad():
+            ref = net(y, m, nlf)
+            hp = dict(sens_pools=pools, padding_size=15, sens_mask_type=mtype, sens_normalize=normalize,
+                      sens_mask_center=mcenter, fft_centered=cen, fft_normalization=nrm, spatial_dims=[-2, -1], coil_dim=1)
+            o = onets.sensitivity_model(sd, hp, y, m, nlf)
+        _close(o, ref, "sens model %d" % i, rtol=1e-5, atol=1e-6)
+        pad, n = Sens.get_pad_and_num_low_freqs(m, nlf)
+        out.update({"sens%d_%s" % (i, k): v for k, v in _np(dict(y=y, mask=m, out=ref, pad=pad, nlf=n)).items()})
+        out.update({"sens%d_w_%s" % (i, k): v.numpy() for k, v in sd.items()})
+        out["sens%d_cfg" % i] = np.asarray([chans, pools, ["1D", "2D"].index(mtype), int(cen),
+                                            ["backward", "ortho", "forward"].index(nrm), int(normalize), int(mcenter),
+                                            -1 if nlf is None else nlf])
+        i += 1
+    out["nsens"] = np.asarray(i)
+    np.savez_compressed(os.path.join(GOLDEN, "sens.npz"), **out)
+    print("sens.npz: %d arrays" % len(out))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
     R = Ref()
     only = set(sys.argv[1:])  # e.g. `python -m oracle.make_golden qmri` regenerates one fixture file
     for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("unet", gen_unet),
-                     ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson)):
+                     ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens)):
         if not only or name in only:
             fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))

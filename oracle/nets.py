@@ -236,3 +236,48 @@ def varnet_block(sd, hp, pred, ref_kspace, sens, mask):
     if not hp["no_dc"]:
         eta = pred - soft_dc - eta
     return eta
+
+
+# --------------------------------------------------------------------------------------------------
+# Sensitivity-estimation network
+# --------------------------------------------------------------------------------------------------
+def sens_pad_and_num_low_freqs(mask, num_low_frequencies=None):
+    """reconstruction/models/base.py:842-878."""
+    if num_low_frequencies is None or num_low_frequencies == 0:
+        sq = mask[:, 0, 0, :, 0].to(torch.int8)
+        cent = sq.shape[1] // 2
+        left = torch.argmin(sq[:, :cent].flip(1), dim=1)
+        right = torch.argmin(sq[:, cent:], dim=1)
+        nlf = torch.max(2 * torch.min(left, right), torch.ones_like(left))
+    else:
+        nlf = num_low_frequencies * torch.ones(mask.shape[0], dtype=mask.dtype, device=mask.device)
+    pad = torch.div(mask.shape[-2] - nlf + 1, 2, rounding_mode="trunc")
+    return pad, nlf
+
+
+def sensitivity_model(sd, hp, masked_kspace, mask, num_low_frequencies=None):
+    """BaseSensitivityModel.forward, reconstruction/models/base.py:880-932.  ``sd`` keys are prefixed ``norm_unet.``;
+    hp keys: sens_pools, padding_size (15), sens_mask_type, sens_normalize, sens_mask_center, fft_centered,
+    fft_normalization, spatial_dims, coil_dim."""
+    x = masked_kspace
+    if hp.get("sens_mask_center", True):
+        pad, nlf = sens_pad_and_num_low_freqs(mask, num_low_frequencies)
+        keep = torch.zeros_like(x)  # utils.batched_mask_center, common/parts/utils.py:379-417
+        if pad.shape[0] == 1:
+            a, b = int(pad), int(pad + nlf)
+            if hp["sens_mask_type"] == "1D":
+                keep[:, :, :, a:b] = x[:, :, :, a:b]
+            elif hp["sens_mask_type"] == "2D":
+                keep[:, :, a:b] = x[:, :, a:b]
+        else:
+            for i, (a, b) in enumerate(zip(pad, pad + nlf)):
+                keep[i, :, :, a:b] = x[i, :, :, a:b]
+        x = keep
+    img = mri.ifft2(x, hp["fft_centered"], hp["fft_normalization"], hp.get("spatial_dims") or [-2, -1])
+    b, c, h, w, comp = img.shape
+    out = norm_unet(img.reshape(b * c, 1, h, w, comp), _sub(sd, "norm_unet."), hp["sens_pools"],
+                    hp.get("padding_size", 15), hp.get("sens_normalize", True)).view(b, c, h, w, comp)
+    if hp.get("sens_normalize", True):
+        cd = hp["coil_dim"]
+        out = out / mri.rss_complex(out, dim=cd).unsqueeze(-1).unsqueeze(cd)  # :826-840
+    return out

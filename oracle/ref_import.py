@@ -86,3 +86,20 @@ class Ref:
         self.unet_block = ref("reconstruction.models.unet_base.unet_block")
         self.qrim_utils = ref("quantitative.models.qrim.utils")
         self.qrim_block = ref("quantitative.models.qrim.qrim_block")
+
+
+def ref_class_from_source(rel_path: str, class_name: str, namespace: dict):
+    """Execute ONE class definition of a reference file that cannot be imported as a module (its imports need
+    pytorch_lightning / omegaconf): the class node is cut out of the parsed source and compiled with the file's own
+    name, in a namespace holding the (importable) reference leaf modules it uses.  Nothing is copied into the repo."""
+    import ast
+
+    path = os.path.join(REF_ROOT, rel_path)
+    with open(path) as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), namespace)
+            return namespace[class_name]
+    raise LookupError("%s not found in %s" % (class_name, path))

@@ -478,3 +478,56 @@ def test_dc_hybrid_row_form_vs_oracle_and_three_pass(B, C, H, W):
     m2d = (torch.rand(1, 1, H, W, 1, generator=g) < 0.5).to(torch.uint8)
     if H > 1:
         assert _ops.dc_hybrid_prepare(y.cuda(), m2d.cuda(), True) is None
+
+
+# ---------------------------------------------------------------------------------------------- sens-net (8f rank 1)
+def test_sensitivity_model_golden(golden):
+    """BaseSensitivityModel (reconstruction/models/base.py:715-932) vs the outputs of the reference class."""
+    import mridc_b200 as mb
+    from test_oracle_golden import _sens_case
+
+    g = golden("sens")
+    for i in range(int(g["nsens"])):
+        hp, nlf = _sens_case(g, i)
+        net = mb.BaseSensitivityModel(hp["sens_chans"], hp["sens_pools"], fft_centered=hp["fft_centered"],
+                                      fft_normalization=hp["fft_normalization"], spatial_dims=[-2, -1], coil_dim=1,
+                                      mask_type=hp["sens_mask_type"], normalize=hp["sens_normalize"],
+                                      mask_center=hp["sens_mask_center"]).cuda().eval()
+        net.load_state_dict(golden.weights(g, "sens%d_w_" % i), strict=True)
+        y, m = cu(g["sens%d_y" % i]), cu(g["sens%d_mask" % i])
+        pad, n = net.get_pad_and_num_low_freqs(m, nlf)
+        assert np.array_equal(pad.cpu().numpy(), g["sens%d_pad" % i])  # integer bookkeeping: bit-exact
+        assert np.array_equal(n.cpu().numpy(), g["sens%d_nlf" % i])
+        out = net(y, m, nlf)
+        assert out.shape == y.shape
+        e = rel_l2(out, g["sens%d_out" % i])
+        assert e < 1e-5, (i, e)
+        if hp["sens_normalize"]:  # maps have unit root-sum-of-squares over coils
+            assert torch.allclose(mb.rss_complex(out, dim=1), torch.ones_like(out[:, 0, ..., 0]), atol=1e-5)
+
+
+def test_e2e_varnet_with_sens_net_vs_oracle():
+    """The 'end-to-end' half of E2EVN: sens_net(kspace, mask) -> VarNet.forward, 15 coils 320x320 (configs[1] geometry,
+    4 cascades to keep the CPU oracle short)."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+    from oracle import nets as onets
+
+    d = synth.make_batch(1, 15, 320, 320, mask_func=synth.Gaussian1DMask([0.7], [4]), seed=123, mask_dtype="float32")
+    cfg = dict(synth.varnet_cfg(num_cascades=4), use_sens_net=True, sens_chans=8, sens_pools=4, sens_mask_type="2D",
+               sens_normalize=True, sens_mask_center=True)
+    torch.manual_seed(5)
+    model = mb.VarNet(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    y, m = d["y"].cuda(), d["mask"].cuda()
+    S = model.sens_net(y, m)
+    out = model(y, S, m, None, d["target"].cuda())
+    hp = dict(sens_pools=4, padding_size=15, sens_mask_type="2D", sens_normalize=True, sens_mask_center=True,
+              fft_centered=False, fft_normalization="backward", spatial_dims=[-2, -1], coil_dim=1)
+    S_ref = onets.sensitivity_model({k[len("sens_net."):]: v for k, v in sd.items() if k.startswith("sens_net.")}, hp,
+                                    d["y"], d["mask"])
+    assert rel_l2(S, S_ref) < 1e-4, rel_l2(S, S_ref)
+    ref = omodels.varnet_forward(sd, cfg, d["y"], S_ref, d["mask"], None, d["target"])
+    assert rel_l2(out, ref) < 1e-4, rel_l2(out, ref)

@@ -196,3 +196,36 @@ def test_qrim_initialisers_reproduce_reference_weights():
         assert sorted(a) == sorted(b)
         for k in a:
             assert torch.equal(a[k], b[k]), (layer, k)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
+def test_sens_net_initialiser_and_bookkeeping_match_reference():
+    import mridc_b200 as mb
+    from oracle.make_golden import _ref_sens_model
+
+    Sens = _ref_sens_model(ref_import.Ref())
+    torch.manual_seed(9)
+    a = Sens(4, 3, mask_type="1D").state_dict()
+    torch.manual_seed(9)
+    b = mb.BaseSensitivityModel(4, 3, mask_type="1D").state_dict()
+    assert sorted(a) == sorted(b) and all(torch.equal(a[k], b[k]) for k in a)
+    g = torch.Generator().manual_seed(3)
+    for _ in range(5):
+        m = (torch.rand(3, 1, 1, 24, 1, generator=g) < 0.5).float()
+        m[:, 0, 0, 10:14, 0] = 1
+        for nlf in (None, 0, 4):
+            pa, na = Sens.get_pad_and_num_low_freqs(m, nlf)
+            pb, nb = mb.BaseSensitivityModel.get_pad_and_num_low_freqs(m, nlf)
+            assert torch.equal(pa, pb) and torch.equal(na, nb)
+    # a model with use_sens_net builds the network first (base.py:81-94): same keys / RNG order as the reference
+    from mridc_b200 import synth
+
+    cfg = dict(synth.varnet_cfg(num_cascades=1), use_sens_net=True, sens_chans=4, sens_pools=2, sens_mask_type="2D",
+               sens_normalize=True, sens_mask_center=True)
+    torch.manual_seed(11)
+    ours = mb.VarNet(cfg).state_dict()
+    torch.manual_seed(11)
+    ref_first = Sens(4, 2, fft_centered=False, fft_normalization="backward", spatial_dims=[-2, -1], coil_dim=1,
+                     mask_type="2D", normalize=True, mask_center=True).state_dict()
+    for k, v in ref_first.items():
+        assert torch.equal(ours["sens_net." + k], v), k
