@@ -264,6 +264,21 @@ int mrb_qrim_eta_update(void* eta, int eta_channels, int eta_offset, const void*
 int mrb_scale_batch(const void* x, void* out, int B, long long per_batch, const float* scales, int take_abs,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * On-device evaluation: what test_step computes on the host after .cpu()
+ * (mridc/collections/reconstruction/models/base.py:415-436, common/metrics/reconstruction_metrics.py:11-41).
+ * ------------------------------------------------------------------------------------------------- */
+/* bytes of the device workspace both calls below take (B = slices) */
+size_t mrb_metrics_workspace_bytes(int B);
+/* base.py:415-420: out[i] = |x[i]| / max_j |x[j]|; x: n complex64 (is_complex) or fp32 values, out: n fp32 */
+int mrb_abs_max_normalize(const void* x, long long n, int is_complex, void* out, void* ws, void* stream);
+/* gt, pred [B,H,W] fp32 -> res (device, 5 doubles) = mse, nmse, psnr, ssim, data range used.  maxval_mode 0: max(gt)
+ * (reconstruction_metrics.py:23,35), 1: max(pred) - min(pred) (base.py:431,434), 2: `maxval`.  SSIM = skimage
+ * structural_similarity defaults (7x7 uniform window, sample covariance, K1 0.01, K2 0.03, 3-px border crop, float64),
+ * averaged over slices; PSNR = 10 log10(R^2 / mse). */
+int mrb_recon_metrics(const void* gt, const void* pred, int B, int H, int W, int maxval_mode, double maxval, void* res,
+                      void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,5 +21,6 @@ from .qrim import (  # noqa: F401
 )
 from .models import CIRIM, VarNet, UNet, ZF, qCIRIM  # noqa: F401
 from .pipeline import HostPrefetcher  # noqa: F401
+from . import metrics  # noqa: F401
 
 __version__ = "0.1.0"

@@ -61,6 +61,9 @@ SIGNATURES = {
     "mrb_tc_conv5x5x4_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrb_tc_gru_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrb_metrics_workspace_bytes": (_sz, [_i]),
+    "mrb_abs_max_normalize": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
+    "mrb_recon_metrics": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp]),
     "mrb_megre_signal": (_i, [_vp, _vp, _vp, _vp, _fp, _dp, _i, _d, _i, _ll, _i, _vp, _vp]),
     "mrb_megre_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _fp, _dp, _i, _d, _i, _ll, _f, _i, _vp, _i, _vp]),
     "mrb_qrim_eta_update": (_i, [_vp, _i, _i, _vp, _vp, _i, _ll, _vp]),

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmridc_b200.so")
 STAMP = os.path.join(PKG_DIR, "csrc", ".build_stamp")
-SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "tc_microbench.cu", "qmri.cu"]
+SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "tc_microbench.cu", "qmri.cu", "metrics.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -531,3 +531,40 @@ def test_e2e_varnet_with_sens_net_vs_oracle():
     assert rel_l2(S, S_ref) < 1e-4, rel_l2(S, S_ref)
     ref = omodels.varnet_forward(sd, cfg, d["y"], S_ref, d["mask"], None, d["target"])
     assert rel_l2(out, ref) < 1e-4, rel_l2(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------- metrics (8f rank 3)
+@pytest.mark.parametrize("B,H,W", [(1, 7, 7), (2, 20, 33), (3, 320, 320)])
+def test_on_device_metrics_vs_oracle(B, H, W):
+    """MSE / NMSE / PSNR / SSIM on the GPU vs the oracle restatement of numpy + scikit-image (float64): agreement far
+    inside the north star's '4 decimals'."""
+    import mridc_b200 as mb
+    from oracle import metrics as om
+
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    gt = torch.rand(B, H, W, generator=g)
+    pred = (gt + 0.05 * torch.randn(B, H, W, generator=g)).clamp_min(0)
+    a, b = gt.numpy(), pred.numpy()
+    G, P = gt.cuda(), pred.cuda()
+    assert abs(mb.metrics.mse(G, P) - om.mse(a, b)) < 1e-5 * om.mse(a, b)  # numpy sums in float32
+    assert abs(mb.metrics.nmse(G, P) - om.nmse(a, b)) < 1e-5 * om.nmse(a, b)
+    assert abs(mb.metrics.psnr(G, P) - om.psnr(a, b)) < 1e-5
+    assert abs(mb.metrics.psnr(G, P, maxval=0.7) - om.psnr(a, b, 0.7)) < 1e-5
+    assert abs(mb.metrics.ssim(G, P) - om.ssim(a, b)) < 1e-7
+    assert abs(mb.metrics.ssim(G, P, maxval=0.7) - om.ssim(a, b, 0.7)) < 1e-7
+    assert abs(mb.metrics.ssim(G, G) - 1.0) < 1e-12
+    with pytest.raises(ValueError, match="Unexpected number of dimensions"):
+        mb.metrics.ssim(G[0], P[0])
+    # the test_step block (base.py:415-436) on complex predictions
+    cp = torch.complex(pred, 0.3 * gt)
+    ct = torch.complex(gt, 0.1 * pred)
+    out = np.abs(cp.numpy()); out = out / out.max()
+    tgt = np.abs(ct.numpy()); tgt = tgt / tgt.max()
+    R = out.max() - out.min()
+    ev = mb.metrics.evaluate(cp.cuda(), ct.cuda())
+    assert abs(ev["mse"] - om.mse(tgt, out)) < 1e-5 * om.mse(tgt, out)
+    assert abs(ev["nmse"] - om.nmse(tgt, out)) < 1e-5 * om.nmse(tgt, out)
+    assert abs(ev["psnr"] - om.psnr(tgt, out, R)) < 1e-4
+    assert abs(ev["ssim"] - om.ssim(tgt, out, R)) < 1e-5
+    nm = mb.metrics.normalized_magnitude(cp.cuda())
+    assert rel_l2(nm, out) < 1e-6 and nm.max().item() == 1.0
