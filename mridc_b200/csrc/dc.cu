@@ -484,6 +484,247 @@ __global__ void __maxnreg__(MRB_ROWDC_REGS) row_dc_kernel(const float2* __restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// W = 320 fast path of the hybrid-space gradient (both fastMRI geometries have 320 columns): register-resident
+// two-pass transforms, 320 = 16 x 20.
+//
+// Thread (c = tid / 20, t = tid % 20) of a 320-thread CTA (one image row, up to 16 coils):
+//   pass 1 (t = n2):  loads S[c][20*n1 + t] * eta for n1 < 16 straight into registers, 16-point DFT over n1,
+//                     twiddle w320^(t*k1), one shared-memory exchange (xch[c][k1][n2]);
+//   pass 2 (t = k1 < 16): 20-point DFT over n2 -> X[k1 + 16*k2]; k-space residual against the (cp.async-prefetched)
+//                     hybrid k-space row; inverse 20-point DFT over k2 of the SAME registers, twiddle, second exchange;
+//   pass 3 (t = n2):  inverse 16-point DFT over k1 -> x[20*n1 + t], the ownership of pass 1, so conj(S) is still in
+//                     registers; the coil sum goes through shared memory in coil order (rim_utils.py:61-62).
+// Two exchanges per forward + inverse pair instead of six Stockham passes (3.5x fewer shared-memory wavefronts, all
+// conflict free: k1 rows are 22 float2 apart, coils 356) and no per-stage index arithmetic.
+// ---------------------------------------------------------------------------------------------------------------
+namespace r320 {
+constexpr int N = 320, N1 = 16, N2 = 20, XS = 22, CS = N1 * XS + 4, THREADS = 320, MAXC = 16, RS = N + 4;
+
+template <bool INV>
+__device__ __forceinline__ float2 mulw(float2 a, float wr, float wi) {  // a * (wr + i*wi), conjugated for the inverse
+    return INV ? make_float2(a.x * wr + a.y * wi, a.y * wr - a.x * wi) : make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+}
+
+// 16-point DFT in registers, natural order in and out (4 x 4 Cooley-Tukey: n = i + 4m, k = q + 4p)
+template <bool INV>
+__device__ __forceinline__ void dft16(float2* v) {
+    constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, H = 0.70710678118654752440f;
+    float2 a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 u[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
+        butterfly<4, INV>(u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[i][q] = u[q];
+    }
+    // twiddles w16^(i*q) = exp(-2*pi*i * i*q / 16)
+    a[1][1] = mulw<INV>(a[1][1], C1, -S1);
+    a[1][2] = mulw<INV>(a[1][2], H, -H);
+    a[1][3] = mulw<INV>(a[1][3], S1, -C1);
+    a[2][1] = mulw<INV>(a[2][1], H, -H);
+    a[2][2] = mul_mi<INV>(a[2][2]);
+    a[2][3] = mulw<INV>(a[2][3], -H, -H);
+    a[3][1] = mulw<INV>(a[3][1], S1, -C1);
+    a[3][2] = mulw<INV>(a[3][2], -H, -H);
+    a[3][3] = mulw<INV>(a[3][3], -C1, S1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 u[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
+        butterfly<4, INV>(u);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[q + 4 * p] = u[p];
+    }
+}
+
+// 20-point DFT in registers, natural order in and out (4 x 5: n = 5*n1 + n2, k = k1 + 4*k2)
+template <bool INV>
+__device__ __forceinline__ void dft20(float2* v) {
+    // w20^j = (cos(2*pi*j/20), -sin(2*pi*j/20)) for the exponents n2*k1 that occur
+    constexpr float c1 = 0.95105651629515357212f, s1 = 0.30901699437494742410f;   // j = 1
+    constexpr float c2 = 0.80901699437494742410f, s2 = 0.58778525229247312917f;   // j = 2
+    constexpr float c3 = 0.58778525229247312917f, s3 = 0.80901699437494742410f;   // j = 3
+    constexpr float c4 = 0.30901699437494742410f, s4 = 0.95105651629515357212f;   // j = 4
+    float2 a[5][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        float2 u[4] = {v[n2], v[n2 + 5], v[n2 + 10], v[n2 + 15]};
+        butterfly<4, INV>(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) a[n2][k1] = u[k1];
+    }
+    a[1][1] = mulw<INV>(a[1][1], c1, -s1);    // j = 1
+    a[1][2] = mulw<INV>(a[1][2], c2, -s2);    // 2
+    a[1][3] = mulw<INV>(a[1][3], c3, -s3);    // 3
+    a[2][1] = mulw<INV>(a[2][1], c2, -s2);    // 2
+    a[2][2] = mulw<INV>(a[2][2], c4, -s4);    // 4
+    a[2][3] = mulw<INV>(a[2][3], -c4, -s4);   // 6: cos(108 deg) = -c4, sin = s4
+    a[3][1] = mulw<INV>(a[3][1], c3, -s3);    // 3
+    a[3][2] = mulw<INV>(a[3][2], -c4, -s4);   // 6
+    a[3][3] = mulw<INV>(a[3][3], -c1, -s1);   // 9: cos(162 deg) = -c1, sin = s1
+    a[4][1] = mulw<INV>(a[4][1], c4, -s4);    // 4
+    a[4][2] = mulw<INV>(a[4][2], -c2, -s2);   // 8: cos(144 deg) = -c2, sin = s2
+    a[4][3] = mulw<INV>(a[4][3], -c2, s2);    // 12: cos(216 deg) = -c2, sin = -s2
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        float2 u[5] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1], a[4][k1]};
+        butterfly<5, INV>(u);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) v[k1 + 4 * k2] = u[k2];
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+
+inline size_t smem_bytes(int C) {
+    return (size_t)MAXC * CS * sizeof(float2) + (size_t)C * N * sizeof(float2) + 2 * (size_t)N * sizeof(float2) +
+           (size_t)N * sizeof(float) + 2 * (size_t)N * sizeof(unsigned short) + 16;
+}
+
+template <int OUT_MODE>
+__global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __restrict__ eta, const float2* __restrict__ S,
+                                                               const float2* __restrict__ yh, float* __restrict__ out, int C,
+                                                               int H, const float2* __restrict__ tw, int rw, float fscale,
+                                                               float oscale, MaskDesc mask) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;                              // [MAXC][CS]; reused as the coil-sum buffer [C][RS]
+    float2* yh_s = xch + MAXC * CS;                   // [C][ns2] packed hybrid k-space rows
+    float2* tw_s = yh_s + (size_t)C * N;              // [N] exp(-2 pi i k / 320)
+    float2* eta_s = tw_s + N;                         // [N] the eta row (storage order)
+    float* mval_s = reinterpret_cast<float*>(eta_s + N);                      // [N] mask value by un-centred k
+    unsigned short* pos_s = reinterpret_cast<unsigned short*>(mval_s + N);    // [N] un-centred k -> packed index
+    unsigned short* cols_s = pos_s + N;                                       // [N] packed index -> un-centred k
+    __shared__ int scan_scratch[33];
+    const int tid = threadIdx.x;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int c = tid / N2, t = tid - c * N2;
+    const bool active = c < C;
+    const long long cstride = (long long)H * N;
+    const long long rowoff = ((long long)b * C * H + h) * N;
+    const float2* erow = eta + ((long long)b * H + h) * N;
+
+    // Centring (rw = W/2) costs no index rotation here: a circular shift of the transform input by N/2 multiplies its
+    // output by (-1)^k, and the same holds for the inverse, so the row is transformed in STORAGE order and only the
+    // measured term changes sign on odd k:  (-1)^k m (fs (-1)^k X_s[k] - yh[k]) = m (fs X_s[k] - (-1)^k yh[k]).
+    // k = t + 16*k2 has the parity of t: one sign per thread.
+    // ---- pass 1 loads first: their latency overlaps the table set-up ----
+    float2 sreg[N1];
+    if (active) {
+        const float2* sp = S + rowoff + (long long)c * cstride + t;
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) sreg[n1] = LDSTREAM(sp + N2 * n1);
+    }
+    tw_s[tid] = tw[tid];
+    eta_s[tid] = __ldg(&erow[tid]);
+    pos_s[tid] = 0;  // unsampled k: any valid slot (its mask value is 0)
+    mval_s[tid] = mask_value(mask, b, 0, rot_add(tid, rw, N));
+    const int ns = build_active_cols(mask, b, N, rw, true, cols_s, scan_scratch);  // ends with a barrier
+    if (tid < ns) pos_s[cols_s[tid]] = (unsigned short)tid;
+    const int ns2 = max(2, (ns + 1) & ~1);
+    {
+        const int per = ns2 >> 1, total = C * per;
+        for (int i = tid; i < total; i += THREADS) {
+            const int cc = i / per, q = i - cc * per;
+            cp_async16(yh_s + (size_t)cc * ns2 + 2 * q, yh + rowoff + (long long)cc * cstride + 2 * q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float2* xc = xch + (size_t)c * CS;
+    if (active) {
+        float2 v[N1];
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) {
+            const float2 e = eta_s[N2 * n1 + t], s0 = sreg[n1];
+            v[n1] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);  // rim_utils.py:47-48
+        }
+        dft16<false>(v);
+        xc[t] = v[0];
+        const float2* twt = tw_s;
+#pragma unroll
+        for (int k1 = 1; k1 < N1; ++k1) {
+            twt += t;  // tw_s[t * k1]
+            const float2 w = *twt;
+            xc[k1 * XS + t] = mulw<false>(v[k1], w.x, w.y);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- pass 2: forward 20-point DFT, residual, inverse 20-point DFT (thread t = k1) ----
+    if (active && t < N1) {
+        float2 v[N2];
+        float4* row = reinterpret_cast<float4*>(xc + t * XS);
+#pragma unroll
+        for (int i = 0; i < N2 / 2; ++i) {
+            const float4 q = row[i];
+            v[2 * i] = make_float2(q.x, q.y);
+            v[2 * i + 1] = make_float2(q.z, q.w);
+        }
+        dft20<false>(v);
+        const float2* yc = yh_s + (size_t)c * ns2;
+        const float ysgn = (rw != 0 && (t & 1)) ? -1.f : 1.f;
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) {
+            const int k = t + N1 * k2;
+            const float m = mval_s[k];  // 0 on unsampled columns: the residual vanishes there
+            const float2 yv = yc[pos_s[k]];
+            v[k2] = make_float2(m * (v[k2].x * fscale - ysgn * yv.x), m * (v[k2].y * fscale - ysgn * yv.y));  // rim_utils.py:54
+        }
+        dft20<true>(v);
+        const float2* twt = tw_s;
+#pragma unroll
+        for (int n2 = 1; n2 < N2; ++n2) {
+            twt += t;  // tw_s[n2 * t]
+            const float2 w = *twt;
+            v[n2] = mulw<true>(v[n2], w.x, w.y);
+        }
+#pragma unroll
+        for (int i = 0; i < N2 / 2; ++i) row[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+    }
+    __syncthreads();
+    // ---- pass 3: inverse 16-point DFT over k1 (thread t = n2), conj(S), coil sum ----
+    float2 v[N1];
+    if (active) {
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) v[k1] = xc[k1 * XS + t];
+        dft16<true>(v);
+    }
+    __syncthreads();  // every thread has read its exchange data: the buffer becomes the coil-sum buffer
+    if (active) {
+        float2* rc = xch + (size_t)c * RS + t;
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) {
+            const float2 s0 = sreg[n1], x = v[n1];
+            rc[N2 * n1] = make_float2(x.x * s0.x + x.y * s0.y, x.y * s0.x - x.x * s0.y);  // x * conj(S)
+        }
+    }
+    __syncthreads();
+    {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int cc = 0; cc < C; ++cc) {
+            const float2 r = xch[(size_t)cc * RS + tid];
+            acc.x += r.x;
+            acc.y += r.y;
+        }
+        const int d = tid;
+        const float2 e = eta_s[d];
+        if (OUT_MODE == 2) {
+            reinterpret_cast<float4*>(out)[((long long)b * H + h) * N + d] = make_float4(e.x, e.y, acc.x * oscale, acc.y * oscale);
+        } else {
+            const long long HW = (long long)H * N;
+            float* o = out + (long long)b * 4 * HW + (long long)h * N + d;
+            o[0] = e.x;
+            o[HW] = e.y;
+            o[2 * HW] = acc.x * oscale;
+            o[3 * HW] = acc.y * oscale;
+        }
+    }
+}
+}  // namespace r320
+
 struct DcGeom {
     FftPlan pw, ph;
     int cc;       // coils per smem chunk in the row kernels
@@ -643,6 +884,23 @@ extern "C" int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const voi
     const float fs = norm_scale(norm, 0, npts);
     const float os = norm_scale(norm, 1, npts) * (float)H * inv_sigma2;
     const size_t smem = g.smem_row + (size_t)W * sizeof(unsigned short);
+    if (W == r320::N && C <= r320::MAXC && !getenv("MRIDC_B200_DC_STOCKHAM")) {
+        // register-resident two-pass row transforms (both fastMRI geometries have 320 columns)
+        const size_t sm = r320::smem_bytes(C);
+        if (out_nhwc) {
+            if ((rc = set_smem(r320::row_dc320_kernel<2>))) return rc;
+            r320::row_dc320_kernel<2><<<dim3(H, B), r320::THREADS, sm, st>>>((const float2*)eta, (const float2*)S,
+                                                                             (const float2*)yh, (float*)out, C, H, g.pw.tw, rw,
+                                                                             fs, os, m);
+        } else {
+            if ((rc = set_smem(r320::row_dc320_kernel<1>))) return rc;
+            r320::row_dc320_kernel<1><<<dim3(H, B), r320::THREADS, sm, st>>>((const float2*)eta, (const float2*)S,
+                                                                             (const float2*)yh, (float*)out, C, H, g.pw.tw, rw,
+                                                                             fs, os, m);
+        }
+        MRB_LAUNCHED();
+        return MRB_OK;
+    }
     const bool keep = g.threads_row >= W && g.cc <= 8;
 #define MRB_ROW_DC(MODE, KEEP)                                                                                        \
     do {                                                                                                              \

@@ -444,7 +444,8 @@ def test_host_prefetcher_streams_batches_in_order():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (1, 2, 5, 3), (3, 5, 33, 17), (2, 15, 64, 48), (1, 9, 40, 36), (1, 4, 320, 320)])
+@pytest.mark.parametrize("B,C,H,W", [(1, 1, 1, 1), (1, 2, 5, 3), (3, 5, 33, 17), (2, 15, 64, 48), (1, 9, 40, 36), (1, 4, 320, 320),
+                                     (2, 15, 6, 320), (1, 16, 3, 320), (1, 1, 2, 320), (1, 17, 2, 320)])
 def test_dc_hybrid_row_form_vs_oracle_and_three_pass(B, C, H, W):
     """1-D masks: the single-kernel hybrid-space gradient (H transforms cancelled analytically) equals the reference
     formula and the general three-pass operator; masks that depend on k_h are refused."""
