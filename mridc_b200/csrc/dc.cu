@@ -597,8 +597,7 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     float2* eta_s = tw_s + N;                         // [N] the eta row (storage order)
     float* mval_s = reinterpret_cast<float*>(eta_s + N);                      // [N] mask value by un-centred k
     unsigned short* pos_s = reinterpret_cast<unsigned short*>(mval_s + N);    // [N] un-centred k -> packed index
-    unsigned short* cols_s = pos_s + N;                                       // [N] packed index -> un-centred k
-    __shared__ int scan_scratch[33];
+    __shared__ int scan_s[THREADS / 32];
     const int tid = threadIdx.x;
     const int h = blockIdx.x, b = blockIdx.y;
     const int c = tid / N2, t = tid - c * N2;
@@ -620,19 +619,34 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     }
     tw_s[tid] = tw[tid];
     eta_s[tid] = __ldg(&erow[tid]);
-    pos_s[tid] = 0;  // unsampled k: any valid slot (its mask value is 0)
-    mval_s[tid] = mask_value(mask, b, 0, rot_add(tid, rw, N));
-    const int ns = build_active_cols(mask, b, N, rw, true, cols_s, scan_scratch);  // ends with a barrier
-    if (tid < ns) pos_s[cols_s[tid]] = (unsigned short)tid;
-    const int ns2 = max(2, (ns + 1) & ~1);
+    // Thread k owns un-centred k-space column k: its mask value, and (ballot scan) its slot in the packed row.
+    const float mk = mask_value(mask, b, 0, rot_add(tid, rw, N));
+    mval_s[tid] = mk;
+    int ns;
     {
-        const int per = ns2 >> 1, total = C * per;
-        for (int i = tid; i < total; i += THREADS) {
-            const int cc = i / per, q = i - cc * per;
-            cp_async16(yh_s + (size_t)cc * ns2 + 2 * q, yh + rowoff + (long long)cc * cstride + 2 * q);
+        const int lane = tid & 31, wid = tid >> 5;
+        const unsigned bal = __ballot_sync(0xffffffffu, mk != 0.f);
+        if (lane == 0) scan_s[wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) {
+            const int cnt = scan_s[w];
+            woff += w < wid ? cnt : 0;
+            tot += cnt;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        ns = tot;
+        // unsampled k: any valid slot (its mask value is 0, so the residual vanishes)
+        pos_s[tid] = mk != 0.f ? (unsigned short)(woff + __popc(bal & ((1u << lane) - 1u))) : (unsigned short)0;
     }
+    const int ns2 = max(2, (ns + 1) & ~1);
+    if (active) {  // each coil's 20 threads prefetch that coil's packed hybrid k-space row (16-byte chunks)
+        const float2* ysrc = yh + rowoff + (long long)c * cstride;
+        float2* ydst = yh_s + (size_t)c * ns2;
+#pragma unroll 1
+        for (int q = 2 * t; q < ns2; q += 2 * N2) cp_async16(ydst + q, ysrc + q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     float2* xc = xch + (size_t)c * CS;
     if (active) {
         float2 v[N1];
