@@ -507,32 +507,98 @@ __device__ __forceinline__ float2 mulw(float2 a, float wr, float wi) {  // a * (
     return INV ? make_float2(a.x * wr + a.y * wi, a.y * wr - a.x * wi) : make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
 }
 
+// Packed complex arithmetic: a complex value lives in one 64-bit register pair and the additions / real scalings of
+// the butterflies are single add / sub / fma .f32x2 instructions (the kernel is instruction-issue bound); multiplications
+// by +-i and by constant twiddles stay scalar (immediate-operand FMUL / FFMA on the two halves).
+typedef unsigned long long cx;
+__device__ __forceinline__ cx pk(float x, float y) {
+    cx r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ cx pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 upk(cx a) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ cx add2(cx a, cx b) {
+    cx r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx sub2(cx a, cx b) {
+    cx r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx mul2(cx a, cx b) {
+    cx r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx fma2(cx a, cx b, cx c) {
+    cx r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+template <bool INV>
+__device__ __forceinline__ cx mulwp(cx a, float wr, float wi) { return pk(mulw<INV>(upk(a), wr, wi)); }
+// t + (-i) d and t - (-i) d (forward; +i for the inverse)
+template <bool INV>
+__device__ __forceinline__ void rot_pm(cx t, cx d, cx& plus, cx& minus) {
+    const float2 a = upk(t), e = upk(d);
+    const cx p = pk(a.x + e.y, a.y - e.x), m = pk(a.x - e.y, a.y + e.x);
+    plus = INV ? m : p;
+    minus = INV ? p : m;
+}
+template <bool INV>
+__device__ __forceinline__ void fft4p(cx* u) {
+    const cx t0 = add2(u[0], u[2]), t1 = sub2(u[0], u[2]), t2 = add2(u[1], u[3]), d = sub2(u[1], u[3]);
+    u[0] = add2(t0, t2);
+    u[2] = sub2(t0, t2);
+    rot_pm<INV>(t1, d, u[1], u[3]);
+}
+template <bool INV>
+__device__ __forceinline__ void dft5p(cx* u) {
+    constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const cx p1 = add2(u[1], u[4]), m1 = sub2(u[1], u[4]), p2 = add2(u[2], u[3]), m2 = sub2(u[2], u[3]), a0 = u[0];
+    const cx A = fma2(p2, pk(c2, c2), fma2(p1, pk(c1, c1), a0));
+    const cx B = fma2(p2, pk(c1, c1), fma2(p1, pk(c2, c2), a0));
+    const cx U = fma2(m2, pk(s2, s2), mul2(m1, pk(s1, s1)));    // s1*m1 + s2*m2
+    const cx V = fma2(m2, pk(-s1, -s1), mul2(m1, pk(s2, s2)));  // s2*m1 - s1*m2
+    u[0] = add2(add2(a0, p1), p2);
+    rot_pm<INV>(A, U, u[1], u[4]);
+    rot_pm<INV>(B, V, u[2], u[3]);
+}
+
 // 16-point DFT in registers, natural order in and out (4 x 4 Cooley-Tukey: n = i + 4m, k = q + 4p)
 template <bool INV>
-__device__ __forceinline__ void dft16(float2* v) {
+__device__ __forceinline__ void dft16(cx* v) {
     constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, H = 0.70710678118654752440f;
-    float2 a[4][4];
+    cx a[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 u[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
-        butterfly<4, INV>(u);
+        cx u[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
+        fft4p<INV>(u);
 #pragma unroll
         for (int q = 0; q < 4; ++q) a[i][q] = u[q];
     }
     // twiddles w16^(i*q) = exp(-2*pi*i * i*q / 16)
-    a[1][1] = mulw<INV>(a[1][1], C1, -S1);
-    a[1][2] = mulw<INV>(a[1][2], H, -H);
-    a[1][3] = mulw<INV>(a[1][3], S1, -C1);
-    a[2][1] = mulw<INV>(a[2][1], H, -H);
-    a[2][2] = mul_mi<INV>(a[2][2]);
-    a[2][3] = mulw<INV>(a[2][3], -H, -H);
-    a[3][1] = mulw<INV>(a[3][1], S1, -C1);
-    a[3][2] = mulw<INV>(a[3][2], -H, -H);
-    a[3][3] = mulw<INV>(a[3][3], -C1, S1);
+    a[1][1] = mulwp<INV>(a[1][1], C1, -S1);
+    a[1][2] = mulwp<INV>(a[1][2], H, -H);
+    a[1][3] = mulwp<INV>(a[1][3], S1, -C1);
+    a[2][1] = mulwp<INV>(a[2][1], H, -H);
+    a[2][2] = pk(mul_mi<INV>(upk(a[2][2])));
+    a[2][3] = mulwp<INV>(a[2][3], -H, -H);
+    a[3][1] = mulwp<INV>(a[3][1], S1, -C1);
+    a[3][2] = mulwp<INV>(a[3][2], -H, -H);
+    a[3][3] = mulwp<INV>(a[3][3], -C1, S1);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float2 u[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
-        butterfly<4, INV>(u);
+        cx u[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
+        fft4p<INV>(u);
 #pragma unroll
         for (int p = 0; p < 4; ++p) v[q + 4 * p] = u[p];
     }
@@ -540,36 +606,36 @@ __device__ __forceinline__ void dft16(float2* v) {
 
 // 20-point DFT in registers, natural order in and out (4 x 5: n = 5*n1 + n2, k = k1 + 4*k2)
 template <bool INV>
-__device__ __forceinline__ void dft20(float2* v) {
+__device__ __forceinline__ void dft20(cx* v) {
     // w20^j = (cos(2*pi*j/20), -sin(2*pi*j/20)) for the exponents n2*k1 that occur
     constexpr float c1 = 0.95105651629515357212f, s1 = 0.30901699437494742410f;   // j = 1
     constexpr float c2 = 0.80901699437494742410f, s2 = 0.58778525229247312917f;   // j = 2
     constexpr float c3 = 0.58778525229247312917f, s3 = 0.80901699437494742410f;   // j = 3
     constexpr float c4 = 0.30901699437494742410f, s4 = 0.95105651629515357212f;   // j = 4
-    float2 a[5][4];
+    cx a[5][4];
 #pragma unroll
     for (int n2 = 0; n2 < 5; ++n2) {
-        float2 u[4] = {v[n2], v[n2 + 5], v[n2 + 10], v[n2 + 15]};
-        butterfly<4, INV>(u);
+        cx u[4] = {v[n2], v[n2 + 5], v[n2 + 10], v[n2 + 15]};
+        fft4p<INV>(u);
 #pragma unroll
         for (int k1 = 0; k1 < 4; ++k1) a[n2][k1] = u[k1];
     }
-    a[1][1] = mulw<INV>(a[1][1], c1, -s1);    // j = 1
-    a[1][2] = mulw<INV>(a[1][2], c2, -s2);    // 2
-    a[1][3] = mulw<INV>(a[1][3], c3, -s3);    // 3
-    a[2][1] = mulw<INV>(a[2][1], c2, -s2);    // 2
-    a[2][2] = mulw<INV>(a[2][2], c4, -s4);    // 4
-    a[2][3] = mulw<INV>(a[2][3], -c4, -s4);   // 6: cos(108 deg) = -c4, sin = s4
-    a[3][1] = mulw<INV>(a[3][1], c3, -s3);    // 3
-    a[3][2] = mulw<INV>(a[3][2], -c4, -s4);   // 6
-    a[3][3] = mulw<INV>(a[3][3], -c1, -s1);   // 9: cos(162 deg) = -c1, sin = s1
-    a[4][1] = mulw<INV>(a[4][1], c4, -s4);    // 4
-    a[4][2] = mulw<INV>(a[4][2], -c2, -s2);   // 8: cos(144 deg) = -c2, sin = s2
-    a[4][3] = mulw<INV>(a[4][3], -c2, s2);    // 12: cos(216 deg) = -c2, sin = -s2
+    a[1][1] = mulwp<INV>(a[1][1], c1, -s1);    // j = 1
+    a[1][2] = mulwp<INV>(a[1][2], c2, -s2);    // 2
+    a[1][3] = mulwp<INV>(a[1][3], c3, -s3);    // 3
+    a[2][1] = mulwp<INV>(a[2][1], c2, -s2);    // 2
+    a[2][2] = mulwp<INV>(a[2][2], c4, -s4);    // 4
+    a[2][3] = mulwp<INV>(a[2][3], -c4, -s4);   // 6: cos(108 deg) = -c4, sin = s4
+    a[3][1] = mulwp<INV>(a[3][1], c3, -s3);    // 3
+    a[3][2] = mulwp<INV>(a[3][2], -c4, -s4);   // 6
+    a[3][3] = mulwp<INV>(a[3][3], -c1, -s1);   // 9: cos(162 deg) = -c1, sin = s1
+    a[4][1] = mulwp<INV>(a[4][1], c4, -s4);    // 4
+    a[4][2] = mulwp<INV>(a[4][2], -c2, -s2);   // 8: cos(144 deg) = -c2, sin = s2
+    a[4][3] = mulwp<INV>(a[4][3], -c2, s2);    // 12: cos(216 deg) = -c2, sin = -s2
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
-        float2 u[5] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1], a[4][k1]};
-        butterfly<5, INV>(u);
+        cx u[5] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1], a[4][k1]};
+        dft5p<INV>(u);
 #pragma unroll
         for (int k2 = 0; k2 < 5; ++k2) v[k1 + 4 * k2] = u[k2];
     }
@@ -581,8 +647,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 
 inline size_t smem_bytes(int C) {
-    return (size_t)MAXC * CS * sizeof(float2) + (size_t)C * N * sizeof(float2) + 2 * (size_t)N * sizeof(float2) +
-           (size_t)N * sizeof(float) + 2 * (size_t)N * sizeof(unsigned short) + 16;
+    return (size_t)MAXC * CS * sizeof(float2) + (size_t)C * RS * sizeof(float2) + 3 * (size_t)N * sizeof(float2) +
+           (size_t)N * sizeof(float) + (size_t)N * sizeof(unsigned short) + 16;
 }
 
 template <int OUT_MODE>
@@ -591,10 +657,11 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
                                                                int H, const float2* __restrict__ tw, int rw, float fscale,
                                                                float oscale, MaskDesc mask) {
     extern __shared__ float2 smem[];
-    float2* xch = smem;                              // [MAXC][CS]; reused as the coil-sum buffer [C][RS]
-    float2* yh_s = xch + MAXC * CS;                   // [C][ns2] packed hybrid k-space rows
-    float2* tw_s = yh_s + (size_t)C * N;              // [N] exp(-2 pi i k / 320)
-    float2* eta_s = tw_s + N;                         // [N] the eta row (storage order)
+    float2* xch = smem;                              // [MAXC][CS] exchange buffer of the two transposes
+    float2* yh_s = xch + MAXC * CS;                   // [C][ns2] packed hybrid k-space rows; later the coil-sum buffer [C][RS]
+    float2* tw1_s = yh_s + (size_t)C * RS;            // [k1][t]  w320^(t*k1): pass-1 twiddles, lanes read consecutive t
+    float2* tw2_s = tw1_s + N;                        // [n2][k1] w320^(n2*k1): pass-2 twiddles, lanes read consecutive k1
+    float2* eta_s = tw2_s + N;                        // [N] the eta row (storage order)
     float* mval_s = reinterpret_cast<float*>(eta_s + N);                      // [N] mask value by un-centred k
     unsigned short* pos_s = reinterpret_cast<unsigned short*>(mval_s + N);    // [N] un-centred k -> packed index
     __shared__ int scan_s[THREADS / 32];
@@ -609,7 +676,7 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     // Centring (rw = W/2) costs no index rotation here: a circular shift of the transform input by N/2 multiplies its
     // output by (-1)^k, and the same holds for the inverse, so the row is transformed in STORAGE order and only the
     // measured term changes sign on odd k:  (-1)^k m (fs (-1)^k X_s[k] - yh[k]) = m (fs X_s[k] - (-1)^k yh[k]).
-    // k = t + 16*k2 has the parity of t: one sign per thread.
+    // k = k1 + 16*k2 has the parity of k1: one sign per thread.
     // ---- pass 1 loads first: their latency overlaps the table set-up ----
     float2 sreg[N1];
     if (active) {
@@ -617,7 +684,8 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
 #pragma unroll
         for (int n1 = 0; n1 < N1; ++n1) sreg[n1] = LDSTREAM(sp + N2 * n1);
     }
-    tw_s[tid] = tw[tid];
+    tw1_s[tid] = __ldg(&tw[c * t]);                  // tid = 20*c + t  -> (k1 = c, t)
+    tw2_s[tid] = __ldg(&tw[(tid >> 4) * (tid & 15)]);  // tid = 16*n2 + k1
     eta_s[tid] = __ldg(&erow[tid]);
     // Thread k owns un-centred k-space column k: its mask value, and (ballot scan) its slot in the packed row.
     const float mk = mask_value(mask, b, 0, rot_add(tid, rw, N));
@@ -649,69 +717,67 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     asm volatile("cp.async.commit_group;" ::: "memory");
     float2* xc = xch + (size_t)c * CS;
     if (active) {
-        float2 v[N1];
+        cx v[N1];
 #pragma unroll
         for (int n1 = 0; n1 < N1; ++n1) {
             const float2 e = eta_s[N2 * n1 + t], s0 = sreg[n1];
-            v[n1] = make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);  // rim_utils.py:47-48
+            v[n1] = pk(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);  // rim_utils.py:47-48
         }
         dft16<false>(v);
-        xc[t] = v[0];
-        const float2* twt = tw_s;
+        xc[t] = upk(v[0]);
 #pragma unroll
         for (int k1 = 1; k1 < N1; ++k1) {
-            twt += t;  // tw_s[t * k1]
-            const float2 w = *twt;
-            xc[k1 * XS + t] = mulw<false>(v[k1], w.x, w.y);
+            const float2 w = tw1_s[k1 * N2 + t];
+            xc[k1 * XS + t] = mulw<false>(upk(v[k1]), w.x, w.y);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // ---- pass 2: forward 20-point DFT, residual, inverse 20-point DFT (thread t = k1) ----
-    if (active && t < N1) {
-        float2 v[N2];
-        float4* row = reinterpret_cast<float4*>(xc + t * XS);
+    // ---- pass 2: forward 20-point DFT, residual, inverse 20-point DFT.  Only 16 lines per coil: the threads are re-dealt as
+    // (coil = tid / 16, k1 = tid % 16) so that the 16*C busy lanes fill whole warps (7.5 instead of 10 at C = 15) ----
+    const int c2 = tid >> 4, kk = tid & (N1 - 1);
+    if (c2 < C) {
+        cx v[N2];
+        float4* row = reinterpret_cast<float4*>(xch + (size_t)c2 * CS + kk * XS);
 #pragma unroll
         for (int i = 0; i < N2 / 2; ++i) {
             const float4 q = row[i];
-            v[2 * i] = make_float2(q.x, q.y);
-            v[2 * i + 1] = make_float2(q.z, q.w);
+            v[2 * i] = pk(q.x, q.y);
+            v[2 * i + 1] = pk(q.z, q.w);
         }
         dft20<false>(v);
-        const float2* yc = yh_s + (size_t)c * ns2;
-        const float ysgn = (rw != 0 && (t & 1)) ? -1.f : 1.f;
+        const float2* yc = yh_s + (size_t)c2 * ns2;
+        const float ysgn = (rw != 0 && (kk & 1)) ? -1.f : 1.f;
 #pragma unroll
         for (int k2 = 0; k2 < N2; ++k2) {
-            const int k = t + N1 * k2;
+            const int k = kk + N1 * k2;
             const float m = mval_s[k];  // 0 on unsampled columns: the residual vanishes there
-            const float2 yv = yc[pos_s[k]];
-            v[k2] = make_float2(m * (v[k2].x * fscale - ysgn * yv.x), m * (v[k2].y * fscale - ysgn * yv.y));  // rim_utils.py:54
+            const float2 yv = yc[pos_s[k]], X = upk(v[k2]);
+            v[k2] = pk(m * (X.x * fscale - ysgn * yv.x), m * (X.y * fscale - ysgn * yv.y));  // rim_utils.py:54
         }
         dft20<true>(v);
-        const float2* twt = tw_s;
+        float2 o[N2];
+        o[0] = upk(v[0]);
 #pragma unroll
         for (int n2 = 1; n2 < N2; ++n2) {
-            twt += t;  // tw_s[n2 * t]
-            const float2 w = *twt;
-            v[n2] = mulw<true>(v[n2], w.x, w.y);
+            const float2 w = tw2_s[n2 * N1 + kk];
+            o[n2] = mulw<true>(upk(v[n2]), w.x, w.y);
         }
 #pragma unroll
-        for (int i = 0; i < N2 / 2; ++i) row[i] = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
+        for (int i = 0; i < N2 / 2; ++i) row[i] = make_float4(o[2 * i].x, o[2 * i].y, o[2 * i + 1].x, o[2 * i + 1].y);
     }
     __syncthreads();
     // ---- pass 3: inverse 16-point DFT over k1 (thread t = n2), conj(S), coil sum ----
-    float2 v[N1];
+    cx v[N1];
     if (active) {
 #pragma unroll
-        for (int k1 = 0; k1 < N1; ++k1) v[k1] = xc[k1 * XS + t];
+        for (int k1 = 0; k1 < N1; ++k1) v[k1] = pk(xc[k1 * XS + t]);
         dft16<true>(v);
-    }
-    __syncthreads();  // every thread has read its exchange data: the buffer becomes the coil-sum buffer
-    if (active) {
-        float2* rc = xch + (size_t)c * RS + t;
+        // the coil-sum buffer aliases the hybrid k-space rows, which nobody reads after pass 2
+        float2* rc = yh_s + (size_t)c * RS + t;
 #pragma unroll
         for (int n1 = 0; n1 < N1; ++n1) {
-            const float2 s0 = sreg[n1], x = v[n1];
+            const float2 s0 = sreg[n1], x = upk(v[n1]);
             rc[N2 * n1] = make_float2(x.x * s0.x + x.y * s0.y, x.y * s0.x - x.x * s0.y);  // x * conj(S)
         }
     }
@@ -719,7 +785,7 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     {
         float2 acc = make_float2(0.f, 0.f);
         for (int cc = 0; cc < C; ++cc) {
-            const float2 r = xch[(size_t)cc * RS + tid];
+            const float2 r = yh_s[(size_t)cc * RS + tid];
             acc.x += r.x;
             acc.y += r.y;
         }
