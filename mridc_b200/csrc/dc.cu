@@ -501,6 +501,10 @@ __global__ void __maxnreg__(MRB_ROWDC_REGS) row_dc_kernel(const float2* __restri
 // ---------------------------------------------------------------------------------------------------------------
 namespace r320 {
 constexpr int N = 320, N1 = 16, N2 = 20, XS = 22, CS = N1 * XS + 4, THREADS = 320, MAXC = 16, RS = N + 4;
+#ifndef MRB_DC_PF_DIST
+#define MRB_DC_PF_DIST 444
+#endif
+constexpr int PF_DIST = MRB_DC_PF_DIST;  // ~1.5 rounds of 2 CTAs x 148 SMs
 
 template <bool INV>
 __device__ __forceinline__ float2 mulw(float2 a, float wr, float wi) {  // a * (wr + i*wi), conjugated for the inverse
@@ -683,6 +687,20 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
         const float2* sp = S + rowoff + (long long)c * cstride + t;
 #pragma unroll
         for (int n1 = 0; n1 < N1; ++n1) sreg[n1] = LDSTREAM(sp + N2 * n1);
+    }
+    {
+        // L2 prefetch for the CTA that will run PF_DIST rows later (rows are scheduled in block-index order): its S row
+        // (C x 2560 B = 20*C lines of 128 B) and the head of its hybrid k-space row then come from L2 instead of HBM.
+        long long rid = (long long)b * H + h + PF_DIST;
+        if (rid < (long long)gridDim.y * H) {
+            const long long pb = rid / H, ph = rid - pb * H;
+            const long long proff = (pb * C * H + ph) * N;
+            if (tid < 20 * C) {
+                const int pc = tid / 20, pl = tid - pc * 20;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(S + proff + (long long)pc * cstride + pl * 16));
+                if (pl < 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(yh + proff + (long long)pc * cstride + pl * 16));
+            }
+        }
     }
     tw1_s[tid] = __ldg(&tw[c * t]);                  // tid = 20*c + t  -> (k1 = c, t)
     tw2_s[tid] = __ldg(&tw[(tid >> 4) * (tid & 15)]);  // tid = 16*n2 + k1
