@@ -39,6 +39,21 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def dc_traffic(B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one DC-gradient launch, from the committed `ncu --set full` capture
+    (profiles/*_traffic.json, written by tools/summarise_profiles.py; captured at B = 4 and scaled linearly to B)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        t = json.load(open(files[-1]))["row_dc"]
+        return t["dram_bytes_per_launch"] * B / t["slices"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -280,10 +295,11 @@ def run_ours(args):
         dc_bytes = B * DC_BYTES_PER_SLICE + mcan.numel() * mcan.element_size()
         dc_gbs = dc_bytes / (dc_ms * 1e-3) / 1e9
         roof_dc = {"bound": "hbm",
-                   "kernel": "DC gradient, hybrid-space row form (row_dc_kernel: S*eta -> FFT_W -> mask*(. - yh) -> IFFT_W "
-                             "-> sum_c conj(S)*.; the H transforms cancel for 1-D masks, yh prepared once per batch)",
+                   "kernel": "DC gradient, hybrid-space row form (row_dc320_kernel: S*eta -> FFT_W -> mask*(. - yh) -> IFFT_W "
+                             "-> sum_c conj(S)*., register-resident 16x20 transforms; the H transforms cancel for 1-D "
+                             "masks, yh prepared once per batch)",
                    "achieved": dc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": dc_gbs / peaks["hbm_gbs"],
-                   "frac_of_nominal_8000": dc_gbs / 8000.0, "traffic": None, "peak_src": peaks["src"],
+                   "frac_of_nominal_8000": dc_gbs / 8000.0, "traffic": dc_traffic(B), "peak_src": peaks["src"],
                    "ms_per_launch_group": dc_ms, "algorithmic_bytes": dc_bytes,
                    "general_three_pass_ms": dc3_ms, "general_three_pass_gbs": dc_bytes / (dc3_ms * 1e-3) / 1e9,
                    "note": "algorithmic bytes = SURVEY 8(d) contract figure (S and y once, eta in, 4-channel out); the row "

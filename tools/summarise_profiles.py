@@ -42,6 +42,20 @@ if os.path.exists(f):
     for r in rows[2:]:
         out.append("| `%s` | " % r[ki].split("(")[0][:40] + " | ".join(r[i][:12] for i, _ in cols) + " |")
     out.append("")
+    # DRAM traffic of the DC gradient per launch (bench.py's roofline.traffic reads this file)
+    try:
+        ri, wi = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        dc = [r for r in rows[2:] if "row_dc" in r[ki]]
+        if dc:
+            tot = sum(float(r[ri].replace(",", "")) * mult[rows[1][ri]] + float(r[wi].replace(",", "")) * mult[rows[1][wi]]
+                      for r in dc) / len(dc)
+            json.dump({"row_dc": {"dram_bytes_per_launch": tot, "slices": 4, "kernel": dc[0][ki].split("(")[0],
+                                  "source": "%s_hot_raw.csv (ncu --set full, B=4, 15x320x320)" % R}},
+                      open(os.path.join(pr, "%s_traffic.json" % R), "w"))
+            out += ["DC gradient DRAM traffic per launch (B=4): %.1f MB (algorithmic: 108.1 MB)" % (tot / 1e6), ""]
+    except ValueError:
+        pass
 f = os.path.join(go, "%s_bench.json" % R)
 if os.path.exists(f):
     line = open(f).read().strip().splitlines()[-1]
