@@ -16,6 +16,9 @@ def _enabled():
     return os.environ.get("MRIDC_B200_DISABLE_TC", "0") != "1"
 
 
+_ZERO_STATE = {}
+
+
 class RimTcEngine:
     def __init__(self, block):
         self.block = block
@@ -124,20 +127,26 @@ class RimTcEngine:
         packs = self.packs()
         st = _lib.stream_ptr()
 
-        def nhwc_state(t):
-            if t is None:
-                return torch.zeros((B, H, W, 64), dtype=torch.float32, device=dev)
-            return t.permute(0, 2, 3, 1).contiguous()
-
-        h = [nhwc_state(hx[0] if hx is not None else None), nhwc_state(hx[1] if hx is not None else None)]
-        h_alt = [torch.empty_like(h[0]), torch.empty_like(h[1])]
+        if hx is None:
+            # zero initial state (rim_block.py:188-193): one cached, read-only zero buffer feeds the first time step of
+            # every cascade instead of a fresh 26 MB-per-slice fill per layer and cascade
+            key = (B, H, W, str(dev))
+            if _ZERO_STATE.get("key") != key:  # one buffer shared by all cascades / engines (latest geometry only)
+                _ZERO_STATE.update(key=key, buf=torch.zeros((B, H, W, 64), dtype=torch.float32, device=dev))
+            h = [_ZERO_STATE["buf"], _ZERO_STATE["buf"]]
+        else:
+            h = [hx[0].permute(0, 2, 3, 1).contiguous(), hx[1].permute(0, 2, 3, 1).contiguous()]
+        h_alt = [torch.empty((B, H, W, 64), dtype=torch.float32, device=dev) for _ in range(2)]
         xbuf = torch.empty((B, H, W, 64), dtype=torch.float32, device=dev)
         g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         etas = []
         eta = eta.contiguous()
-        for _ in range(b.time_steps):
+        for step in range(b.time_steps):
             _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
                              ws=ws, nhwc=True, y_hybrid=y_hybrid)
             eta = self.conv_stack(g4, h, h_alt, xbuf, eta, packs)
+            if step == 0 and hx is None:
+                # the ping-pong swap left the shared zero buffer in h_alt: it must never be written
+                h_alt = [torch.empty_like(h[0]), torch.empty_like(h[1])]
             etas.append(eta)
         return etas, [h[0].permute(0, 3, 1, 2), h[1].permute(0, 3, 1, 2)]
