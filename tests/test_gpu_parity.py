@@ -393,6 +393,31 @@ def test_cirim_full_config_vs_oracle(centered, norm):
     assert rel_l2(out[0][0], ref[0][0]) <= 1e-5
 
 
+def test_cirim_brain_geometry_vs_oracle():
+    """Config 4 geometry: 16-coil 640 x 320 brain-shaped slices, 8x mask (2 cascades keep the CPU oracle short); the
+    on-device metrics agree with the host evaluation of the oracle's output to 4 decimals."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    cfg = synth.cirim_cfg("GRU", num_cascades=2)
+    batch = synth.make_batch(2, 16, 640, 320, mask_func=synth.Equispaced1DMask([0.04], [8]))
+    torch.manual_seed(2)
+    model = mb.CIRIM(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = omodels.cirim_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None,
+                                    batch["target"])
+    out = next(model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
+                            batch["target"].cuda()))
+    assert out[-1][-1].shape == (2, 640, 320)
+    e = rel_l2(out[-1][-1], ref[-1][-1])
+    assert e <= 1e-4, e
+    ev = mb.metrics.evaluate(out[-1][-1], batch["target"].cuda())
+    host = _metrics(ref[-1][-1].numpy(), batch["target"].numpy())  # (ssim, psnr)
+    assert _same_to_4_decimals((ev["ssim"], ev["psnr"]), host), (ev, host)
+
+
 def test_varnet_full_config_vs_oracle():
     """Config 2: E2EVN 12 cascades, 14 channels, 2 pools, 15 x 320 x 320, Gaussian-1D 4x mask."""
     import mridc_b200 as mb
