@@ -230,6 +230,10 @@ int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const void* bias, vo
 /* ConvGRUCell (kernel size 1): x, h, h_out [B,H,W,64]; b_ih [192] or null */
 int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, const void* b_ih, void* h_out, int B, int H,
                     int W, int ch, void* stream);
+/* IndRNNCell (kernel size 1, rnn_cells.py:264-391): x, h, h_out [B,H,W,ch]; wpack = mrb_tc_pack_conv of ih.weight
+ * [ch, 64, 1, 1]; b_ih [ch] or null; hh [ch] (the per-channel recurrent weight): h_out = ReLU(ih(x) + hh * h) */
+int mrb_tc_indrnn_nhwc(const void* x, const void* h, const void* wpack, const void* b_ih, const void* hh, void* h_out,
+                       int B, int H, int W, int ch, void* stream);
 /* Final RIM conv (rim_block.py:239-248): k x k (odd), dilation dil, replicate padding, cin -> 2 channels, no bias,
  * x [B,H,W,cin] channels-last, out [B,H,W,2] = eta + conv(x). */
 int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out, int B,

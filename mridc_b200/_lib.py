@@ -60,6 +60,7 @@ SIGNATURES = {
     "mrb_tc_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_tc_conv5x5x4_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrb_tc_gru_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mrb_tc_indrnn_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_metrics_workspace_bytes": (_sz, [_i]),
     "mrb_abs_max_normalize": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),

@@ -62,7 +62,8 @@ struct Params {
     int cs[2];               // channels per pixel of each source
     const float* wpack;      // packed weights: [half][nseg_w][hi|lo][n rows x 128 B swizzled]
     const float* bias;       // conv: [Cout]; GRU: b_ih [3*Ch] (may be null)
-    const float* hprev;      // GRU: previous hidden state NHWC [P, Ch]
+    const float* hprev;      // GRU / IndRNN: previous hidden state NHWC [P, Ch]
+    const float* add_scale;  // conv modes, IndRNN (rnn_cells.py:391): out = act(conv + bias + add_scale[c] * hprev[p][c]); null = off
     float* out;              // NHWC [P, Cout]
     int B, H, W;
     long long P;             // B*H*W pixels
@@ -454,6 +455,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const float b = P.bias ? P.bias[i] : 0.f;
             bias_s[i] = (GRU && i < 2 * P.cout) ? -kLog2e * b : b;
         }
+        if (!GRU && P.add_scale)  // IndRNN recurrent weights, second row of the table
+            for (int i = threadIdx.x; i < P.cout; i += THREADS) bias_s[256 + i] = P.add_scale[i];
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
@@ -1113,6 +1116,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     for (int jb = 0; jb < 8; ++jb) {
                         const float4 bi = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 4));
                         float4 v = make_float4(o[jb * 4 + 0] + bi.x, o[jb * 4 + 1] + bi.y, o[jb * 4 + 2] + bi.z, o[jb * 4 + 3] + bi.w);
+                        if (P.add_scale) {  // IndRNN: + hh * h_prev (rnn_cells.py:391)
+                            const float4 hv = __ldg(reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j_lo) + jb);
+                            const float4 sc = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j_lo + jb * 4));
+                            v = make_float4(v.x + sc.x * hv.x, v.y + sc.y * hv.y, v.z + sc.z * hv.z, v.w + sc.w * hv.w);
+                        }
                         if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
                         op[jb] = v;
                     }
@@ -1146,9 +1154,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                         const float4 bi1 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j + 4));
                         const float bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
                         const bool relu = P.mode == MODE_CONV_RELU;
+                        float hs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (P.add_scale) {  // IndRNN: + hh * h_prev (rnn_cells.py:391)
+                            const float4* hp4 = reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j);
+                            const float4 h0 = __ldg(hp4), h1 = __ldg(hp4 + 1);
+                            const float4 s0 = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j));
+                            const float4 s1 = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j + 4));
+                            hs[0] = s0.x * h0.x; hs[1] = s0.y * h0.y; hs[2] = s0.z * h0.z; hs[3] = s0.w * h0.w;
+                            hs[4] = s1.x * h1.x; hs[5] = s1.y * h1.y; hs[6] = s1.z * h1.z; hs[7] = s1.w * h1.w;
+                        }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const float v = a[q] + bi[q];
+                            const float v = (a[q] + bi[q]) + hs[q];
                             o[q] = relu ? fmaxf(v, 0.f) : v;
                         }
                         float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
@@ -1320,8 +1337,25 @@ static int tc_common(tc::Params& P, int B, int H, int W) {
 }
 
 // ConvNonlinear k x k (dilated, replicate padding), 64 -> cout channels, NHWC, bias + optional ReLU.
+static int tc_conv_launch(const void* x, const void* wpack, const void* bias, const void* hprev, const void* add_scale,
+                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream);
+
 extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
                                 int cout, int k, int dil, int relu, void* stream) {
+    return tc_conv_launch(x, wpack, bias, nullptr, nullptr, out, B, H, W, cout, k, dil, relu, stream);
+}
+
+// IndRNNCell with kernel size 1 (rnn_cells.py:264-391): ReLU(ih(x) + hh * h) = the 1x1 conv with the recurrent term in the
+// epilogue
+extern "C" int mrb_tc_indrnn_nhwc(const void* x, const void* h, const void* wpack, const void* b_ih, const void* hh,
+                                  void* h_out, int B, int H, int W, int ch, void* stream) {
+    MRB_REQUIRE(h && hh, MRB_EINVAL, "mrb_tc_indrnn_nhwc: null pointer");
+    MRB_REQUIRE(h != h_out, MRB_EINVAL, "mrb_tc_indrnn_nhwc: h_out must not alias h");
+    return tc_conv_launch(x, wpack, b_ih, h, hh, h_out, B, H, W, ch, 1, 1, 1, stream);
+}
+
+static int tc_conv_launch(const void* x, const void* wpack, const void* bias, const void* hprev, const void* add_scale,
+                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv_nhwc: null pointer");
     MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS && dil >= 1,
                 MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: unsupported geometry");
@@ -1331,6 +1365,7 @@ extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bi
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = nullptr; P.cs[1] = 0;
     P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
+    P.hprev = (const float*)hprev; P.add_scale = (const float*)add_scale;
     // All output channels in one CTA (stacked MMAs of N = 2*cout and cout: half the MMA instructions of a channel
     // split, which is what bounds this kernel); the k*k*2 weight chunks (2*cout*128 B each) do not fit shared memory
     // next to the staging tiles, so each loader group streams the chunk of its segment from L2.

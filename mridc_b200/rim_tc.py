@@ -21,20 +21,25 @@ _ZERO_STATE = {}
 
 class RimTcEngine:
     def __init__(self, block):
+        from .rim import IndRNNCell
+
         self.block = block
+        self._indrnn = isinstance(block.layers[0].rnn, IndRNNCell)
         self._key = None
         self._packs = None
 
     # ---------------------------------------------------------------------------------------------
     @staticmethod
     def supported(block) -> bool:
-        from .rim import ConvGRUCell, ConvNonlinear
+        from .rim import ConvGRUCell, ConvNonlinear, IndRNNCell
 
         if not _enabled() or len(block.layers) != 2:
             return False
         for i, st in enumerate(block.layers):
             c, r = st.convs, st.rnn
-            if not isinstance(c, ConvNonlinear) or not isinstance(r, ConvGRUCell):
+            if not isinstance(c, ConvNonlinear) or not isinstance(r, (ConvGRUCell, IndRNNCell)):
+                return False
+            if type(r) is not type(block.layers[0].rnn):
                 return False
             if c._act != _ops.ACT_RELU or c.features != 64 or r.hidden_size != 64 or r.input_size != 64:
                 return False
@@ -58,7 +63,7 @@ class RimTcEngine:
         b = self.block
         ps = []
         for st in b.layers:
-            ps += [st.convs.conv_layer.weight, st.rnn.ih.weight, st.rnn.hh.weight]
+            ps += [st.convs.conv_layer.weight, st.rnn.ih.weight, st.rnn.hh if self._indrnn else st.rnn.hh.weight]
         return ps
 
     def packs(self):
@@ -80,13 +85,26 @@ class RimTcEngine:
             else:
                 pc = torch.empty(lib.mrb_tc_packed_floats(0, 64, 64, c.kernel_size), dtype=torch.float32, device=dev)
                 _lib.check(lib.mrb_tc_pack_conv(_lib.ptr(w), _lib.ptr(pc), 64, 64, c.kernel_size, st))
-            pg = torch.empty(lib.mrb_tc_packed_floats(1, 64, 64, 1), dtype=torch.float32, device=dev)
             wih = r.ih.weight.detach().contiguous()
-            whh = r.hh.weight.detach().contiguous()
-            _lib.check(lib.mrb_tc_pack_gru(_lib.ptr(wih), _lib.ptr(whh), _lib.ptr(pg), 64, 64, st))
+            if self._indrnn:  # the 1x1 ih conv; the per-channel recurrent weight goes to the kernel's epilogue
+                pg = torch.empty(lib.mrb_tc_packed_floats(0, 64, 64, 1), dtype=torch.float32, device=dev)
+                _lib.check(lib.mrb_tc_pack_conv(_lib.ptr(wih), _lib.ptr(pg), 64, 64, 1, st))
+            else:
+                pg = torch.empty(lib.mrb_tc_packed_floats(1, 64, 64, 1), dtype=torch.float32, device=dev)
+                whh = r.hh.weight.detach().contiguous()
+                _lib.check(lib.mrb_tc_pack_gru(_lib.ptr(wih), _lib.ptr(whh), _lib.ptr(pg), 64, 64, st))
             out.append((pc, pg))
         self._key, self._packs = key, out
         return out
+
+    def _cell(self, lib, x, h, pack, rnn, h_out, B, H, W, st):
+        """ConvGRUCell (rnn_cells.py:93-127) or IndRNNCell (:367-391) with kernel size 1 on channels-last buffers."""
+        if self._indrnn:
+            _lib.check(lib.mrb_tc_indrnn_nhwc(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pack), _lib.ptr(rnn.ih.bias),
+                                              _lib.ptr(rnn.hh.detach().reshape(-1)), _lib.ptr(h_out), B, H, W, 64, st))
+        else:
+            _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pack), _lib.ptr(rnn.ih.bias),
+                                           _lib.ptr(h_out), B, H, W, 64, st))
 
     # ---------------------------------------------------------------------------------------------
     def conv_stack(self, g4, h, h_alt, xbuf, eta, packs=None):
@@ -102,13 +120,11 @@ class RimTcEngine:
         fin = b.final_layer[0]
         _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias),
                                              _lib.ptr(xbuf), B, H, W, 64, 1, st))
-        _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xbuf), _lib.ptr(h[0]), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias),
-                                       _lib.ptr(h_alt[0]), B, H, W, 64, st))
+        self._cell(lib, xbuf, h[0], packs[0][1], r0, h_alt[0], B, H, W, st)
         h[0], h_alt[0] = h_alt[0], h[0]
         _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(h[0]), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias),
                                         _lib.ptr(xbuf), B, H, W, 64, c1.kernel_size, c1.dilation, 1, st))
-        _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xbuf), _lib.ptr(h[1]), _lib.ptr(packs[1][1]), _lib.ptr(r1.ih.bias),
-                                       _lib.ptr(h_alt[1]), B, H, W, 64, st))
+        self._cell(lib, xbuf, h[1], packs[1][1], r1, h_alt[1], B, H, W, st)
         h[1], h_alt[1] = h_alt[1], h[1]
         new_eta = torch.empty_like(eta)
         _lib.check(lib.mrb_conv_c2_nhwc_residual(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight),

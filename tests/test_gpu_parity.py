@@ -369,14 +369,16 @@ def _same_to_4_decimals(a, b):
     return all(abs(x - y) < 1e-4 for x, y in zip(a, b))
 
 
-@pytest.mark.parametrize("centered,norm", [(False, "backward"), (True, "ortho")])
-def test_cirim_full_config_vs_oracle(centered, norm):
-    """Config 3: CIRIM 5 cascades x 8 steps, ConvGRU 64 filters, 15 x 320 x 320, 4x equispaced mask."""
+@pytest.mark.parametrize("layer,centered,norm", [("GRU", False, "backward"), ("GRU", True, "ortho"),
+                                                 ("IndRNN", False, "backward")])
+def test_cirim_full_config_vs_oracle(layer, centered, norm):
+    """Config 3: CIRIM 5 cascades x 8 steps, 64 filters, 15 x 320 x 320, 4x equispaced mask; ConvGRU (base_rim_run.yaml)
+    and the IndRNN cell that base_cirim_run.yaml ships as its default."""
     import mridc_b200 as mb
     from mridc_b200 import synth
     from oracle import models as omodels
 
-    cfg = synth.cirim_cfg("GRU", centered=centered, normalization=norm)
+    cfg = synth.cirim_cfg(layer, centered=centered, normalization=norm)
     batch = synth.make_batch(1, 15, 320, 320, centered=centered, normalization=norm)
     torch.manual_seed(1)
     model = mb.CIRIM(cfg).eval()

@@ -87,6 +87,15 @@ def test_tc_ops_vs_oracle(B, H, W):
     _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pg), _lib.ptr(bihd), _lib.ptr(out), B, H, W, 64,
                                    st))
     _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "gru")
+    # IndRNN cell, kernel size 1: ReLU(ih(x) + hh * h) (rnn_cells.py:391) = 1x1 tensor-core conv + recurrent epilogue
+    wi = torch.randn(64, 64, 1, 1, generator=g) * 0.1
+    bi = torch.randn(64, generator=g)
+    hhw = torch.randn(1, 64, 1, 1, generator=g)
+    ref = onets.indrnn_cell(x, h, wi, bi, hhw, 1, 1)
+    pi, bid, hhd = _pack(0, wi.cuda(), k=1), bi.cuda(), hhw.reshape(-1).cuda()
+    _lib.check(lib.mrb_tc_indrnn_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pi), _lib.ptr(bid), _lib.ptr(hhd), _lib.ptr(out),
+                                      B, H, W, 64, st))
+    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "indrnn")
     # final conv 64 -> 2 with the eta update
     w3 = torch.randn(2, 64, 3, 3, generator=g) * 0.05
     eta = torch.randn(B, H, W, 2, generator=g)
@@ -112,14 +121,15 @@ def test_dc_nhwc_layout_matches_nchw():
     assert torch.equal(a, b.permute(0, 3, 1, 2))
 
 
-def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch):
-    """The shipped geometry (64 filters, GRU k=1): tensor-core engine == exact-fp32 kernels == oracle."""
+@pytest.mark.parametrize("layer", ["GRU", "IndRNN"])
+def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch, layer):
+    """The shipped geometries (64 filters, GRU or IndRNN with k=1): tensor-core engine == exact-fp32 kernels == oracle."""
     from mridc_b200 import synth
     from mridc_b200.rim import RIMBlock
     from mridc_b200.rim_tc import RimTcEngine
     from oracle import nets as onets
 
-    cfg = synth.cirim_cfg("GRU", centered=True, normalization="ortho")
+    cfg = synth.cirim_cfg(layer, centered=True, normalization="ortho")
     kw = {k: cfg[k] for k in ("recurrent_layer", "conv_filters", "conv_kernels", "conv_dilations", "conv_bias",
                               "recurrent_filters", "recurrent_kernels", "recurrent_dilations", "recurrent_bias",
                               "depth", "time_steps", "conv_dim", "no_dc", "fft_centered", "fft_normalization",
@@ -130,6 +140,9 @@ def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch):
         for st in blk.layers:
             st.convs.conv_layer.bias.normal_(0, 0.1)
             st.rnn.ih.bias.normal_(0, 0.1)
+            if layer == "IndRNN":  # the default init (std 1/128) makes the recurrent term numerically invisible
+                st.rnn.hh.normal_(0, 0.5)
+                st.rnn.ih.weight.normal_(0, 0.1)
     sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
     batch = synth.make_batch(2, 6, 48, 40, centered=True, normalization="ortho")
     y, S, m = batch["y"], batch["sensitivity_maps"], batch["mask"]
