@@ -1,8 +1,8 @@
 """Tensor-core time-step engine for RIMBlock (channels-last activations, tcgen05 3xTF32 kernels of conv_tc.cu).
 
 Used by ``RIMBlock.forward`` when the block has the geometry of the shipped CIRIM/RIM configs
-(projects/reconstruction/model_zoo/conf/base_{cirim,rim}_run.yaml with recurrent_layer GRU): two
-ConvNonlinear(ReLU)+ConvGRUCell(kernel 1) stages with 64 channels and a final 64->2 ConvNonlinear.  Anything else
+(projects/reconstruction/model_zoo/conf/base_{cirim,rim}_run.yaml, recurrent_layer GRU or IndRNN): two
+ConvNonlinear(ReLU) + ConvGRUCell / IndRNNCell (kernel 1) stages with 64 channels and a final 64->2 ConvNonlinear.  Anything else
 runs on the generic exact-fp32 CUDA-core kernels.  Both paths are CUDA; neither is a CPU fallback.
 """
 import os
