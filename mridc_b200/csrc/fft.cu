@@ -6,6 +6,8 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "fft.cuh"
 
 namespace mrb {
@@ -125,6 +127,114 @@ __global__ void fft1d_cols_kernel(const float2* __restrict__ in, float2* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 320-point fast path (both fastMRI geometries): 16 lines per CTA of 320 threads, register-resident 16 x 20 transform
+// with one shared-memory transpose (the building blocks of the DC gradient kernel, fft.cuh r320::).
+//   ROWS (inner == 1): thread (line l = tid / 20, t = tid % 20) -- a line's 20 threads read 160 contiguous bytes per step.
+//   COLS (inner > 1):  thread (t = tid / 16, column l = tid % 16) -- 16 adjacent columns = 128 contiguous bytes per row.
+// Centring needs no index rotation: x'[j] = x[j + N/2] multiplies the output by (-1)^k and out[d] = X[d - N/2] equals
+// a (-1)^j modulation of the input, so the rotations of fft1d_launch (0 or N/2 each) become two thread-constant signs
+// (j = 20*n1 + t has the parity of t, k = k1 + 16*k2 the parity of k1).
+// In-place use is fine: a CTA reads its 16 lines into registers before the first barrier and writes only those lines.
+// ---------------------------------------------------------------------------------------------------------------
+namespace r320 {
+constexpr int FN = 320, FN1 = 16, FN2 = 20, FXS = 22, FLINES = 16, FTHREADS = 320;
+
+template <bool INV, bool COLS>
+__global__ void __launch_bounds__(FTHREADS, 3) fft320_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                             long long nlines, long long inner, const float2* __restrict__ tw,
+                                                             int in_sign, int out_sign, float scale) {
+    // line stride of the exchange buffer: ROWS wants 16-byte aligned rows read with 128-bit loads by lanes that walk k1
+    // (356 = 16*22 + 4), COLS has lanes walking the 16 lines with 64-bit accesses (odd stride: 2 banks per lane)
+    constexpr int CS = COLS ? FN1 * FXS + 1 : FN1 * FXS + 4;
+    extern __shared__ float2 smem[];
+    float2* xch = smem;               // [FLINES][CS]
+    float2* tw1_s = xch + FLINES * CS;  // [k1][t]  w320^(t*k1)
+    const int tid = threadIdx.x;
+    const int l = COLS ? (tid & 15) : tid / FN2, t = COLS ? (tid >> 4) : tid - (tid / FN2) * FN2;
+    const long long lid = (long long)blockIdx.x * FLINES + l;  // line (ROWS) or column (COLS) index
+    const bool valid = COLS ? lid < inner : lid < nlines;
+    const long long base = COLS ? (long long)blockIdx.y * FN * inner + lid : lid * FN;
+    const long long stride = COLS ? inner : 1;
+    cx v[FN1];
+    if (valid) {
+        const float2* g = in + base + (long long)t * stride;
+        float2 x[FN1];
+#pragma unroll
+        for (int n1 = 0; n1 < FN1; ++n1) x[n1] = __ldg(g + (long long)(FN2 * n1) * stride);
+        const float sg = (in_sign && (t & 1)) ? -1.f : 1.f;
+#pragma unroll
+        for (int n1 = 0; n1 < FN1; ++n1) v[n1] = pk(x[n1].x * sg, x[n1].y * sg);
+    }
+    {
+        const int a = tid / FN2, b = tid - a * FN2;
+        tw1_s[tid] = __ldg(&tw[a * b]);  // tid = 20*k1 + t
+    }
+    __syncthreads();
+    float2* xl = xch + (size_t)l * CS;
+    if (valid) {
+        dft16<INV>(v);
+        xl[t] = upk(v[0]);
+#pragma unroll
+        for (int k1 = 1; k1 < FN1; ++k1) {
+            const float2 w = tw1_s[k1 * FN2 + t];
+            xl[k1 * FXS + t] = mulw<INV>(upk(v[k1]), w.x, w.y);
+        }
+    }
+    __syncthreads();
+    // pass 2: 16 lines x 16 k1 = 256 threads, 20-point DFT over n2, store X[k1 + 16*k2]
+    if (tid < FLINES * FN1) {
+        const int l2 = COLS ? (tid & 15) : (tid >> 4), k1 = COLS ? (tid >> 4) : (tid & 15);
+        const long long lid2 = (long long)blockIdx.x * FLINES + l2;
+        const bool valid2 = COLS ? lid2 < inner : lid2 < nlines;
+        if (valid2) {
+            cx u[FN2];
+            const float2* row = xch + (size_t)l2 * CS + k1 * FXS;
+            if (COLS) {
+#pragma unroll
+                for (int i = 0; i < FN2; ++i) u[i] = pk(row[i]);
+            } else {
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+                for (int i = 0; i < FN2 / 2; ++i) {
+                    const float4 q = row4[i];
+                    u[2 * i] = pk(q.x, q.y);
+                    u[2 * i + 1] = pk(q.z, q.w);
+                }
+            }
+            dft20<INV>(u);
+            const float sc = (out_sign && (k1 & 1)) ? -scale : scale;
+            const long long base2 = COLS ? (long long)blockIdx.y * FN * inner + lid2 : lid2 * FN;
+            float2* o = out + base2 + (long long)k1 * stride;
+#pragma unroll
+            for (int k2 = 0; k2 < FN2; ++k2) {
+                const float2 r = upk(u[k2]);
+                o[(long long)(FN1 * k2) * stride] = make_float2(r.x * sc, r.y * sc);
+            }
+        }
+    }
+}
+
+template <bool INV, bool COLS>
+static int launch_fft320(const float2* in, float2* out, long long outer, long long inner, const float2* tw, int in_sign,
+                         int out_sign, float scale, cudaStream_t st) {
+    constexpr int CS = COLS ? FN1 * FXS + 1 : FN1 * FXS + 4;
+    const size_t smem = (size_t)(FLINES * CS + FN) * sizeof(float2);
+    auto k = fft320_kernel<INV, COLS>;
+    MRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (COLS) {
+        const long long gx = (inner + FLINES - 1) / FLINES;
+        k<<<dim3((unsigned)gx, (unsigned)outer), FTHREADS, smem, st>>>(in, out, 0, inner, tw, in_sign, out_sign, scale);
+    } else {
+        const long long gx = (outer + FLINES - 1) / FLINES;
+        k<<<(unsigned)gx, FTHREADS, smem, st>>>(in, out, outer, 1, tw, in_sign, out_sign, scale);
+    }
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+}  // namespace r320
+
 static int choose_lines(const FftPlan& p, int want_min_threads_work, long long avail_lines, size_t max_smem) {
     // lines per CTA: enough butterflies for 256 threads, bounded by shared memory and by what exists.
     int lines = 1;
@@ -143,6 +253,19 @@ int fft1d_launch(const float2* in, float2* out, long long outer, int n, long lon
     MRB_REQUIRE(in_rot >= 0 && in_rot < n && out_rot >= 0 && out_rot < n, MRB_EINVAL, "rotation out of range");
     const size_t max_smem = device_max_smem_optin();
     MRB_REQUIRE(fft_smem_bytes(p, 1) <= max_smem, MRB_EUNSUPPORTED, "fft length %d does not fit shared memory", n);
+    if (n == r320::FN && (in_rot == 0 || in_rot == n / 2) && (out_rot == 0 || out_rot == n / 2) &&
+        !getenv("MRIDC_B200_FFT_STOCKHAM")) {
+        const long long gx = inner == 1 ? (outer + 15) / 16 : (inner + 15) / 16;
+        if (gx <= 2147483647LL && (inner == 1 || outer <= 65535)) {
+            // x'[j] = x[j + N/2] -> (-1)^k on the output; out[d] = X[d - N/2] -> (-1)^j on the input
+            const int in_sign = out_rot != 0, out_sign = in_rot != 0;
+            if (inner == 1)
+                return inverse ? r320::launch_fft320<true, false>(in, out, outer, 1, p.tw, in_sign, out_sign, scale, st)
+                               : r320::launch_fft320<false, false>(in, out, outer, 1, p.tw, in_sign, out_sign, scale, st);
+            return inverse ? r320::launch_fft320<true, true>(in, out, outer, inner, p.tw, in_sign, out_sign, scale, st)
+                           : r320::launch_fft320<false, true>(in, out, outer, inner, p.tw, in_sign, out_sign, scale, st);
+        }
+    }
     const int threads = 256;
     if (inner == 1) {
         int lpb = choose_lines(p, 512, outer, max_smem < 98304 ? max_smem : 98304);

@@ -252,4 +252,150 @@ __device__ __forceinline__ void block_fft(float2* A, float2* B, int nlines, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident building blocks of the 320-point transforms (320 = 16 x 20): used by the fused hybrid-space DC
+// gradient (dc.cu, r320::row_dc320_kernel) and by the standalone 320-point line / column FFT (fft.cu).
+// ---------------------------------------------------------------------------------------------------------------
+namespace r320 {
+template <bool INV>
+__device__ __forceinline__ float2 mulw(float2 a, float wr, float wi) {  // a * (wr + i*wi), conjugated for the inverse
+    return INV ? make_float2(a.x * wr + a.y * wi, a.y * wr - a.x * wi) : make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+}
+
+// Packed complex arithmetic: a complex value lives in one 64-bit register pair and the additions / real scalings of
+// the butterflies are single add / sub / fma .f32x2 instructions (the kernel is instruction-issue bound); multiplications
+// by +-i and by constant twiddles stay scalar (immediate-operand FMUL / FFMA on the two halves).
+typedef unsigned long long cx;
+__device__ __forceinline__ cx pk(float x, float y) {
+    cx r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ cx pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 upk(cx a) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ cx add2(cx a, cx b) {
+    cx r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx sub2(cx a, cx b) {
+    cx r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx mul2(cx a, cx b) {
+    cx r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ cx fma2(cx a, cx b, cx c) {
+    cx r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+template <bool INV>
+__device__ __forceinline__ cx mulwp(cx a, float wr, float wi) { return pk(mulw<INV>(upk(a), wr, wi)); }
+// t + (-i) d and t - (-i) d (forward; +i for the inverse)
+template <bool INV>
+__device__ __forceinline__ void rot_pm(cx t, cx d, cx& plus, cx& minus) {
+    const float2 a = upk(t), e = upk(d);
+    const cx p = pk(a.x + e.y, a.y - e.x), m = pk(a.x - e.y, a.y + e.x);
+    plus = INV ? m : p;
+    minus = INV ? p : m;
+}
+template <bool INV>
+__device__ __forceinline__ void fft4p(cx* u) {
+    const cx t0 = add2(u[0], u[2]), t1 = sub2(u[0], u[2]), t2 = add2(u[1], u[3]), d = sub2(u[1], u[3]);
+    u[0] = add2(t0, t2);
+    u[2] = sub2(t0, t2);
+    rot_pm<INV>(t1, d, u[1], u[3]);
+}
+template <bool INV>
+__device__ __forceinline__ void dft5p(cx* u) {
+    constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    const cx p1 = add2(u[1], u[4]), m1 = sub2(u[1], u[4]), p2 = add2(u[2], u[3]), m2 = sub2(u[2], u[3]), a0 = u[0];
+    const cx A = fma2(p2, pk(c2, c2), fma2(p1, pk(c1, c1), a0));
+    const cx B = fma2(p2, pk(c1, c1), fma2(p1, pk(c2, c2), a0));
+    const cx U = fma2(m2, pk(s2, s2), mul2(m1, pk(s1, s1)));    // s1*m1 + s2*m2
+    const cx V = fma2(m2, pk(-s1, -s1), mul2(m1, pk(s2, s2)));  // s2*m1 - s1*m2
+    u[0] = add2(add2(a0, p1), p2);
+    rot_pm<INV>(A, U, u[1], u[4]);
+    rot_pm<INV>(B, V, u[2], u[3]);
+}
+
+// 16-point DFT in registers, natural order in and out (4 x 4 Cooley-Tukey: n = i + 4m, k = q + 4p)
+template <bool INV>
+__device__ __forceinline__ void dft16(cx* v) {
+    constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, H = 0.70710678118654752440f;
+    cx a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        cx u[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
+        fft4p<INV>(u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[i][q] = u[q];
+    }
+    // twiddles w16^(i*q) = exp(-2*pi*i * i*q / 16)
+    a[1][1] = mulwp<INV>(a[1][1], C1, -S1);
+    a[1][2] = mulwp<INV>(a[1][2], H, -H);
+    a[1][3] = mulwp<INV>(a[1][3], S1, -C1);
+    a[2][1] = mulwp<INV>(a[2][1], H, -H);
+    a[2][2] = pk(mul_mi<INV>(upk(a[2][2])));
+    a[2][3] = mulwp<INV>(a[2][3], -H, -H);
+    a[3][1] = mulwp<INV>(a[3][1], S1, -C1);
+    a[3][2] = mulwp<INV>(a[3][2], -H, -H);
+    a[3][3] = mulwp<INV>(a[3][3], -C1, S1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cx u[4] = {a[0][q], a[1][q], a[2][q], a[3][q]};
+        fft4p<INV>(u);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[q + 4 * p] = u[p];
+    }
+}
+
+// 20-point DFT in registers, natural order in and out (4 x 5: n = 5*n1 + n2, k = k1 + 4*k2)
+template <bool INV>
+__device__ __forceinline__ void dft20(cx* v) {
+    // w20^j = (cos(2*pi*j/20), -sin(2*pi*j/20)) for the exponents n2*k1 that occur
+    constexpr float c1 = 0.95105651629515357212f, s1 = 0.30901699437494742410f;   // j = 1
+    constexpr float c2 = 0.80901699437494742410f, s2 = 0.58778525229247312917f;   // j = 2
+    constexpr float c3 = 0.58778525229247312917f, s3 = 0.80901699437494742410f;   // j = 3
+    constexpr float c4 = 0.30901699437494742410f, s4 = 0.95105651629515357212f;   // j = 4
+    cx a[5][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        cx u[4] = {v[n2], v[n2 + 5], v[n2 + 10], v[n2 + 15]};
+        fft4p<INV>(u);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) a[n2][k1] = u[k1];
+    }
+    a[1][1] = mulwp<INV>(a[1][1], c1, -s1);    // j = 1
+    a[1][2] = mulwp<INV>(a[1][2], c2, -s2);    // 2
+    a[1][3] = mulwp<INV>(a[1][3], c3, -s3);    // 3
+    a[2][1] = mulwp<INV>(a[2][1], c2, -s2);    // 2
+    a[2][2] = mulwp<INV>(a[2][2], c4, -s4);    // 4
+    a[2][3] = mulwp<INV>(a[2][3], -c4, -s4);   // 6: cos(108 deg) = -c4, sin = s4
+    a[3][1] = mulwp<INV>(a[3][1], c3, -s3);    // 3
+    a[3][2] = mulwp<INV>(a[3][2], -c4, -s4);   // 6
+    a[3][3] = mulwp<INV>(a[3][3], -c1, -s1);   // 9: cos(162 deg) = -c1, sin = s1
+    a[4][1] = mulwp<INV>(a[4][1], c4, -s4);    // 4
+    a[4][2] = mulwp<INV>(a[4][2], -c2, -s2);   // 8: cos(144 deg) = -c2, sin = s2
+    a[4][3] = mulwp<INV>(a[4][3], -c2, s2);    // 12: cos(216 deg) = -c2, sin = -s2
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cx u[5] = {a[0][k1], a[1][k1], a[2][k1], a[3][k1], a[4][k1]};
+        dft5p<INV>(u);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) v[k1 + 4 * k2] = u[k2];
+    }
+}
+
+}  // namespace r320
+
 }  // namespace mrb
