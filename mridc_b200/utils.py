@@ -56,6 +56,8 @@ def complex_mul(x: torch.Tensor, y: torch.Tensor, _conj_y: bool = False) -> torc
     if len(shape) > 6:
         xe, ye = xe.contiguous().reshape(-1), ye.contiguous().reshape(-1)
     out = torch.empty(shape, dtype=torch.complex64, device=x.device)
+    if out.numel() == 0:  # empty batch: nothing to launch (data_ptr() is null)
+        return torch.view_as_real(out)
     nd = xe.dim()
     arr = ctypes.c_longlong * max(nd, 1)
     _lib.check(_lib.load().mrb_complex_mul(
@@ -71,6 +73,8 @@ def complex_conj(x: torch.Tensor) -> torch.Tensor:
     _lib.require_cuda(x, "x")
     x = x.contiguous()
     out = torch.empty_like(x)
+    if out.numel() == 0:
+        return out
     _lib.check(_lib.load().mrb_complex_conj(_lib.ptr(x), _lib.ptr(out), x.numel() // 2, _lib.stream_ptr()))
     return out
 
@@ -81,6 +85,8 @@ def _abs(data, squared):
     _lib.require_cuda(data, "data")
     data = data.contiguous()
     out = torch.empty(data.shape[:-1], dtype=torch.float32, device=data.device)
+    if out.numel() == 0:
+        return out
     _lib.check(_lib.load().mrb_complex_abs(_lib.ptr(data), _lib.ptr(out), out.numel(), int(squared),
                                            _lib.stream_ptr()))
     return out
@@ -118,6 +124,8 @@ def rss(data: torch.Tensor, dim: int = 0) -> torch.Tensor:
     d = dim % data.dim()
     outer, C, inner = _split(data.shape, d)
     out = torch.empty(data.shape[:d] + data.shape[d + 1:], dtype=torch.float32, device=data.device)
+    if out.numel() == 0 or C == 0:  # empty batch / no coils: an empty sum
+        return out.zero_()
     _lib.check(_lib.load().mrb_rss(_lib.ptr(data), _lib.ptr(out), outer, C, inner, _lib.stream_ptr()))
     return out
 
@@ -132,6 +140,8 @@ def rss_complex(data: torch.Tensor, dim: int = 0) -> torch.Tensor:
     cshape = data.shape[:-1]
     outer, C, inner = _split(cshape, d)
     out = torch.empty(cshape[:d] + cshape[d + 1:], dtype=torch.float32, device=data.device)
+    if out.numel() == 0 or C == 0:
+        return out.zero_()
     _lib.check(_lib.load().mrb_rss_complex(_lib.ptr(data), _lib.ptr(out), outer, C, inner, _lib.stream_ptr()))
     return out
 
@@ -150,6 +160,8 @@ def sense(data: torch.Tensor, sensitivity_maps: torch.Tensor, dim: int = 0) -> t
     cshape = data.shape[:-1]
     outer, C, inner = _split(cshape, d)
     out = torch.empty(cshape[:d] + cshape[d + 1:] + (2,), dtype=torch.float32, device=data.device)
+    if out.numel() == 0 or C == 0:
+        return out.zero_()
     _lib.check(_lib.load().mrb_sense_combine(_lib.ptr(data), _lib.ptr(sensitivity_maps), _lib.ptr(out), outer, C,
                                              inner, _lib.stream_ptr()))
     return out

@@ -596,3 +596,26 @@ def test_on_device_metrics_vs_oracle(B, H, W):
     assert abs(ev["ssim"] - om.ssim(tgt, out, R)) < 1e-5
     nm = mb.metrics.normalized_magnitude(cp.cuda())
     assert rel_l2(nm, out) < 1e-6 and nm.max().item() == 1.0
+
+
+def test_empty_and_ragged_inputs():
+    """Zero-sized batches flow through (shapes as torch / the reference give them), non-contiguous inputs are accepted,
+    inputs are never written."""
+    import mridc_b200 as mb
+    from oracle import mri as omri
+
+    e = torch.zeros(0, 3, 8, 6, 2).cuda()
+    assert mb.fft2(e).shape == e.shape and mb.ifft2(e, centered=True, normalization="ortho").shape == e.shape
+    assert mb.complex_mul(e, e).shape == e.shape and mb.complex_conj(e).shape == e.shape
+    assert mb.complex_abs(e).shape == e.shape[:-1]
+    assert mb.rss_complex(e, dim=1).shape == (0, 8, 6) and mb.sense(e, e, dim=1).shape == (0, 8, 6, 2)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 10, 12, 2, generator=g)
+    xt = x.cuda().transpose(2, 3)  # non-contiguous view [2, 3, 12, 10, 2]
+    keep = xt.clone()
+    for cen in (False, True):
+        assert rel_l2(mb.fft2(xt, centered=cen, normalization="ortho"), omri.fft2(x.transpose(2, 3), cen, "ortho")) < 2e-6
+    assert torch.equal(xt, keep)
+    s = torch.randn(2, 3, 10, 12, 2, generator=g)
+    assert rel_l2(mb.coil_combination(x.cuda()[:, :, ::2], s.cuda()[:, :, ::2], "SENSE", 1),
+                  omri.coil_combination(x[:, :, ::2], s[:, :, ::2], "SENSE", 1)) < 2e-6
