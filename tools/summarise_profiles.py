@@ -26,6 +26,7 @@ if os.path.exists(f):
 # ---- full capture
 f = os.path.join(go, "%s_hot_raw.csv" % R)
 if os.path.exists(f):
+    import shutil; shutil.copy(f, os.path.join(pr, os.path.basename(f)))  # raw capture travels with its summary
     rows = list(csv.reader(open(f)))
     h = rows[0]
     want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
