@@ -201,19 +201,14 @@ int mrb_normunet_out(const void* x, const void* mean_std, void* out, int B, int 
                      int normalize, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * Tensor-core (tcgen05 / TMEM, error-compensated 3xTF32) RIM regulariser, channels-last fp32 activations.
- * Same arithmetic as mrb_conv2d / mrb_gru_cell_1x1 to fp32 round-off; used by RIMBlock's time loop
- * (rim_block.py:217-249) when the layer geometry matches (64 channels, GRU kernel size 1).
- * Weights are packed once per parameter version into the UMMA shared-memory layout (hi/lo split).
+ * Tensor-core (tcgen05 / TMEM, error-compensated bf16 hi/lo split, fp32 accumulation) RIM regulariser,
+ * channels-last fp32 activations.  Same arithmetic as mrb_conv2d / mrb_gru_cell_1x1 to ~3e-6 relative per operator
+ * (products are evaluated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with 16-17 significant bits per operand); used by
+ * RIMBlock's time loop (rim_block.py:217-249) when the layer geometry matches (64 channels, cell kernel size 1).
+ * Weights are packed once per parameter version into the UMMA shared-memory layout (bf16 hi/lo split).
+ * (The profiling hooks of this kernel live in the tools-only build, tools/libmridc_b200_tools.so.)
  * ------------------------------------------------------------------------------------------------- */
-/* profiling switches for the tensor-core kernel (bit 0: skip MMAs, 1: skip global loads, 2: skip epilogue);
- * results are garbage when non-zero -- used only by tools/ to attribute time to the kernel's roles. */
-void mrb_tc_set_debug(int flags);
-/* device buffer of 148*16 uint64 cycle counters written by the kernel's roles (null = off; tools/ only) */
-void mrb_tc_set_prof(void* buf);
-/* tcgen05.mma issue/dependency micro-benchmark (tools/ only): out[0] = issue cycles, out[1] = cycles to completion */
-int mrb_tc_microbench(int N, int nacc, int iters, int a_in_tmem, void* out, void* stream);
-/* floats needed by the pack: kind 0 = conv k x k (cin 64), 1 = GRU 1x1 (64 -> 64), 2 = conv 5x5 over 4 channels */
+/* size of the packed weights in 4-byte units: kind 0 = conv k x k (cin 64), 1 = GRU 1x1 (64 -> 64), 2 = conv 5x5 over 4 channels */
 size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k);
 /* w [cout, 64, k, k] (conv_layers.py:78-85) */
 int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int k, void* stream);

@@ -50,9 +50,6 @@ SIGNATURES = {
     "mrb_pad2d": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_normunet_in": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
     "mrb_normunet_out": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
-    "mrb_tc_set_debug": (None, [_i]),
-    "mrb_tc_set_prof": (None, [_vp]),
-    "mrb_tc_microbench": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "mrb_tc_packed_floats": (_sz, [_i, _i, _i, _i]),
     "mrb_tc_pack_conv": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mrb_tc_pack_gru": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

@@ -14,7 +14,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmridc_b200.so")
 STAMP = os.path.join(PKG_DIR, "csrc", ".build_stamp")
-SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "tc_microbench.cu", "qmri.cu", "metrics.cu"]
+SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "qmri.cu", "metrics.cu"]
+# tools-only library (tools/libmridc_b200_tools.so): the tensor-core kernels with their per-role cycle counters and role
+# switches compiled in (-DMRB_TC_PROF) plus the tcgen05 issue micro-benchmark; never loaded by the package
+TOOLS_SOURCES = ["core.cu", "conv_tc.cu", "conv.cu", "tc_microbench.cu"]
+TOOLS_LIB_PATH = os.path.join(PKG_DIR, "..", "tools", "libmridc_b200_tools.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -77,5 +81,26 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_tools():
+    """tools/libmridc_b200_tools.so: profiling build of the tensor-core kernels (see TOOLS_SOURCES)."""
+    nvcc = _nvcc()
+    objdir = os.path.join(PKG_DIR, "csrc", "build", "tools")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in TOOLS_SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-DMRB_TC_PROF", "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+    subprocess.check_call([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", TOOLS_LIB_PATH] + objs + ["-lcudart"])
+    return TOOLS_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--tools" in sys.argv:
+        print(build_tools())

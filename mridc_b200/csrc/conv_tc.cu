@@ -3,25 +3,30 @@
 // Reference behaviour: ConvNonlinear (rim/conv_layers.py:36-123, replicate padding) and ConvGRUCell with
 // kernel_size 1 (rim/rnn_cells.py:93-127), as used by RIMBlock's time loop (rim/rim_block.py:217-249).
 //
-// Numerics: the reference is fp32 and the end-to-end tolerance (rel-L2 1e-4) rules out plain TF32 (SURVEY
-// section 7: 9.3e-4).  Every product is therefore evaluated as an error-compensated 3xTF32 sum
-//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,    x_hi = rn_tf32(x), x_lo = rn_tf32(x - x_hi)
-// with fp32 accumulation in TMEM (split error and dropped term a_lo*b_lo are both ~2^-24 relative).
+// Numerics: the reference is fp32 and the end-to-end tolerance (rel-L2 1e-4) rules out plain TF32 / BF16 operands
+// (9.3e-4 / 9.9e-3).  Every product is therefore evaluated as an error-compensated split sum
+//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,    x_hi = rn_bf16(x), x_lo = rn_bf16(x - x_hi)
+// on tcgen05.mma.kind::f16 (bf16 operands, fp32 accumulation in TMEM).  hi + lo carries 16-17 significant bits
+// (|x - hi - lo| <= 2^-18 |x|), the dropped a_lo*b_lo term is <= 2^-18 relative: ~3e-6 rms per operator, 2.5e-5
+// end to end over the 40 time steps of CIRIM 5x8 (measured with a CPU emulation of this arithmetic against the fp32
+// oracle; the budget is 1e-4).  Round 1 used 3xTF32 (22 bits, 2.6e-6 end to end): same three MMAs per product but
+// at half the tensor-pipe rate and twice the instruction count (K = 8 instead of 16 per MMA) -- the kernels were
+// bound by exactly those two.
 //
 // Structure: one persistent CTA per SM.  Work item = (128-pixel tile, half of the output channels).
 //   * B operand = the weights of the CTA's channel half (hi and lo, pre-packed in the UMMA K-major SWIZZLE_128B
 //     layout): copied to shared memory once and resident for the whole kernel.
 //   * A operand = activations, held in TENSOR MEMORY (tcgen05.mma with A from TMEM): a ring of TMEM stages of
-//     64 columns (32 hi + 32 lo tf32 columns = one 32-channel K chunk for the 128 pixels/lanes).  Shared memory
+//     64 columns (32 hi + 32 lo columns of packed bf16 pairs = one 64-channel K chunk for the 128 pixels/lanes).  Shared memory
 //     therefore carries no activation traffic for the MMAs, and the ring is deep (5-6 stages) although the
 //     resident weights fill most of shared memory -- the mbarrier round trip loader -> MMA -> commit -> loader
 //     measured at ~2k cycles needs that depth.
-//   loader warps (2 groups x 4, alternating segments): coalesced gather of a [128 px x 32 ch] fp32 chunk per
+//   loader warps (2 groups x 4, alternating segments): coalesced gather of a [128 px x 64 ch] fp32 chunk per
 //                     "segment" (source tensor, tap offset with replicate clamp, channel chunk) with the next
 //                     segment's loads in flight in registers; a per-warp 4 KB swizzled staging tile turns the
 //                     coalesced (4 rows x 128 B per instruction) view into row ownership (thread = pixel = TMEM
 //                     lane); split into hi/lo and tcgen05.st into the stage;
-//   MMA warp (1 lane) 4 k-steps x 3 tcgen05.mma.kind::tf32 per segment (A from TMEM, B descriptor in smem) and
+//   MMA warp (1 lane) 4 k-steps (K = 16) x 3 tcgen05.mma.kind::f16 per segment (A from TMEM, B descriptor in smem) and
 //                     tcgen05.commit of the stage back to the loaders / of the accumulator to the epilogue;
 //   epilogue warps (8) tcgen05.ld the accumulator (one pixel per thread, 2 warps per lane quadrant), apply
 //                     bias + ReLU or the GRU gates, and write NHWC.
@@ -31,36 +36,49 @@ namespace mrb {
 namespace tc {
 
 constexpr int TILE_M = 128;
-constexpr int KC = 32;                        // channels per K chunk (32 tf32 columns of TMEM / one 128-byte B row)
+constexpr int KC = 32;                        // TMEM columns of one K chunk half (hi or lo): 64 bf16 channels, packed in pairs
+constexpr int KCH = 64;                       // channels per K chunk (one 128-byte row of bf16 in the B operand)
 constexpr int A_STAGE_COLS = 2 * KC;          // hi + lo
 constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant (each takes half of the channels)
 constexpr int LOAD_GROUPS = 2, LOAD_WARPS = 4 * LOAD_GROUPS;  // loader groups alternate segments
 constexpr int MMA_WARPS = 2;                  // two issuing lanes (alternate segments): one thread cannot feed the pipe
 constexpr int THREADS = (EPI_WARPS + LOAD_WARPS + MMA_WARPS + 1) * 32;  // + weight-streaming warp
 constexpr int B_STAGES = 6;                   // max depth of the streamed-weights ring (Params::b_stages)
-constexpr int MAX_SEGS = 20;
+constexpr int MAX_SEGS = 25;
 constexpr int MAX_STAGES = 6;
-constexpr int TBUF_BYTES = 32 * 128;          // per loader warp staging tile
+constexpr int TBUF_BYTES = 2 * 32 * 128;      // per loader warp staging tile: 32 pixels x 64 fp32 channels, as two
+                                              // [32 rows x 128 B] swizzled halves (channels 0-31 | 32-63)
 constexpr int EPI_ROW_BYTES = 80;             // 64 B of payload per pixel, padded: conflict-free for both access patterns
 constexpr int EPI_TILE_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int HALO_ROWS = 40;                 // halo mode: 32 pixels + 2*pad on each side of up to two image-row pieces
 
 enum Mode { MODE_CONV_RELU = 0, MODE_GRU = 1, MODE_CONV_NOACT = 2 };
 
+// Profiling hooks (per-role cycle counters, role switches) exist only in the tools build (-DMRB_TC_PROF,
+// tools/libmridc_b200_tools.so); the product kernel carries none of them.
+#ifdef MRB_TC_PROF
+#define TCP(...) __VA_ARGS__
+#define TC_DBG(P, flag) (((P).debug & (flag)) != 0)
+#else
+#define TCP(...)
+#define TC_DBG(P, flag) false
+#endif
+
 struct Segment {
     short src;     // 0 / 1: which input tensor
     short dy, dx;  // pixel offset of this tap (replicate clamp)
-    short c0;      // first channel of the chunk in the source (or im2col chunk index when im2col != 0)
-    short wchunk;  // resident weight chunk index
+    short c0;      // first channel of the 64-channel chunk in the source (or im2col chunk index when im2col != 0)
+    short wchunk;  // weight chunk index
     short dcol;    // accumulator column offset
     short n;       // MMA N for this segment
-    short first;   // 1: first contribution to its accumulator columns (overwrite); 2: GRU x-part (see umma_first_split)
+    short first;   // non-stacked issue: 1: first contribution to its accumulator columns (overwrite); 2: GRU x-part
+                   // (see umma_first_split).  Stacked issue derives "first" from the segment index (see the issuers).
 };
 
 struct Params {
     const float* src[2];     // NHWC inputs [B, H, W, cs]
     int cs[2];               // channels per pixel of each source
-    const float* wpack;      // packed weights: [half][nseg_w][hi|lo][n rows x 128 B swizzled]
+    const void* wpack;       // packed bf16 weights: [half][chunk][hi|lo][n rows x 128 B swizzled]
     const float* bias;       // conv: [Cout]; GRU: b_ih [3*Ch] (may be null)
     const float* hprev;      // GRU / IndRNN: previous hidden state NHWC [P, Ch]
     const float* add_scale;  // conv modes, IndRNN (rnn_cells.py:391): out = act(conv + bias + add_scale[c] * hprev[p][c]); null = off
@@ -68,8 +86,9 @@ struct Params {
     int B, H, W;
     long long P;             // B*H*W pixels
     int n_tiles;
-    int nseg;
-    int wchunk_rows;         // rows (N) of one resident weight chunk
+    int nseg;                // segments (64-channel K chunks) per tile; the global segment stream s = item * nseg + sgi
+                             // is dealt round-robin to the loader groups, the TMEM stages, the weight ring and the issuers
+    int wchunk_rows;         // rows (N) of one weight chunk
     int n_wchunks;
     int acc_cols;            // TMEM columns of one accumulator buffer
     int acc_bufs;            // 1 or 2 accumulator buffers
@@ -78,25 +97,30 @@ struct Params {
     int n_split;             // 1 or 2: CTAs per pixel tile (each takes cout / n_split output channels)
     int nhalf;               // output channels handled per item (cout / n_split)
     int mode;
-    int stream_b;            // 1: weights are not resident; each loader group streams the B chunk of its segment
-                             // (hi rows | lo rows, wchunk_rows*256 B) into its own ring of tb_depth slots
+    int stream_b;            // 1: weights are not resident; a dedicated lane streams the B chunk of every segment
+                             // (hi rows | lo rows, wchunk_rows*256 B) through a ring of b_stages slots
     int b_stages;            // depth of the streamed-weights ring (<= B_STAGES)
     int tb_depth;            // cp.async staging tiles per loader warp (2 or 3)
-    int tb_bytes;            // bytes of one staging tile (32 rows, or HALO_ROWS rows in halo mode)
+    int tb_half;             // bytes of one staging half (32 rows x 128 B, or HALO_ROWS rows in halo mode)
+    int tb_bytes;            // bytes of one staging tile (2 halves)
     int halo;                // 1: k x k conv, one gather per (tile, kernel row) feeds the k taps of that row (see loaders)
     int ksz, dil;            // conv geometry (halo mode)
     int stages;              // A stages in TMEM (columns acc_bufs*acc_cols + 64*s)
-    int im2col;              // != 0: source 0 is [B,H,W,4] and chunk c0 holds taps 8*c0 .. 8*c0+7 of a 5x5 window
+    int im2col;              // != 0: source 0 is [B,H,W,4] and chunk c0 holds taps 16*c0 .. 16*c0+15 of a 5x5 window
                              // (1: gathered tap by tap from global memory, 2: from a halo patch in shared memory)
-    unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py); null in production
-    int debug;               // profiling switches (mrb_tc_set_debug): 1 skip MMAs, 2 skip global loads, 4 skip epilogue math
     int ngroups;             // conv: number of independent accumulator groups (each [hi*hi | cross], 2*nhalf columns);
                              // the tensor core's fp32 accumulation truncates, so its error grows linearly with the
                              // chain length -- short chains summed in the epilogue (RN fp32) keep it at fp32 level
-    int n_issuers;           // 1 or 2 MMA-issuing lanes (2: segments alternate; each issuer owns its accumulator group)
+    int group_cols;          // TMEM columns between the accumulator groups of the two issuers (0 with one group)
+    int n_issuers;           // 1 or 2 MMA-issuing lanes (2: the global segment stream alternates; issuer i owns
+                             // accumulator group i)
     int stacked;             // 1: stacked-B issue (2 MMAs per k-step); requires small_off == n of every segment
     int small_off;           // != 0: the two cross terms (lo*hi, hi*lo) accumulate in columns dcol + small_off, so the
                              // long hi*hi chain sees 3x fewer (truncating) tensor-core accumulations; summed in the epilogue
+#ifdef MRB_TC_PROF
+    unsigned long long* prof; // optional [gridDim.x][16] cycle counters (tools/tc_roles.py)
+    int debug;                // role switches: 1 skip MMAs, 2 skip global loads, 4 skip epilogue math, 8 skip tcgen05.st
+#endif
     Segment seg[MAX_SEGS];
 };
 
@@ -176,24 +200,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
         "}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M = 128, K = 8
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 operands), M = 128, K = 16
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 tf32 columns starting at a_tmem
+// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 columns (16 packed bf16) starting at a_tmem
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -220,18 +244,18 @@ __device__ __forceinline__ void umma_segment_ts(uint32_t d, uint32_t ds, uint32_
         "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
         "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
         "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
-        "@pf tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, ps;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %6, pb;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah1], bl1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah2], bl2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah3], bl3, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %6, pt;\n\t"
+        "@pf tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %4, %6, ps;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %5, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %4, %6, pb;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bl1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah2], bl2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al3], bh3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah3], bl3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah3], bh3, %6, pt;\n\t"
         "}\n" ::"r"(d),
         "r"(ds), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small0), "r"(acc_big0), "r"(skip_first)
         : "memory");
@@ -248,8 +272,8 @@ __device__ __forceinline__ void umma_first_split(uint32_t ds, uint32_t a, uint64
         "elect.sync _|pe, 0xffffffff;\n\t"
         "setp.eq.b32 pt, 0, 0;\n\t"
         "setp.ne.b32 pz, 0, 0;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %4, %6, pz;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %4, %6, pz;\n\t"
         "}\n" ::"r"(ds),
         "r"(ds + n_acc), "r"(a), "l"(db), "l"(db2), "r"(idesc_acc), "r"(idesc_new)
         : "memory");
@@ -270,14 +294,14 @@ __device__ __forceinline__ void umma_segment_ts_stacked(uint32_t d, uint32_t dsm
         "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
         "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
         "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %5, pa;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al3], bh3, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %4, %5, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %4, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah1], bh1, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah2], bh2, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al2], bh2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah3], bh3, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al3], bh3, %6, pt;\n\t"
         "}\n" ::"r"(d),
         "r"(dsm), "r"(a_hi), "r"(a_lo), "l"(dbh), "r"(idesc2n), "r"(idescn), "r"(acc0)
         : "memory");
@@ -290,13 +314,11 @@ struct SegIssue {  // per-segment operands of the MMA issuer
     uint32_t idesc, first, idesc2n;
 };
 // registers -> TMEM: 16 consecutive columns of this thread's lane
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -351,15 +373,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// round-to-nearest (ties away, like cvt.rna) fp32 -> tf32 (10-bit mantissa, low 13 bits zero).  Used for both split
-// terms so that the tensor core's own operand truncation is a no-op: a = hi + lo + O(2^-24 |a|).
-// Two integer instructions; cvt.rna.tf32.f32 itself compiles to four on sm_100a (add, |x| >= inf test, select, mask)
-// and the loaders are instruction-issue bound.  Inf / NaN pass through unchanged (the mask clears the added bit).
-__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// fp32 pair -> packed bf16 hi pair + packed bf16 lo pair (element 0 in the low half, as tcgen05 reads packed A rows).
+// hi = rn_bf16(x); lo = rn_bf16(x - hi): the subtraction is exact in fp32 and |x - hi - lo| <= 2^-18 |x|.
+// Five instructions per pair (cvt.pack, shl, and, packed sub, cvt.pack): the loaders are instruction-issue bound.
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));  // first source -> upper half
+    return r;
+}
+__device__ __forceinline__ void sub2(float x0, float x1, float y0, float y1, float& r0, float& r1);
+__device__ __forceinline__ void split_bf16x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(e0, e1);
+    float l0, l1;
+    sub2(e0, e1, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u), l0, l1);
+    lo = pack_bf16x2(l0, l1);
+}
+__host__ __device__ inline uint16_t bf16_rn_bits(float v) {  // host/pack-kernel side rounding (RNE), NaN/Inf pass through
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -409,13 +448,13 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 12
 template <bool GRU>
 __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // layout: [weights resident][loader staging tiles][barriers]
+    // layout: [weights resident][loader staging tiles][streamed-weights ring][barriers][bias][epilogue exchange]
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int wbytes_chunk = P.wchunk_rows * 128;
+    const int wbytes_chunk = P.wchunk_rows * 128;  // bytes of the hi (or lo) rows of one weight chunk
     uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
-    uint8_t* tb_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [LOAD_WARPS][depth][32 rows x 128 B]
-    uint8_t* bst_s = tb_s + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes;  // [B_STAGES][2*wbytes_chunk] if stream_b
-    uint64_t* bars = (uint64_t*)(bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0));
+    uint8_t* bst_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [b_stages][2*wbytes_chunk] if stream_b
+    uint8_t* tb_s = bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0);  // [LOAD_WARPS][depth][tb_bytes]
+    uint64_t* bars = (uint64_t*)(tb_s + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes);
     uint64_t* full = bars;                          // [MAX_STAGES]
     uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
     uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [2]
@@ -477,167 +516,72 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_col0 = (uint32_t)(P.acc_bufs * P.acc_cols);  // first TMEM column of the A ring
+    int n_items = 0;
+    for (int t = first_tile; t < P.n_tiles; t += tile_stride) ++n_items;
     if (warp >= EPI_WARPS && warp < EPI_WARPS + LOAD_WARPS) {
         // ============================== LOADERS ==============================
+        // The global segment stream s = item * nseg + sgi is dealt to the two loader groups (generic / patch mode:
+        // alternate segments; halo mode: alternate (tile, kernel row) units of k segments); segment s goes to TMEM stage
+        // s % stages.
         const int lw = warp - EPI_WARPS;
-        const int grp = lw >> 2;                     // loader group: handles segments grp, grp + 2, ...
+        const int grp = lw >> 2;                     // loader group
         const int quad = lw & 3;                     // == warp % 4: the TMEM lane quadrant this warp may write
-        const int c16 = lane & 7;                    // 16-byte chunk within the 128-byte row (coalesced view)
+        const int c16 = lane & 7;                    // 16-byte chunk within a 128-byte half row (coalesced view)
         const int rl0 = lane >> 3;                   // rows rl0 + 4*i of the warp's 32 rows (coalesced view)
-        uint8_t* tbuf = tb_s + (size_t)lw * P.tb_depth * P.tb_bytes;  // tb_depth staging tiles of this warp
+        const uint32_t tb_u32 = smem_u32(tb_s + (size_t)lw * P.tb_depth * P.tb_bytes);  // tb_depth staging tiles of this warp
+        const uint32_t HB = (uint32_t)P.tb_half;     // channels 32-63 of a staging row live HB bytes after channels 0-31
         const uint32_t W32 = (uint32_t)P.W, H32 = (uint32_t)P.H;
-        int pb[8], py[8], px[8];
-        bool pv[8];
-        int coords_tile = -1;
-        bool uniform_rows = false;
+        const bool ld_on = !TC_DBG(P, 2);
+        TCP(long long t_start = clock64(), t_wait = 0, t_st = 0, t_issue = 0, t_stw = 0, c0;)
 
-        // cp.async gather of one segment into staging tile `slot` (no registers held while in flight)
-        // all gathers bypass L1 (.cg): measured 144 -> 122 us for the GRU (every activation read once) and still 7 % faster
-        // for the 3x3 taps although they re-read their neighbours (from L2 instead of L1)
-        const bool cg = !(P.debug & 16);
-        auto issue_loads = [&](int tile, int sgi, int slot) {
-            const Segment sg = P.seg[sgi];
-            const float* src = P.src[sg.src];
-            const int cs = P.cs[sg.src];
-            uint8_t* tb = tbuf + (size_t)slot * P.tb_bytes;
-            if (!P.im2col && sg.dy == 0 && sg.dx == 0) {
-                // centre tap / 1x1 kernel: pixel p is row p of the [P, cs] matrix -- no (b, y, x) decomposition, no clamp
-                const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
-                const float* g = src + p0 * cs + sg.c0 + c16 * 4;
-                const uint32_t sbase = smem_u32(tb);
-                const long long gstep = 4ll * cs;
-                const bool on = !(P.debug & 2);
-                if ((long long)(tile + 1) * TILE_M <= P.P) {  // whole tile inside the image stack: no per-row predicate
-                    const uint32_t nbytes = on ? 16u : 0u;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        cp_async16(sbase + swz(rl0 + 4 * i, c16), g + i * gstep, nbytes, cg);
-                    }
-                    return;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool ok = p0 + 4 * i < P.P;
-                    cp_async16(sbase + swz(rl0 + 4 * i, c16), ok ? g + i * gstep : src, (ok && on) ? 16u : 0u, cg);
-                }
-                return;
-            }
-            if (tile != coords_tile) {
-                coords_tile = tile;
-                // one division pair per tile; rows rl0 + 4*i follow by carry (x -> y -> b)
-                const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
-                const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;  // P.P < 2^31 (checked on the host)
-                const uint32_t t = q / W32;
-                int x = (int)(q - t * W32);
-                const uint32_t b0 = t / H32;
-                int y = (int)(t - b0 * H32), b = (int)b0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    pv[i] = p0 + 4 * i < P.P;
-                    px[i] = pv[i] ? x : 0; py[i] = pv[i] ? y : 0; pb[i] = pv[i] ? b : 0;
-                    x += 4;
-                    while (x >= P.W) {
-                        x -= P.W;
-                        if (++y == P.H) { y = 0; ++b; }
-                    }
-                }
-                uniform_rows = pv[7] && py[7] == py[0] && pb[7] == pb[0];
-            }
-            if (!P.im2col && uniform_rows) {
-                // fast path: rows rl0 + 4*i are 4 pixels apart on one image row; only y may clamp (uniformly)
-                const int xlo = px[0] + sg.dx, xhi = px[0] + 28 + sg.dx;
-                if (xlo >= 0 && xhi < P.W) {
-                    const int yy = min(max(py[0] + sg.dy, 0), P.H - 1);
-                    const float* g = src + (((long long)pb[0] * P.H + yy) * P.W + xlo) * cs + sg.c0 + c16 * 4;
-                    const uint32_t nbytes = (P.debug & 2) ? 0u : 16u;
-                    const uint32_t sbase = smem_u32(tb);
-                    const long long gstep = 4ll * cs;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        cp_async16(sbase + swz(rl0 + 4 * i, c16), g + i * gstep, nbytes, cg);
-                    return;
-                }
-            }
-            int dy = sg.dy, dx = sg.dx, coff = sg.c0 + c16 * 4;
-            bool tap_ok = true;
-            if (P.im2col) {
-                // chunk c16 of im2col row = tap t of the 5x5 window (4 channels = one float4)
-                const int t = sg.c0 * 8 + c16;
-                tap_ok = t < 25;
-                dy = t / 5 - 2; dx = t % 5 - 2; coff = 0;
-                if (uniform_rows && px[0] >= 2 && px[0] + 30 < P.W) {
-                    // interior of an image row: no x clamp for any tap, y clamps uniformly; rows are 4 pixels apart
-                    const int yy = min(max(py[0] + dy, 0), P.H - 1);
-                    const float* g = src + (((long long)pb[0] * P.H + yy) * P.W + px[0] + dx) * cs;
-                    const uint32_t nbytes = (tap_ok && !(P.debug & 2)) ? 16u : 0u;
-                    const uint32_t sbase = smem_u32(tb);
-                    const long long gstep = 4ll * cs;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cp_async16(sbase + swz(rl0 + 4 * i, c16), g + i * gstep, nbytes, cg);
-                    return;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rl0 + 4 * i;
-                const int yy = min(max(py[i] + dy, 0), P.H - 1);
-                const int xx = min(max(px[i] + dx, 0), P.W - 1);
-                const float* g = src + (((long long)pb[i] * P.H + yy) * P.W + xx) * cs + coff;
-                const uint32_t nbytes = (pv[i] && tap_ok && !(P.debug & 2)) ? 16u : 0u;  // 0 -> zero fill
-                cp_async16(smem_u32(tb + swz(r, c16)), g, nbytes, cg);
-            }
+        int stage = 0;
+        uint32_t phase = 0;
+        auto stage_set = [&](long long s) { stage = (int)(s % P.stages); phase = (uint32_t)(s / P.stages) & 1u; };
+        auto stage_adv = [&](int n) {
+            stage += n;
+            while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
         };
-
-        // this group's segment sequence (every LOAD_GROUPS-th global segment); all indices advance incrementally --
-        // the loader warps are instruction-issue bound, so no divisions in the per-segment path
-        const int spg = P.nseg / LOAD_GROUPS;
-        int n_items = 0;
-        for (int t = first_tile; t < P.n_tiles; t += tile_stride) ++n_items;
-        const int n_total = n_items * spg;
-        long long t_start = clock64(), t_wait = 0, t_st = 0, t_issue = 0, t_stw = 0, c0;
-        const int D = P.tb_depth;
-        // prefetch cursor
-        int pf_n = 0, pf_tile = first_tile, pf_sgi = grp, pf_slot = 0;
-        auto prefetch_next = [&]() {
-            if (pf_n < n_total) issue_loads(pf_tile, pf_sgi, pf_slot);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            ++pf_n;
-            pf_sgi += LOAD_GROUPS;
-            if (pf_sgi >= P.nseg) { pf_sgi = grp; pf_tile += tile_stride; }
-            if (++pf_slot == D) pf_slot = 0;
-        };
-        // staging row `row` of tile tb -> hi/lo split -> TMEM stage (thread = pixel = TMEM lane quad*32 + lane)
-        auto store_stage = [&](uint32_t tb, int row, int stage) {
-            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
+        // staging row `row` of tile tb (64 fp32 channels) -> bf16 hi/lo split -> TMEM stage (thread = pixel = TMEM lane
+        // quad*32 + lane): columns [0,32) = hi pairs, [32,64) = lo pairs
+        auto store_stage = [&](uint32_t tb, int row, int stg) {
+            const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stg * A_STAGE_COLS);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                float hi[16], lo[16];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 a = lds128(tb + swz(row, hf * 4 + c));
-                    // hi = rn_tf32(a) (exact tf32); lo = a - hi is exact in fp32 with |lo| <= 2^-12 |a|, and the tensor
-                    // core's own truncation of lo to tf32 costs <= 2^-23 |a|: no second conversion needed.
-                    // The subtractions are packed (sub.f32x2): the loaders are instruction-issue bound.
-                    hi[4 * c + 0] = tf32_rn(a.x); hi[4 * c + 1] = tf32_rn(a.y);
-                    hi[4 * c + 2] = tf32_rn(a.z); hi[4 * c + 3] = tf32_rn(a.w);
-                    sub2(a.x, a.y, hi[4 * c + 0], hi[4 * c + 1], lo[4 * c + 0], lo[4 * c + 1]);
-                    sub2(a.z, a.w, hi[4 * c + 2], hi[4 * c + 3], lo[4 * c + 2], lo[4 * c + 3]);
+                for (int c = 0; c < 8; ++c) {
+                    const float4 a = lds128(tb + hf * HB + swz(row, c));
+                    split_bf16x2(a.x, a.y, hi[2 * c], lo[2 * c]);
+                    split_bf16x2(a.z, a.w, hi[2 * c + 1], lo[2 * c + 1]);
                 }
-                if (!(P.debug & 8)) {
+                if (!TC_DBG(P, 8)) {
                     tmem_st16(ta + hf * 16, hi);
                     tmem_st16(ta + KC + hf * 16, lo);
                 }
             }
         };
-        int stage = grp % P.stages;
-        uint32_t phase = (uint32_t)(grp / P.stages) & 1u;
+        // wait for the stage, convert + store one staging row per lane, hand the stage to the issuers
+        auto fill_stage = [&](uint32_t tb, int row) {
+            TCP(c0 = clock64();)
+            mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+            TCP(t_wait += clock64() - c0;)
+            tc_fence_after();
+            TCP(c0 = clock64();)
+            store_stage(tb, row, stage);
+            TCP(const long long c2 = clock64();)
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&full[stage]);
+            TCP(t_st += clock64() - c0; t_stw += clock64() - c2;)
+        };
+
         if (P.halo) {
-            // ---- halo mode (k x k conv, group = K chunk) ----
+            // ---- halo mode (k x k conv over 64 channels) ----
             // The k taps of one kernel row read the same image row shifted by dil pixels.  One gather per (tile, kernel
             // row) brings the warp's 32 pixels plus pad = dil*(k-1)/2 pixels on each side (replicate clamp applied to the
             // source column) into a staging tile; tap kx then reads staging row lane + kx*dil.  A warp's 32 pixels may
             // straddle two image rows: the second piece gets its own 2*pad halo (rows shifted by another 2*pad).
-            // Cuts the gathers (issue slots and L2 traffic) by k.
+            // Cuts the gathers (issue slots and L2 traffic) by k.  The two loader groups take alternate units.
             const int k = P.ksz, dil = P.dil, pad = dil * (k - 1) / 2;
             const int cs = P.cs[0];
             const float* src = P.src[0];
@@ -678,65 +622,59 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             auto issue_halo = [&](int tile, int ky, int slot) {
                 if (tile != geo_tile) { geo_tile = tile; tile_geometry(tile); }
                 const int dy = ky * dil - pad;
-                const float* gA = src + (rowA + min(max(yA + dy, 0), P.H - 1)) * P.W * cs + grp * KC + c16 * 4;
-                const float* gB = src + (rowB + min(max(yB + dy, 0), P.H - 1)) * P.W * cs + grp * KC + c16 * 4;
-                const uint32_t sbase = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
-                const bool on = !(P.debug & 2);
+                const float* gA = src + (rowA + min(max(yA + dy, 0), P.H - 1)) * P.W * cs + c16 * 4;
+                const float* gB = src + (rowB + min(max(yB + dy, 0), P.H - 1)) * P.W * cs + c16 * 4;
+                const uint32_t sbase = tb_u32 + (uint32_t)(slot * P.tb_bytes);
 #pragma unroll
                 for (int i = 0; i < HALO_ROWS / 4; ++i) {
                     const bool ok = (rowok >> i) & 1u;
                     const float* g = (((selB >> i) & 1u) ? gB : gA) + xoff[i];
-                    cp_async16(sbase + swz(rl0 + 4 * i, c16), ok ? (const void*)g : (const void*)src, (ok && on) ? 16u : 0u, cg);
+                    const uint32_t nb = (ok && ld_on) ? 16u : 0u;
+                    cp_async16(sbase + swz(rl0 + 4 * i, c16), ok ? (const void*)g : (const void*)src, nb, true);
+                    cp_async16(sbase + HB + swz(rl0 + 4 * i, c16), ok ? (const void*)(g + 32) : (const void*)src, nb, true);
                 }
             };
-            int pf_u = 0, pf_tile = first_tile, pf_ky = 0, pf_slot = 0;
+            int pf_u = grp, pf_tile = first_tile, pf_ky = grp, pf_slot = 0;
+            while (pf_ky >= k) { pf_ky -= k; pf_tile += tile_stride; }
             auto prefetch_unit = [&]() {
                 if (pf_u < n_units) issue_halo(pf_tile, pf_ky, pf_slot);
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                ++pf_u;
-                if (++pf_ky == k) { pf_ky = 0; pf_tile += tile_stride; }
+                pf_u += LOAD_GROUPS;
+                pf_ky += LOAD_GROUPS;
+                while (pf_ky >= k) { pf_ky -= k; pf_tile += tile_stride; }
                 pf_slot ^= 1;
             };
             prefetch_unit();
-            int slot = 0, ky = 0, tile = first_tile;
-            int nA_cur = 32;
-            for (int u = 0; u < n_units; ++u) {
-                if (ky == 0) {  // nA of the tile being consumed (the prefetch cursor may already be on the next tile)
-                    const long long p0 = (long long)tile * TILE_M + quad * 32;
-                    const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
-                    nA_cur = min(32, P.W - (int)(q % W32));
-                }
-                c0 = clock64();
+            int slot = 0, ky = grp, tile = first_tile;
+            while (ky >= k) { ky -= k; tile += tile_stride; }
+            stage_set((long long)grp * k);
+            for (int u = grp; u < n_units; u += LOAD_GROUPS) {
+                // nA of the tile being consumed (the prefetch cursor may already be on the next tile)
+                const long long p0 = (long long)tile * TILE_M + quad * 32;
+                const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
+                const int nA_cur = min(32, P.W - (int)(q % W32));
+                TCP(c0 = clock64();)
                 prefetch_unit();
-                t_issue += clock64() - c0;
+                TCP(t_issue += clock64() - c0;)
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
-                const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const uint32_t tb = tb_u32 + (uint32_t)(slot * P.tb_bytes);
                 const int row0 = lane + (lane >= nA_cur ? 2 * pad : 0);
                 for (int kx = 0; kx < k; ++kx) {
-                    c0 = clock64();
-                    mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
-                    t_wait += clock64() - c0;
-                    tc_fence_after();
-                    c0 = clock64();
-                    store_stage(tb, row0 + kx * dil, stage);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&full[stage]);
-                    t_st += clock64() - c0;
-                    stage += LOAD_GROUPS;
-                    while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+                    fill_stage(tb, row0 + kx * dil);
+                    stage_adv(1);
                 }
                 __syncwarp();  // every lane has read its rows before the slot is refilled
+                stage_adv(k * (LOAD_GROUPS - 1));  // the other group's unit
                 slot ^= 1;
-                if (++ky == k) { ky = 0; tile += tile_stride; }
+                ky += LOAD_GROUPS;
+                while (ky >= k) { ky -= k; tile += tile_stride; }
             }
         } else if (P.im2col == 2) {
-            // ---- 5x5 x 4-channel im2col from a halo patch ----
+            // ---- 5x5 x 4-channel im2col from a halo patch (nseg == LOAD_GROUPS: group g assembles K chunk g) ----
             // One gather per tile brings the warp's 32 pixels (+2 on each side, two-piece layout as above) of the five
-            // image rows y-2..y+2 into a [5][HALO_ROWS] x 16 B patch; the four K chunks (8 taps each) are then assembled
-            // from shared memory: tap (ky, kx) of pixel `lane` is patch[ky][row0 + kx].  Replaces 32 scattered 16-byte
-            // gathers per pixel and tile by ~6.
+            // image rows y-2..y+2 into a [5][HALO_ROWS] x 16 B patch; the two K chunks (16 taps x 4 channels each, taps
+            // 25..31 zero) are then assembled from shared memory: tap (ky, kx) of pixel `lane` is patch[ky][row0 + kx].
             const float* src = P.src[0];
             constexpr int PAD = 2, NE = (5 * HALO_ROWS + 31) / 32;  // patch elements per lane
             int eoff[NE];      // clamped source column (in floats) of patch element e = lane + 32*i
@@ -772,8 +710,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             };
             auto issue_patch = [&](int tile, int slot) {
                 tile_geometry(tile);
-                const uint32_t sbase = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
-                const bool on = !(P.debug & 2);
+                const uint32_t sbase = tb_u32 + (uint32_t)(slot * P.tb_bytes);
 #pragma unroll
                 for (int i = 0; i < NE; ++i) {
                     const int e = lane + 32 * i;
@@ -782,7 +719,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     const bool inB = (eB >> i) & 1u;
                     const int yy = min(max((inB ? yB : yA) + ky - PAD, 0), P.H - 1);
                     const float* g = src + ((inB ? rowB : rowA) + yy) * P.W * 4 + eoff[i];
-                    cp_async16(sbase + 16u * (uint32_t)e, ok ? (const void*)g : (const void*)src, (ok && on) ? 16u : 0u, cg);
+                    cp_async16(sbase + 16u * (uint32_t)e, ok ? (const void*)g : (const void*)src, (ok && ld_on) ? 16u : 0u, true);
                 }
             };
             int pf_t = 0, pf_tile = first_tile, pf_slot = 0;
@@ -795,114 +732,206 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             };
             prefetch_patch();
             int slot = 0, tile = first_tile;
+            stage_set(grp);
             for (int it = 0; it < n_items; ++it, tile += tile_stride) {
                 const long long p0 = (long long)tile * TILE_M + quad * 32;
                 const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
                 const int nA_cur = min(32, P.W - (int)(q % W32));
-                c0 = clock64();
+                TCP(c0 = clock64();)
                 prefetch_patch();
-                t_issue += clock64() - c0;
+                TCP(t_issue += clock64() - c0;)
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
-                const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
+                const uint32_t tb = tb_u32 + (uint32_t)(slot * P.tb_bytes);
                 const int row0 = lane + (lane >= nA_cur ? 2 * PAD : 0);
-                for (int sgi = grp; sgi < P.nseg; sgi += LOAD_GROUPS) {
-                    c0 = clock64();
-                    mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
-                    t_wait += clock64() - c0;
-                    tc_fence_after();
-                    c0 = clock64();
-                    const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
+                TCP(c0 = clock64();)
+                mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
+                TCP(t_wait += clock64() - c0;)
+                tc_fence_after();
+                TCP(c0 = clock64();)
+                const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float hi[16], lo[16];
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int t = sgi * 8 + hf * 4 + c;       // tap index (K chunk sgi holds taps 8*sgi .. 8*sgi+7)
-                            const int ky = (t * 13) >> 6, kx = t - 5 * ky;  // t / 5, t % 5 for t < 32
-                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (t < 25) a = lds128(tb + 16u * (uint32_t)(ky * HALO_ROWS + row0 + kx));
-                            hi[4 * c + 0] = tf32_rn(a.x); hi[4 * c + 1] = tf32_rn(a.y);
-                            hi[4 * c + 2] = tf32_rn(a.z); hi[4 * c + 3] = tf32_rn(a.w);
-                            sub2(a.x, a.y, hi[4 * c + 0], hi[4 * c + 1], lo[4 * c + 0], lo[4 * c + 1]);
-                            sub2(a.z, a.w, hi[4 * c + 2], hi[4 * c + 3], lo[4 * c + 2], lo[4 * c + 3]);
-                        }
-                        if (!(P.debug & 8)) {
-                            tmem_st16(ta + hf * 16, hi);
-                            tmem_st16(ta + KC + hf * 16, lo);
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        const int t = grp * 16 + hf * 8 + c;            // tap index (K chunk g holds taps 16g .. 16g+15)
+                        const int ky = (t * 13) >> 6, kx = t - 5 * ky;  // t / 5, t % 5 for t < 32
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t < 25) a = lds128(tb + 16u * (uint32_t)(ky * HALO_ROWS + row0 + kx));
+                        split_bf16x2(a.x, a.y, hi[2 * c], lo[2 * c]);
+                        split_bf16x2(a.z, a.w, hi[2 * c + 1], lo[2 * c + 1]);
                     }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&full[stage]);
-                    t_st += clock64() - c0;
-                    stage += LOAD_GROUPS;
-                    while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
+                    if (!TC_DBG(P, 8)) {
+                        tmem_st16(ta + hf * 16, hi);
+                        tmem_st16(ta + KC + hf * 16, lo);
+                    }
                 }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&full[stage]);
+                TCP(t_st += clock64() - c0;)
+                stage_adv(LOAD_GROUPS);
                 __syncwarp();  // every lane has read its taps before the slot is refilled
                 slot ^= 1;
             }
         } else {
-        for (int n = 0; n < D - 1; ++n) prefetch_next();
-        // consume cursor: global segment index advances by LOAD_GROUPS (nseg is a multiple of it)
-        int slot = 0;
-        for (int n = 0; n < n_total; ++n) {
-            c0 = clock64();
-            prefetch_next();
-            t_issue += clock64() - c0;
-            if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 2;" ::: "memory");
-            __syncwarp();
-            const uint32_t tb = smem_u32(tbuf) + (uint32_t)(slot * P.tb_bytes);
-            c0 = clock64();
-            mbar_wait_sleep(&empty[stage], phase ^ 1, 40);
-            t_wait += clock64() - c0;
-            tc_fence_after();
-            c0 = clock64();
-            store_stage(tb, lane, stage);
-            const long long c2 = clock64();
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&full[stage]);
-            __syncwarp();  // every lane has read its row before the slot is refilled
-            t_st += clock64() - c0;
-            t_stw += clock64() - c2;
-            if (++slot == D) slot = 0;
-            stage += LOAD_GROUPS;
-            while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
-        }
+            // ---- generic path: one gather per segment (1x1 kernels: GRU / IndRNN; small images) ----
+            int pb[8], py[8], px[8];
+            bool pv[8];
+            int coords_tile = -1;
+            bool uniform_rows = false;
+            // cp.async gather of one segment into staging tile `slot` (no registers held while in flight); all gathers
+            // bypass L1 (.cg): every activation is read once
+            auto issue_loads = [&](int tile, int sgi, int slot) {
+                const Segment sg = P.seg[sgi];
+                const float* src = P.src[sg.src];
+                const int cs = P.cs[sg.src];
+                const uint32_t sbase = tb_u32 + (uint32_t)(slot * P.tb_bytes);
+                const long long gstep = 4ll * cs;
+                if (!P.im2col && sg.dy == 0 && sg.dx == 0) {
+                    // centre tap / 1x1 kernel: pixel p is row p of the [P, cs] matrix -- no (b, y, x) decomposition, no clamp
+                    const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
+                    const float* g = src + p0 * cs + sg.c0 + c16 * 4;
+                    if ((long long)(tile + 1) * TILE_M <= P.P) {  // whole tile inside the image stack: no per-row predicate
+                        const uint32_t nbytes = ld_on ? 16u : 0u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            cp_async16(sbase + swz(rl0 + 4 * i, c16), g + i * gstep, nbytes, true);
+                            cp_async16(sbase + HB + swz(rl0 + 4 * i, c16), g + i * gstep + 32, nbytes, true);
+                        }
+                        return;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = p0 + 4 * i < P.P;
+                        const uint32_t nbytes = (ok && ld_on) ? 16u : 0u;
+                        cp_async16(sbase + swz(rl0 + 4 * i, c16), ok ? g + i * gstep : src, nbytes, true);
+                        cp_async16(sbase + HB + swz(rl0 + 4 * i, c16), ok ? g + i * gstep + 32 : src, nbytes, true);
+                    }
+                    return;
+                }
+                if (tile != coords_tile) {
+                    coords_tile = tile;
+                    // one division pair per tile; rows rl0 + 4*i follow by carry (x -> y -> b)
+                    const long long p0 = (long long)tile * TILE_M + quad * 32 + rl0;
+                    const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;  // P.P < 2^31 (checked on the host)
+                    const uint32_t t = q / W32;
+                    int x = (int)(q - t * W32);
+                    const uint32_t b0 = t / H32;
+                    int y = (int)(t - b0 * H32), b = (int)b0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pv[i] = p0 + 4 * i < P.P;
+                        px[i] = pv[i] ? x : 0; py[i] = pv[i] ? y : 0; pb[i] = pv[i] ? b : 0;
+                        x += 4;
+                        while (x >= P.W) {
+                            x -= P.W;
+                            if (++y == P.H) { y = 0; ++b; }
+                        }
+                    }
+                    uniform_rows = pv[7] && py[7] == py[0] && pb[7] == pb[0];
+                }
+                if (!P.im2col && uniform_rows) {
+                    // fast path: rows rl0 + 4*i are 4 pixels apart on one image row; only y may clamp (uniformly)
+                    const int xlo = px[0] + sg.dx, xhi = px[0] + 28 + sg.dx;
+                    if (xlo >= 0 && xhi < P.W) {
+                        const int yy = min(max(py[0] + sg.dy, 0), P.H - 1);
+                        const float* g = src + (((long long)pb[0] * P.H + yy) * P.W + xlo) * cs + sg.c0 + c16 * 4;
+                        const uint32_t nbytes = ld_on ? 16u : 0u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            cp_async16(sbase + swz(rl0 + 4 * i, c16), g + i * gstep, nbytes, true);
+                            cp_async16(sbase + HB + swz(rl0 + 4 * i, c16), g + i * gstep + 32, nbytes, true);
+                        }
+                        return;
+                    }
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    int dy = sg.dy, dx = sg.dx, coff = sg.c0 + hf * 32 + c16 * 4;
+                    bool tap_ok = true;
+                    if (P.im2col) {
+                        // chunk (hf, c16) of the im2col row = tap t of the 5x5 window (4 channels = one float4)
+                        const int t = sg.c0 * 16 + hf * 8 + c16;
+                        tap_ok = t < 25;
+                        dy = t / 5 - 2; dx = t % 5 - 2; coff = 0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int yy = min(max(py[i] + dy, 0), P.H - 1);
+                        const int xx = min(max(px[i] + dx, 0), P.W - 1);
+                        const float* g = src + (((long long)pb[i] * P.H + yy) * P.W + xx) * cs + coff;
+                        const uint32_t nbytes = (pv[i] && tap_ok && ld_on) ? 16u : 0u;  // 0 -> zero fill
+                        cp_async16(sbase + hf * HB + swz(rl0 + 4 * i, c16), g, nbytes, true);
+                    }
+                }
+            };
+            const long long n_total = (long long)n_items * P.nseg;  // length of the global segment stream
+            const int D = P.tb_depth;
+            // prefetch cursor over this group's segments s = grp, grp + LOAD_GROUPS, ...
+            long long pf_s = grp;
+            int pf_tile = first_tile, pf_sgi = grp, pf_slot = 0;
+            while (pf_sgi >= P.nseg) { pf_sgi -= P.nseg; pf_tile += tile_stride; }
+            auto prefetch_next = [&]() {
+                if (pf_s < n_total) issue_loads(pf_tile, pf_sgi, pf_slot);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                pf_s += LOAD_GROUPS;
+                pf_sgi += LOAD_GROUPS;
+                while (pf_sgi >= P.nseg) { pf_sgi -= P.nseg; pf_tile += tile_stride; }
+                if (++pf_slot == D) pf_slot = 0;
+            };
+            for (int n = 0; n < D - 1; ++n) prefetch_next();
+            int slot = 0;
+            stage_set(grp);
+            for (long long s = grp; s < n_total; s += LOAD_GROUPS) {
+                TCP(c0 = clock64();)
+                prefetch_next();
+                TCP(t_issue += clock64() - c0;)
+                if (D == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 2;" ::: "memory");
+                __syncwarp();
+                fill_stage(tb_u32 + (uint32_t)(slot * P.tb_bytes), lane);
+                __syncwarp();  // every lane has read its row before the slot is refilled
+                if (++slot == D) slot = 0;
+                stage_adv(LOAD_GROUPS);
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef MRB_TC_PROF
         if (P.prof && lane == 0 && lw == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
             o[0] = clock64() - t_start; o[1] = t_wait; o[2] = t_st; o[3] = t_issue; o[13] = t_stw;
         }
+#endif
     } else if (warp >= EPI_WARPS + LOAD_WARPS && warp < EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
         // ============================== MMA ISSUERS ==============================
-        // Issuer mi handles segments mi, mi + 2, ... of every tile (the same split as the loader groups).  All MMAs
-        // of one issuer go to its own accumulator group, so the two issue streams need no mutual ordering.
+        // Issuer mi handles segments s = mi, mi + NI, ... of the global segment stream.  All MMAs of one issuer go to its
+        // own accumulator group, so the two issue streams need no mutual ordering; the assignment is a fixed function of
+        // the geometry, so results are bit-reproducible.
         const int mi = warp - (EPI_WARPS + LOAD_WARPS);
         if (mi < P.n_issuers) {  // whole warp, warp-uniform control flow (see umma_commit)
             const int NI = P.n_issuers;
-            const bool prof = P.prof != nullptr;
+            TCP(const bool prof = P.prof != nullptr;)
             int stage = mi % P.stages;
             uint32_t phase = (uint32_t)(mi / P.stages) & 1u;
             int bs = mi % P.b_stages;
             uint32_t bphase = (uint32_t)(mi / P.b_stages) & 1u;
-            int it = 0;
-            long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, t_prep = 0, c0 = 0, c1 = 0;
+            TCP(long long t_start = clock64(), t_wfull = 0, t_wacc = 0, t_mma = 0, t_commit = 0, t_wb = 0, t_prep = 0, c0 = 0, c1 = 0;)
             int buf = 0;
             uint32_t acc_phase = 0;
             const uint32_t tmem_u = uni(tmem_base);
             const uint32_t w_u32 = smem_u32(w_s), bst_u32 = smem_u32(bst_s);
-            for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
-                if (prof) c0 = clock64();
+            const uint32_t grp_off = (uint32_t)(mi * P.group_cols);
+            int sgi = mi;  // segment index within the current tile
+            for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
+                TCP(if (prof) c0 = clock64();)
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
-                if (prof) t_wacc += clock64() - c0;
+                TCP(if (prof) t_wacc += clock64() - c0;)
                 tc_fence_after();
-                const uint32_t d_base = tmem_u + (uint32_t)(buf * P.acc_cols);
-                for (int sgi = mi; sgi < P.nseg; sgi += NI) {
-                    if (prof) c1 = clock64();
+                const uint32_t d_base = tmem_u + (uint32_t)(buf * P.acc_cols) + grp_off;
+                for (; sgi < P.nseg; sgi += NI) {
+                    TCP(if (prof) c1 = clock64();)
                     // every MMA operand is derived from kernel parameters and uniform loop state (no shared-memory
                     // table, no shuffles): it stays in uniform registers, and it is ready before the waits return
                     const Segment sg = P.seg[sgi];
@@ -917,23 +946,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     const uint32_t a_hi = tmem_u + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
                     const uint32_t d = d_base + (uint32_t)sg.dcol;
                     if (P.stream_b) {
-                        if (prof) c0 = clock64();
+                        TCP(if (prof) c0 = clock64();)
                         mbar_wait(&b_full[bs], bphase);
-                        if (prof) t_wb += clock64() - c0;
+                        TCP(if (prof) t_wb += clock64() - c0;)
                     }
-                    if (prof) c0 = clock64();
+                    TCP(if (prof) c0 = clock64();)
                     mbar_wait(&full[stage], phase);
-                    if (prof) t_wfull += clock64() - c0;
+                    TCP(if (prof) t_wfull += clock64() - c0;)
                     tc_fence_after();
-                    if (prof) { c0 = clock64(); t_prep += c0 - c1; }
-                    if (P.debug & 1) {
+                    TCP(if (prof) { c0 = clock64(); t_prep += c0 - c1; })
+                    if (TC_DBG(P, 1)) {
                     } else if (P.stacked) {
-                        // si.first: first segment of its accumulator group -> the N = 2n MMA of k-step 0 overwrites
-                        // [main | cross]; everything after it accumulates (MMAs of one thread execute in order)
+                        // first segment of this issuer's accumulator group in this tile (sgi < NI): the N = 2n MMA of
+                        // k-step 0 overwrites [main | cross]; everything after it accumulates (MMAs of one thread
+                        // execute in order)
                         umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc,
-                                                si.first ? 0u : 1u);
+                                                sgi < NI ? 0u : 1u);
                     } else if (si.first == 2) {
-                        // GRU x-part, first chunk: r/z columns accumulate onto the h-part, the i_n columns start here
+                        // GRU x-part: r/z columns accumulate onto the h-part, the i_n columns start here
                         umma_first_split(d, a_hi + KC, si.dbh, make_idesc(TILE_M, 2 * P.nhalf), make_idesc(TILE_M, P.nhalf),
                                          (uint32_t)(2 * P.nhalf));
                         umma_segment_ts(d, d, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc, 1u, 1u, 1u);
@@ -941,24 +971,27 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                         umma_segment_ts(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.dbl, si.idesc,
                                         si.first ? 0u : 1u, 1u, 0u);
                     }
-                    if (prof) { t_mma += clock64() - c0; c0 = clock64(); }
+                    TCP(if (prof) { t_mma += clock64() - c0; c0 = clock64(); })
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (P.stream_b) {
                         umma_commit(&b_empty[bs]);
                         bs += NI;
                         while (bs >= P.b_stages) { bs -= P.b_stages; bphase ^= 1u; }
                     }
-                    if (prof) t_commit += clock64() - c0;
+                    TCP(if (prof) t_commit += clock64() - c0;)
                     stage += NI;
                     while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
                 }
+                sgi -= P.nseg;
                 umma_commit(&acc_full[buf]);
                 if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
             }
+#ifdef MRB_TC_PROF
             if (prof && mi == 0 && lane == 0) {
                 unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
                 o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb; o[12] = t_prep;
             }
+#endif
         }
     } else if (warp == EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
         // ============================== WEIGHT STREAMER (stream_b) ==============================
@@ -967,7 +1000,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             int bs = 0;
             uint32_t bphase = 0;
             const uint32_t bytes = (uint32_t)(2 * wbytes_chunk);
-            for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
+            for (int it = 0; it < n_items; ++it) {
                 for (int sgi = 0; sgi < P.nseg; ++sgi) {
                     mbar_wait_sleep(&b_empty[bs], bphase ^ 1, 64);
                     const uint8_t* gsrc = reinterpret_cast<const uint8_t*>(P.wpack) + (size_t)P.seg[sgi].wchunk * bytes;
@@ -1012,8 +1045,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        if (GRU && !(P.debug & 4)) fetch_hprev(first_tile, et0);
-        long long e_start = clock64(), e_wait = 0;
+        if (GRU && !TC_DBG(P, 4)) fetch_hprev(first_tile, et0);
+        TCP(long long e_start = clock64(), e_wait = 0;)
         int buf = 0;
         uint32_t acc_phase = 0;
         for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride, ++it) {
@@ -1023,16 +1056,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const int ch0 = half * P.nhalf;
             bool released = false;
             const uint32_t et = et0 + (uint32_t)((it & 1) * EPI_TILE_BYTES);
-            if (GRU && !(P.debug & 4)) {
+            if (GRU && !TC_DBG(P, 4)) {
                 fetch_hprev(tile + tile_stride, et0 + (uint32_t)(((it + 1) & 1) * EPI_TILE_BYTES));  // next tile, other buffer
                 asm volatile("cp.async.wait_group 1;" ::: "memory");                                 // this tile's has landed
                 __syncwarp();
             }
-            long long c0 = clock64();
+            TCP(long long c0 = clock64();)
             mbar_wait_sleep(&acc_full[buf], acc_phase, 64);
-            e_wait += clock64() - c0;
+            TCP(e_wait += clock64() - c0;)
             tc_fence_after();
-            if (P.debug & 4) {
+            if (TC_DBG(P, 4)) {
             } else if (GRU) {
                 // nhalf == 32: this warp owns 16 channels (64 B) of its 32 pixels.  Thread = pixel is what TMEM dictates,
                 // but as a global access pattern it touches 32 different 128-byte lines per instruction (the L1 data
@@ -1180,10 +1213,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             }
             if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
         }
+#ifdef MRB_TC_PROF
         if (P.prof && threadIdx.x == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
             o[8] = clock64() - e_start; o[9] = e_wait;
         }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -1194,12 +1229,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------
-// dst chunk layout: [rows x 128 B] SWIZZLE_128B, hi then lo.  Source value for (half, chunk, row n, col k) is
-// given by a small descriptor evaluated on the device.
+// dst chunk layout: [rows x 128 B] SWIZZLE_128B (64 bf16 K elements per row), hi rows then lo rows.  Source value for
+// (half, chunk, row n, col k) is given by a small descriptor evaluated on the device.
 struct PackDesc {
     const float* w;       // conv: [Cout][Cin][k][k]; GRU: w_ih [3Ch][Cx] then w_hh via w2
     const float* w2;
-    int mode;             // 0 conv taps (chunk = tap*2 + kchunk), 1 GRU (chunks 0,1 = ih ; 2,3 = hh), 2 im2col 5x5x4
+    int mode;             // 0 conv taps (chunk = tap), 1 GRU (chunk 0 = hh, 1 = ih), 2 im2col 5x5x4 (chunk = 16 taps)
     int cout, cin, ksz;   // conv geometry
     int nhalf;            // output channels per split part
     int rows;             // rows per chunk
@@ -1207,43 +1242,43 @@ struct PackDesc {
     int n_split;
 };
 
-__global__ void pack_weights_kernel(PackDesc D, float* dst) {
-    const int total = D.n_split * D.n_chunks * D.rows * KC;
+__global__ void pack_weights_kernel(PackDesc D, uint16_t* dst) {
+    const int total = D.n_split * D.n_chunks * D.rows * KCH;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        int k = t % KC;
-        int r = (t / KC) % D.rows;
-        int ch = (t / (KC * D.rows)) % D.n_chunks;
-        int half = t / (KC * D.rows * D.n_chunks);
+        int k = t % KCH;
+        int r = (t / KCH) % D.rows;
+        int ch = (t / (KCH * D.rows)) % D.n_chunks;
+        int half = t / (KCH * D.rows * D.n_chunks);
         float v = 0.f;
         if (D.mode == 0) {
-            const int tap = ch >> 1, kc = ch & 1;
-            const int co = half * D.nhalf + r, ci = kc * KC + k;
+            const int tap = ch;
+            const int co = half * D.nhalf + r, ci = k;
             if (co < D.cout && ci < D.cin) v = D.w[((long long)co * D.cin + ci) * D.ksz * D.ksz + tap];
         } else if (D.mode == 1) {
-            // chunks 0,1: w_hh with rows [n ; r ; z] of this half (accumulator columns [0, 3*nhalf));
-            // chunks 2,3: w_ih with rows [r ; z ; n] (columns [nhalf, 4*nhalf)): the r and z columns are shared
+            // chunk 0: w_hh with rows [n ; r ; z] of this half (accumulator columns [0, 3*nhalf));
+            // chunk 1: w_ih with rows [r ; z ; n] (columns [nhalf, 4*nhalf)): the r and z columns are shared
             const int Ch = D.cout;
             const int blk = r / D.nhalf, j = r % D.nhalf;
-            const bool is_hh = ch < 2;
+            const bool is_hh = ch == 0;
             const int g = is_hh ? ((blk + 2) % 3) : blk;  // hh order n,r,z -> gate index 2,0,1
             const int row = g * Ch + half * D.nhalf + j;
             const float* w = is_hh ? D.w2 : D.w;
-            const int ci = (ch & 1) * KC + k;
-            v = w[(long long)row * D.cin + ci];
+            v = w[(long long)row * D.cin + k];
         } else {
-            // im2col of a 5x5 window over 4 channels: K index = tap*4 + ci, chunk ch covers taps 8*ch .. 8*ch+7
-            const int kk = ch * KC + k;
+            // im2col of a 5x5 window over 4 channels: K index = tap*4 + ci, chunk ch covers taps 16*ch .. 16*ch+15
+            const int kk = ch * KCH + k;
             const int tap = kk >> 2, ci = kk & 3;
             const int co = half * D.nhalf + r;
             if (tap < 25 && co < D.cout) v = D.w[((long long)co * 4 + ci) * 25 + tap];
         }
-        const float hi = tf32_rn(v);
-        const float lo = tf32_rn(v - hi);
-        const size_t chunk_floats = (size_t)D.rows * KC;
-        float* base = dst + ((size_t)half * D.n_chunks + ch) * 2 * chunk_floats;
-        const uint32_t off = (uint32_t)(r * 128 + (((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4);
-        base[off / 4] = hi;
-        base[chunk_floats + off / 4] = lo;
+        const uint16_t hi = bf16_rn_bits(v);
+        const float hif = __uint_as_float((uint32_t)hi << 16);
+        const uint16_t lo = bf16_rn_bits(v - hif);
+        const size_t chunk_elems = (size_t)D.rows * KCH;
+        uint16_t* base = dst + ((size_t)half * D.n_chunks + ch) * 2 * chunk_elems;
+        const uint32_t off = (uint32_t)(r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+        base[off / 2] = hi;
+        base[chunk_elems + off / 2] = lo;
     }
 }
 
@@ -1254,26 +1289,37 @@ static size_t smem_needed(const Params& P) {
            (P.mode == MODE_GRU ? (size_t)EPI_WARPS * 2 * EPI_TILE_BYTES : 0);
 }
 
+#ifdef MRB_TC_PROF
 static int g_debug = 0;
 static unsigned long long* g_prof = nullptr;
+#endif
 
 static int launch(Params& P, cudaStream_t st) {
+#ifdef MRB_TC_PROF
     P.debug = g_debug;
     P.prof = g_prof;
+#endif
     const size_t max_smem = device_max_smem_optin();
     P.tmem_cols = 512;
     P.stages = (512 - P.acc_bufs * P.acc_cols) / A_STAGE_COLS;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     MRB_REQUIRE(P.stages >= 2, MRB_EUNSUPPORTED, "tensor-core conv: accumulator leaves no room for the TMEM A ring");
     MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
-    MRB_REQUIRE((P.nseg % LOAD_GROUPS) == 0, MRB_EUNSUPPORTED, "tensor-core conv: odd segment count");
-    if (P.b_stages == 0) P.b_stages = B_STAGES;
-    P.tb_bytes = P.halo ? HALO_ROWS * 128 : TBUF_BYTES;
+    MRB_REQUIRE(P.nseg >= P.n_issuers && P.nseg <= MAX_SEGS, MRB_EUNSUPPORTED, "tensor-core conv: bad segment count");
+    MRB_REQUIRE(P.im2col != 2 || P.nseg == LOAD_GROUPS, MRB_EUNSUPPORTED, "tensor-core conv: patch mode needs one K chunk per loader group");
+    P.tb_half = (P.halo ? HALO_ROWS : 32) * 128;
+    P.tb_bytes = 2 * P.tb_half;
     P.tb_depth = P.halo ? 2 : 3;  // halo mode: one staging tile feeds k segments, current + next is enough
+    if (P.b_stages == 0) P.b_stages = B_STAGES;
     if (smem_needed(P) > max_smem) P.tb_depth = 2;
+    while (P.stream_b && P.b_stages > 2 && smem_needed(P) > max_smem) --P.b_stages;
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
-    MRB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    MRB_CUDA(cudaFuncSetAttribute(tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    static bool attr_set = false;  // per-process, not per launch (the attribute calls are not free)
+    if (!attr_set) {
+        MRB_CUDA(cudaFuncSetAttribute(tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        MRB_CUDA(cudaFuncSetAttribute(tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        attr_set = true;
+    }
     int sms = device_sm_count();
     int grid = (sms / P.n_split) * P.n_split;  // groups of n_split CTAs share a pixel tile
     if (grid > P.n_split * P.n_tiles) grid = P.n_split * P.n_tiles;
@@ -1288,22 +1334,26 @@ static int launch(Params& P, cudaStream_t st) {
 
 using namespace mrb;
 
+#ifdef MRB_TC_PROF
 extern "C" void mrb_tc_set_debug(int flags) { tc::g_debug = flags; }
 extern "C" void mrb_tc_set_prof(void* buf) { tc::g_prof = (unsigned long long*)buf; }
+#endif
 
 extern "C" size_t mrb_tc_packed_floats(int kind, int cout, int cin, int k) {
-    // kind 0: conv k x k (cin multiple of 32); 1: GRU 1x1 (cout = hidden, cin = 64 for both inputs); 2: conv 5x5 x 4ch
-    if (kind == 0) return (size_t)(k * k * (cin / 32)) * 2 * cout * 32;
-    if (kind == 1) return (size_t)2 * 4 * 2 * (3 * cout / 2) * 32;
-    return (size_t)4 * 2 * cout * 32;
+    // kind 0: conv k x k (cin == 64); 1: GRU 1x1 (cout = hidden, cin = 64 for both inputs); 2: conv 5x5 x 4ch.
+    // Size of the packed bf16 hi/lo image, in 4-byte units (one chunk = 2 x rows x 128 B = 2 * rows * 32 floats).
+    (void)cin;
+    if (kind == 0) return (size_t)(k * k) * 2 * cout * 32;
+    if (kind == 1) return (size_t)2 * 2 * 2 * (3 * cout / 2) * 32;
+    return (size_t)2 * 2 * cout * 32;
 }
 
 extern "C" int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int k, void* stream) {
     MRB_REQUIRE(w && dst, MRB_EINVAL, "mrb_tc_pack_conv: null pointer");
-    MRB_REQUIRE(cin == 64 && (cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS,
-                MRB_EUNSUPPORTED, "mrb_tc_pack_conv: need cin == 64, cout multiple of 32, k*k*2 <= %d", tc::MAX_SEGS);
-    tc::PackDesc D{(const float*)w, nullptr, 0, cout, cin, k, cout, cout, k * k * 2, 1};
-    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
+    MRB_REQUIRE(cin == 64 && (cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k <= tc::MAX_SEGS,
+                MRB_EUNSUPPORTED, "mrb_tc_pack_conv: need cin == 64, cout multiple of 32, k*k <= %d", tc::MAX_SEGS);
+    tc::PackDesc D{(const float*)w, nullptr, 0, cout, cin, k, cout, cout, k * k, 1};
+    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (uint16_t*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -1311,8 +1361,8 @@ extern "C" int mrb_tc_pack_conv(const void* w, void* dst, int cout, int cin, int
 extern "C" int mrb_tc_pack_gru(const void* w_ih, const void* w_hh, void* dst, int ch, int cx, void* stream) {
     MRB_REQUIRE(w_ih && w_hh && dst, MRB_EINVAL, "mrb_tc_pack_gru: null pointer");
     MRB_REQUIRE(ch == 64 && cx == 64, MRB_EUNSUPPORTED, "mrb_tc_pack_gru: tensor-core GRU needs 64 input and hidden channels");
-    tc::PackDesc D{(const float*)w_ih, (const float*)w_hh, 1, ch, cx, 1, ch / 2, 3 * ch / 2, 4, 2};
-    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
+    tc::PackDesc D{(const float*)w_ih, (const float*)w_hh, 1, ch, cx, 1, ch / 2, 3 * ch / 2, 2, 2};
+    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (uint16_t*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -1320,8 +1370,8 @@ extern "C" int mrb_tc_pack_gru(const void* w_ih, const void* w_hh, void* dst, in
 extern "C" int mrb_tc_pack_conv5x5x4(const void* w, void* dst, int cout, void* stream) {
     MRB_REQUIRE(w && dst, MRB_EINVAL, "mrb_tc_pack_conv5x5x4: null pointer");
     MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128, MRB_EUNSUPPORTED, "mrb_tc_pack_conv5x5x4: bad cout");
-    tc::PackDesc D{(const float*)w, nullptr, 2, cout, 4, 5, cout, cout, 4, 1};  // not split: N = cout per CTA
-    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (float*)dst);
+    tc::PackDesc D{(const float*)w, nullptr, 2, cout, 4, 5, cout, cout, 2, 1};  // not split: N = cout per CTA
+    tc::pack_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(D, (uint16_t*)dst);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -1357,46 +1407,47 @@ extern "C" int mrb_tc_indrnn_nhwc(const void* x, const void* h, const void* wpac
 static int tc_conv_launch(const void* x, const void* wpack, const void* bias, const void* hprev, const void* add_scale,
                           void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv_nhwc: null pointer");
-    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k * 2 <= tc::MAX_SEGS && dil >= 1,
+    MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k <= tc::MAX_SEGS && dil >= 1,
                 MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: unsupported geometry");
     tc::Params P;
     memset(&P, 0, sizeof(P));
     int rc = tc_common(P, B, H, W);
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = nullptr; P.cs[1] = 0;
-    P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
+    P.wpack = wpack; P.bias = (const float*)bias; P.out = (float*)out;
     P.hprev = (const float*)hprev; P.add_scale = (const float*)add_scale;
     // All output channels in one CTA (stacked MMAs of N = 2*cout and cout: half the MMA instructions of a channel
-    // split, which is what bounds this kernel); the k*k*2 weight chunks (2*cout*128 B each) do not fit shared memory
-    // next to the staging tiles, so each loader group streams the chunk of its segment from L2.
+    // split).  One segment per tap (64 input channels = one 128-byte bf16 row of B); the k*k weight chunks
+    // (2*cout*128 B each: hi rows | lo rows) are streamed from L2 through a small ring -- resident they would leave
+    // no room for the halo staging tiles.
     P.n_split = 1;
     P.stream_b = 1;
     P.cout = cout; P.nhalf = cout;
-    P.wchunk_rows = cout; P.n_wchunks = k * k * 2;
-    // accumulator groups (short accumulation chains, see Params::ngroups): as many as TMEM allows next to a 4-stage A ring
-    // two accumulator groups, one per MMA issuer (= K-chunk parity): fixed accumulation order inside a group
-    // (bit-reproducible), half-length chains (see Params::ngroups); the epilogue adds the groups
-    P.ngroups = 2;
-    P.n_issuers = 2;
+    P.wchunk_rows = cout; P.n_wchunks = k * k;
+    P.nseg = k * k;
+    // two accumulator groups, one per MMA issuer (the global segment stream alternates between them): fixed
+    // accumulation order inside a group (bit-reproducible), half-length chains (see Params::ngroups); the epilogue
+    // adds the groups.  A 1x1 kernel has a single segment per tile: one issuer, one group, two accumulator buffers.
+    P.n_issuers = P.nseg >= 2 ? 2 : 1;
+    P.ngroups = P.n_issuers;
+    P.group_cols = 2 * cout;
     MRB_REQUIRE(P.ngroups * 2 * cout <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");
     P.acc_cols = P.ngroups * 2 * cout;  // per group: hi*hi chain + cross-term chain
     P.small_off = cout;
     P.stacked = 1;
-    P.acc_bufs = 1;
+    P.acc_bufs = (P.ngroups == 1 && 2 * P.acc_cols <= 512 - 2 * tc::A_STAGE_COLS) ? 2 : 1;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
-    P.nseg = k * k * 2;
     const int pad = dil * (k - 1) / 2;
     P.ksz = k; P.dil = dil;
     // halo gathers need the two-piece staging layout to hold (4*pad extra rows) and a warp's 32 pixels on <= 2 image rows
     P.halo = (4 * pad <= tc::HALO_ROWS - 32 && W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 1 : 0;
-    for (int t = 0; t < k * k; ++t)
-        for (int kc = 0; kc < 2; ++kc) {
-            tc::Segment& s = P.seg[t * 2 + kc];
-            s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
-            s.c0 = (short)(kc * 32); s.wchunk = (short)(t * 2 + kc); s.dcol = (short)(kc * 2 * cout);
-            s.n = (short)cout;
-            s.first = (short)(t == 0);  // one accumulator group per K-chunk parity = per issuer
-        }
+    for (int t = 0; t < k * k; ++t) {
+        tc::Segment& s = P.seg[t];
+        s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
+        s.c0 = 0; s.wchunk = (short)t; s.dcol = 0;
+        s.n = (short)cout;
+        s.first = 0;  // stacked issue: derived from the segment index
+    }
     return tc::launch(P, (cudaStream_t)stream);
 }
 
@@ -1410,24 +1461,25 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
     int rc = tc_common(P, B, H, W);
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 4;
-    P.wpack = (const float*)wpack; P.bias = (const float*)bias; P.out = (float*)out;
-    P.n_split = 1;  // all output channels in one CTA: weights (4 chunks x 2 x cout x 128 B) stay resident
+    P.wpack = wpack; P.bias = (const float*)bias; P.out = (float*)out;
+    P.n_split = 1;  // all output channels in one CTA: weights (2 chunks x 2 x cout x 128 B) stay resident
     P.cout = cout; P.nhalf = cout;
-    P.wchunk_rows = cout; P.n_wchunks = 4;
+    P.wchunk_rows = cout; P.n_wchunks = 2;
     P.ngroups = 1;
     P.n_issuers = 1;
+    P.group_cols = 0;
     P.acc_cols = 2 * cout;
     P.small_off = cout;
     P.stacked = 1;
     P.acc_bufs = 2;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
     P.im2col = (W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 2 : 1;  // 2: taps assembled from a shared-memory halo patch
-    P.nseg = 4;
-    for (int c = 0; c < 4; ++c) {
+    P.nseg = 2;  // K = 25 taps x 4 channels = 100, padded to two 64-wide chunks
+    for (int c = 0; c < 2; ++c) {
         tc::Segment& s = P.seg[c];
         s.src = 0; s.dy = 0; s.dx = 0; s.c0 = (short)c; s.wchunk = (short)c; s.dcol = 0;
         s.n = (short)cout;
-        s.first = (short)(c == 0);
+        s.first = 0;
     }
     return tc::launch(P, (cudaStream_t)stream);
 }
@@ -1443,29 +1495,26 @@ extern "C" int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, 
     int rc = tc_common(P, B, H, W);
     if (rc) return rc;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = (const float*)h; P.cs[1] = 64;
-    P.wpack = (const float*)wpack; P.bias = (const float*)b_ih; P.hprev = (const float*)h; P.out = (float*)h_out;
+    P.wpack = wpack; P.bias = (const float*)b_ih; P.hprev = (const float*)h; P.out = (float*)h_out;
     // Channel split (two CTAs per pixel tile, N = 96 MMAs), weights resident, two 128-column accumulator buffers.
-    // The alternative -- all 192 gate rows in one CTA with streamed weights (N = 192, execution-bound MMAs) -- was
-    // measured equal (221 vs 188-219 us at B=4): 256 accumulator columns leave no room for a second buffer, and the gate
-    // epilogue (TMEM read 64 B/clk + 6 SFU ops per output) then serialises with the MMAs.
     P.n_split = 2;
     P.cout = ch; P.nhalf = ch / 2;
-    P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 4;
+    P.wchunk_rows = 3 * ch / 2; P.n_wchunks = 2;
     // accumulator columns (nh = ch/2): [0,nh) = hh_n, [nh,2nh) = r, [2nh,3nh) = z (hh + ih summed by the tensor core),
-    // [3nh,4nh) = ih_n.  h-part: N = 3nh at column 0; x-part: N = 3nh at column nh.  The first h chunk overwrites its
-    // columns, the first x chunk accumulates onto r/z and overwrites ih_n (Segment::first = 2).
+    // [3nh,4nh) = ih_n.  h-part: N = 3nh at column 0; x-part: N = 3nh at column nh.  The h segment overwrites its
+    // columns, the x segment accumulates onto r/z and overwrites ih_n (Segment::first = 2).
     P.ngroups = 1;
     P.n_issuers = 1;
+    P.group_cols = 0;
     P.acc_cols = 4 * (ch / 2);
     P.acc_bufs = 2;
     P.mode = tc::MODE_GRU;
-    P.nseg = 4;
-    for (int i = 0; i < 4; ++i) {
+    P.nseg = 2;  // segment 0: h (64 channels), segment 1: x
+    for (int i = 0; i < 2; ++i) {
         tc::Segment& s = P.seg[i];
-        const int is_x = i >> 1;
-        s.src = (short)(is_x ? 0 : 1); s.dy = 0; s.dx = 0; s.c0 = (short)((i & 1) * 32); s.wchunk = (short)i;
-        s.dcol = (short)(is_x ? ch / 2 : 0); s.n = (short)(3 * ch / 2);
-        s.first = (short)(i == 0 ? 1 : (i == 2 ? 2 : 0));
+        s.src = (short)(i ? 0 : 1); s.dy = 0; s.dx = 0; s.c0 = 0; s.wchunk = (short)i;
+        s.dcol = (short)(i ? ch / 2 : 0); s.n = (short)(3 * ch / 2);
+        s.first = (short)(i == 0 ? 1 : 2);
     }
     return tc::launch(P, (cudaStream_t)stream);
 }

@@ -392,7 +392,7 @@ def test_cirim_full_config_vs_oracle(layer, centered, norm):
     assert e <= 1e-4, e
     assert _same_to_4_decimals(_metrics(out[-1][-1].cpu().numpy(), batch["target"].numpy()),
                                _metrics(ref[-1][-1].numpy(), batch["target"].numpy()))
-    assert rel_l2(out[0][0], ref[0][0]) <= 1e-5
+    assert rel_l2(out[0][0], ref[0][0]) <= 3e-5  # one time step on the split-bf16 tensor-core kernels (~3e-6 per operator)
 
 
 def test_cirim_brain_geometry_vs_oracle():

@@ -1,7 +1,8 @@
-"""GPU: tensor-core (tcgen05 / TMEM, 3xTF32) RIM regulariser kernels against the CPU oracle and the exact-fp32
-CUDA-core kernels.  Tolerance: rel-L2 <= 5e-6 per operator: the error-compensated 3xTF32 products are fp32-grade
-(~2^-23); what remains is the tensor core's truncating fp32 accumulation over the K chain (measured 1e-6 .. 3e-6
-at K = 576).  Plain TF32 would sit at ~5e-4; the end-to-end budget is 1e-4 with ~2x amplification."""
+"""GPU: tensor-core (tcgen05 / TMEM, bf16 hi/lo split) RIM regulariser kernels against the CPU oracle and the
+exact-fp32 CUDA-core kernels.  Tolerance: rel-L2 <= 1e-5 per operator: every operand is carried as hi + lo bf16
+(16-17 significant bits) and a_lo*b_lo is dropped, ~3e-6 rms per product, plus the tensor core's truncating fp32
+accumulation over the K chain.  Plain BF16 would sit at ~4e-3, plain TF32 at ~5e-4; the end-to-end budget is 1e-4
+(rel-L2 on the reconstruction) and a CPU emulation of this arithmetic over CIRIM 5x8 lands at 2.5e-5."""
 import numpy as np
 import pytest
 import torch
@@ -14,6 +15,7 @@ pytestmark = pytest.mark.gpu
 def _diag(out_nchw, ref, tol, what):
     """rel-L2 check that reports where the error sits (pixels / channels) when it fails."""
     e = rel_l2(out_nchw, ref)
+    print("[tc parity] %-16s rel-L2 %.2e (tol %.0e)" % (what, e, tol))  # visible with pytest -s
     if e >= tol:
         o = torch.as_tensor(out_nchw).detach().cpu().float()
         d = (o - ref).abs()
@@ -65,7 +67,7 @@ def test_tc_ops_vs_oracle(B, H, W):
     out = torch.empty(B, H, W, 64, device="cuda")
     x4d, p1, b1d = nhwc(x4), _pack(2, w1.cuda()), b1.cuda()
     _lib.check(lib.mrb_tc_conv5x5x4_nhwc(_lib.ptr(x4d), _lib.ptr(p1), _lib.ptr(b1d), _lib.ptr(out), B, H, W, 64, 1, st))
-    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "conv5x5x4")
+    _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "conv5x5x4")
     # conv 3x3 dilation 2 (and dilation 1), 64 -> 64
     x = torch.randn(B, 64, H, W, generator=g)
     xd = nhwc(x)
@@ -76,7 +78,7 @@ def test_tc_ops_vs_oracle(B, H, W):
         p2, b2d = _pack(0, w2.cuda(), k=3), b2.cuda()
         _lib.check(lib.mrb_tc_conv_nhwc(_lib.ptr(xd), _lib.ptr(p2), _lib.ptr(b2d), _lib.ptr(out), B, H, W, 64, 3, dil,
                                         relu, st))
-        _diag(out.permute(0, 3, 1, 2), ref, 5e-6, "conv3x3 dil %d" % dil)
+        _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "conv3x3 dil %d" % dil)
     # ConvGRU cell, kernel size 1
     h = torch.randn(B, 64, H, W, generator=g)
     wih = torch.randn(192, 64, 1, 1, generator=g) * 0.1
@@ -86,7 +88,7 @@ def test_tc_ops_vs_oracle(B, H, W):
     hd, pg, bihd = nhwc(h), _pack(1, wih.cuda(), whh.cuda()), bih.cuda()
     _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pg), _lib.ptr(bihd), _lib.ptr(out), B, H, W, 64,
                                    st))
-    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "gru")
+    _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "gru")
     # IndRNN cell, kernel size 1: ReLU(ih(x) + hh * h) (rnn_cells.py:391) = 1x1 tensor-core conv + recurrent epilogue
     wi = torch.randn(64, 64, 1, 1, generator=g) * 0.1
     bi = torch.randn(64, generator=g)
@@ -95,7 +97,7 @@ def test_tc_ops_vs_oracle(B, H, W):
     pi, bid, hhd = _pack(0, wi.cuda(), k=1), bi.cuda(), hhw.reshape(-1).cuda()
     _lib.check(lib.mrb_tc_indrnn_nhwc(_lib.ptr(xd), _lib.ptr(hd), _lib.ptr(pi), _lib.ptr(bid), _lib.ptr(hhd), _lib.ptr(out),
                                       B, H, W, 64, st))
-    _diag(out.permute(0, 3, 1, 2), ref, 2e-6, "indrnn")
+    _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "indrnn")
     # final conv 64 -> 2 with the eta update
     w3 = torch.randn(2, 64, 3, 3, generator=g) * 0.05
     eta = torch.randn(B, H, W, 2, generator=g)
@@ -153,18 +155,18 @@ def test_rim_block_tc_vs_fp32_and_oracle(monkeypatch, layer):
     etas, hx = blk(y.cuda(), y.cuda(), S.cuda(), m.cuda(), None, None, 1.0, False)
     assert blk._tc_engine and len(etas) == 8
     assert hx[0].shape == (2, 64, 48, 40)
-    for a, b in zip(etas, ref):
-        assert rel_l2(a, b) < 1e-5
-    assert rel_l2(hx[0], ref_h[0]) < 1e-5 and rel_l2(hx[1], ref_h[1]) < 1e-5
+    for a, b in zip(etas, ref):  # 8 time steps of split-bf16 convs: ~3e-6 per operator, budget 3e-5 per block
+        assert rel_l2(a, b) < 3e-5
+    assert rel_l2(hx[0], ref_h[0]) < 3e-5 and rel_l2(hx[1], ref_h[1]) < 3e-5
     monkeypatch.setenv("MRIDC_B200_DISABLE_TC", "1")
     etas32, hx32 = blk(y.cuda(), y.cuda(), S.cuda(), m.cuda(), None, None, 1.0, False)
-    assert rel_l2(etas[-1], etas32[-1]) < 1e-5 and rel_l2(hx[1], hx32[1]) < 1e-5
+    assert rel_l2(etas[-1], etas32[-1]) < 3e-5 and rel_l2(hx[1], hx32[1]) < 3e-5
     # continuing from given hidden states (NCHW in, as the reference API)
     monkeypatch.delenv("MRIDC_B200_DISABLE_TC")
     e2, h2 = blk(etas, y.cuda(), S.cuda(), m.cuda(), None, [t.contiguous() for t in hx32], 1.0, True)
     with torch.no_grad():
         r2, _ = onets.rim_block(sd, dict(cfg), ref, y, S, m, None, [t.clone() for t in ref_h], 1.0, True)
-    assert rel_l2(e2[-1], r2[-1]) < 2e-5
+    assert rel_l2(e2[-1], r2[-1]) < 5e-5
 
 
 def test_tc_kernels_are_deterministic():

@@ -1,7 +1,8 @@
 #!/bin/bash
-# One GPU-box visit: smoke, parity tests, bench, ncu launch list.  Logs land in gpurun_out/.
+# One GPU-box visit: TC parity first (fast fail), full parity suite, role profile, bench.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== smoke" ; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -5 gpurun_out/smoke.log
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -40 gpurun_out/pytest_gpu.log
-echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+echo "== tc tests"; timeout 900 python -m pytest tests/test_gpu_tc.py -x -q -s --timeout=600 > gpurun_out/pytest_tc.log 2>&1; echo "tc rc=$?"; grep -E "tc parity|passed|failed|Error|error" gpurun_out/pytest_tc.log | tail -40
+echo "== roles"; timeout 300 python tools/tc_roles.py 4 > gpurun_out/roles.log 2>&1; echo "roles rc=$?"; tail -12 gpurun_out/roles.log
+echo "== pytest gpu"; timeout 1800 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.log; tail -5 gpurun_out/bench.err

@@ -2,7 +2,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mridc_b200 import _lib
-lib = _lib.load(); st = _lib.stream_ptr()
+import _toolslib
+lib = _toolslib.load(); st = _lib.stream_ptr()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 iters = 960
 print("tcgen05.mma kind::tf32 M=128 K=8: cycles per MMA (issue / to-completion), %d MMAs" % iters)
@@ -12,7 +13,7 @@ for a_tmem in (2, 6):
         for nacc in (1,):
             if nacc * N > 448:
                 continue
-            _lib.check(lib.mrb_tc_microbench(N, nacc, iters, a_tmem, _lib.ptr(out), st))
+            assert 0 == (lib.mrb_tc_microbench(N, nacc, iters, a_tmem, _lib.ptr(out), st))
             torch.cuda.synchronize()
             o = out.tolist()
             row.append("nacc=%d: %5.1f / %5.1f" % (nacc, o[0] / iters, o[1] / iters))

@@ -5,7 +5,8 @@ import torch
 import mridc_b200 as mb
 from mridc_b200 import _lib, synth
 from mridc_b200.rim_tc import RimTcEngine
-lib = _lib.load(); st = _lib.stream_ptr()
+import _toolslib
+lib = _toolslib.load(); st = _lib.stream_ptr()   # profiling build of the same kernels (weights packed by the product library)
 B, H, W = int(sys.argv[1]) if len(sys.argv) > 1 else 1, 320, 320
 dev = torch.device("cuda")
 model = mb.CIRIM(synth.cirim_cfg("GRU")).cuda().eval()
