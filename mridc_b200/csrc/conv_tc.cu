@@ -906,9 +906,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
 #endif
     } else if (warp >= EPI_WARPS + LOAD_WARPS && warp < EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
         // ============================== MMA ISSUERS ==============================
-        // Issuer mi handles segments s = mi, mi + NI, ... of the global segment stream.  All MMAs of one issuer go to its
-        // own accumulator group, so the two issue streams need no mutual ordering; the assignment is a fixed function of
-        // the geometry, so results are bit-reproducible.
+        // Issuer mi handles segments mi, mi + NI, ... of every tile.  All MMAs of one issuer go to its own accumulator
+        // group, so the two issue streams need no mutual ordering; the assignment does not depend on the tile index,
+        // so a pixel's result is bit-identical run to run and whatever the batch it is part of.
         const int mi = warp - (EPI_WARPS + LOAD_WARPS);
         if (mi < P.n_issuers) {  // whole warp, warp-uniform control flow (see umma_commit)
             const int NI = P.n_issuers;
@@ -923,14 +923,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             const uint32_t tmem_u = uni(tmem_base);
             const uint32_t w_u32 = smem_u32(w_s), bst_u32 = smem_u32(bst_s);
             const uint32_t grp_off = (uint32_t)(mi * P.group_cols);
-            int sgi = mi;  // segment index within the current tile
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
                 TCP(if (prof) c0 = clock64();)
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
                 TCP(if (prof) t_wacc += clock64() - c0;)
                 tc_fence_after();
                 const uint32_t d_base = tmem_u + (uint32_t)(buf * P.acc_cols) + grp_off;
-                for (; sgi < P.nseg; sgi += NI) {
+                for (int sgi = mi; sgi < P.nseg; sgi += NI) {
                     TCP(if (prof) c1 = clock64();)
                     // every MMA operand is derived from kernel parameters and uniform loop state (no shared-memory
                     // table, no shuffles): it stays in uniform registers, and it is ready before the waits return
@@ -957,7 +956,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     TCP(if (prof) { c0 = clock64(); t_prep += c0 - c1; })
                     if (TC_DBG(P, 1)) {
                     } else if (P.stacked) {
-                        // first segment of this issuer's accumulator group in this tile (sgi < NI): the N = 2n MMA of
+                        // first segment of this issuer's accumulator group in this tile (sgi == mi): the N = 2n MMA of
                         // k-step 0 overwrites [main | cross]; everything after it accumulates (MMAs of one thread
                         // execute in order)
                         umma_segment_ts_stacked(d, d + (uint32_t)P.small_off, a_hi, a_hi + KC, si.dbh, si.idesc2n, si.idesc,
@@ -973,16 +972,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                     }
                     TCP(if (prof) { t_mma += clock64() - c0; c0 = clock64(); })
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    // distance (in the global segment stream) to this issuer's next segment: NI inside the tile, else
+                    // to segment mi of the next tile
+                    const int delta = (sgi + NI < P.nseg) ? NI : (P.nseg - sgi + mi);
                     if (P.stream_b) {
                         umma_commit(&b_empty[bs]);
-                        bs += NI;
+                        bs += delta;
                         while (bs >= P.b_stages) { bs -= P.b_stages; bphase ^= 1u; }
                     }
                     TCP(if (prof) t_commit += clock64() - c0;)
-                    stage += NI;
+                    stage += delta;
                     while (stage >= P.stages) { stage -= P.stages; phase ^= 1u; }
                 }
-                sgi -= P.nseg;
                 umma_commit(&acc_full[buf]);
                 if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
             }

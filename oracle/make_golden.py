@@ -564,13 +564,57 @@ def gen_sens(R):
     print("sens.npz: %d arrays" % len(out))
 
 
+def gen_apply_mask(R):
+    """common/parts/utils.py:293-343: the reference's apply_mask on seeded k-space with its own mask functions
+    (seeded 1-D equispaced / random, padding zeroing, fftshift of a 2-D mask); mridc_b200.utils.apply_mask must
+    reproduce data, mask and acceleration bit for bit (tests/test_host_logic.py, tests/test_gpu_parity.py)."""
+    from mridc_b200 import synth, utils as mutils
+
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    cases = [
+        ("equi", R.subsample.Equispaced1DMaskFunc, synth.Equispaced1DMask, [0.08], [4], (3, 24, 40, 2), 123, None, False),
+        ("rand_pad", R.subsample.RandomMaskFunc, synth.RandomMask1D, [0.08], [4], (2, 3, 16, 48, 2), (1, 2, 3), (6, 40), False),
+        ("equi2d_shift", R.subsample.Equispaced2DMaskFunc, None, [0.08], [4], (2, 30, 36, 2), 5, None, True),
+        ("rand_pad0", R.subsample.RandomMaskFunc, synth.RandomMask1D, [0.04], [8], (1, 12, 64, 2), 9, (0, 50), False),
+    ]
+    for i, (name, rcls, mcls, cf, acc, shape, seed, padding, shift) in enumerate(cases):
+        data = torch.randn(*shape, generator=g)
+        data[..., 0, 0, :] = -0.0  # the "+ 0.0" of utils.py:341 must clear the sign of zeros
+        rd, rm, ra = R.utils.apply_mask(data.clone(), rcls(cf, acc), seed=seed, padding=padding, shift=shift)
+        if mcls is None:
+            # 2-D mask functions are not restated in the package (a23 covers the 1-D ones + Gaussian + the cached
+            # Poisson mask): replay the reference's raw mask through a fixed mask function
+            shp = np.array(data.shape); shp[:-3] = 1
+            raw, racc = rcls(cf, acc)(shp, seed, half_scan_percentage=0.0, scale=0.02)
+            out["am%d_raw" % i] = raw.numpy()
+
+            def fixed(shape, seed, half_scan_percentage=0.0, scale=0.02, _m=raw, _a=racc):
+                return _m.clone(), _a
+
+            md, mm, ma = mutils.apply_mask(data.clone(), fixed, seed=seed, padding=padding, shift=shift)
+        else:
+            md, mm, ma = mutils.apply_mask(data.clone(), mcls(cf, acc), seed=seed, padding=padding, shift=shift)
+        assert torch.equal(rd, md) and torch.equal(rm, mm) and ra == ma, name
+        assert torch.equal(torch.signbit(rd), torch.signbit(md)), name
+        out.update({"am%d_in" % i: data.numpy(), "am%d_out" % i: rd.numpy(), "am%d_mask" % i: rm.numpy(),
+                    "am%d_acc" % i: np.asarray(ra), "am%d_seed" % i: np.asarray(seed),
+                    "am%d_pad" % i: np.asarray(padding if padding is not None else (-1, -1)),
+                    "am%d_cfg" % i: np.asarray([["equi", "rand_pad", "equi2d_shift", "rand_pad0"].index(name), int(shift)]),
+                    "am%d_cf" % i: np.asarray(cf), "am%d_accs" % i: np.asarray(acc)})
+    out["nam"] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(GOLDEN, "apply_mask.npz"), **out)
+    print("apply_mask: %d cases" % len(cases))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
     R = Ref()
     only = set(sys.argv[1:])  # e.g. `python -m oracle.make_golden qmri` regenerates one fixture file
     for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("unet", gen_unet),
-                     ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens)):
+                     ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens),
+                     ("apply_mask", gen_apply_mask)):
         if not only or name in only:
             fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))

@@ -230,6 +230,13 @@ def test_cpu_tensor_raises():
         mb.complex_mul(x, x)
 
 
+def test_apply_mask_on_device_golden(golden):
+    """apply_mask (a10) with the k-space already on the GPU: same bits as the reference on the CPU."""
+    from test_host_logic import _replay_apply_mask
+
+    _replay_apply_mask(golden, "cuda")
+
+
 # ---------------------------------------------------------------------------------------------- blocks
 def _rim_block(hp, sd):
     from mridc_b200.rim import RIMBlock
@@ -363,6 +370,18 @@ def _metrics(pred, target):
     return float(om.ssim(t, o, maxval=R)), float(om.psnr(t, o, maxval=R))
 
 
+def _fp64(sd):
+    return {k: v.double() for k, v in sd.items()}
+
+
+def _report(name, out, ref32, ref64):
+    """Distance of the CUDA result to the fp32 oracle (the contract, <= 1e-4) and to an fp64 run of the same oracle
+    (the fp32 CPU run is itself ~3e-5 away from fp64 for the 40-step random-init network)."""
+    e32, e64, f = rel_l2(out, ref32), rel_l2(out, ref64), rel_l2(ref32, ref64)
+    print("[parity] %-38s rel-L2 vs fp32 oracle %.2e | vs fp64 oracle %.2e | fp32 oracle vs fp64 %.2e" % (name, e32, e64, f))
+    return e32
+
+
 def _same_to_4_decimals(a, b):
     """"Equal to 4 decimals": the two values agree to within one unit of the 4th decimal (a plain round()==round()
     comparison flips on rounding boundaries for differences of 1e-6)."""
@@ -386,9 +405,11 @@ def test_cirim_full_config_vs_oracle(layer, centered, norm):
     with torch.no_grad():
         ref = omodels.cirim_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None,
                                     batch["target"])
+        ref64 = omodels.cirim_forward(_fp64(sd), cfg, batch["y"].double(), batch["sensitivity_maps"].double(),
+                                      batch["mask"], None, batch["target"])
     out = next(model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
                             batch["target"].cuda()))
-    e = rel_l2(out[-1][-1], ref[-1][-1])
+    e = _report("CIRIM 5x8 %s centered=%s %s" % (layer, centered, norm), out[-1][-1], ref[-1][-1], ref64[-1][-1])
     assert e <= 1e-4, e
     assert _same_to_4_decimals(_metrics(out[-1][-1].cpu().numpy(), batch["target"].numpy()),
                                _metrics(ref[-1][-1].numpy(), batch["target"].numpy()))
@@ -420,27 +441,69 @@ def test_cirim_brain_geometry_vs_oracle():
     assert _same_to_4_decimals((ev["ssim"], ev["psnr"]), host), (ev, host)
 
 
-def test_varnet_full_config_vs_oracle():
-    """Config 2: E2EVN 12 cascades, 14 channels, 2 pools, 15 x 320 x 320, Gaussian-1D 4x mask."""
+@pytest.mark.parametrize("accel", [4, 8])
+def test_varnet_full_config_vs_oracle(accel):
+    """Config 2: E2EVN 12 cascades, 14 channels, 2 pools, 15 x 320 x 320, Gaussian-1D 4x and 8x masks."""
     import mridc_b200 as mb
     from mridc_b200 import synth
     from oracle import models as omodels
 
     cfg = synth.varnet_cfg()
     np.random.seed(123)
-    batch = synth.make_batch(1, 15, 320, 320, synth.Gaussian1DMask([0.7], [4]), seed=None)
+    batch = synth.make_batch(1, 15, 320, 320, synth.Gaussian1DMask([0.7], [accel]), seed=None)
     torch.manual_seed(1)
     model = mb.VarNet(cfg).eval()
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     with torch.no_grad():
         ref = omodels.varnet_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None,
                                      batch["target"])
+        ref64 = omodels.varnet_forward(_fp64(sd), cfg, batch["y"].double(), batch["sensitivity_maps"].double(),
+                                       batch["mask"], None, batch["target"])
     out = model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
                        batch["target"].cuda())
-    e = rel_l2(out, ref)
+    e = _report("E2EVN 12 cascades Gaussian1D %dx" % accel, out, ref, ref64)
     assert e <= 1e-4, e
     assert _same_to_4_decimals(_metrics(out.cpu().numpy(), batch["target"].numpy()),
                                _metrics(ref.numpy(), batch["target"].numpy()))
+
+
+def test_config3_brain_full_depth_vs_oracle():
+    """Config 4 (BASELINE.json configs[3]) at full depth, one brain-shaped slice (16 x 640 x 320, 8x equispaced mask):
+    CIRIM 5 cascades x 8 steps and E2EVN 12 cascades against the CPU oracle, with the distance to fp64 reported."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    batch = synth.make_batch(1, 16, 640, 320, mask_func=synth.Equispaced1DMask([0.04], [8]))
+    dev = [batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None, batch["target"].cuda()]
+    cfg = synth.cirim_cfg("GRU")
+    torch.manual_seed(2)
+    model = mb.CIRIM(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = omodels.cirim_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None, batch["target"])
+        ref64 = omodels.cirim_forward(_fp64(sd), cfg, batch["y"].double(), batch["sensitivity_maps"].double(),
+                                      batch["mask"], None, batch["target"])
+    out = next(model.cuda()(*dev))
+    assert len(out) == 5 and len(out[0]) == 8 and out[-1][-1].shape == (1, 640, 320)
+    e = _report("CIRIM 5x8 GRU brain 16x640x320 8x", out[-1][-1], ref[-1][-1], ref64[-1][-1])
+    assert e <= 1e-4, e
+    assert _same_to_4_decimals(_metrics(out[-1][-1].cpu().numpy(), batch["target"].numpy()),
+                               _metrics(ref[-1][-1].numpy(), batch["target"].numpy()))
+    vcfg = synth.varnet_cfg()
+    torch.manual_seed(3)
+    vn = mb.VarNet(vcfg).eval()
+    vsd = {k: v.detach().clone() for k, v in vn.state_dict().items()}
+    with torch.no_grad():
+        vref = omodels.varnet_forward(vsd, vcfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None, batch["target"])
+        vref64 = omodels.varnet_forward(_fp64(vsd), vcfg, batch["y"].double(), batch["sensitivity_maps"].double(),
+                                        batch["mask"], None, batch["target"])
+    vo = vn.cuda()(*dev)
+    assert vo.shape == (1, 640, 320)
+    e = _report("E2EVN 12 cascades brain 16x640x320 8x", vo, vref, vref64)
+    assert e <= 1e-4, e
+    assert _same_to_4_decimals(_metrics(vo.cpu().numpy(), batch["target"].numpy()),
+                               _metrics(vref.numpy(), batch["target"].numpy()))
 
 
 def test_zf_config1_vs_oracle_and_crop():

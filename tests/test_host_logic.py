@@ -229,3 +229,38 @@ def test_sens_net_initialiser_and_bookkeeping_match_reference():
                      mask_type="2D", normalize=True, mask_center=True).state_dict()
     for k, v in ref_first.items():
         assert torch.equal(ours["sens_net." + k], v), k
+
+
+def _replay_apply_mask(golden, device):
+    """tests/golden/apply_mask.npz (oracle/make_golden.py::gen_apply_mask): the reference's apply_mask
+    (common/parts/utils.py:293-343) on seeded k-space -- data, mask and acceleration must come back bit for bit,
+    including the cleared sign of zeros (":341 + 0.0"), the padding zeroing (:332-335) and the mask fftshift (:337-338)."""
+    from mridc_b200 import synth, utils as mutils
+
+    g = golden("apply_mask")
+    for i in range(int(g["nam"])):
+        kind, shift = (int(v) for v in g["am%d_cfg" % i])
+        cf, acc = [float(v) for v in g["am%d_cf" % i]], [int(v) for v in g["am%d_accs" % i]]
+        seed = g["am%d_seed" % i]
+        seed = int(seed) if seed.ndim == 0 else tuple(int(v) for v in seed)
+        pad = tuple(int(v) for v in g["am%d_pad" % i])
+        pad = None if pad == (-1, -1) else pad
+        if kind == 2:  # 2-D equispaced mask drawn by the reference, replayed through a fixed mask function
+            raw, racc = torch.from_numpy(g["am%d_raw" % i]), float(g["am%d_acc" % i])
+
+            def fn(shape, seed, half_scan_percentage=0.0, scale=0.02, _m=raw, _a=racc):
+                return _m.clone(), _a
+        else:
+            fn = (synth.Equispaced1DMask if kind == 0 else synth.RandomMask1D)(cf, acc)
+        data = torch.from_numpy(g["am%d_in" % i]).to(device)
+        out, mask, a = mutils.apply_mask(data, fn, seed=seed, padding=pad, shift=bool(shift))
+        assert out.device == data.device and mask.device == data.device
+        ref = torch.from_numpy(g["am%d_out" % i])
+        assert torch.equal(out.cpu(), ref), i
+        assert torch.equal(torch.signbit(out.cpu()), torch.signbit(ref)), i
+        assert torch.equal(mask.cpu(), torch.from_numpy(g["am%d_mask" % i])), i
+        assert float(a) == float(g["am%d_acc" % i]), i
+
+
+def test_apply_mask_golden(golden):
+    _replay_apply_mask(golden, "cpu")
