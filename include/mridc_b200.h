@@ -229,6 +229,37 @@ int mrb_tc_gru_nhwc(const void* x, const void* h, const void* wpack, const void*
  * [ch, 64, 1, 1]; b_ih [ch] or null; hh [ch] (the per-channel recurrent weight): h_out = ReLU(ih(x) + hh * h) */
 int mrb_tc_indrnn_nhwc(const void* x, const void* h, const void* wpack, const void* b_ih, const void* hh, void* h_out,
                        int B, int H, int W, int ch, void* stream);
+/* ---------------------------------------------------------------------------------------------------
+ * Second-generation tensor-core engine: split-bf16 ("BH") activations, TMA + shared-memory operands.
+ * BH layout: [B][H+4][W+4][hi 64 bf16 | lo 64 bf16] (x ~= hi + lo; 256 B per pixel; replicate border of 2 pixels, which
+ * is ConvNonlinear's ReplicationPad2d, conv_layers.py:72-76, materialised once by the producer).
+ * ------------------------------------------------------------------------------------------------- */
+/* bytes of a BH tensor for B images of H x W pixels (64 channels) */
+size_t mrb_bh_bytes(int B, int H, int W);
+/* fp32 channels-last [B,H,W,64] -> BH (split + replicate border) and back (interior, hi + lo) */
+int mrb_bh_from_nhwc(const void* x, void* bh, int B, int H, int W, void* stream);
+int mrb_bh_to_nhwc(const void* bh, void* x, int B, int H, int W, void* stream);
+/* packed ConvGRUCell weights for mrb_tc2_gru: w_ih, w_hh [192, 64] (rnn_cells.py:23-38) */
+size_t mrb_tc2_gru_packed_bytes(void);
+int mrb_tc2_pack_gru(const void* w_ih, const void* w_hh, void* dst, int ch, int cx, void* stream);
+/* ConvNonlinear on BH tensors (conv_layers.py:36-123): 5x5 over the fp32 4-channel RIM gradient [B,H,W,4] -> BH, and
+ * k x k (dilation dil, dil*(k-1)/2 <= 2) BH -> BH; wpack as for mrb_tc_conv5x5x4_nhwc / mrb_tc_conv_nhwc; cout == 64.
+ * x_bh needs a valid replicate border; the border of the outputs is not a replicate copy. */
+int mrb_tc_conv5x5x4_bh(const void* x, const void* wpack, const void* bias, void* out_bh, int B, int H, int W, int cout,
+                        int relu, void* stream);
+int mrb_tc_conv_bh(const void* x_bh, const void* wpack, const void* bias, void* out_bh, int B, int H, int W, int cout, int k,
+                   int dil, int relu, void* stream);
+/* final RIM conv (rim_block.py:239-248) on a BH source with a valid border: out [B,H,W,2] = eta + conv3x3(x) (+ bias) */
+int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H,
+                            int W, void* stream);
+/* edge pixels -> replicate border of a BH tensor (after a pointwise producer, before a spatial consumer) */
+int mrb_bh_fix_border(void* bh, int B, int H, int W, void* stream);
+/* ConvGRUCell, kernel size 1, 64 -> 64 (rnn_cells.py:93-127): x, h, out in BH layout; b_ih [192] or null; out must not
+ * alias x or h.  Pointwise over all (H+4)(W+4) positions: the interior of out is the cell output, its border is NOT a
+ * replicate copy (follow with mrb_bh_fix_border before a spatial consumer); the border of x and h is never read for an
+ * interior result. */
+int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack, const void* b_ih, void* out_bh, int B, int H, int W,
+                void* stream);
 /* Final RIM conv (rim_block.py:239-248): k x k (odd), dilation dil, replicate padding, cin -> 2 channels, no bias,
  * x [B,H,W,cin] channels-last, out [B,H,W,2] = eta + conv(x). */
 int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out, int B,

@@ -58,6 +58,16 @@ SIGNATURES = {
     "mrb_tc_conv5x5x4_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrb_tc_gru_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mrb_tc_indrnn_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mrb_bh_bytes": (_sz, [_i, _i, _i]),
+    "mrb_bh_from_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mrb_bh_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mrb_tc_conv5x5x4_bh": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mrb_tc_conv_bh": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mrb_conv_c2_bh_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mrb_bh_fix_border": (_i, [_vp, _i, _i, _i, _vp]),
+    "mrb_tc2_gru_packed_bytes": (_sz, []),
+    "mrb_tc2_pack_gru": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mrb_tc2_gru": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_metrics_workspace_bytes": (_sz, [_i]),
     "mrb_abs_max_normalize": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),

@@ -14,10 +14,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmridc_b200.so")
 STAMP = os.path.join(PKG_DIR, "csrc", ".build_stamp")
-SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "qmri.cu", "metrics.cu"]
+SOURCES = ["core.cu", "fft.cu", "dc.cu", "conv.cu", "unet.cu", "conv_tc.cu", "conv_tc2.cu", "qmri.cu", "metrics.cu"]
 # tools-only library (tools/libmridc_b200_tools.so): the tensor-core kernels with their per-role cycle counters and role
 # switches compiled in (-DMRB_TC_PROF) plus the tcgen05 issue micro-benchmark; never loaded by the package
-TOOLS_SOURCES = ["core.cu", "conv_tc.cu", "conv.cu", "tc_microbench.cu"]
+TOOLS_SOURCES = ["core.cu", "conv_tc.cu", "conv_tc2.cu", "conv.cu", "tc_microbench.cu"]
 TOOLS_LIB_PATH = os.path.join(PKG_DIR, "..", "tools", "libmridc_b200_tools.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -398,7 +398,7 @@ __device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float b0,
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
 }
-template <int ROWS, int F_CH>
+template <int ROWS, int F_CH, bool BH>
 __global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ eta,
                                                          float* __restrict__ out, int B, int H, int W, int cin) {
@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict
     const int x0 = tx * F_TX, y0 = ty * F_TY;
     const int b = blockIdx.y;
     const int lx = threadIdx.x & 31, yg = threadIdx.x >> 5;  // pixels (lx, ROWS*yg + i), i = 0..ROWS-1
-    const float* xb = x + (long long)b * H * W * cin;
+    // BH source (conv_tc2.cu): [B][H+4][W+4][64 hi bf16 | 64 lo bf16] with a valid replicate border: taps are plain offsets;
+    // a staged position holds [F_CH hi | F_CH lo] bf16 (F_CH/2 + F_CH/2 words) and the fp32 value is rebuilt as hi + lo
+    const int Hp = H + 4, Wp = W + 4;
+    const float* xb = BH ? x + (long long)b * Hp * Wp * 64 : x + (long long)b * H * W * cin;
     const uint32_t patch_u32 = (uint32_t)__cvta_generic_to_shared(patch);
     // staging list of this thread: float4 t = tid + 128*i of the [F_PH*F_PW pixels][2 quads] chunk; the clamped source
     // offsets are the same for every chunk (computed once), the shared-memory offset is linear in i
@@ -427,13 +430,19 @@ __global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict
         const int t = threadIdx.x + 128 * i;
         const int q = t % NQ, pp = t / NQ;
         const int py = pp / F_PW, px = pp - py * F_PW;
-        const int gy = min(max(y0 - 1 + py, 0), H - 1), gx = min(max(x0 - 1 + px, 0), W - 1);
-        goff[i] = t < F_PH * F_PW * NQ ? (gy * W + gx) * cin + q * 4 : -1;  // H*W*cin < 2^31 (checked on the host)
+        if (BH) {
+            // quads 0 .. NQ/2-1: the chunk's hi bf16 (16 B each), NQ/2 .. NQ-1: its lo bf16 (128 B further)
+            const int gy = min(max(y0 + 1 + py, 0), Hp - 1), gx = min(max(x0 + 1 + px, 0), Wp - 1);
+            goff[i] = t < F_PH * F_PW * NQ ? (gy * Wp + gx) * 64 + (q < NQ / 2 ? q * 4 : 32 + (q - NQ / 2) * 4) : -1;
+        } else {
+            const int gy = min(max(y0 - 1 + py, 0), H - 1), gx = min(max(x0 - 1 + px, 0), W - 1);
+            goff[i] = t < F_PH * F_PW * NQ ? (gy * W + gx) * cin + q * 4 : -1;  // H*W*cin < 2^31 (checked on the host)
+        }
     }
     const uint32_t soff0 = (uint32_t)(((threadIdx.x / NQ) * F_PS + (threadIdx.x % NQ) * 4) * 4);
     auto stage = [&](int chunk, int buf) {
         const uint32_t dst = patch_u32 + (uint32_t)(buf * F_PH * F_PW * F_PS * 4) + soff0;
-        const float* g = xb + chunk * F_CH;
+        const float* g = xb + chunk * (BH ? F_CH / 2 : F_CH);  // BH: F_CH bf16 = F_CH/2 words per chunk and half
 #pragma unroll
         for (int i = 0; i < kStage; ++i)
             if (goff[i] >= 0)
@@ -461,8 +470,19 @@ __global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict
             for (int q = 0; q < NQ; ++q) {
                 float4 xr[ROWS + 2];
 #pragma unroll
-                for (int r = 0; r < ROWS + 2; ++r)
-                    xr[r] = *reinterpret_cast<const float4*>(pb + (size_t)((ROWS * yg + r) * F_PW + lx + dx) * F_PS + q * 4);
+                for (int r = 0; r < ROWS + 2; ++r) {
+                    const float* pp = pb + (size_t)((ROWS * yg + r) * F_PW + lx + dx) * F_PS;
+                    if (BH) {
+                        const uint2 hw = *reinterpret_cast<const uint2*>(pp + q * 2);
+                        const uint2 lw = *reinterpret_cast<const uint2*>(pp + F_CH / 2 + q * 2);
+                        xr[r] = make_float4(__uint_as_float(hw.x << 16) + __uint_as_float(lw.x << 16),
+                                            __uint_as_float(hw.x & 0xffff0000u) + __uint_as_float(lw.x & 0xffff0000u),
+                                            __uint_as_float(hw.y << 16) + __uint_as_float(lw.y << 16),
+                                            __uint_as_float(hw.y & 0xffff0000u) + __uint_as_float(lw.y & 0xffff0000u));
+                    } else {
+                        xr[r] = *reinterpret_cast<const float4*>(pp + q * 4);
+                    }
+                }
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
                     const float4* wp = wq + (size_t)((dy * 3 + dx) * (cin / 4) + c * NQ + q) * 2;
@@ -493,16 +513,22 @@ __global__ void __launch_bounds__(128) conv_c2_k3_kernel(const float* __restrict
     }
 }
 
-template <int ROWS, int F_CH>
+template <int ROWS, int F_CH, bool BH>
 static int launch_c2_k3(const float* x, const float* w, const float* bias, const float* eta, float* out, int B, int H, int W,
                         int cin, cudaStream_t st) {
     constexpr int F_TY = 4 * ROWS, F_PH = F_TY + 2, F_PS = F_CH + 4;
     const size_t smem3 = (size_t)9 * (cin / 4) * 2 * sizeof(float4) + (size_t)2 * F_PH * F_PW * F_PS * sizeof(float);
     MRB_REQUIRE(smem3 <= 200 * 1024 && (long long)H * W * cin < 2147483647LL, MRB_EUNSUPPORTED,
                 "mrb_conv_c2_nhwc_residual: image or channel count too large");
-    MRB_CUDA(cudaFuncSetAttribute(conv_c2_k3_kernel<ROWS, F_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MRB_REQUIRE(!BH || ((long long)(H + 4) * (W + 4) * 64 < 2147483647LL && cin == 64), MRB_EUNSUPPORTED,
+                "mrb_conv_c2_bh_residual: needs 64 channels and < 2^31 words per image");
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRB_CUDA(cudaFuncSetAttribute(conv_c2_k3_kernel<ROWS, F_CH, BH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
     dim3 grid3((unsigned)(ceil_div(W, F_TX) * ceil_div(H, F_TY)), (unsigned)B);
-    conv_c2_k3_kernel<ROWS, F_CH><<<grid3, 128, smem3, st>>>(x, w, bias, eta, out, B, H, W, cin);
+    conv_c2_k3_kernel<ROWS, F_CH, BH><<<grid3, 128, smem3, st>>>(x, w, bias, eta, out, B, H, W, cin);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -519,7 +545,7 @@ extern "C" int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const voi
     if (k == 3 && dil == 1 && (cin % 32) == 0 && !getenv("MRB_C2_GENERIC")) {
         // 4 rows per thread, 16-channel chunks (98 KB, two CTAs per SM): 48.5 us at B=4 vs 53.8 (8-channel chunks, three
         // CTAs), 57-59 (2 rows per thread) and 87 for the generic kernel below
-        return launch_c2_k3<4, 16>((const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W,
+        return launch_c2_k3<4, 16, false>((const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W,
                                    cin, (cudaStream_t)stream);
     }
     const int pad = dil * (k - 1) / 2;
@@ -532,6 +558,15 @@ extern "C" int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const voi
         (const float*)x, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H, W, cin, k, dil);
     MRB_LAUNCHED();
     return MRB_OK;
+}
+
+// The same final conv on a BH source (64 channels, k = 3, dilation 1; the border of x must be valid: mrb_bh_fix_border)
+extern "C" int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B,
+                                       int H, int W, void* stream) {
+    MRB_REQUIRE(x_bh && w && eta && out, MRB_EINVAL, "mrb_conv_c2_bh_residual: null pointer");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1 && B <= 65535, MRB_EINVAL, "mrb_conv_c2_bh_residual: bad shape");
+    return launch_c2_k3<4, 16, true>((const float*)x_bh, (const float*)w, (const float*)bias, (const float*)eta, (float*)out, B, H,
+                                     W, 64, (cudaStream_t)stream);
 }
 
 extern "C" int mrb_conv2d(const void* x, long long x_bstride, const void* w, const void* bias, void* out,

@@ -30,7 +30,9 @@
 //                     tcgen05.commit of the stage back to the loaders / of the accumulator to the epilogue;
 //   epilogue warps (8) tcgen05.ld the accumulator (one pixel per thread, 2 warps per lane quadrant), apply
 //                     bias + ReLU or the GRU gates, and write NHWC.
-#include "common.cuh"
+#include <cuda.h>
+
+#include "tc_ptx.cuh"
 
 namespace mrb {
 namespace tc {
@@ -53,6 +55,10 @@ constexpr int EPI_TILE_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int HALO_ROWS = 40;                 // halo mode: 32 pixels + 2*pad on each side of up to two image-row pieces
 
 enum Mode { MODE_CONV_RELU = 0, MODE_GRU = 1, MODE_CONV_NOACT = 2 };
+constexpr int BH_PAD = 2;                     // replicate border of the BH activation layout (conv_tc2.cu)
+constexpr int BH_PX_BYTES = 256;              // 64 hi + 64 lo bf16 per position
+constexpr int OUT_BOX_BYTES = TILE_M * 128;   // one [128 positions x 64 bf16] TMA box
+constexpr int BIAS_FLOATS = 384;              // GRU: 3 x 64 gate biases; conv: bias [0,128) | IndRNN recurrent weights [128,256)
 
 // Profiling hooks (per-role cycle counters, role switches) exist only in the tools build (-DMRB_TC_PROF,
 // tools/libmridc_b200_tools.so); the product kernel carries none of them.
@@ -111,6 +117,12 @@ struct Params {
     int ngroups;             // conv: number of independent accumulator groups (each [hi*hi | cross], 2*nhalf columns);
                              // the tensor core's fp32 accumulation truncates, so its error grows linearly with the
                              // chain length -- short chains summed in the epilogue (RN fp32) keep it at fp32 level
+    int pos_padded;          // tiles run over the flat positions of the BH layout, [B][H+4][W+4] (P = B (H+4)(W+4)); H, W stay
+                             // the image size.  Required by src_bh / out_bh.
+    int src_bh;              // source 0 is a BH tensor (bf16 hi | lo per position, replicate border valid): the loaders
+                             // copy rows to TMEM without conversion and address taps as plain offsets (no clamping)
+    int out_bh;              // the epilogue splits its fp32 results into hi / lo bf16, stages the tile in the TMA box layout
+                             // and stores it with two TMA box stores (tm_out); cout == 64
     int group_cols;          // TMEM columns between the accumulator groups of the two issuers (0 with one group)
     int n_issuers;           // 1 or 2 MMA-issuing lanes (2: the global segment stream alternates; issuer i owns
                              // accumulator group i)
@@ -124,334 +136,14 @@ struct Params {
     Segment seg[MAX_SEGS];
 };
 
-// ---- PTX wrappers ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// polling wait with back-off: waiting warps must not steal issue slots from the single MMA-issuing thread
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// long waits (loaders on a free stage, epilogue on a finished tile): try_wait with a suspend-time hint parks the warp in
-// hardware until the phase completes (or the hint expires) instead of spinning through issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(ns)
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// The MMA-issuing warps run warp-uniform code and elect one lane per tcgen05 instruction (elect.sync picks the same
-// lane for the same full mask): with every operand provably uniform the MMAs issue straight from uniform registers.
-// Issued from a single-lane branch instead, each MMA costs a 12-instruction R2UR "waterfall" (~45 cycles measured).
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-        "}\n" ::"r"(smem_u32(bar))
-        : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 operands), M = 128, K = 16
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T: A = 128 lanes x 8 columns (16 packed bf16) starting at a_tmem
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// One segment = 4 k-steps x (lo*hi, hi*lo -> ds ; hi*hi -> d), issued from a single asm block: the issuing thread is
-// latency-bound (one dependent scalar instruction every few cycles, ~45 cycles minimum between MMAs measured with
-// tools/tc_microbench.py), so nothing but the MMAs themselves may sit between them.
-// skip_first != 0: the first MMA (lo*hi of k-step 0) has been issued separately by umma_first_split().
-__device__ __forceinline__ void umma_segment_ts(uint32_t d, uint32_t ds, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
-                                                uint64_t dbl, uint32_t idesc, uint32_t acc_small0, uint32_t acc_big0,
-                                                uint32_t skip_first) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred ps, pb, pt, pe, pf;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "setp.eq.b32 pf, %9, 0;\n\t"
-        "and.pred pf, pf, pe;\n\t"
-        ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
-        ".reg .b64 bh1, bh2, bh3, bl1, bl2, bl3;\n\t"
-        "setp.ne.b32 ps, %7, 0;\n\t"
-        "setp.ne.b32 pb, %8, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
-        "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
-        "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
-        "add.u64 bl1, %5, 2;\n\t add.u64 bl2, %5, 4;\n\t add.u64 bl3, %5, 6;\n\t"
-        "@pf tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %4, %6, ps;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %5, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %4, %6, pb;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah1], bl1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah2], bl2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al3], bh3, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [ah3], bl3, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah3], bh3, %6, pt;\n\t"
-        "}\n" ::"r"(d),
-        "r"(ds), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_small0), "r"(acc_big0), "r"(skip_first)
-        : "memory");
-}
-// First MMA of a segment whose accumulator columns are partly shared with an earlier segment (GRU x-part: the r and z
-// columns already hold the h-part, the n columns are fresh): rows [0, n_acc) of the B chunk accumulate, rows
-// [n_acc, n_acc + n_new) overwrite.  Replaces the epilogue's re-zeroing of the accumulators.
-__device__ __forceinline__ void umma_first_split(uint32_t ds, uint32_t a, uint64_t db, uint32_t idesc_acc, uint32_t idesc_new,
-                                                 uint32_t n_acc) {
-    const uint64_t db2 = db + (uint64_t)((n_acc * 128u) >> 4);  // n_acc is a multiple of 8: whole 1024-byte row groups
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pe, pt, pz;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "setp.ne.b32 pz, 0, 0;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], %4, %6, pz;\n\t"
-        "}\n" ::"r"(ds),
-        "r"(ds + n_acc), "r"(a), "l"(db), "l"(db2), "r"(idesc_acc), "r"(idesc_new)
-        : "memory");
-}
-// Stacked-B variant (2 MMAs per k-step instead of 3): the packed weight chunk holds the hi rows immediately followed
-// by the lo rows, so ONE descriptor with N = 2n multiplies a_hi by [b_hi ; b_lo] -> columns [d, d+n) = a_hi*b_hi and
-// [d+n, d+2n) = a_hi*b_lo; the second MMA adds a_lo*b_hi (N = n) onto the cross-term columns [d+n, d+2n).
-__device__ __forceinline__ void umma_segment_ts_stacked(uint32_t d, uint32_t dsm, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
-                                                        uint32_t idesc2n, uint32_t idescn, uint32_t acc0) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pa, pt, pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        ".reg .b32 ah1, ah2, ah3, al1, al2, al3;\n\t"
-        ".reg .b64 bh1, bh2, bh3;\n\t"
-        "setp.ne.b32 pa, %7, 0;\n\t"
-        "setp.eq.b32 pt, 0, 0;\n\t"
-        "add.u32 ah1, %2, 8;\n\t add.u32 ah2, %2, 16;\n\t add.u32 ah3, %2, 24;\n\t"
-        "add.u32 al1, %3, 8;\n\t add.u32 al2, %3, 16;\n\t add.u32 al3, %3, 24;\n\t"
-        "add.u64 bh1, %4, 2;\n\t add.u64 bh2, %4, 4;\n\t add.u64 bh3, %4, 6;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %4, %5, pa;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], %4, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah1], bh1, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al1], bh1, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah2], bh2, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al2], bh2, %6, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [ah3], bh3, %5, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], [al3], bh3, %6, pt;\n\t"
-        "}\n" ::"r"(d),
-        "r"(dsm), "r"(a_hi), "r"(a_lo), "l"(dbh), "r"(idesc2n), "r"(idescn), "r"(acc0)
-        : "memory");
-}
-// lane-0 broadcast: tells the compiler that a value is warp-uniform (see umma_commit)
-__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
-__device__ __forceinline__ uint64_t uni64(uint64_t v) { return ((uint64_t)uni((uint32_t)(v >> 32)) << 32) | uni((uint32_t)v); }
-struct SegIssue {  // per-segment operands of the MMA issuer
-    uint64_t dbh, dbl;
-    uint32_t idesc, first, idesc2n;
-};
-// registers -> TMEM: 16 consecutive columns of this thread's lane
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// TMEM -> registers: 8 consecutive columns of this thread's lane.  The wait is part of the same asm statement so
-// that no consumer of v[] can be scheduled before the asynchronous load has landed.
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-// four 8-column loads with a single wait (GRU epilogue: hh_n, r, z, ih_n blocks)
-__device__ __forceinline__ void tmem_ld8x4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, float* v0, float* v1, float* v2,
-                                           float* v3) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%32];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%33];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%34];\n\t"
-        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%35];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        v0[i] = __uint_as_float(r[i]);
-        v1[i] = __uint_as_float(r[8 + i]);
-        v2[i] = __uint_as_float(r[16 + i]);
-        v3[i] = __uint_as_float(r[24 + i]);
-    }
-}
-__device__ __forceinline__ void tmem_ld_wait() {}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
-    d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major), 16 B
-    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 1024 B between 8-row groups
-    d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, K-major A and B, N>>3 @17, M>>4 @24
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// fp32 pair -> packed bf16 hi pair + packed bf16 lo pair (element 0 in the low half, as tcgen05 reads packed A rows).
-// hi = rn_bf16(x); lo = rn_bf16(x - hi): the subtraction is exact in fp32 and |x - hi - lo| <= 2^-18 |x|.
-// Five instructions per pair (cvt.pack, shl, and, packed sub, cvt.pack): the loaders are instruction-issue bound.
-__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));  // first source -> upper half
-    return r;
-}
-__device__ __forceinline__ void sub2(float x0, float x1, float y0, float y1, float& r0, float& r1);
-__device__ __forceinline__ void split_bf16x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
-    hi = pack_bf16x2(e0, e1);
-    float l0, l1;
-    sub2(e0, e1, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u), l0, l1);
-    lo = pack_bf16x2(l0, l1);
-}
-__host__ __device__ inline uint16_t bf16_rn_bits(float v) {  // host/pack-kernel side rounding (RNE), NaN/Inf pass through
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-// 16-byte global -> shared async copy (src_bytes 0 = zero fill); bypass_l1: .cg (streamed once) vs .ca (re-read by taps)
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, uint32_t src_bytes, bool bypass_l1) {
-    if (bypass_l1)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes) : "memory");
-}
-// explicit shared-space 128-bit load (a generic pointer would compile to LD.E)
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
-    return v;
-}
-// gate non-linearities on the SFU: one ex2.approx and one rcp.approx each (~2 ulp, |error| ~1e-7 on outputs in
-// [-1, 1]); the raw PTX forms skip the range fix-ups of __expf / __fdividef (saturation is already exact: ex2 -> 0 or
-// +inf, rcp(inf) = 0)
-__device__ __forceinline__ float ex2_approx(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float v) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-constexpr float kLog2e = 1.4426950408889634f;
-// sigmoid(a + b) with bs = -log2(e) * b folded on the host side of the epilogue (bias table)
-__device__ __forceinline__ float sigmoid_fused(float a, float bs) { return rcp_approx(1.f + ex2_approx(fmaf(a, -kLog2e, bs))); }
-__device__ __forceinline__ float tanh_acc(float v) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(v * (2.f * kLog2e))), 1.f); }
-
-// (x0, x1) - (y0, y1) as one packed fp32x2 instruction (same IEEE result as two scalar subtractions)
-__device__ __forceinline__ void sub2(float x0, float x1, float y0, float y1, float& r0, float& r1) {
-    unsigned long long x, y, r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
-}
-
-// byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
-
 template <bool GRU>
-__global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
+__global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ CUtensorMap tm_out, const Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // layout: [weights resident][loader staging tiles][streamed-weights ring][barriers][bias][epilogue exchange]
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int wbytes_chunk = P.wchunk_rows * 128;  // bytes of the hi (or lo) rows of one weight chunk
-    uint8_t* w_s = smem;                                              // [n_wchunks][hi|lo][rows*128]
+    uint8_t* out_s = smem;                                            // out_bh: [hi box | lo box] output tile (1024-aligned)
+    uint8_t* w_s = smem + (P.out_bh ? 2 * OUT_BOX_BYTES : 0);         // [n_wchunks][hi|lo][rows*128]
     uint8_t* bst_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [b_stages][2*wbytes_chunk] if stream_b
     uint8_t* tb_s = bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0);  // [LOAD_WARPS][depth][tb_bytes]
     uint64_t* bars = (uint64_t*)(tb_s + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes);
@@ -462,8 +154,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
     uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
     uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
-    float* bias_s = (float*)(b_empty + B_STAGES);  // [3 * 256]: bias staged once per CTA (epilogue reads it per tile)
-    uint8_t* epi_s = (uint8_t*)(bias_s + 3 * 256); // GRU: [EPI_WARPS][2][32 px][EPI_ROW_BYTES] per-warp exchange tiles
+    uint64_t* out_free = acc_empty + 3;             // [1] out_bh: the TMA stores of the previous tile have read out_s
+    float* bias_s = (float*)(b_empty + B_STAGES);   // [BIAS_FLOATS] (16-byte aligned): bias staged once per CTA
+    uint8_t* epi_s = (uint8_t*)(bias_s + BIAS_FLOATS);  // GRU: [EPI_WARPS][2][32 px][EPI_ROW_BYTES] per-warp exchange tiles
 
     // warp index through a shuffle: provably warp-uniform for the compiler (role branches and the MMA issuers' operands
     // then live in uniform registers)
@@ -485,6 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             mbar_init(&b_full[b], 1);   // the producer's arrive.expect_tx; the bulk copy completes the transaction bytes
             mbar_init(&b_empty[b], 1);  // tcgen05.commit of the MMAs that read the slot
         }
+        mbar_init(out_free, 1);
         fence_barrier_init();
     }
     {
@@ -495,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             bias_s[i] = (GRU && i < 2 * P.cout) ? -kLog2e * b : b;
         }
         if (!GRU && P.add_scale)  // IndRNN recurrent weights, second row of the table
-            for (int i = threadIdx.x; i < P.cout; i += THREADS) bias_s[256 + i] = P.add_scale[i];
+            for (int i = threadIdx.x; i < P.cout; i += THREADS) bias_s[128 + i] = P.add_scale[i];
     }
     if (warp == EPI_WARPS + LOAD_WARPS) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
     // resident weights of this half: straight copy (already swizzled by the packer)
@@ -545,6 +239,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         // quad*32 + lane): columns [0,32) = hi pairs, [32,64) = lo pairs
         auto store_stage = [&](uint32_t tb, int row, int stg) {
             const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + a_col0 + (uint32_t)(stg * A_STAGE_COLS);
+            if (P.src_bh) {
+                // BH source: the staging row already holds 64 hi bf16 (half 0) and 64 lo bf16 (half 1) -- straight copy
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 a = lds128(tb + hf * HB + swz(row, c));
+                        v[4 * c] = __float_as_uint(a.x); v[4 * c + 1] = __float_as_uint(a.y);
+                        v[4 * c + 2] = __float_as_uint(a.z); v[4 * c + 3] = __float_as_uint(a.w);
+                    }
+                    if (!TC_DBG(P, 8)) {
+                        tmem_st16(ta + hf * KC, v);
+                        tmem_st16(ta + hf * KC + 16, v + 16);
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t hi[16], lo[16];
@@ -575,7 +287,60 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             TCP(t_st += clock64() - c0; t_stw += clock64() - c2;)
         };
 
-        if (P.halo) {
+        if (P.halo && P.src_bh) {
+            // ---- halo mode on a BH source: flat positions, valid replicate border => taps are plain offsets ----
+            // unit = (tile, kernel row ky): the warp's 32 positions plus pad on each side of flat row offset
+            // (ky*dil - pad) * pitch; tap kx reads staging row lane + kx*dil.  Positions outside the tensor are zero-filled
+            // (they only feed border positions, whose results are not used).
+            const int k = P.ksz, dil = P.dil, pad = dil * (k - 1) / 2;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(P.src[0]);
+            const long long pitch = P.W + 2 * BH_PAD;
+            const int n_units = n_items * k;
+            const int nrows = 32 + 2 * pad;
+            auto issue_halo = [&](int tile, int ky, int slot) {
+                const long long q0 = (long long)tile * TILE_M + quad * 32 - pad + (long long)(ky * dil - pad) * pitch;
+                const uint32_t sbase = tb_u32 + (uint32_t)(slot * P.tb_bytes);
+#pragma unroll
+                for (int i = 0; i < HALO_ROWS / 4; ++i) {
+                    const int sr = rl0 + 4 * i;
+                    if (sr >= nrows) break;  // the staging tile has exactly nrows rows (a zero-fill would land in the lo half)
+                    const long long q = q0 + sr;
+                    const bool ok = q >= 0 && q < P.P;
+                    const uint8_t* g = src + q * BH_PX_BYTES + c16 * 16;
+                    const uint32_t nb = (ok && ld_on) ? 16u : 0u;
+                    cp_async16(sbase + swz(sr, c16), ok ? (const void*)g : (const void*)src, nb, true);
+                    cp_async16(sbase + HB + swz(sr, c16), ok ? (const void*)(g + 128) : (const void*)src, nb, true);
+                }
+            };
+            int pf_u = grp, pf_tile = first_tile, pf_ky = grp, pf_slot = 0;
+            while (pf_ky >= k) { pf_ky -= k; pf_tile += tile_stride; }
+            auto prefetch_unit = [&]() {
+                if (pf_u < n_units) issue_halo(pf_tile, pf_ky, pf_slot);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                pf_u += LOAD_GROUPS;
+                pf_ky += LOAD_GROUPS;
+                while (pf_ky >= k) { pf_ky -= k; pf_tile += tile_stride; }
+                pf_slot ^= 1;
+            };
+            prefetch_unit();
+            int slot = 0;
+            stage_set((long long)grp * k);
+            for (int u = grp; u < n_units; u += LOAD_GROUPS) {
+                TCP(c0 = clock64();)
+                prefetch_unit();
+                TCP(t_issue += clock64() - c0;)
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t tb = tb_u32 + (uint32_t)(slot * P.tb_bytes);
+                for (int kx = 0; kx < k; ++kx) {
+                    fill_stage(tb, lane + kx * dil);
+                    stage_adv(1);
+                }
+                __syncwarp();  // every lane has read its rows before the slot is refilled
+                stage_adv(k * (LOAD_GROUPS - 1));  // the other group's unit
+                slot ^= 1;
+            }
+        } else if (P.halo) {
             // ---- halo mode (k x k conv over 64 channels) ----
             // The k taps of one kernel row read the same image row shifted by dil pixels.  One gather per (tile, kernel
             // row) brings the warp's 32 pixels plus pad = dil*(k-1)/2 pixels on each side (replicate clamp applied to the
@@ -681,28 +446,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             unsigned eB = 0, eok = 0;
             int nA = 32, yA = 0, yB = 0;
             long long rowA = 0, rowB = 0;
+            // pos_padded: the tile's positions are those of the BH layout (rows of W + 4 positions, H + 4 rows per image);
+            // position (yp, xp) reads the source window centred at (yp - 2, xp - 2), clamped -- exact for interior
+            // positions, and the results at border positions are not used
+            const int roff = P.pos_padded ? BH_PAD : 0;                    // position -> source coordinate offset
+            const uint32_t Wq = (uint32_t)(P.W + 2 * roff), Hq = (uint32_t)(P.H + 2 * roff);  // position grid
             auto tile_geometry = [&](int tile) {
                 const long long p0 = (long long)tile * TILE_M + quad * 32;
                 eB = 0; eok = 0;
                 if (p0 >= P.P) return;
                 const uint32_t q = (uint32_t)p0;
-                const uint32_t t = q / W32;
-                const int x0 = (int)(q - t * W32);
-                const uint32_t b0 = t / H32;
-                yA = (int)(t - b0 * H32);
+                const uint32_t t = q / Wq;
+                const int xq = (int)(q - t * Wq);
+                const int x0 = xq - roff;
+                const uint32_t b0 = t / Hq;
+                const int yq = (int)(t - b0 * Hq);
+                yA = yq - roff;
                 rowA = (long long)b0 * P.H;
-                nA = min(32, P.W - x0);
+                nA = min(32, (int)Wq - xq);
                 const bool hasB = nA < 32 && p0 + nA < P.P;
                 yB = yA + 1;
                 rowB = rowA;
-                if (yB == P.H) { yB = 0; rowB += P.H; }
+                if (yq + 1 == (int)Hq) { yB = -roff; rowB += P.H; }
                 const int nrows = 32 + 2 * PAD + (nA < 32 ? 2 * PAD : 0);
 #pragma unroll
                 for (int i = 0; i < NE; ++i) {
                     const int e = lane + 32 * i;
                     const int sr = e % HALO_ROWS;
                     const bool inB = sr >= nA + 2 * PAD;
-                    const int vx = inB ? sr - nA - 3 * PAD : x0 - PAD + sr;
+                    const int vx = inB ? sr - nA - 3 * PAD - roff : x0 - PAD + sr;
                     eoff[i] = min(max(vx, 0), P.W - 1) * 4;
                     if (inB) eB |= 1u << i;
                     if (e < 5 * HALO_ROWS && sr < nrows && (!inB || hasB)) eok |= 1u << i;
@@ -736,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             for (int it = 0; it < n_items; ++it, tile += tile_stride) {
                 const long long p0 = (long long)tile * TILE_M + quad * 32;
                 const uint32_t q = p0 < P.P ? (uint32_t)p0 : 0u;
-                const int nA_cur = min(32, P.W - (int)(q % W32));
+                const int nA_cur = min(32, (int)Wq - (int)(q % Wq));
                 TCP(c0 = clock64();)
                 prefetch_patch();
                 TCP(t_issue += clock64() - c0;)
@@ -1024,6 +796,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
         const int j_lo = chalf * (P.nhalf / 2), j_hi = j_lo + P.nhalf / 2;
         int it = 0;
         const uint32_t bias_u32 = smem_u32(bias_s);
+        const uint32_t out_u32 = smem_u32(out_s);
+        uint32_t oph = 0;
+        // out_bh: 8 consecutive channels (chunk c8 = channel / 8) of this thread's position -> hi / lo bf16 in the output tile
+        auto emit8 = [&](int c8, const float* v) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            sts128u(out_u32 + swz(m, c8), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128u(out_u32 + OUT_BOX_BYTES + swz(m, c8), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        };
         const uint32_t et0 = smem_u32(epi_s) + (uint32_t)(warp * 2 * EPI_TILE_BYTES);  // this warp's two exchange tiles
         // h_prev of a tile (independent of the MMAs): asynchronous coalesced copy into an exchange tile, issued one tile
         // ahead so that its latency never shows
@@ -1143,7 +925,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                 tc_fence_before();
                 mbar_arrive(&acc_empty[buf]);
                 released = true;
-                if (valid) {
+                if (P.out_bh) {
+                    const bool relu = P.mode == MODE_CONV_RELU;
+                    mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
+#pragma unroll
+                    for (int jb = 0; jb < 4; ++jb) {
+                        const float4 b0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8));
+                        const float4 b1 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8 + 4));
+                        float v[8] = {o[jb * 8 + 0] + b0.x, o[jb * 8 + 1] + b0.y, o[jb * 8 + 2] + b0.z, o[jb * 8 + 3] + b0.w,
+                                      o[jb * 8 + 4] + b1.x, o[jb * 8 + 5] + b1.y, o[jb * 8 + 6] + b1.z, o[jb * 8 + 7] + b1.w};
+                        if (relu) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                        }
+                        emit8((ch0 + j_lo) / 8 + jb, v);
+                    }
+                } else if (valid) {
                     const bool relu = P.mode == MODE_CONV_RELU;
                     float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j_lo);
 #pragma unroll
@@ -1152,7 +949,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                         float4 v = make_float4(o[jb * 4 + 0] + bi.x, o[jb * 4 + 1] + bi.y, o[jb * 4 + 2] + bi.z, o[jb * 4 + 3] + bi.w);
                         if (P.add_scale) {  // IndRNN: + hh * h_prev (rnn_cells.py:391)
                             const float4 hv = __ldg(reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j_lo) + jb);
-                            const float4 sc = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j_lo + jb * 4));
+                            const float4 sc = lds128(bias_u32 + 4u * (uint32_t)(128 + ch0 + j_lo + jb * 4));
                             v = make_float4(v.x + sc.x * hv.x, v.y + sc.y * hv.y, v.z + sc.z * hv.z, v.w + sc.w * hv.w);
                         }
                         if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
@@ -1182,7 +979,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                             }
                         }
                     }
-                    if (valid) {
+                    if (P.out_bh && j == j_lo) mbar_wait_sleep(out_free, oph ^ 1, 32);  // previous tile's stores have read out_s
+                    if (valid || P.out_bh) {
                         float o[8];
                         const float4 bi0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j));
                         const float4 bi1 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j + 4));
@@ -1192,8 +990,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                         if (P.add_scale) {  // IndRNN: + hh * h_prev (rnn_cells.py:391)
                             const float4* hp4 = reinterpret_cast<const float4*>(P.hprev + p * P.cout + ch0 + j);
                             const float4 h0 = __ldg(hp4), h1 = __ldg(hp4 + 1);
-                            const float4 s0 = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j));
-                            const float4 s1 = lds128(bias_u32 + 4u * (uint32_t)(256 + ch0 + j + 4));
+                            const float4 s0 = lds128(bias_u32 + 4u * (uint32_t)(128 + ch0 + j));
+                            const float4 s1 = lds128(bias_u32 + 4u * (uint32_t)(128 + ch0 + j + 4));
                             hs[0] = s0.x * h0.x; hs[1] = s0.y * h0.y; hs[2] = s0.z * h0.z; hs[3] = s0.w * h0.w;
                             hs[4] = s1.x * h1.x; hs[5] = s1.y * h1.y; hs[6] = s1.z * h1.z; hs[7] = s1.w * h1.w;
                         }
@@ -1202,15 +1000,32 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
                             const float v = (a[q] + bi[q]) + hs[q];
                             o[q] = relu ? fmaxf(v, 0.f) : v;
                         }
-                        float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
-                        op[0] = make_float4(o[0], o[1], o[2], o[3]);
-                        op[1] = make_float4(o[4], o[5], o[6], o[7]);
+                        if (P.out_bh) {
+                            emit8((ch0 + j) / 8, o);
+                        } else {
+                            float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
+                            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+                            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+                        }
                     }
                 }
             }
             if (!released) {
                 tc_fence_before();
                 mbar_arrive(&acc_empty[buf]);
+            }
+            if (P.out_bh) {
+                // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps are here
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (threadIdx.x == 0) {
+                    tma_store_2d(&tm_out, out_u32, 0, tile * TILE_M);
+                    tma_store_2d(&tm_out, out_u32 + OUT_BOX_BYTES, 64, tile * TILE_M);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(out_free);
+                }
+                oph ^= 1;
             }
             if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
         }
@@ -1220,6 +1035,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
             o[8] = clock64() - e_start; o[9] = e_wait;
         }
 #endif
+        if (P.out_bh && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -1232,17 +1048,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const Params P) {
 // ---- weight packing ----------------------------------------------------------------------------------
 // dst chunk layout: [rows x 128 B] SWIZZLE_128B (64 bf16 K elements per row), hi rows then lo rows.  Source value for
 // (half, chunk, row n, col k) is given by a small descriptor evaluated on the device.
-struct PackDesc {
-    const float* w;       // conv: [Cout][Cin][k][k]; GRU: w_ih [3Ch][Cx] then w_hh via w2
-    const float* w2;
-    int mode;             // 0 conv taps (chunk = tap), 1 GRU (chunk 0 = hh, 1 = ih), 2 im2col 5x5x4 (chunk = 16 taps)
-    int cout, cin, ksz;   // conv geometry
-    int nhalf;            // output channels per split part
-    int rows;             // rows per chunk
-    int n_chunks;
-    int n_split;
-};
-
 __global__ void pack_weights_kernel(PackDesc D, uint16_t* dst) {
     const int total = D.n_split * D.n_chunks * D.rows * KCH;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -1283,11 +1088,17 @@ __global__ void pack_weights_kernel(PackDesc D, uint16_t* dst) {
     }
 }
 
+int pack_launch(const PackDesc& D, void* dst, cudaStream_t st) {
+    pack_weights_kernel<<<64, 256, 0, st>>>(D, (uint16_t*)dst);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 + 2 * B_STAGES * 8 + 3 * 256 * sizeof(float) +
-           (P.mode == MODE_GRU ? (size_t)EPI_WARPS * 2 * EPI_TILE_BYTES : 0);
+    return 1024 + (P.out_bh ? (size_t)2 * OUT_BOX_BYTES : 0) + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 +
+           2 * B_STAGES * 8 + BIAS_FLOATS * sizeof(float) + (P.mode == MODE_GRU ? (size_t)EPI_WARPS * 2 * EPI_TILE_BYTES : 0);
 }
 
 #ifdef MRB_TC_PROF
@@ -1308,7 +1119,17 @@ static int launch(Params& P, cudaStream_t st) {
     MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
     MRB_REQUIRE(P.nseg >= P.n_issuers && P.nseg <= MAX_SEGS, MRB_EUNSUPPORTED, "tensor-core conv: bad segment count");
     MRB_REQUIRE(P.im2col != 2 || P.nseg == LOAD_GROUPS, MRB_EUNSUPPORTED, "tensor-core conv: patch mode needs one K chunk per loader group");
-    P.tb_half = (P.halo ? HALO_ROWS : 32) * 128;
+    MRB_REQUIRE(!(P.src_bh || P.out_bh) || P.pos_padded, MRB_EINVAL, "tensor-core conv: BH tensors need padded positions");
+    MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1), MRB_EUNSUPPORTED, "tensor-core conv: BH output needs 64 channels");
+    CUtensorMap tm_out;
+    memset(&tm_out, 0, sizeof(tm_out));
+    if (P.out_bh) {
+        int rc = tc2::make_bh_tmap(&tm_out, P.out, P.P, TILE_M);
+        if (rc) return rc;
+    }
+    // BH source in halo mode: 32 + 2*pad flat positions per unit (no two-piece layout)
+    const int halo_rows = (P.halo && P.src_bh) ? 32 + P.dil * (P.ksz - 1) : HALO_ROWS;
+    P.tb_half = (P.halo ? halo_rows : 32) * 128;
     P.tb_bytes = 2 * P.tb_half;
     P.tb_depth = P.halo ? 2 : 3;  // halo mode: one staging tile feeds k segments, current + next is enough
     if (P.b_stages == 0) P.b_stages = B_STAGES;
@@ -1324,8 +1145,8 @@ static int launch(Params& P, cudaStream_t st) {
     int sms = device_sm_count();
     int grid = (sms / P.n_split) * P.n_split;  // groups of n_split CTAs share a pixel tile
     if (grid > P.n_split * P.n_tiles) grid = P.n_split * P.n_tiles;
-    if (P.mode == MODE_GRU) tc_kernel<true><<<grid, THREADS, smem_needed(P), st>>>(P);
-    else tc_kernel<false><<<grid, THREADS, smem_needed(P), st>>>(P);
+    if (P.mode == MODE_GRU) tc_kernel<true><<<grid, THREADS, smem_needed(P), st>>>(tm_out, P);
+    else tc_kernel<false><<<grid, THREADS, smem_needed(P), st>>>(tm_out, P);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -1377,10 +1198,11 @@ extern "C" int mrb_tc_pack_conv5x5x4(const void* w, void* dst, int cout, void* s
     return MRB_OK;
 }
 
-static int tc_common(tc::Params& P, int B, int H, int W) {
+static int tc_common(tc::Params& P, int B, int H, int W, int pos_padded = 0) {
     MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "tensor-core conv: bad shape");
     P.B = B; P.H = H; P.W = W;
-    P.P = (long long)B * H * W;
+    P.pos_padded = pos_padded;
+    P.P = pos_padded ? (long long)B * (H + 2 * tc::BH_PAD) * (W + 2 * tc::BH_PAD) : (long long)B * H * W;
     long long nt = (P.P + tc::TILE_M - 1) / tc::TILE_M;
     MRB_REQUIRE(nt <= 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
     P.n_tiles = (int)nt;
@@ -1389,7 +1211,16 @@ static int tc_common(tc::Params& P, int B, int H, int W) {
 
 // ConvNonlinear k x k (dilated, replicate padding), 64 -> cout channels, NHWC, bias + optional ReLU.
 static int tc_conv_launch(const void* x, const void* wpack, const void* bias, const void* hprev, const void* add_scale,
-                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream);
+                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream, int bh = 0);
+
+// The same ConvNonlinear on BH tensors (conv_tc2.cu): x_bh with a valid replicate border (mrb_bh_fix_border), out_bh
+// written at all (H+4)(W+4) positions (interior = the conv output; its border is not a replicate copy).
+extern "C" int mrb_tc_conv_bh(const void* x_bh, const void* wpack, const void* bias, void* out_bh, int B, int H, int W, int cout,
+                              int k, int dil, int relu, void* stream) {
+    MRB_REQUIRE(cout == 64, MRB_EUNSUPPORTED, "mrb_tc_conv_bh: 64 output channels only");
+    MRB_REQUIRE(dil * (k - 1) / 2 <= tc::BH_PAD, MRB_EUNSUPPORTED, "mrb_tc_conv_bh: the receptive field exceeds the BH border");
+    return tc_conv_launch(x_bh, wpack, bias, nullptr, nullptr, out_bh, B, H, W, cout, k, dil, relu, stream, 1);
+}
 
 extern "C" int mrb_tc_conv_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
                                 int cout, int k, int dil, int relu, void* stream) {
@@ -1406,14 +1237,15 @@ extern "C" int mrb_tc_indrnn_nhwc(const void* x, const void* h, const void* wpac
 }
 
 static int tc_conv_launch(const void* x, const void* wpack, const void* bias, const void* hprev, const void* add_scale,
-                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream) {
+                          void* out, int B, int H, int W, int cout, int k, int dil, int relu, void* stream, int bh) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv_nhwc: null pointer");
     MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128 && (k % 2) == 1 && k * k <= tc::MAX_SEGS && dil >= 1,
                 MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: unsupported geometry");
     tc::Params P;
     memset(&P, 0, sizeof(P));
-    int rc = tc_common(P, B, H, W);
+    int rc = tc_common(P, B, H, W, bh);
     if (rc) return rc;
+    P.src_bh = bh; P.out_bh = bh;
     P.src[0] = (const float*)x; P.cs[0] = 64; P.src[1] = nullptr; P.cs[1] = 0;
     P.wpack = wpack; P.bias = (const float*)bias; P.out = (float*)out;
     P.hprev = (const float*)hprev; P.add_scale = (const float*)add_scale;
@@ -1442,6 +1274,7 @@ static int tc_conv_launch(const void* x, const void* wpack, const void* bias, co
     P.ksz = k; P.dil = dil;
     // halo gathers need the two-piece staging layout to hold (4*pad extra rows) and a warp's 32 pixels on <= 2 image rows
     P.halo = (4 * pad <= tc::HALO_ROWS - 32 && W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 1 : 0;
+    if (bh) P.halo = 1;  // flat positions: always the halo loader (32 + 2*pad <= HALO_ROWS rows per unit)
     for (int t = 0; t < k * k; ++t) {
         tc::Segment& s = P.seg[t];
         s.src = 0; s.dy = (short)((t / k) * dil - pad); s.dx = (short)((t % k) * dil - pad);
@@ -1452,15 +1285,28 @@ static int tc_conv_launch(const void* x, const void* wpack, const void* bias, co
     return tc::launch(P, (cudaStream_t)stream);
 }
 
+static int tc_conv5_launch(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W, int cout, int relu,
+                           void* stream, int bh);
 // ConvNonlinear 5x5 over a 4-channel NHWC input (the RIM gradient), cout outputs, bias + ReLU.
 extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W,
                                      int cout, int relu, void* stream) {
+    return tc_conv5_launch(x, wpack, bias, out, B, H, W, cout, relu, stream, 0);
+}
+// The same with a BH output (conv_tc2.cu): x [B,H,W,4] fp32 as above, out_bh written at all (H+4)(W+4) positions
+extern "C" int mrb_tc_conv5x5x4_bh(const void* x, const void* wpack, const void* bias, void* out_bh, int B, int H, int W,
+                                   int cout, int relu, void* stream) {
+    MRB_REQUIRE(cout == 64 && W + 2 * tc::BH_PAD >= 32, MRB_EUNSUPPORTED, "mrb_tc_conv5x5x4_bh: needs 64 output channels and W >= 28");
+    return tc_conv5_launch(x, wpack, bias, out_bh, B, H, W, cout, relu, stream, 1);
+}
+static int tc_conv5_launch(const void* x, const void* wpack, const void* bias, void* out, int B, int H, int W, int cout, int relu,
+                           void* stream, int bh) {
     MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc_conv5x5x4_nhwc: null pointer");
     MRB_REQUIRE((cout % 32) == 0 && cout >= 32 && cout <= 128, MRB_EUNSUPPORTED, "mrb_tc_conv5x5x4_nhwc: bad cout");
     tc::Params P;
     memset(&P, 0, sizeof(P));
-    int rc = tc_common(P, B, H, W);
+    int rc = tc_common(P, B, H, W, bh);
     if (rc) return rc;
+    P.out_bh = bh;
     P.src[0] = (const float*)x; P.cs[0] = 4;
     P.wpack = wpack; P.bias = (const float*)bias; P.out = (float*)out;
     P.n_split = 1;  // all output channels in one CTA: weights (2 chunks x 2 x cout x 128 B) stay resident
@@ -1474,7 +1320,7 @@ extern "C" int mrb_tc_conv5x5x4_nhwc(const void* x, const void* wpack, const voi
     P.stacked = 1;
     P.acc_bufs = 2;
     P.mode = relu ? tc::MODE_CONV_RELU : tc::MODE_CONV_NOACT;
-    P.im2col = (W >= 32 && !getenv("MRB_TC_NO_HALO")) ? 2 : 1;  // 2: taps assembled from a shared-memory halo patch
+    P.im2col = (bh || (W >= 32 && !getenv("MRB_TC_NO_HALO"))) ? 2 : 1;  // 2: taps assembled from a shared-memory halo patch
     P.nseg = 2;  // K = 25 taps x 4 channels = 100, padded to two 64-wide chunks
     for (int c = 0; c < 2; ++c) {
         tc::Segment& s = P.seg[c];

@@ -1,0 +1,583 @@
+// ConvGRU cell on split-bf16 activations: TMA -> shared memory -> tcgen05.mma (A and B from shared memory) -> TMEM ->
+// gate epilogue, one persistent CTA per SM.  Second-generation engine of the RIM regulariser (the first one, conv_tc.cu,
+// keeps A in tensor memory and converts fp32 activations in loader warps; it still runs the convolutions).
+//
+// Reference behaviour: ConvGRUCell with kernel_size 1 (rim/rnn_cells.py:93-127) inside RIMBlock's time loop
+// (rim/rim_block.py:217-249).
+//
+// Activation format "BH" (shared by every kernel of the time step): channels-last, 64 channels per pixel stored as
+// 64 bf16 "hi" values followed by 64 bf16 "lo" values (x ~= hi + lo, |x - hi - lo| <= 2^-18 |x|; 256 bytes per pixel,
+// the same as fp32), every image surrounded by a replicate-padded border of PAD = 2 pixels:
+//     [B][H + 4][W + 4][hi 64 | lo 64]
+// * the producer's epilogue does the hi/lo split once, where the fp32 value sits in a register; consumers feed the
+//   tensor core without touching the data: one 2-D TMA box per operand tile lands in the UMMA K-major SWIZZLE_128B layout;
+// * the replicate border turns ConvNonlinear's ReplicationPad2d (conv_layers.py:72-76) into plain address offsets: spatial
+//   kernels (3x3 dil 2, final 3x3) never clamp; producers of tensors that are read spatially write the border copies;
+// * pointwise kernels (this one) run over all (H+4)(W+4) positions of the flat [Q][128] matrix (2.5 % extra rows) with
+//   no position logic at all; what they leave at border positions is not a replicate copy, so a producer whose output is
+//   read spatially is followed by mrb_bh_fix_border (edge pixels -> border, ~1 % of the tensor).
+//
+// Work item = 128 consecutive positions x all 64 hidden channels (N = 192 gate rows per MMA: 96 tensor-pipe cycles, so
+// the issuing thread's ~50-cycle latency is hidden; the channel-split kernel of the first engine issued N = 96).
+//   TMA lane      four 16 KB boxes per tile: h_hi, h_lo through a two-tile ring (held until the epilogue has taken its
+//                 h_prev values), x_hi, x_lo through a one-tile ring (released by the MMAs); mbarrier transaction counts;
+//   MMA lane      25 tcgen05.mma.kind::f16 per tile (a_hi*b_hi, a_hi*b_lo, a_lo*b_hi for h and x; the r and z gates of
+//                 both parts accumulate in shared columns), two 256-column accumulator buffers: the gate epilogue of
+//                 tile t overlaps the MMAs of tile t+1;
+//   16 epilogue warps (4 per TMEM lane quadrant, 16 channels each): h_prev straight from the TMA-landed operand slots
+//                 (no second global read), batched tcgen05.ld, gates on the SFU, hi/lo split into an output tile in the
+//                 TMA box layout;
+//   TMA store lane  the two box stores of each tile.  No global load or store
+//                 instruction is executed by any warp: a first version that fetched h_prev with cp.async and stored with
+//                 st.global (16 lines per instruction) was bound by L1 wavefronts, not by HBM.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+namespace mrb {
+namespace tc2 {
+using namespace mrb::tc;
+
+constexpr int PADB = 2;            // replicate border of the BH layout
+constexpr int PX_BYTES = 256;      // 64 hi + 64 lo bf16
+constexpr int TILE = 128;
+constexpr int EPI_W = 16;          // epilogue warps
+constexpr int THREADS2 = (EPI_W + 3) * 32;  // + TMA load lane, MMA issuer, TMA store lane
+constexpr int NSLOT = 8;           // 16 KB boxes: h ring 4 (two tiles x (h_hi, h_lo)), x ring 2 (x_hi, x_lo), output tile 2
+constexpr int SLOT_BYTES = TILE * 128;
+constexpr int W_CHUNK = 192 * 128; // hi (or lo) rows of one weight chunk
+
+// ---- TMA ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// A BH tensor as the 2-D matrix [Q positions][128 bf16]; box = 64 columns (the hi or the lo half of a pixel, 128 B) x
+// box_rows positions, written to shared memory in the SWIZZLE_128B pattern the UMMA descriptors expect.  Positions
+// outside [0, Q) are zero-filled.
+int make_bh_tmap(void* mp, const void* base, long long Q, int box_rows) {
+    CUtensorMap* m = reinterpret_cast<CUtensorMap*>(mp);
+    EncodeTiledFn fn = encode_fn();
+    MRB_REQUIRE(fn != nullptr, MRB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {128, (cuuint64_t)Q};
+    cuuint64_t strides[1] = {PX_BYTES};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRB_REQUIRE(r == CUDA_SUCCESS, MRB_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MRB_OK;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(m), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+#ifdef MRB_TC_PROF
+__device__ int g_skip_mma = 0;
+#endif
+// D[tmem] (+)= A[smem] * B[smem]^T issued by one elected lane of a converged warp
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#ifdef MRB_TC_PROF
+    if (g_skip_mma) return;
+#endif
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+#ifdef MRB_TC_PROF
+#define T2P(...) __VA_ARGS__
+#define T2_DBG(P, f) (((P).debug & (f)) != 0)
+#else
+#define T2P(...)
+#define T2_DBG(P, f) false
+#endif
+
+struct Gru2Params {
+    const void* wpack;   // chunk 0 = W_hh rows [n ; r ; z], chunk 1 = W_ih rows [r ; z ; n]; each [hi 192 x 128 B | lo]
+    const float* bias;   // b_ih [192] (r, z, n) or null
+    long long Q;         // B * (H+4) * (W+4) positions
+    int n_tiles;
+#ifdef MRB_TC_PROF
+    int debug;                 // 1 skip MMAs, 2 skip TMA loads, 4 skip gate math, 8 skip global stores, 16 skip h_prev fetch
+    unsigned long long* prof;  // [grid][16]
+#endif
+};
+
+__global__ void __launch_bounds__(THREADS2, 1)
+gru2_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_x,
+            const __grid_constant__ CUtensorMap tm_o, const Gru2Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_s = smem;                                  // [2 chunks][hi | lo][192 x 128 B]
+    uint8_t* ring = w_s + 4 * W_CHUNK;                    // [4] h boxes: tile parity p -> h_hi = 2p, h_lo = 2p + 1
+    uint8_t* xring = ring + 4 * SLOT_BYTES;               // [2] x_hi, x_lo of the tile whose MMAs run next
+    uint8_t* out_s = xring + 2 * SLOT_BYTES;              // [2] output tile: hi box | lo box
+    float* bias_s = (float*)(out_s + 2 * SLOT_BYTES);     // [192]: r, z pre-scaled by -log2(e)
+    uint64_t* hfull = (uint64_t*)(bias_s + 192);          // [4]
+    uint64_t* hempty = hfull + 4;                         // [4] MMA commit + one arrival per epilogue warp (h_prev readers)
+    uint64_t* xfull = hempty + 4;                         // [2]
+    uint64_t* xempty = xfull + 2;                         // [2] MMA commit
+    uint64_t* acc_full = xempty + 2;                      // [2]
+    uint64_t* acc_empty = acc_full + 2;                   // [2]
+    uint64_t* out_ready = acc_empty + 2;                  // [1] every epilogue warp has written its part of the output tile
+    uint64_t* out_free = out_ready + 1;                   // [1] the TMA stores have read the output tile
+    uint32_t* tmem_slot = (uint32_t*)(out_free + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&hfull[i], 1);
+            mbar_init(&hempty[i], 1 + EPI_W);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&xfull[i], 1);
+            mbar_init(&xempty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_W);
+        }
+        mbar_init(out_ready, EPI_W);
+        mbar_init(out_free, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 192; i += THREADS2) {
+        const float b = P.bias ? P.bias[i] : 0.f;
+        bias_s[i] = i < 128 ? -kLog2e * b : b;
+    }
+    if (warp == EPI_W + 1) tmem_alloc(tmem_slot, 512);
+    {
+        const float4* g = reinterpret_cast<const float4*>(P.wpack);
+        const uint32_t s = smem_u32(w_s);
+        for (int i = threadIdx.x; i < 4 * W_CHUNK / 16; i += THREADS2) {
+            const float4 v = __ldg(g + i);
+            sts128(s + 16u * (uint32_t)i, v);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EPI_W) {
+        // ============================== TMA PRODUCER ==============================
+        // order: h(0) | x(0), h(1) | x(1), h(2) | ...: the h boxes run one tile ahead (their slots are free as soon as the
+        // epilogue of two tiles ago has taken its h_prev values), the x boxes follow the MMAs of the previous tile
+        if (lane == 0) {
+            T2P(long long t_pw = 0, t_p0 = clock64(), c0;)
+            auto load = [&](uint64_t* fullb, uint64_t* emptyb, uint32_t parity, uint8_t* dst, const CUtensorMap* tm, int c0e, int q0) {
+                T2P(c0 = clock64();)
+                mbar_wait_sleep(emptyb, parity ^ 1, 64);
+                T2P(t_pw += clock64() - c0;)
+                if (T2_DBG(P, 2)) {
+                    mbar_arrive(fullb);
+                } else {
+                    mbar_expect_tx(fullb, SLOT_BYTES);
+                    tma_load_2d(smem_u32(dst), tm, c0e, q0, smem_u32(fullb));
+                }
+            };
+            int it = 0;
+            uint32_t xph = 0;
+            const int first = blockIdx.x;
+            if (first < P.n_tiles) {
+                load(&hfull[0], &hempty[0], 0, ring, &tm_h, 0, first * TILE);
+                load(&hfull[1], &hempty[1], 0, ring + SLOT_BYTES, &tm_h, 64, first * TILE);
+            }
+            for (int tile = first; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                load(&xfull[0], &xempty[0], xph, xring, &tm_x, 0, tile * TILE);
+                load(&xfull[1], &xempty[1], xph, xring + SLOT_BYTES, &tm_x, 64, tile * TILE);
+                xph ^= 1;
+                const int nt = tile + gridDim.x;
+                if (nt < P.n_tiles) {
+                    const int p = (it + 1) & 1;
+                    const uint32_t hph = (uint32_t)((it + 1) >> 1) & 1u;
+                    load(&hfull[2 * p], &hempty[2 * p], hph, ring + (2 * p) * SLOT_BYTES, &tm_h, 0, nt * TILE);
+                    load(&hfull[2 * p + 1], &hempty[2 * p + 1], hph, ring + (2 * p + 1) * SLOT_BYTES, &tm_h, 64, nt * TILE);
+                }
+            }
+            T2P(if (P.prof) { P.prof[blockIdx.x * 16 + 0] = clock64() - t_p0; P.prof[blockIdx.x * 16 + 1] = t_pw; })
+        }
+    } else if (warp == EPI_W + 1) {
+        // ============================== MMA ISSUER (whole warp, one elected lane per instruction) ==============================
+        const uint32_t tmem_u = uni(tmem_base);
+        const uint32_t ws = smem_u32(w_s), rs = smem_u32(ring);
+        const uint64_t wh_hi = make_desc(ws), wh_lo = make_desc(ws + W_CHUNK);
+        const uint64_t wx_hi = make_desc(ws + 2 * W_CHUNK), wx_lo = make_desc(ws + 3 * W_CHUNK);
+        const uint64_t wx_hi_n = make_desc(ws + 2 * W_CHUNK + 128 * 128);  // rows 128..191 of W_ih (the n gate)
+        constexpr uint32_t id192 = make_idesc(TILE, 192), id128 = make_idesc(TILE, 128), id64 = make_idesc(TILE, 64);
+        const uint32_t xs = smem_u32(xring);
+        int buf = 0, it = 0;
+        uint32_t acc_ph = 0, xph = 0;
+        T2P(long long t_m0 = clock64(), t_wacc = 0, t_wfull = 0, c0;)
+#ifdef MRB_TC_PROF
+#define WAIT_FULL(bar, par) do { c0 = clock64(); mbar_wait(bar, par); t_wfull += clock64() - c0; } while (0)
+#else
+#define WAIT_FULL(bar, par) mbar_wait(bar, par)
+#endif
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int p = it & 1;
+            const uint32_t hph = (uint32_t)(it >> 1) & 1u;
+            T2P(c0 = clock64();)
+            mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+            T2P(t_wacc += clock64() - c0;)
+            tc_fence_after();
+            // accumulator columns: [0,64) hh_n | [64,128) r | [128,192) z | [192,256) ih_n
+            const uint32_t d = tmem_u + (uint32_t)(buf * 256);
+            // h_hi x (Whh_hi, Whh_lo): the first MMA overwrites columns [0,192)
+            WAIT_FULL(&hfull[2 * p], hph);
+            tc_fence_after();
+            uint64_t a = make_desc(rs + (uint32_t)((2 * p) * SLOT_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                umma_ss(d, a + 2 * k, wh_hi + 2 * k, id192, k > 0);
+                umma_ss(d, a + 2 * k, wh_lo + 2 * k, id192, 1);
+            }
+            umma_commit(&hempty[2 * p]);
+            // h_lo x Whh_hi
+            WAIT_FULL(&hfull[2 * p + 1], hph);
+            tc_fence_after();
+            a = make_desc(rs + (uint32_t)((2 * p + 1) * SLOT_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d, a + 2 * k, wh_hi + 2 * k, id192, 1);
+            umma_commit(&hempty[2 * p + 1]);
+            // x_hi x (Wih_hi, Wih_lo): r, z accumulate onto the h part, the ih_n columns start here
+            WAIT_FULL(&xfull[0], xph);
+            tc_fence_after();
+            a = make_desc(xs);
+            umma_ss(d + 64, a, wx_hi, id128, 1);
+            umma_ss(d + 192, a, wx_hi_n, id64, 0);
+            umma_ss(d + 64, a, wx_lo, id192, 1);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                umma_ss(d + 64, a + 2 * k, wx_hi + 2 * k, id192, 1);
+                umma_ss(d + 64, a + 2 * k, wx_lo + 2 * k, id192, 1);
+            }
+            umma_commit(&xempty[0]);
+            // x_lo x Wih_hi
+            WAIT_FULL(&xfull[1], xph);
+            tc_fence_after();
+            a = make_desc(xs + SLOT_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d + 64, a + 2 * k, wx_hi + 2 * k, id192, 1);
+            umma_commit(&xempty[1]);
+            xph ^= 1;
+            umma_commit(&acc_full[buf]);
+            if (++buf == 2) { buf = 0; acc_ph ^= 1; }
+        }
+        T2P(if (P.prof && lane == 0) { P.prof[blockIdx.x * 16 + 2] = clock64() - t_m0; P.prof[blockIdx.x * 16 + 3] = t_wacc; P.prof[blockIdx.x * 16 + 4] = t_wfull; })
+    } else if (warp == EPI_W + 2) {
+        // ============================== TMA STORE LANE ==============================
+        // waits until the 16 epilogue warps have written a tile's output boxes, stores them and frees the output tile as
+        // soon as the stores have read it
+        if (lane == 0) {
+            uint32_t oph = 0;
+            const uint32_t out_u32 = smem_u32(out_s);
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                mbar_wait_sleep(out_ready, oph, 64);
+                if (!T2_DBG(P, 8)) {
+                    tma_store_2d(&tm_o, out_u32, 0, tile * TILE);
+                    tma_store_2d(&tm_o, out_u32 + SLOT_BYTES, 64, tile * TILE);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(out_free);
+                oph ^= 1;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
+        }
+    } else {
+        // ============================== EPILOGUE ==============================
+        const int quad = warp & 3;   // TMEM lane quadrant
+        const int cg = warp >> 2;    // channels 16*cg .. 16*cg + 15
+        const int m = quad * 32 + lane;  // tile row = TMEM lane of this thread
+        const uint32_t bias_u32 = smem_u32(bias_s);
+        // this thread's two 16-byte chunks (8 channels each) of row m inside a [128 x 128 B] SWIZZLE_128B box
+        const uint32_t ch0 = swz(m, 2 * cg), ch1 = swz(m, 2 * cg + 1);
+        const uint32_t ring_u32 = smem_u32(ring), out_u32 = smem_u32(out_s);
+        int buf = 0, it = 0;
+        uint32_t acc_ph = 0, oph = 0;
+        T2P(long long t_e0 = clock64(), t_ew = 0, t_eld = 0, t_emath = 0, t_est = 0, c0;)
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            // ---- h_prev of this thread's row and channels from the landed h_hi / h_lo boxes, which are then released on
+            // behalf of this warp.  (An arrival can never be counted for an earlier phase of the same box: the data this
+            // warp has just waited for was loaded after that earlier phase had completed.)
+            float hp[16];
+            {
+                const int p = it & 1;
+                const uint32_t hph = (uint32_t)(it >> 1) & 1u;
+                uint4 hh[2], hl[2];
+                mbar_wait_sleep(&hfull[2 * p], hph, 32);
+                hh[0] = lds128u(ring_u32 + (uint32_t)((2 * p) * SLOT_BYTES) + ch0);
+                hh[1] = lds128u(ring_u32 + (uint32_t)((2 * p) * SLOT_BYTES) + ch1);
+                mbar_wait_sleep(&hfull[2 * p + 1], hph, 32);
+                hl[0] = lds128u(ring_u32 + (uint32_t)((2 * p + 1) * SLOT_BYTES) + ch0);
+                hl[1] = lds128u(ring_u32 + (uint32_t)((2 * p + 1) * SLOT_BYTES) + ch1);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&hempty[2 * p]);
+                    mbar_arrive(&hempty[2 * p + 1]);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t hw[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w}, lw[4] = {hl[j].x, hl[j].y, hl[j].z, hl[j].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        hp[8 * j + 2 * i] = bf_lo(hw[i]) + bf_lo(lw[i]);
+                        hp[8 * j + 2 * i + 1] = bf_hi(hw[i]) + bf_hi(lw[i]);
+                    }
+                }
+            }
+            T2P(c0 = clock64();)
+            mbar_wait_sleep(&acc_full[buf], acc_ph, 64);
+            T2P(t_ew += clock64() - c0;)
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + cg * 16);
+            float o[16];
+#pragma unroll
+            for (int jb = 0; jb < 2; ++jb) {
+                float hn[8], ar[8], az[8], xn[8];
+                T2P(c0 = clock64();)
+                tmem_ld8x4(t0 + jb * 8, t0 + 64 + jb * 8, t0 + 128 + jb * 8, t0 + 192 + jb * 8, hn, ar, az, xn);
+                T2P(t_eld += clock64() - c0; c0 = clock64();)
+                if (jb == 1) {  // all of this warp's accumulator columns are in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (T2_DBG(P, 4)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[jb * 8 + q] = hn[q] + ar[q] + az[q] + xn[q] + hp[jb * 8 + q];
+                } else
+#pragma unroll
+                for (int q4 = 0; q4 < 8; q4 += 4) {
+                    const int c = cg * 16 + jb * 8 + q4;
+                    const float4 br4 = lds128(bias_u32 + 4u * (uint32_t)c);
+                    const float4 bz4 = lds128(bias_u32 + 4u * (uint32_t)(64 + c));
+                    const float4 bn4 = lds128(bias_u32 + 4u * (uint32_t)(128 + c));
+                    const float br[4] = {br4.x, br4.y, br4.z, br4.w}, bz[4] = {bz4.x, bz4.y, bz4.z, bz4.w};
+                    const float bn[4] = {bn4.x, bn4.y, bn4.z, bn4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = q4 + u;
+                        // rnn_cells.py:121-125 (ih + hh of the r and z gates were summed by the tensor core).
+                        // r = 1/(1+ea), z = 1/(1+eb) share ONE reciprocal: 1/((1+ea)(1+eb)); the exponents are clamped
+                        // so that the product stays finite (a gate below 2^-60 is zero to fp32 in everything it multiplies)
+                        const float ea = 1.f + ex2_approx(fminf(fmaf(ar[q], -kLog2e, br[u]), 60.f));
+                        const float eb = 1.f + ex2_approx(fminf(fmaf(az[q], -kLog2e, bz[u]), 60.f));
+                        const float ip = rcp_approx(ea * eb);
+                        const float r = eb * ip, z = ea * ip;
+                        const float n = tanh_acc(fmaf(r, hn[q], xn[q] + bn[u]));
+                        o[jb * 8 + q] = fmaf(z, hp[jb * 8 + q], n * (1.f - z));
+                    }
+                }
+                T2P(t_emath += clock64() - c0;)
+            }
+            T2P(c0 = clock64();)
+            // ---- hi/lo split into the output tile (rows = positions, same box layout as the inputs) + TMA stores
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_bf16x2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+            mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
+            oph ^= 1;
+            sts128u(out_u32 + ch0, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128u(out_u32 + ch1, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+            sts128u(out_u32 + SLOT_BYTES + ch0, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            sts128u(out_u32 + SLOT_BYTES + ch1, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+            fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(out_ready);
+            T2P(t_est += clock64() - c0;)
+            if (++buf == 2) { buf = 0; acc_ph ^= 1; }
+        }
+        T2P(if (P.prof && threadIdx.x == 0) { unsigned long long* o = P.prof + blockIdx.x * 16; o[5] = clock64() - t_e0; o[6] = t_ew; o[7] = t_eld; o[8] = t_emath; o[9] = t_est; })
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_W + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// edge pixels -> replicate border of a BH tensor (one thread per (border position, 16-byte piece))
+__global__ void bh_fix_border_kernel(uint8_t* __restrict__ bh, int B, int H, int W) {
+    const int Hp = H + 2 * PADB, Wp = W + 2 * PADB;
+    const int nb = Hp * Wp - H * W;  // border positions per image
+    const long long total = (long long)B * nb * 16;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int piece = (int)(t & 15);
+        const long long r = t >> 4;
+        const int i = (int)(r % nb), b = (int)(r / nb);
+        int yp, xp;
+        if (i < 2 * PADB * Wp) {  // top and bottom bands
+            const int row = i / Wp;
+            yp = row < PADB ? row : H + row;  // rows 0,1 and H+2,H+3
+            xp = i - row * Wp;
+        } else {  // left and right bands of the interior rows
+            const int j = i - 2 * PADB * Wp;
+            const int row = j / (2 * PADB), c = j - row * 2 * PADB;
+            yp = PADB + row;
+            xp = c < PADB ? c : W + c;
+        }
+        const int ys = min(max(yp, PADB), H + PADB - 1), xs = min(max(xp, PADB), W + PADB - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(bh + (((long long)b * Hp + ys) * Wp + xs) * PX_BYTES + piece * 16);
+        *reinterpret_cast<uint4*>(bh + (((long long)b * Hp + yp) * Wp + xp) * PX_BYTES + piece * 16) = v;
+    }
+}
+
+// ---- layout converters -------------------------------------------------------------------------------
+// fp32 channels-last [B,H,W,64] -> BH (hi/lo split, replicate border)
+__global__ void bh_from_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ bh, int B, int H, int W) {
+    const int Hp = H + 2 * PADB, Wp = W + 2 * PADB;
+    const long long total = (long long)B * Hp * Wp * 8;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t & 7);
+        const long long q = t >> 3;
+        const int xp = (int)(q % Wp);
+        const long long r = q / Wp;
+        const int yp = (int)(r % Hp), b = (int)(r / Hp);
+        const int xx = min(max(xp - PADB, 0), W - 1), yy = min(max(yp - PADB, 0), H - 1);
+        const float4* s = reinterpret_cast<const float4*>(x + (((long long)b * H + yy) * W + xx) * 64 + g * 8);
+        const float4 a = __ldg(s), c = __ldg(s + 1);
+        uint32_t hi[4], lo[4];
+        split_bf16x2(a.x, a.y, hi[0], lo[0]);
+        split_bf16x2(a.z, a.w, hi[1], lo[1]);
+        split_bf16x2(c.x, c.y, hi[2], lo[2]);
+        split_bf16x2(c.z, c.w, hi[3], lo[3]);
+        uint8_t* d = bh + q * PX_BYTES + g * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(d + 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+// BH -> fp32 channels-last [B,H,W,64] (interior only; x = hi + lo)
+__global__ void bh_to_nhwc_kernel(const uint8_t* __restrict__ bh, float* __restrict__ x, int B, int H, int W) {
+    const int Hp = H + 2 * PADB, Wp = W + 2 * PADB;
+    const long long total = (long long)B * H * W * 8;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t & 7);
+        const long long p = t >> 3;
+        const int xx = (int)(p % W);
+        const long long r = p / W;
+        const int yy = (int)(r % H), b = (int)(r / H);
+        const uint8_t* s = bh + (((long long)b * Hp + yy + PADB) * Wp + xx + PADB) * PX_BYTES + g * 16;
+        const uint4 h = *reinterpret_cast<const uint4*>(s), l = *reinterpret_cast<const uint4*>(s + 128);
+        float4* d = reinterpret_cast<float4*>(x + p * 64 + g * 8);
+        d[0] = make_float4(bf_lo(h.x) + bf_lo(l.x), bf_hi(h.x) + bf_hi(l.x), bf_lo(h.y) + bf_lo(l.y), bf_hi(h.y) + bf_hi(l.y));
+        d[1] = make_float4(bf_lo(h.z) + bf_lo(l.z), bf_hi(h.z) + bf_hi(l.z), bf_lo(h.w) + bf_lo(l.w), bf_hi(h.w) + bf_hi(l.w));
+    }
+}
+
+#ifdef MRB_TC_PROF
+int g_debug2 = 0;
+unsigned long long* g_prof2 = nullptr;
+#endif
+static size_t gru2_smem() { return 1024 + 4 * W_CHUNK + NSLOT * SLOT_BYTES + 192 * 4 + 20 * 8 + 16; }
+
+}  // namespace tc2
+}  // namespace mrb
+
+using namespace mrb;
+
+extern "C" size_t mrb_bh_bytes(int B, int H, int W) {
+    return (size_t)B * (size_t)(H + 2 * tc2::PADB) * (size_t)(W + 2 * tc2::PADB) * tc2::PX_BYTES;
+}
+
+extern "C" int mrb_bh_from_nhwc(const void* x, void* bh, int B, int H, int W, void* stream) {
+    MRB_REQUIRE(x && bh && B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_bh_from_nhwc: bad argument");
+    const long long total = (long long)B * (H + 2 * tc2::PADB) * (W + 2 * tc2::PADB) * 8;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    tc2::bh_from_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (uint8_t*)bh, B, H, W);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_bh_to_nhwc(const void* bh, void* x, int B, int H, int W, void* stream) {
+    MRB_REQUIRE(x && bh && B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_bh_to_nhwc: bad argument");
+    const long long total = (long long)B * H * W * 8;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    tc2::bh_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)bh, (float*)x, B, H, W);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_bh_fix_border(void* bh, int B, int H, int W, void* stream) {
+    MRB_REQUIRE(bh && B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_bh_fix_border: bad argument");
+    const long long nb = (long long)(H + 2 * tc2::PADB) * (W + 2 * tc2::PADB) - (long long)H * W;
+    const long long total = (long long)B * nb * 16;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    tc2::bh_fix_border_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t*)bh, B, H, W);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" size_t mrb_tc2_gru_packed_bytes(void) { return (size_t)4 * tc2::W_CHUNK; }
+
+extern "C" int mrb_tc2_pack_gru(const void* w_ih, const void* w_hh, void* dst, int ch, int cx, void* stream) {
+    MRB_REQUIRE(w_ih && w_hh && dst, MRB_EINVAL, "mrb_tc2_pack_gru: null pointer");
+    MRB_REQUIRE(ch == 64 && cx == 64, MRB_EUNSUPPORTED, "mrb_tc2_pack_gru: 64 input and hidden channels only");
+    tc::PackDesc D{(const float*)w_ih, (const float*)w_hh, 1, ch, cx, 1, ch, 3 * ch, 2, 1};  // no channel split: 192 rows per chunk
+    return tc::pack_launch(D, dst, (cudaStream_t)stream);
+}
+
+extern "C" int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack, const void* b_ih, void* out_bh, int B, int H,
+                           int W, void* stream) {
+    MRB_REQUIRE(x_bh && h_bh && wpack && out_bh, MRB_EINVAL, "mrb_tc2_gru: null pointer");
+    MRB_REQUIRE(out_bh != h_bh && out_bh != x_bh, MRB_EINVAL, "mrb_tc2_gru: the output must not alias an input");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_gru: bad shape");
+    tc2::Gru2Params P;
+    P.wpack = wpack; P.bias = (const float*)b_ih;
+    P.Q = (long long)B * (H + 2 * tc2::PADB) * (W + 2 * tc2::PADB);
+    MRB_REQUIRE(P.Q < 2147483647LL - tc2::TILE, MRB_EUNSUPPORTED, "mrb_tc2_gru: too many pixels");
+    P.n_tiles = (int)((P.Q + tc2::TILE - 1) / tc2::TILE);
+#ifdef MRB_TC_PROF
+    P.debug = tc2::g_debug2; P.prof = tc2::g_prof2;
+    { int skip = (tc2::g_debug2 & 1) ? 1 : 0; cudaMemcpyToSymbol(tc2::g_skip_mma, &skip, sizeof(int)); }
+#endif
+    CUtensorMap tm_h, tm_x, tm_o;
+    int rc = tc2::make_bh_tmap(&tm_h, h_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    rc = tc2::make_bh_tmap(&tm_x, x_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    rc = tc2::make_bh_tmap(&tm_o, out_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    static bool attr_set = false;
+    const size_t smem = tc2::gru2_smem();
+    if (!attr_set) {
+        MRB_REQUIRE(smem <= device_max_smem_optin(), MRB_EUNSUPPORTED, "mrb_tc2_gru: shared memory");
+        MRB_CUDA(cudaFuncSetAttribute(tc2::gru2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = device_sm_count();
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    tc2::gru2_kernel<<<grid, tc2::THREADS2, smem, (cudaStream_t)stream>>>(tm_h, tm_x, tm_o, P);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+#ifdef MRB_TC_PROF
+extern "C" void mrb_tc2_set_debug(int flags) { tc2::g_debug2 = flags; }
+extern "C" void mrb_tc2_set_prof(void* buf) { tc2::g_prof2 = (unsigned long long*)buf; }
+#endif

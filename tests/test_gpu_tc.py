@@ -198,3 +198,115 @@ def test_tc_kernels_are_deterministic():
     for lst in outs:
         for o in lst[1:]:
             assert torch.equal(o, lst[0])
+
+
+def _bh_roundtrip(x_nhwc):
+    """fp32 [B,H,W,64] -> BH -> (raw BH view [B,H+4,W+4,128] bf16, fp32 back)"""
+    from mridc_b200 import _lib
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    B, H, W, _ = x_nhwc.shape
+    bh = torch.empty(lib.mrb_bh_bytes(B, H, W), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_bh_from_nhwc(_lib.ptr(x_nhwc), _lib.ptr(bh), B, H, W, st))
+    back = torch.empty_like(x_nhwc)
+    _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(bh), _lib.ptr(back), B, H, W, st))
+    return bh, back
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (2, 5, 100), (1, 320, 320)])
+def test_tc2_gru_vs_oracle(B, H, W):
+    """Second-generation GRU kernel (TMA + smem operands, BH activations): converters, cell arithmetic, replicate border."""
+    from mridc_b200 import _lib
+    from oracle import nets as onets
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(H + 1)
+    x = torch.randn(B, 64, H, W, generator=g)
+    h = torch.randn(B, 64, H, W, generator=g)
+    wih = torch.randn(192, 64, 1, 1, generator=g) * 0.1
+    whh = torch.randn(192, 64, 1, 1, generator=g) * 0.1
+    bih = torch.randn(192, generator=g)
+    ref = onets.conv_gru_cell(x, h, wih, bih, whh, 1, 1)
+    xd, hd = x.permute(0, 2, 3, 1).contiguous().cuda(), h.permute(0, 2, 3, 1).contiguous().cuda()
+    xb, xback = _bh_roundtrip(xd)
+    hb, _ = _bh_roundtrip(hd)
+    assert rel_l2(xback, xd) < 4e-6  # hi + lo carries 16-17 significant bits
+    raw = xb.view(torch.bfloat16).view(B, H + 4, W + 4, 128).float()
+    assert torch.equal(raw[:, 0, 0], raw[:, 2, 2]) and torch.equal(raw[:, -1, -1], raw[:, -3, -3])  # replicate border
+    assert torch.equal(raw[:, 1, 5 % (W + 4)], raw[:, 2, min(max(5 % (W + 4), 2), W + 1)])
+    wd, w2d, bd = wih.cuda().contiguous(), whh.cuda().contiguous(), bih.cuda()
+    pk = torch.empty(lib.mrb_tc2_gru_packed_bytes(), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_tc2_pack_gru(_lib.ptr(wd), _lib.ptr(w2d), _lib.ptr(pk), 64, 64, st))
+    ob = torch.full((lib.mrb_bh_bytes(B, H, W),), 0x7f, dtype=torch.uint8, device="cuda")  # poison: every byte must be written
+    # garbage (NaN patterns) in the border of x must not reach any interior result
+    xb.view(torch.bfloat16).view(B, H + 4, W + 4, 128)[:, :2] = float("nan")
+    xb.view(torch.bfloat16).view(B, H + 4, W + 4, 128)[:, :, -2:] = float("nan")
+    _lib.check(lib.mrb_tc2_gru(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(ob), B, H, W, st))
+    _lib.check(lib.mrb_bh_fix_border(_lib.ptr(ob), B, H, W, st))
+    out = torch.empty_like(xd)
+    _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(ob), _lib.ptr(out), B, H, W, st))
+    _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "gru (tc2)")
+    rawo = ob.view(torch.bfloat16).view(B, H + 4, W + 4, 128).float()
+    inner = rawo[:, 2:-2, 2:-2]
+    pad = torch.nn.functional.pad(inner.permute(0, 3, 1, 2), (2, 2, 2, 2), mode="replicate").permute(0, 2, 3, 1)
+    assert torch.equal(pad, rawo)  # the replicate border of the output is complete and exact
+    # run-to-run determinism
+    ob2 = torch.empty_like(ob)
+    _lib.check(lib.mrb_tc2_gru(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(ob2), B, H, W, st))
+    _lib.check(lib.mrb_bh_fix_border(_lib.ptr(ob2), B, H, W, st))
+    assert torch.equal(ob, ob2)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 64, 32), (2, 33, 28), (1, 320, 320)])
+def test_tc2_conv_ops_vs_oracle(B, H, W):
+    """The convolutions of the time step on BH activations: conv5x5 (fp32 gradient -> BH), conv3x3 (BH -> BH, replicate
+    padding = the BH border), final conv (BH -> eta)."""
+    from mridc_b200 import _lib
+    from oracle import nets as onets
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(W)
+    nb = lib.mrb_bh_bytes(B, H, W)
+
+    def from_bh(buf):
+        out = torch.empty(B, H, W, 64, device="cuda")
+        _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(buf), _lib.ptr(out), B, H, W, st))
+        return out.permute(0, 3, 1, 2)
+
+    x4 = torch.randn(B, 4, H, W, generator=g)
+    w1 = torch.randn(64, 4, 5, 5, generator=g) * 0.2
+    b1 = torch.randn(64, generator=g)
+    ref = onets.conv_nonlinear(x4, w1, b1, 5, 1, "relu")
+    x4d, p1, b1d = x4.permute(0, 2, 3, 1).contiguous().cuda(), _pack(2, w1.cuda()), b1.cuda()
+    ob = torch.full((nb,), 0x7f, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(x4d), _lib.ptr(p1), _lib.ptr(b1d), _lib.ptr(ob), B, H, W, 64, 1, st))
+    _diag(from_bh(ob), ref, 1e-5, "conv5x5x4 (bh)")
+
+    x = torch.randn(B, 64, H, W, generator=g)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    xb, _ = _bh_roundtrip(xd)
+    for dil, relu in ((2, 1), (1, 0)):
+        w2 = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+        b2 = torch.randn(64, generator=g)
+        ref = onets.conv_nonlinear(x, w2, b2, 3, dil, "relu" if relu else None)
+        p2, b2d = _pack(0, w2.cuda(), k=3), b2.cuda()
+        ob = torch.full((nb,), 0x7f, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.mrb_tc_conv_bh(_lib.ptr(xb), _lib.ptr(p2), _lib.ptr(b2d), _lib.ptr(ob), B, H, W, 64, 3, dil, relu, st))
+        _diag(from_bh(ob), ref, 1e-5, "conv3x3 dil %d (bh)" % dil)
+        ob2 = torch.empty_like(ob)
+        _lib.check(lib.mrb_tc_conv_bh(_lib.ptr(xb), _lib.ptr(p2), _lib.ptr(b2d), _lib.ptr(ob2), B, H, W, 64, 3, dil, relu, st))
+        a_, b_ = from_bh(ob), from_bh(ob2)
+        assert torch.equal(a_, b_)  # run-to-run determinism (interior)
+
+    w3 = torch.randn(2, 64, 3, 3, generator=g) * 0.05
+    eta = torch.randn(B, H, W, 2, generator=g)
+    ref = eta + onets.conv_nonlinear(x, w3, None, 3, 1, None).permute(0, 2, 3, 1)
+    o2 = torch.empty(B, H, W, 2, device="cuda")
+    w3d, etad = w3.cuda(), eta.cuda()
+    _lib.check(lib.mrb_conv_c2_bh_residual(_lib.ptr(xb), _lib.ptr(w3d), None, _lib.ptr(etad), _lib.ptr(o2), B, H, W, st))
+    e = rel_l2(o2, ref)
+    print("[tc parity] %-16s rel-L2 %.2e" % ("conv_c2 (bh)", e))
+    assert e < 5e-6  # exact fp32 arithmetic on x = hi + lo (2^-18 relative representation error)

@@ -12,11 +12,14 @@ def load():
         _build.build_tools()
     lib = ctypes.CDLL(os.path.abspath(_build.TOOLS_LIB_PATH))
     for name in ("mrb_tc_packed_floats", "mrb_tc_pack_conv", "mrb_tc_pack_gru", "mrb_tc_pack_conv5x5x4", "mrb_tc_conv_nhwc",
-                 "mrb_tc_conv5x5x4_nhwc", "mrb_tc_gru_nhwc", "mrb_tc_indrnn_nhwc", "mrb_conv_c2_nhwc_residual", "mrb_last_error"):
+                 "mrb_tc_conv5x5x4_nhwc", "mrb_tc_gru_nhwc", "mrb_tc_indrnn_nhwc", "mrb_conv_c2_nhwc_residual", "mrb_last_error",
+                 "mrb_bh_bytes", "mrb_bh_from_nhwc", "mrb_bh_to_nhwc", "mrb_tc2_gru_packed_bytes", "mrb_tc2_pack_gru", "mrb_tc2_gru"):
         res, args = _lib.SIGNATURES[name]
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     lib.mrb_tc_set_debug.restype, lib.mrb_tc_set_debug.argtypes = None, [_i]
     lib.mrb_tc_set_prof.restype, lib.mrb_tc_set_prof.argtypes = None, [_vp]
+    lib.mrb_tc2_set_debug.restype, lib.mrb_tc2_set_debug.argtypes = None, [_i]
+    lib.mrb_tc2_set_prof.restype, lib.mrb_tc2_set_prof.argtypes = None, [_vp]
     lib.mrb_tc_microbench.restype, lib.mrb_tc_microbench.argtypes = _i, [_i, _i, _i, _i, _vp, _vp]
     return lib
