@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
     uint64_t* b_full = acc_empty + 4;               // [B_STAGES]
     uint64_t* b_empty = b_full + B_STAGES;          // [B_STAGES]
     uint64_t* out_free = acc_empty + 3;             // [1] out_bh: the TMA stores of the previous tile have read out_s
-    float* bias_s = (float*)(b_empty + B_STAGES);   // [BIAS_FLOATS] (16-byte aligned): bias staged once per CTA
+    uint64_t* out_ready = b_empty + B_STAGES;       // [1] out_bh: every epilogue warp has written its part of the output tile
+    float* bias_s = (float*)(out_ready + 2);        // [BIAS_FLOATS] (16-byte aligned): bias staged once per CTA
     uint8_t* epi_s = (uint8_t*)(bias_s + BIAS_FLOATS);  // GRU: [EPI_WARPS][2][32 px][EPI_ROW_BYTES] per-warp exchange tiles
 
     // warp index through a shuffle: provably warp-uniform for the compiler (role branches and the MMA issuers' operands
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
             mbar_init(&b_empty[b], 1);  // tcgen05.commit of the MMAs that read the slot
         }
         mbar_init(out_free, 1);
+        mbar_init(out_ready, EPI_WARPS);
         fence_barrier_init();
     }
     {
@@ -1015,16 +1017,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                 mbar_arrive(&acc_empty[buf]);
             }
             if (P.out_bh) {
-                // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps are here
+                // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps have arrived
+                // (mbarriers only: no warp-aligned instruction is executed while lane 0 of warp 0 is busy with the stores)
                 fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(out_ready);
                 if (threadIdx.x == 0) {
+                    mbar_wait_sleep(out_ready, oph, 32);
                     tma_store_2d(&tm_out, out_u32, 0, tile * TILE_M);
                     tma_store_2d(&tm_out, out_u32 + OUT_BOX_BYTES, 64, tile * TILE_M);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     mbar_arrive(out_free);
                 }
+                __syncwarp();
                 oph ^= 1;
             }
             if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
@@ -1118,6 +1124,8 @@ static int launch(Params& P, cudaStream_t st) {
     MRB_REQUIRE(P.stages >= 2, MRB_EUNSUPPORTED, "tensor-core conv: accumulator leaves no room for the TMEM A ring");
     MRB_REQUIRE(P.P < 2147483647LL, MRB_EUNSUPPORTED, "tensor-core conv: too many pixels");
     MRB_REQUIRE(P.nseg >= P.n_issuers && P.nseg <= MAX_SEGS, MRB_EUNSUPPORTED, "tensor-core conv: bad segment count");
+    // two issuers share the rings safely only if a slot / stage is always revisited by the same issuer inside a tile
+    // (tiles are separated by the accumulator hand-shake): ring depths must be even
     MRB_REQUIRE(P.im2col != 2 || P.nseg == LOAD_GROUPS, MRB_EUNSUPPORTED, "tensor-core conv: patch mode needs one K chunk per loader group");
     MRB_REQUIRE(!(P.src_bh || P.out_bh) || P.pos_padded, MRB_EINVAL, "tensor-core conv: BH tensors need padded positions");
     MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1), MRB_EUNSUPPORTED, "tensor-core conv: BH output needs 64 channels");
@@ -1135,6 +1143,10 @@ static int launch(Params& P, cudaStream_t st) {
     if (P.b_stages == 0) P.b_stages = B_STAGES;
     if (smem_needed(P) > max_smem) P.tb_depth = 2;
     while (P.stream_b && P.b_stages > 2 && smem_needed(P) > max_smem) --P.b_stages;
+    if (P.n_issuers == 2) {  // see above: even ring depths for two issuers
+        if (P.stream_b && (P.b_stages & 1)) --P.b_stages;
+        if (P.stages & 1) --P.stages;
+    }
     MRB_REQUIRE(smem_needed(P) <= max_smem, MRB_EUNSUPPORTED, "tensor-core conv: weights do not fit shared memory");
     static bool attr_set = false;  // per-process, not per launch (the attribute calls are not free)
     if (!attr_set) {
@@ -1145,8 +1157,12 @@ static int launch(Params& P, cudaStream_t st) {
     int sms = device_sm_count();
     int grid = (sms / P.n_split) * P.n_split;  // groups of n_split CTAs share a pixel tile
     if (grid > P.n_split * P.n_tiles) grid = P.n_split * P.n_tiles;
-    if (P.mode == MODE_GRU) tc_kernel<true><<<grid, THREADS, smem_needed(P), st>>>(tm_out, P);
-    else tc_kernel<false><<<grid, THREADS, smem_needed(P), st>>>(tm_out, P);
+    // Every launch asks for the full opt-in shared memory (one CTA per SM anyway): all tensor-core kernels of the time
+    // step then run with the same shared-memory carve-out.  Alternating this kernel between a ~195 KB and a ~227 KB
+    // configuration (two different carve-outs) produced sporadic "Warp Illegal Instruction" traps in the weight streamer
+    // and hangs on the B200 (reproduced with tools/stress_bh.py conv3+conv5; same-size sequences never failed).
+    if (P.mode == MODE_GRU) tc_kernel<true><<<grid, THREADS, max_smem, st>>>(tm_out, P);
+    else tc_kernel<false><<<grid, THREADS, max_smem, st>>>(tm_out, P);
     MRB_LAUNCHED();
     return MRB_OK;
 }
@@ -1261,7 +1277,12 @@ static int tc_conv_launch(const void* x, const void* wpack, const void* bias, co
     // two accumulator groups, one per MMA issuer (the global segment stream alternates between them): fixed
     // accumulation order inside a group (bit-reproducible), half-length chains (see Params::ngroups); the epilogue
     // adds the groups.  A 1x1 kernel has a single segment per tile: one issuer, one group, two accumulator buffers.
-    P.n_issuers = P.nseg >= 2 ? 2 : 1;
+    // BH variant: ONE issuer.  Its staging tiles leave room for a 3-slot weight ring only, and a ring slot whose consecutive
+    // fills belong to different issuers breaks the parity waits (the issuer that is ahead sees the parity of the previous
+    // phase as "complete" and consumes the slot one fill early -- sporadic traps / hangs on the B200).  With K = 16 per MMA
+    // one issuing thread keeps the pipe fed (64 + 32 pipe cycles per k-step), and the 128-column accumulator can be
+    // double-buffered, so the epilogue overlaps the next tile.
+    P.n_issuers = (P.nseg >= 2 && !bh) ? 2 : 1;
     P.ngroups = P.n_issuers;
     P.group_cols = 2 * cout;
     MRB_REQUIRE(P.ngroups * 2 * cout <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");

@@ -564,9 +564,9 @@ extern "C" int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack
     rc = tc2::make_bh_tmap(&tm_o, out_bh, P.Q, tc2::TILE);
     if (rc) return rc;
     static bool attr_set = false;
-    const size_t smem = tc2::gru2_smem();
+    const size_t smem = device_max_smem_optin();  // the full opt-in size: same carve-out as the other tensor-core kernels
     if (!attr_set) {
-        MRB_REQUIRE(smem <= device_max_smem_optin(), MRB_EUNSUPPORTED, "mrb_tc2_gru: shared memory");
+        MRB_REQUIRE(tc2::gru2_smem() <= smem, MRB_EUNSUPPORTED, "mrb_tc2_gru: shared memory");
         MRB_CUDA(cudaFuncSetAttribute(tc2::gru2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }

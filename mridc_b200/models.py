@@ -121,7 +121,7 @@ class CIRIM(_BaseModel):
         hybrid_cache = {}  # hybrid-space k-space of y: prepared by the first cascade, reused by the others
         for i, cascade in enumerate(self.cirim):
             prediction, _ = cascade(prediction, y, sensitivity_maps, mask, init_pred, hx, sigma,
-                                    keep_eta=False if i == 0 else self.keep_eta, y_hybrid=hybrid_cache)
+                                    keep_eta=False if i == 0 else self.keep_eta, y_hybrid=hybrid_cache, want_hx=False)
             cascades_etas.append([self.process_intermediate_pred(pred, sensitivity_maps, target)
                                   for pred in prediction])
         yield cascades_etas

@@ -274,9 +274,11 @@ class RIMBlock(nn.Module):
     @torch.no_grad()
     def forward(self, pred: torch.Tensor, masked_kspace: torch.Tensor, sense: torch.Tensor, mask: torch.Tensor,
                 eta: torch.Tensor = None, hx: torch.Tensor = None, sigma: float = 1.0,
-                keep_eta: bool = False, y_hybrid: Optional[dict] = None) -> Tuple[Any, Union[list, torch.Tensor, None]]:
-        """rim_block.py:134-269.  ``y_hybrid`` (not in the reference signature): a dict the caller keeps across cascades so
-        that the hybrid-space k-space of ``masked_kspace`` (dc_hybrid_prepare) is computed once per slice batch."""
+                keep_eta: bool = False, y_hybrid: Optional[dict] = None,
+                want_hx: bool = True) -> Tuple[Any, Union[list, torch.Tensor, None]]:
+        """rim_block.py:134-269.  Not in the reference signature: ``y_hybrid``, a dict the caller keeps across cascades so
+        that the hybrid-space k-space of ``masked_kspace`` (dc_hybrid_prepare) is computed once per slice batch; and
+        ``want_hx=False``, with which a caller that drops the hidden states (CIRIM.forward) spares their export."""
         _ops.check_spatial_dims(self.spatial_dims)
         if self.coil_dim != 1:
             raise NotImplementedError("mridc_b200: RIMBlock expects coil_dim == 1")
@@ -313,8 +315,9 @@ class RIMBlock(nn.Module):
             self._tc_engine = RimTcEngine(self) if RimTcEngine.supported(self) else False
         use_tc = bool(self._tc_engine) and RimTcEngine.supported(self) and _lib.require_cuda(eta, "eta") is not None
         if use_tc:
-            # tensor-core (tcgen05, 3xTF32) channels-last engine for the whole time loop
-            etas, hx = self._tc_engine.run(eta, masked_kspace, sense, mcan, sigma, hx if hx_given else None, ws, yhyb)
+            # tensor-core (tcgen05, split-bf16) engine for the whole time loop
+            etas, hx = self._tc_engine.run(eta, masked_kspace, sense, mcan, sigma, hx if hx_given else None, ws, yhyb,
+                                           want_hx=want_hx or not self.no_dc)
         for _ in range(0 if use_tc else self.time_steps):  # :217-249 (generic exact-fp32 kernels)
             grad_eta = _ops.dc_rim_grad(eta, masked_kspace, sense, mcan, sigma, self.fft_centered,
                                         self.fft_normalization, ws=ws, y_hybrid=yhyb)

@@ -1,9 +1,14 @@
-"""Tensor-core time-step engine for RIMBlock (channels-last activations, tcgen05 3xTF32 kernels of conv_tc.cu).
+"""Tensor-core time-step engine for RIMBlock (tcgen05 / TMEM kernels of conv_tc.cu and conv_tc2.cu, split-bf16 products).
 
 Used by ``RIMBlock.forward`` when the block has the geometry of the shipped CIRIM/RIM configs
 (projects/reconstruction/model_zoo/conf/base_{cirim,rim}_run.yaml, recurrent_layer GRU or IndRNN): two
 ConvNonlinear(ReLU) + ConvGRUCell / IndRNNCell (kernel 1) stages with 64 channels and a final 64->2 ConvNonlinear.  Anything else
 runs on the generic exact-fp32 CUDA-core kernels.  Both paths are CUDA; neither is a CPU fallback.
+
+ConvGRU blocks run on the second-generation kernels: every activation of the time loop lives in the "BH" layout
+([B][H+4][W+4][64 hi bf16 | 64 lo bf16], see conv_tc2.cu) -- the hi/lo split is done once by the producing kernel's epilogue,
+the ConvGRU cell is fed by TMA, and the replicate padding of ConvNonlinear is the tensor's own border.  IndRNN blocks use the
+first-generation kernels on fp32 channels-last activations.
 """
 import os
 
@@ -25,8 +30,7 @@ class RimTcEngine:
 
         self.block = block
         self._indrnn = isinstance(block.layers[0].rnn, IndRNNCell)
-        self._key = None
-        self._packs = None
+        self._packs = {}
 
     # ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -49,7 +53,7 @@ class RimTcEngine:
                 if not (c.input_size == 4 and c.kernel_size == 5 and c.dilation == 1):
                     return False
             else:
-                if c.input_size != 64 or c.kernel_size % 2 != 1 or 2 * c.kernel_size**2 > 20:
+                if c.input_size != 64 or c.kernel_size % 2 != 1 or c.kernel_size**2 > 25:
                     return False
         f = block.final_layer[0]
         if not isinstance(f, ConvNonlinear) or f.features != 2 or f.input_size != 64 or f._act != _ops.ACT_NONE:
@@ -59,6 +63,14 @@ class RimTcEngine:
         return True
 
     # ---------------------------------------------------------------------------------------------
+    def use_bh(self, W) -> bool:
+        """BH-layout engine: ConvGRU, second conv with a receptive field inside the 2-pixel border, final conv 3x3, and
+        rows of at least 32 positions (W + 4 >= 32)."""
+        b = self.block
+        c1, f = b.layers[1].convs, b.final_layer[0]
+        return (not self._indrnn and os.environ.get("MRIDC_B200_TC_GEN1", "0") != "1" and W >= 28
+                and c1.dilation * (c1.kernel_size - 1) // 2 <= 2 and f.kernel_size == 3 and f.dilation == 1)
+
     def _params(self):
         b = self.block
         ps = []
@@ -66,11 +78,12 @@ class RimTcEngine:
             ps += [st.convs.conv_layer.weight, st.rnn.ih.weight, st.rnn.hh if self._indrnn else st.rnn.hh.weight]
         return ps
 
-    def packs(self):
+    def packs(self, bh=False):
         """Packed (hi/lo split, UMMA-swizzled) weights, rebuilt only when a parameter changes."""
         key = tuple((p.data_ptr(), p._version, str(p.device)) for p in self._params())
-        if key == self._key:
-            return self._packs
+        hit = self._packs.get(bh)
+        if hit is not None and hit[0] == key:
+            return hit[1]
         lib = _lib.load()
         st = _lib.stream_ptr()
         b = self.block
@@ -89,12 +102,16 @@ class RimTcEngine:
             if self._indrnn:  # the 1x1 ih conv; the per-channel recurrent weight goes to the kernel's epilogue
                 pg = torch.empty(lib.mrb_tc_packed_floats(0, 64, 64, 1), dtype=torch.float32, device=dev)
                 _lib.check(lib.mrb_tc_pack_conv(_lib.ptr(wih), _lib.ptr(pg), 64, 64, 1, st))
+            elif bh:  # all 192 gate rows in one CTA (conv_tc2.cu)
+                pg = torch.empty(lib.mrb_tc2_gru_packed_bytes(), dtype=torch.uint8, device=dev)
+                whh = r.hh.weight.detach().contiguous()
+                _lib.check(lib.mrb_tc2_pack_gru(_lib.ptr(wih), _lib.ptr(whh), _lib.ptr(pg), 64, 64, st))
             else:
                 pg = torch.empty(lib.mrb_tc_packed_floats(1, 64, 64, 1), dtype=torch.float32, device=dev)
                 whh = r.hh.weight.detach().contiguous()
                 _lib.check(lib.mrb_tc_pack_gru(_lib.ptr(wih), _lib.ptr(whh), _lib.ptr(pg), 64, 64, st))
             out.append((pc, pg))
-        self._key, self._packs = key, out
+        self._packs[bh] = (key, out)
         return out
 
     def _cell(self, lib, x, h, pack, rnn, h_out, B, H, W, st):
@@ -133,9 +150,107 @@ class RimTcEngine:
         return new_eta
 
     # ---------------------------------------------------------------------------------------------
-    def run(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid=None):
+    def conv_stack_bh(self, g4, h, h_alt, xbuf, eta, packs, B, H, W):
+        """One time step of the regulariser (rim_block.py:233-248) on BH buffers (conv_tc2.cu): conv5x5 -> ConvGRU -> border
+        -> conv3x3(dil) -> ConvGRU -> border -> final conv + eta update.  h / h_alt are ping-pong lists, swapped in place."""
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        b = self.block
+        c0, c1 = b.layers[0].convs, b.layers[1].convs
+        r0, r1 = b.layers[0].rnn, b.layers[1].rnn
+        fin = b.final_layer[0]
+        _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias), _lib.ptr(xbuf),
+                                           B, H, W, 64, 1, st))
+        _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[0]), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias),
+                                   _lib.ptr(h_alt[0]), B, H, W, st))
+        h[0], h_alt[0] = h_alt[0], h[0]
+        _lib.check(lib.mrb_bh_fix_border(_lib.ptr(h[0]), B, H, W, st))  # the dilated 3x3 reads it spatially
+        _lib.check(lib.mrb_tc_conv_bh(_lib.ptr(h[0]), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias), _lib.ptr(xbuf),
+                                      B, H, W, 64, c1.kernel_size, c1.dilation, 1, st))
+        _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[1]), _lib.ptr(packs[1][1]), _lib.ptr(r1.ih.bias),
+                                   _lib.ptr(h_alt[1]), B, H, W, st))
+        h[1], h_alt[1] = h_alt[1], h[1]
+        _lib.check(lib.mrb_bh_fix_border(_lib.ptr(h[1]), B, H, W, st))  # the final 3x3 reads it spatially
+        new_eta = torch.empty_like(eta)
+        _lib.check(lib.mrb_conv_c2_bh_residual(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight), _lib.ptr(fin.conv_layer.bias),
+                                               _lib.ptr(eta), _lib.ptr(new_eta), B, H, W, st))
+        return new_eta
+
+    def bench_step(self, B, H, W, dev):
+        """-> (callable running the conv stack of ONE time step on random buffers in this engine's layout, description)."""
+        g4 = torch.randn((B, H, W, 4), device=dev)
+        eta = torch.randn((B, H, W, 2), device=dev)
+        if self.use_bh(W):
+            lib = _lib.load()
+            nb = lib.mrb_bh_bytes(B, H, W)
+            h, h_alt = [], [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
+            for _ in range(2):
+                t = torch.randn((B, H, W, 64), device=dev) * 0.1
+                buf = torch.empty(nb, dtype=torch.uint8, device=dev)
+                _lib.check(lib.mrb_bh_from_nhwc(_lib.ptr(t), _lib.ptr(buf), B, H, W, _lib.stream_ptr()))
+                h.append(buf)
+            xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+            packs = self.packs(bh=True)
+            return (lambda: self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W),
+                    "split-bf16 tcgen05 ConvGRU stack of one time step on BH activations (conv5x5x4, TMA-fed ConvGRU, border, "
+                    "conv3x3d2, ConvGRU, border, conv3x3->2 + eta)")
+        h = [torch.randn((B, H, W, 64), device=dev) * 0.1 for _ in range(2)]
+        h_alt = [torch.empty_like(t) for t in h]
+        xbuf = torch.empty((B, H, W, 64), device=dev)
+        return (lambda: self.conv_stack(g4, h, h_alt, xbuf, eta),
+                "split-bf16 tcgen05 stack of one time step on fp32 channels-last activations (conv5x5x4, cell 1x1, conv3x3d2, "
+                "cell 1x1, conv3x3->2 + eta)")
+
+    def _run_bh(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid, want_hx):
+        lib = _lib.load()
+        b = self.block
+        B, C, H, W, _ = masked_kspace.shape
+        dev = masked_kspace.device
+        packs = self.packs(bh=True)
+        st = _lib.stream_ptr()
+        nb = lib.mrb_bh_bytes(B, H, W)
+        if hx is None:
+            # zero initial state (rim_block.py:188-193): one cached, read-only zero buffer (its border is zero too)
+            key = ("bh", B, H, W, str(dev))
+            if _ZERO_STATE.get("key") != key:
+                _ZERO_STATE.update(key=key, buf=torch.zeros(nb, dtype=torch.uint8, device=dev))
+            h = [_ZERO_STATE["buf"], _ZERO_STATE["buf"]]
+        else:
+            h = []
+            for t in hx:  # NCHW fp32 in (the reference API) -> BH; the caller's tensors are never written
+                src = _lib.require_cuda(t, "hx").permute(0, 2, 3, 1).contiguous()
+                buf = torch.empty(nb, dtype=torch.uint8, device=dev)
+                _lib.check(lib.mrb_bh_from_nhwc(_lib.ptr(src), _lib.ptr(buf), B, H, W, st))
+                h.append(buf)
+        h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
+        xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        etas = []
+        eta = eta.contiguous()
+        for step in range(b.time_steps):
+            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
+                             ws=ws, nhwc=True, y_hybrid=y_hybrid)
+            eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W)
+            if step == 0 and hx is None:
+                # the ping-pong swap left the shared zero buffer in h_alt: it must never be written
+                h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
+            etas.append(eta)
+        if not want_hx:
+            return etas, None
+        out = []
+        for buf in h:  # BH -> fp32, NCHW-shaped like the reference's hidden states
+            t = torch.empty((B, H, W, 64), dtype=torch.float32, device=dev)
+            _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(buf), _lib.ptr(t), B, H, W, st))
+            out.append(t.permute(0, 3, 1, 2))
+        return etas, out
+
+    # ---------------------------------------------------------------------------------------------
+    def run(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid=None, want_hx=True):
         """The time loop of rim_block.py:217-249.  eta [B,H,W,2]; hx: list of 2 NCHW-shaped tensors or None.
-        Returns (list of etas, [h0, h1]) with the hidden states NCHW-shaped (channels-last strides)."""
+        Returns (list of etas, [h0, h1]) with the hidden states NCHW-shaped (channels-last strides); ``want_hx=False``
+        (CIRIM.forward, which drops them, cirim.py:156-163) skips the export of the hidden states."""
+        if self.use_bh(masked_kspace.shape[3]):
+            return self._run_bh(eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid, want_hx)
         lib = _lib.load()
         b = self.block
         B, C, H, W, _ = masked_kspace.shape
@@ -151,7 +266,9 @@ class RimTcEngine:
                 _ZERO_STATE.update(key=key, buf=torch.zeros((B, H, W, 64), dtype=torch.float32, device=dev))
             h = [_ZERO_STATE["buf"], _ZERO_STATE["buf"]]
         else:
-            h = [hx[0].permute(0, 2, 3, 1).contiguous(), hx[1].permute(0, 2, 3, 1).contiguous()]
+            # never write the caller's tensors: .contiguous() is a no-op for channels-last inputs, so clone explicitly
+            h = [hx[0].permute(0, 2, 3, 1).clone(memory_format=torch.contiguous_format),
+                 hx[1].permute(0, 2, 3, 1).clone(memory_format=torch.contiguous_format)]
         h_alt = [torch.empty((B, H, W, 64), dtype=torch.float32, device=dev) for _ in range(2)]
         xbuf = torch.empty((B, H, W, 64), dtype=torch.float32, device=dev)
         g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
