@@ -697,6 +697,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
             const uint32_t tmem_u = uni(tmem_base);
             const uint32_t w_u32 = smem_u32(w_s), bst_u32 = smem_u32(bst_s);
             const uint32_t grp_off = (uint32_t)(mi * P.group_cols);
+            // loop-invariant operands of the stacked issue (segments of a conv all have N = nhalf, wchunk = segment index)
+            const uint64_t desc0 = make_desc(w_u32);
+            const uint32_t idesc_n = make_idesc(TILE_M, P.nhalf), idesc_2n = make_idesc(TILE_M, 2 * P.nhalf);
             for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
                 TCP(if (prof) c0 = clock64();)
                 mbar_wait(&acc_empty[buf], acc_phase ^ 1);
@@ -707,17 +710,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                     TCP(if (prof) c1 = clock64();)
                     // every MMA operand is derived from kernel parameters and uniform loop state (no shared-memory
                     // table, no shuffles): it stays in uniform registers, and it is ready before the waits return
-                    const Segment sg = P.seg[sgi];
-                    const uint32_t b_hi = P.stream_b ? bst_u32 + (uint32_t)(bs * 2 * wbytes_chunk)
-                                                     : w_u32 + (uint32_t)(sg.wchunk * 2 * wbytes_chunk);
                     SegIssue si;
-                    si.dbh = make_desc(b_hi);
-                    si.dbl = make_desc(b_hi + wbytes_chunk);
-                    si.idesc = make_idesc(TILE_M, sg.n);
-                    si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
-                    si.first = (uint32_t)sg.first;
+                    uint32_t d = d_base;
+                    if (P.stacked) {
+                        // stacked convs: every segment has the same N and accumulator columns; only the weight chunk moves
+                        const uint32_t b_hi = P.stream_b ? bst_u32 + (uint32_t)(bs * 2 * wbytes_chunk)
+                                                         : w_u32 + (uint32_t)(sgi * 2 * wbytes_chunk);
+                        si.dbh = desc0 + (uint64_t)((b_hi - w_u32) >> 4);
+                        si.dbl = 0;
+                        si.idesc = idesc_n;
+                        si.idesc2n = idesc_2n;
+                        si.first = 0;
+                    } else {
+                        const Segment sg = P.seg[sgi];
+                        const uint32_t b_hi = P.stream_b ? bst_u32 + (uint32_t)(bs * 2 * wbytes_chunk)
+                                                         : w_u32 + (uint32_t)(sg.wchunk * 2 * wbytes_chunk);
+                        si.dbh = make_desc(b_hi);
+                        si.dbl = make_desc(b_hi + wbytes_chunk);
+                        si.idesc = make_idesc(TILE_M, sg.n);
+                        si.idesc2n = make_idesc(TILE_M, 2 * sg.n);
+                        si.first = (uint32_t)sg.first;
+                        d += (uint32_t)sg.dcol;
+                    }
                     const uint32_t a_hi = tmem_u + a_col0 + (uint32_t)(stage * A_STAGE_COLS);
-                    const uint32_t d = d_base + (uint32_t)sg.dcol;
                     if (P.stream_b) {
                         TCP(if (prof) c0 = clock64();)
                         mbar_wait(&b_full[bs], bphase);
@@ -767,6 +782,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                 o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb; o[12] = t_prep;
             }
 #endif
+        } else if (P.out_bh && mi == 1 && lane == 0) {
+            // ============================== TMA STORE LANE (out_bh; requires n_issuers == 1) ==============================
+            const uint32_t out_u32 = smem_u32(out_s);
+            uint32_t oph = 0;
+            for (int tile = first_tile; tile < P.n_tiles; tile += tile_stride) {
+                mbar_wait_sleep(out_ready, oph, 64);
+                tma_store_2d(&tm_out, out_u32, 0, tile * TILE_M);
+                tma_store_2d(&tm_out, out_u32 + OUT_BOX_BYTES, 64, tile * TILE_M);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(out_free);
+                oph ^= 1;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
         }
     } else if (warp == EPI_WARPS + LOAD_WARPS + MMA_WARPS) {
         // ============================== WEIGHT STREAMER (stream_b) ==============================
@@ -912,6 +941,38 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                     }
                 }
                 __syncwarp();  // stores have read the tile before the next h_prev block lands in it
+            } else if (P.out_bh && P.ngroups == 1 && P.nhalf == 64 && P.small_off == 64) {
+                // BH output, one accumulator group [main | cross]: all 32 channels of this thread with two batched loads,
+                // the buffer goes back to the MMA issuer before any arithmetic
+                float o[32];
+#pragma unroll
+                for (int jb = 0; jb < 2; ++jb) {
+                    const int j = j_lo + jb * 16;
+                    float a[8], a2[8], b1[8], b2[8];
+                    tmem_ld8x4(t0 + j, t0 + 64 + j, t0 + j + 8, t0 + 64 + j + 8, a, a2, b1, b2);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o[jb * 16 + q] = a[q] + a2[q];
+                        o[jb * 16 + 8 + q] = b1[q] + b2[q];
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[buf]);
+                released = true;
+                const bool relu = P.mode == MODE_CONV_RELU;
+                mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) {
+                    const float4 b0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8));
+                    const float4 b1 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8 + 4));
+                    float v[8] = {o[jb * 8 + 0] + b0.x, o[jb * 8 + 1] + b0.y, o[jb * 8 + 2] + b0.z, o[jb * 8 + 3] + b0.w,
+                                  o[jb * 8 + 4] + b1.x, o[jb * 8 + 5] + b1.y, o[jb * 8 + 6] + b1.z, o[jb * 8 + 7] + b1.w};
+                    if (relu) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                    }
+                    emit8((ch0 + j_lo) / 8 + jb, v);
+                }
             } else if (P.ngroups == 2 && P.nhalf == 64 && P.acc_bufs == 1) {
                 // single accumulator buffer (3x3 conv): sum the four accumulator regions into registers first and hand
                 // the buffer back to the MMA issuers BEFORE the bias / ReLU / global stores
@@ -1017,20 +1078,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                 mbar_arrive(&acc_empty[buf]);
             }
             if (P.out_bh) {
-                // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps have arrived
-                // (mbarriers only: no warp-aligned instruction is executed while lane 0 of warp 0 is busy with the stores)
+                // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps have
+                // arrived; the TMA store lane (second MMA warp) takes it from there
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(out_ready);
-                if (threadIdx.x == 0) {
-                    mbar_wait_sleep(out_ready, oph, 32);
-                    tma_store_2d(&tm_out, out_u32, 0, tile * TILE_M);
-                    tma_store_2d(&tm_out, out_u32 + OUT_BOX_BYTES, 64, tile * TILE_M);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    mbar_arrive(out_free);
-                }
-                __syncwarp();
                 oph ^= 1;
             }
             if (++buf == P.acc_bufs) { buf = 0; acc_phase ^= 1u; }
@@ -1041,7 +1093,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
             o[8] = clock64() - e_start; o[9] = e_wait;
         }
 #endif
-        if (P.out_bh && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -1128,7 +1179,8 @@ static int launch(Params& P, cudaStream_t st) {
     // (tiles are separated by the accumulator hand-shake): ring depths must be even
     MRB_REQUIRE(P.im2col != 2 || P.nseg == LOAD_GROUPS, MRB_EUNSUPPORTED, "tensor-core conv: patch mode needs one K chunk per loader group");
     MRB_REQUIRE(!(P.src_bh || P.out_bh) || P.pos_padded, MRB_EINVAL, "tensor-core conv: BH tensors need padded positions");
-    MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1), MRB_EUNSUPPORTED, "tensor-core conv: BH output needs 64 channels");
+    MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1 && P.n_issuers == 1), MRB_EUNSUPPORTED,
+                "tensor-core conv: BH output needs 64 channels and one MMA issuer (the second MMA warp stores)");
     CUtensorMap tm_out;
     memset(&tm_out, 0, sizeof(tm_out));
     if (P.out_bh) {
