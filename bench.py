@@ -173,6 +173,102 @@ def workload_config(batch, n_gpus):
                   % (batch * 2 * CHW8 / 1e6, batch * 4 * 64 * H * W * 4 / 1e6)}
 
 
+def run_extras(model, d, dev, e0, e1):
+    """Secondary, driver-visible measurements (rank 0, N = 1): single-slice latency (the reference ships batch_size 1,
+    base_cirim_run.yaml:71), E2EVN (BASELINE.json configs[1]) and the brain geometry of configs[3] on one GPU."""
+    import numpy as np
+    import torch
+    import mridc_b200 as mb
+    from mridc_b200 import _ops, synth
+
+    def timed(fn, n, w=3):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+    # ---- B = 1 latency through CIRIM.forward (inputs resident; the time loop of each cascade replays a CUDA graph) ----
+    one = {k: (d[k][:1].contiguous() if d[k].shape[0] > 1 else d[k]) for k in ("y", "sensitivity_maps", "mask", "target")}
+
+    def fwd1():
+        return next(model(one["y"], one["sensitivity_maps"], one["mask"], None, one["target"]))[-1][-1]
+
+    lat = timed(fwd1, 20, 5)
+    eng = model.cirim[0]._tc_engine
+    kern = None
+    if eng:
+        step1, _ = eng.bench_step(1, H, W, dev)
+        mcan = _ops.canonical_mask(one["mask"], 1, H, W)[0]
+        yh1 = _ops.dc_hybrid_prepare(one["y"], mcan, False)
+        eta1 = torch.randn((1, H, W, 2), device=dev)
+        g41 = torch.empty((1, H, W, 4), device=dev)
+        dc1 = timed(lambda: _ops.dc_rim_grad(eta1, one["y"], one["sensitivity_maps"], mcan, 1.0, False, "backward", out=g41,
+                                             nhwc=True, y_hybrid=yh1), 40)
+        kern = 40 * (timed(step1, 20) + dc1)
+    out["latency_b1"] = {"ms": lat, "kernel_ms": kern, "ratio": (lat / kern) if kern else None,
+                         "note": "CIRIM.forward on ONE slice, inputs resident; kernel_ms = 40 x (conv stack + DC gradient) "
+                                 "timed back to back at B = 1"}
+    # ---- E2EVN, configs[1] ----
+    Bv = 8
+    np.random.seed(123)
+    dv = synth.make_batch(Bv, C, H, W, mask_func=synth.Gaussian1DMask([0.7], [4]), seed=123, mask_dtype="uint8")
+    torch.manual_seed(1)
+    vn = mb.VarNet(synth.varnet_cfg()).eval().to(dev)
+    hv = {k: dv[k].pin_memory() for k in ("y", "sensitivity_maps", "mask", "target")}
+    gv = {k: v.to(dev) for k, v in hv.items()}
+    ms = timed(lambda: vn(gv["y"], gv["sensitivity_maps"], gv["mask"], None, gv["target"]), 8)
+
+    def vn_e2e():
+        t = {k: v.to(dev, non_blocking=True) for k, v in hv.items()}
+        return vn(t["y"], t["sensitivity_maps"], t["mask"], None, t["target"]).cpu()
+
+    ms_e = timed(vn_e2e, 8)
+    wsv = torch.empty((2, Bv, C, H, W, 2), device=dev)
+    img = torch.randn(Bv, H, W, 2, device=dev)
+    dcw = torch.ones(1, device=dev)
+    o5 = torch.empty_like(gv["y"])
+
+    def dc_block():
+        _ops.sens_reduce(gv["y"], gv["sensitivity_maps"], False, "backward", ws=wsv)
+        _ops.sens_expand_softdc(img, gv["sensitivity_maps"], gv["y"], gv["y"], gv["y"], gv["mask"], dcw, False, False,
+                                "backward", out=o5, ws=wsv)
+
+    ms_dc = timed(dc_block, 20)
+    dcb = Bv * (6 * CHW8 + 2 * HW8)
+    peaks = load_peaks()
+    out["e2evn"] = {"metric": "e2evn_320x320x15coil_slices_per_sec", "value": Bv / ms * 1e3,
+                    "e2e": Bv / ms_e * 1e3, "unit": "slices/s", "slices_per_step": Bv,
+                    "workload": "E2EVN 12 cascades, U-Net 14 ch / 2 pools, 15x320x320, 4x Gaussian 1-D (BASELINE.json configs[1])",
+                    "soft_dc_block": {"ms": ms_dc, "algorithmic_bytes": dcb, "achieved_gbs": dcb / ms_dc / 1e6,
+                                      "frac": dcb / ms_dc / 1e6 / peaks["hbm_gbs"], "share_of_step": 12 * ms_dc / ms}}
+    del vn, gv, wsv, o5
+    # ---- configs[3]: CIRIM on 16-coil 640x320 brain-shaped slices, 8x equispaced mask (one GPU's share) ----
+    Bb, Cb, Hb = 8, 16, 640
+    db = synth.make_batch(Bb, Cb, Hb, W, mask_func=synth.Equispaced1DMask([0.04], [8]))
+    gb = {k: db[k].to(dev) for k in ("y", "sensitivity_maps", "mask", "target")}
+    msb = timed(lambda: next(model(gb["y"], gb["sensitivity_maps"], gb["mask"], None, gb["target"]))[-1][-1], 5, 2)
+    mcb = _ops.canonical_mask(gb["mask"], Bb, Hb, W)[0]
+    yhb = _ops.dc_hybrid_prepare(gb["y"], mcb, False)
+    etab = torch.randn((Bb, Hb, W, 2), device=dev)
+    g4b = torch.empty((Bb, Hb, W, 4), device=dev)
+    dcb_ms = timed(lambda: _ops.dc_rim_grad(etab, gb["y"], gb["sensitivity_maps"], mcb, 1.0, False, "backward", out=g4b,
+                                            nhwc=True, y_hybrid=yhb), 40)
+    bytes_b = Bb * (2 * Cb * Hb * W * 8 + 3 * Hb * W * 8) + W
+    out["brain_cirim"] = {"metric": "cirim_640x320x16coil_slices_per_sec", "value": Bb / msb * 1e3, "unit": "slices/s",
+                          "slices_per_step": Bb,
+                          "workload": "CIRIM 5x8 ConvGRU, 16-coil 640x320 brain-shaped slices, 8x equispaced mask "
+                                      "(BASELINE.json configs[3], one GPU's share of the batch)",
+                          "dc_gradient": {"ms": dcb_ms, "algorithmic_bytes": bytes_b, "achieved_gbs": bytes_b / dcb_ms / 1e6,
+                                          "frac": bytes_b / dcb_ms / 1e6 / peaks["hbm_gbs"]}}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -199,10 +295,22 @@ def run_ours(args):
     d = {k: v.to(dev) for k, v in pinned.items()}
     n_global = B * world
 
+    pending = []
+
     def step_resident():
         out = next(model(d["y"], d["sensitivity_maps"], d["mask"], None, d["target"]))
         rec = out[-1][-1]
-        return sharding.gather_reconstructions(rec, n_global) if world > 1 else rec
+        if world == 1:
+            return rec
+        # only rank 0 needs the volume (the reference's test_epoch_end): point-to-point gather on NCCL's own stream,
+        # waited for one step later so that it overlaps with the next step's kernels
+        if pending:
+            pending.pop().wait()
+        pending.append(sharding.gather_reconstructions(rec, n_global, dst=0, async_op=True))
+        return rec
+
+    def drain():
+        return pending.pop().wait() if pending else None
 
     def barrier_sync():
         if world > 1:
@@ -212,6 +320,17 @@ def run_ours(args):
     # ---- device-resident timing --------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if world > 1:
+        # outside the timed region: what rank 0 gathered must equal, bit for bit, what each rank computed locally
+        full = drain()
+        local_rec = step_resident()
+        drain()
+        lr = torch.view_as_real(local_rec).contiguous()  # NCCL has no complex type
+        mine = [torch.zeros_like(lr) for _ in range(world)] if rank == 0 else None
+        dist.gather(lr, mine, dst=0)
+        if rank == 0:
+            assert full is not None and torch.equal(torch.view_as_real(full), torch.cat(mine, 0)), \
+                "gathered volume != per-rank results"
     barrier_sync()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -221,6 +340,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         step_resident()
+    drain()
     e1.record()
     barrier_sync()
     launches = _lib.launch_count()
@@ -243,7 +363,8 @@ def run_ours(args):
             out = next(model(bt["y"], bt["sensitivity_maps"], bt["mask"], None, d["target"]))
             rec = out[-1][-1]
             if world > 1:
-                rec = sharding.gather_reconstructions(rec, n_global)[rank * B:(rank + 1) * B]
+                full = sharding.gather_reconstructions(rec, n_global, dst=0)
+                rec = full[:B] if rank == 0 else rec
             out_host.copy_(rec, non_blocking=True)
 
     run_e2e(2)
@@ -344,6 +465,8 @@ def run_ours(args):
         roof = roof_conv if cv_ms > dc_ms else roof_dc
         roof = dict(roof)
         extra = {"roofline_dc": roof_dc, "roofline_conv": roof_conv, "kernel_shares": share}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra["extras"] = run_extras(model, d, dev, e0, e1)
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -385,6 +508,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="slices per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (latency, E2EVN, brain)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

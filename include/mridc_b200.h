@@ -53,6 +53,8 @@ int mrb_version(void);
  * (bench.py's "gpu_launches"). */
 long long mrb_launch_count(void);
 void mrb_reset_launch_count(void);
+/* account for kernel launches replayed from a CUDA graph (captured launches are counted once, at capture time) */
+void mrb_add_launch_count(long long n);
 
 /* ---------------------------------------------------------------------------------------------------
  * L1 primitives -- mc/common/parts/fft.py, utils.py

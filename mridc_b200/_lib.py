@@ -22,6 +22,7 @@ SIGNATURES = {
     "mrb_version": (_i, []),
     "mrb_launch_count": (_ll, []),
     "mrb_reset_launch_count": (None, []),
+    "mrb_add_launch_count": (None, [_ll]),
     "mrb_fft1d_c2c": (_i, [_vp, _vp, _ll, _i, _ll, _i, _i, _i, _f, _vp]),
     "mrb_fft2_c2c": (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "mrb_roll": (_i, [_vp, _vp, _ll, _ll, _ll, _i, _ll, _vp]),

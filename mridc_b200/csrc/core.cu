@@ -163,6 +163,7 @@ extern "C" const char* mrb_last_error(void) { return g_err; }
 extern "C" int mrb_version(void) { return 100; }
 extern "C" long long mrb_launch_count(void) { return g_launches; }
 extern "C" void mrb_reset_launch_count(void) { g_launches = 0; }
+extern "C" void mrb_add_launch_count(long long n) { mrb::g_launches += n; }
 
 extern "C" int mrb_complex_mul(const void* x, const void* y, void* out, int ndim, const long long* shape,
                                const long long* xstride, const long long* ystride, int conj_y, void* stream) {

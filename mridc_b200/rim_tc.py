@@ -22,6 +22,20 @@ def _enabled():
 
 
 _ZERO_STATE = {}
+_YH_STATIC = {}      # (B, C, H, W, device) -> [static hybrid k-space buffer, id of the tensor last copied into it]
+_GRAPH_POOL = {}     # device -> CUDA-graph memory pool shared by all cascades (they replay one after the other)
+
+
+def _graphs_enabled(n_px):
+    """CUDA-graph replay of a cascade's time loop: MRIDC_B200_GRAPHS=1 always, =0 never; default "auto" = only in the
+    launch-bound regime (at most two 320x320 slices per call -- the reference ships batch_size 1,
+    base_cirim_run.yaml:71).  Measured on the B200: at 16 slices per call the kernels run back to back anyway (no gain
+    device-resident) and a stream of alternating input buffers pays for the captures; at one slice per call the 49
+    launches of a cascade cost more than its kernels."""
+    v = os.environ.get("MRIDC_B200_GRAPHS", "auto")
+    if v == "auto":
+        return n_px <= 2 * 320 * 320
+    return v != "0"
 
 
 class RimTcEngine:
@@ -31,6 +45,7 @@ class RimTcEngine:
         self.block = block
         self._indrnn = isinstance(block.layers[0].rnn, IndRNNCell)
         self._packs = {}
+        self._graphs = {}  # key -> "warm" | (CUDAGraph, static eta, static outputs)
 
     # ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -201,14 +216,37 @@ class RimTcEngine:
                 "split-bf16 tcgen05 stack of one time step on fp32 channels-last activations (conv5x5x4, cell 1x1, conv3x3d2, "
                 "cell 1x1, conv3x3->2 + eta)")
 
-    def _run_bh(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid, want_hx):
+    def _steps_bh(self, eta, masked_kspace, sense, mask_can, sigma, h, y_hybrid, ws, fresh_state):
+        """The time loop on BH buffers.  h: two BH state buffers (never written); returns (etas, final states)."""
         lib = _lib.load()
         b = self.block
         B, C, H, W, _ = masked_kspace.shape
         dev = masked_kspace.device
         packs = self.packs(bh=True)
+        nb = lib.mrb_bh_bytes(B, H, W)
+        h = list(h)
+        h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
+        xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
+        g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        etas = []
+        for step in range(b.time_steps):
+            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
+                             ws=ws, nhwc=True, y_hybrid=y_hybrid)
+            eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W)
+            if step == 0 and fresh_state:
+                # the ping-pong swap left the caller's / the shared zero buffers in h_alt: they must never be written
+                h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
+            etas.append(eta)
+        return etas, h
+
+    def _run_bh(self, eta, masked_kspace, sense, mask_can, sigma, hx, ws, y_hybrid, want_hx):
+        lib = _lib.load()
+        b = self.block
+        B, C, H, W, _ = masked_kspace.shape
+        dev = masked_kspace.device
         st = _lib.stream_ptr()
         nb = lib.mrb_bh_bytes(B, H, W)
+        eta = eta.contiguous()
         if hx is None:
             # zero initial state (rim_block.py:188-193): one cached, read-only zero buffer (its border is zero too)
             key = ("bh", B, H, W, str(dev))
@@ -222,19 +260,50 @@ class RimTcEngine:
                 buf = torch.empty(nb, dtype=torch.uint8, device=dev)
                 _lib.check(lib.mrb_bh_from_nhwc(_lib.ptr(src), _lib.ptr(buf), B, H, W, st))
                 h.append(buf)
-        h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
-        xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
-        g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
-        etas = []
-        eta = eta.contiguous()
-        for step in range(b.time_steps):
-            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
-                             ws=ws, nhwc=True, y_hybrid=y_hybrid)
-            eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W)
-            if step == 0 and hx is None:
-                # the ping-pong swap left the shared zero buffer in h_alt: it must never be written
-                h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
-            etas.append(eta)
+        # ---- CUDA-graph replay of the whole time loop (49 launches) when nothing but eta changes between calls: zero initial
+        # state, hidden states not wanted (CIRIM.forward), 1-D mask (hybrid k-space), same input tensors as a previous call
+        if (hx is None and not want_hx and y_hybrid is not None and _graphs_enabled(B * H * W)
+                and not torch.cuda.is_current_stream_capturing()):
+            ykey = (B, C, H, W, str(dev))
+            ent = _YH_STATIC.get(ykey)
+            if ent is None:
+                ent = _YH_STATIC[ykey] = [torch.empty_like(y_hybrid), None]
+            tag = (y_hybrid.data_ptr(), y_hybrid._version, id(y_hybrid))
+            if ent[1] != tag:  # once per forward: the five cascades share one hybrid k-space tensor
+                ent[0].copy_(y_hybrid)
+                ent[1] = tag
+            yh = ent[0]
+            pkey = tuple((p.data_ptr(), p._version) for p in self._params())
+            gkey = (masked_kspace.data_ptr(), sense.data_ptr(), mask_can.data_ptr(), tuple(masked_kspace.shape),
+                    str(mask_can.dtype), tuple(mask_can.shape), float(sigma), bool(b.fft_centered), str(b.fft_normalization),
+                    pkey, b.time_steps)
+            g = self._graphs.get(gkey)
+            if g is None:
+                # first sight of these tensors: run eagerly (doubles as the warm-up the capture needs), capture next time
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[gkey] = "warm"
+            else:
+                if g == "warm":
+                    pool = _GRAPH_POOL.get(str(dev))
+                    if pool is None:
+                        pool = _GRAPH_POOL[str(dev)] = torch.cuda.graph_pool_handle()
+                    graph = torch.cuda.CUDAGraph()
+                    eta_in = eta.clone()
+                    n0 = _lib.launch_count()
+                    with torch.cuda.graph(graph, pool=pool):
+                        outs, _ = self._steps_bh(eta_in, masked_kspace, sense, mask_can, sigma, h, yh, ws, True)
+                        outs = torch.stack(outs)
+                    n_launch = _lib.launch_count() - n0  # launches of this library inside the graph
+                    lib.mrb_add_launch_count(-n_launch)   # captured, not executed
+                    # the tuple keeps every tensor the graph reads alive
+                    g = self._graphs[gkey] = (graph, eta_in, outs, n_launch, (masked_kspace, sense, mask_can, yh, h))
+                graph, eta_in, outs, n_launch = g[0], g[1], g[2], g[3]
+                eta_in.copy_(eta)
+                graph.replay()
+                lib.mrb_add_launch_count(n_launch)
+                return list(outs.clone().unbind(0)), None  # the static outputs are overwritten by the next replay
+        etas, h = self._steps_bh(eta, masked_kspace, sense, mask_can, sigma, h, y_hybrid, ws, True)
         if not want_hx:
             return etas, None
         out = []

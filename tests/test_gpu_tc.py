@@ -310,3 +310,32 @@ def test_tc2_conv_ops_vs_oracle(B, H, W):
     e = rel_l2(o2, ref)
     print("[tc parity] %-16s rel-L2 %.2e" % ("conv_c2 (bh)", e))
     assert e < 5e-6  # exact fp32 arithmetic on x = hi + lo (2^-18 relative representation error)
+
+
+def test_cirim_graph_replay_equals_eager(monkeypatch):
+    """CUDA-graph replay of the time loop (third call with the same input tensors) == eager launches, bit for bit; new
+    eta values, new k-space values in the same tensors and a different cascade state are all picked up."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+
+    cfg = synth.cirim_cfg("GRU", num_cascades=2)
+    batch = synth.make_batch(2, 6, 64, 48)
+    torch.manual_seed(4)
+    model = mb.CIRIM(cfg).cuda().eval()
+    y, S, m, tgt = (batch[k].cuda() for k in ("y", "sensitivity_maps", "mask", "target"))
+
+    def run():
+        return torch.stack([torch.stack(c) for c in next(model(y, S, m, None, tgt))])
+
+    monkeypatch.setenv("MRIDC_B200_GRAPHS", "0")
+    ref = run()
+    monkeypatch.setenv("MRIDC_B200_GRAPHS", "auto")  # 2 x 64 x 48 pixels: launch-bound -> graphs
+    a = run()   # eager (first sight of these tensors)
+    b = run()   # captures + replays
+    c = run()   # replays
+    assert any(isinstance(g, tuple) for blk in model.cirim for g in blk._tc_engine._graphs.values())
+    assert torch.equal(a, ref) and torch.equal(b, ref) and torch.equal(c, ref)
+    y.mul_(0.5)  # same tensors, new contents
+    d = run()
+    monkeypatch.setenv("MRIDC_B200_GRAPHS", "0")
+    assert torch.equal(d, run()) and not torch.equal(d, ref)
