@@ -44,14 +44,26 @@ def dc_traffic(B):
     (profiles/*_traffic.json, written by tools/summarise_profiles.py; captured at B = 4 and scaled linearly to B)."""
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
-    if not files:
-        return None
-    try:
-        t = json.load(open(files[-1]))["row_dc"]
-        return t["dram_bytes_per_launch"] * B / t["slices"]
-    except Exception:
-        return None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(f))["row_dc"]
+            return t["dram_bytes_per_launch"] * B / t["slices"]
+        except Exception:
+            continue
+    return None
+
+
+def conv_traffic(B):
+    """DRAM bytes of the regulariser kernels of one time step, from the same committed capture (scaled from B = 4)."""
+    import glob
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(f))["conv_stack"]
+            return t["dram_bytes_per_time_step"] * B / t["slices"]
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -455,7 +467,7 @@ def run_ours(args):
         cv_ms = e0.elapsed_time(e1) / 10
         tf = B * CONV_FLOPS_PER_STEP / (cv_ms * 1e-3) / 1e12
         roof_conv = {"bound": "tensor", "kernel": kname, "achieved": tf, "peak": peaks["bf16_tflops_sustained"],
-                     "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": conv_traffic(B),
                      "peak_src": peaks["src"], "ms_per_time_step": cv_ms, "note": note,
                      # an fp32-grade result costs 3 bf16 products per MAC: the same time expressed against that
                      # ceiling (peak / 3)

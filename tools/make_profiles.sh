@@ -1,13 +1,13 @@
 #!/bin/bash
 # Round profile pass (run under gpurun, 1 GPU).  Outputs land in gpurun_out/; tools/summarise_profiles.py turns
 # them into the tracked profiles/ summaries.  Numbers printed under ncu are never bench values.
-R=${1:-r01}
+R=${1:-r02}
 mkdir -p gpurun_out
 # (1) launch list of the bench command itself (cold-cache, serialised: compare shares, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${R}_bench_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file gpurun_out/${R}_bench_launches.csv \
     python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline > gpurun_out/${R}_bench_under_ncu.log 2>&1
 # (2) full capture of the hot kernels at the bench geometry (B=4, 15x320x320)
-ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|row_dc|conv_c2" -s 6 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|gru2_kernel|row_dc|conv_c2|bh_fix" -s 9 -c 9 \
     -o gpurun_out/${R}_hot python tools/prof_ops.py 4 2 all > gpurun_out/${R}_hot.log 2>&1
 ncu -i gpurun_out/${R}_hot.ncu-rep --page raw --csv > gpurun_out/${R}_hot_raw.csv 2>/dev/null
 # (3) the real bench line, outside any profiler

@@ -21,17 +21,14 @@ model = mb.CIRIM(cfg).cuda().eval()
 blk = model.cirim[0]
 from mridc_b200.rim_tc import RimTcEngine
 eng = RimTcEngine(blk)
-g4 = torch.randn(B, H, W, 4, device=dev)
-hx = [torch.randn(B, H, W, 64, device=dev) * 0.1 for _ in range(2)]
-hx_alt = [torch.empty_like(t) for t in hx]
-xbuf = torch.empty(B, H, W, 64, device=dev)
+conv_step, _ = eng.bench_step(B, H, W, dev)   # one time step of the regulariser in the engine's own layout
 yhyb = _ops.dc_hybrid_prepare(y, mask, False, ws=ws[0])
 g4o = torch.empty(B, H, W, 4, device=dev)
 for _ in range(reps):
     if what in ("all", "dc"):
         _ops.dc_rim_grad(eta, y, S, mask, 1.0, False, "backward", out=g4o, nhwc=True, y_hybrid=yhyb)
     if what in ("all", "conv"):
-        eng.conv_stack(g4, hx, hx_alt, xbuf, eta)
+        conv_step()
     if what in ("all", "vn"):
         pass
 torch.cuda.synchronize()

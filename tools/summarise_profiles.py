@@ -1,6 +1,6 @@
 """Turn gpurun_out/<round>_* ncu outputs into the tracked summaries under profiles/."""
 import collections, csv, json, os, sys
-R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 go, pr = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
 os.makedirs(pr, exist_ok=True)
@@ -47,14 +47,26 @@ if os.path.exists(f):
     try:
         ri, wi = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        def dram(r):
+            return float(r[ri].replace(",", "")) * mult[rows[1][ri]] + float(r[wi].replace(",", "")) * mult[rows[1][wi]]
         dc = [r for r in rows[2:] if "row_dc" in r[ki]]
+        # the regulariser kernels of ONE time step = the launches between two DC gradients of the capture
+        idx = [i for i, r in enumerate(rows[2:]) if "row_dc" in r[ki]]
+        stack = rows[2:][idx[0] + 1:idx[1]] if len(idx) >= 2 else [r for r in rows[2:] if "row_dc" not in r[ki]]
+        tj = {}
         if dc:
-            tot = sum(float(r[ri].replace(",", "")) * mult[rows[1][ri]] + float(r[wi].replace(",", "")) * mult[rows[1][wi]]
-                      for r in dc) / len(dc)
-            json.dump({"row_dc": {"dram_bytes_per_launch": tot, "slices": 4, "kernel": dc[0][ki].split("(")[0],
-                                  "source": "%s_hot_raw.csv (ncu --set full, B=4, 15x320x320)" % R}},
-                      open(os.path.join(pr, "%s_traffic.json" % R), "w"))
+            tot = sum(dram(r) for r in dc) / len(dc)
+            tj["row_dc"] = {"dram_bytes_per_launch": tot, "slices": 4, "kernel": dc[0][ki].split("(")[0],
+                            "source": "%s_hot_raw.csv (ncu --set full, B=4, 15x320x320)" % R}
             out += ["DC gradient DRAM traffic per launch (B=4): %.1f MB (algorithmic: 108.1 MB)" % (tot / 1e6), ""]
+        if stack:
+            tots = sum(dram(r) for r in stack)
+            tj["conv_stack"] = {"dram_bytes_per_time_step": tots, "slices": 4, "launches": len(stack),
+                                "kernels": [r[ki].split("(")[0][:40] for r in stack],
+                                "source": "%s_hot_raw.csv (ncu --set full, B=4, 15x320x320)" % R}
+            out += ["Regulariser DRAM traffic per time step (B=4, %d launches): %.1f MB" % (len(stack), tots / 1e6), ""]
+        if tj:
+            json.dump(tj, open(os.path.join(pr, "%s_traffic.json" % R), "w"))
     except ValueError:
         pass
 f = os.path.join(go, "%s_bench.json" % R)
