@@ -121,8 +121,10 @@ struct Params {
                              // the image size.  Required by src_bh / out_bh.
     int src_bh;              // source 0 is a BH tensor (bf16 hi | lo per position, replicate border valid): the loaders
                              // copy rows to TMEM without conversion and address taps as plain offsets (no clamping)
-    int out_bh;              // the epilogue splits its fp32 results into hi / lo bf16, stages the tile in the TMA box layout
-                             // and stores it with two TMA box stores (tm_out); cout == 64
+    int out_bh;              // the epilogue splits its fp32 results into hi / lo bf16 (cout == 64).  1: the tile is staged in the
+                             // TMA box layout and stored by a TMA store lane (one issuer); 2: straight st.global from the
+                             // thread that owns the position (used where the 32 KB of the output tile buy a deeper weight
+                             // ring and a second MMA issuer instead)
     int group_cols;          // TMEM columns between the accumulator groups of the two issuers (0 with one group)
     int n_issuers;           // 1 or 2 MMA-issuing lanes (2: the global segment stream alternates; issuer i owns
                              // accumulator group i)
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int wbytes_chunk = P.wchunk_rows * 128;  // bytes of the hi (or lo) rows of one weight chunk
     uint8_t* out_s = smem;                                            // out_bh: [hi box | lo box] output tile (1024-aligned)
-    uint8_t* w_s = smem + (P.out_bh ? 2 * OUT_BOX_BYTES : 0);         // [n_wchunks][hi|lo][rows*128]
+    uint8_t* w_s = smem + (P.out_bh == 1 ? 2 * OUT_BOX_BYTES : 0);         // [n_wchunks][hi|lo][rows*128]
     uint8_t* bst_s = w_s + (P.stream_b ? 0 : (size_t)P.n_wchunks * 2 * wbytes_chunk);  // [b_stages][2*wbytes_chunk] if stream_b
     uint8_t* tb_s = bst_s + (P.stream_b ? (size_t)P.b_stages * 2 * wbytes_chunk : 0);  // [LOAD_WARPS][depth][tb_bytes]
     uint64_t* bars = (uint64_t*)(tb_s + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes);
@@ -168,12 +170,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) {
-            mbar_init(&full[s], 128);  // one loader group (4 warps) fills a stage
+            mbar_init(&full[s], 4);    // one loader group fills a stage: one arrival per warp (lane 0, after __syncwarp)
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], P.n_issuers);
-            mbar_init(&acc_empty[b], EPI_WARPS * 32);
+            mbar_init(&acc_empty[b], EPI_WARPS);  // one arrival per epilogue warp
         }
         for (int b = 0; b < B_STAGES; ++b) {
             mbar_init(&b_full[b], 1);   // the producer's arrive.expect_tx; the bulk copy completes the transaction bytes
@@ -285,7 +287,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
             TCP(const long long c2 = clock64();)
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&full[stage]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
             TCP(t_st += clock64() - c0; t_stw += clock64() - c2;)
         };
 
@@ -543,7 +546,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&full[stage]);
+                __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
                 TCP(t_st += clock64() - c0;)
                 stage_adv(LOAD_GROUPS);
                 __syncwarp();  // every lane has read its taps before the slot is refilled
@@ -782,7 +786,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                 o[4] = clock64() - t_start; o[5] = t_wfull; o[6] = t_wacc; o[7] = t_mma; o[10] = t_commit; o[11] = t_wb; o[12] = t_prep;
             }
 #endif
-        } else if (P.out_bh && mi == 1 && lane == 0) {
+        } else if (P.out_bh == 1 && mi == 1 && lane == 0) {
             // ============================== TMA STORE LANE (out_bh; requires n_issuers == 1) ==============================
             const uint32_t out_u32 = smem_u32(out_s);
             uint32_t oph = 0;
@@ -830,12 +834,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
         const uint32_t out_u32 = smem_u32(out_s);
         uint32_t oph = 0;
         // out_bh: 8 consecutive channels (chunk c8 = channel / 8) of this thread's position -> hi / lo bf16 in the output tile
-        auto emit8 = [&](int c8, const float* v) {
+        auto emit8 = [&](int c8, const float* v, long long pos, bool ok) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-            sts128u(out_u32 + swz(m, c8), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-            sts128u(out_u32 + OUT_BOX_BYTES + swz(m, c8), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            if (P.out_bh == 1) {  // output tile in the TMA box layout (stored by the TMA store lane)
+                sts128u(out_u32 + swz(m, c8), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                sts128u(out_u32 + OUT_BOX_BYTES + swz(m, c8), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            } else if (ok) {      // out_bh == 2: straight to global memory from the thread that owns the position
+                uint8_t* g = reinterpret_cast<uint8_t*>(P.out) + pos * BH_PX_BYTES + c8 * 16;
+                *reinterpret_cast<uint4*>(g) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(g + 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
         };
         const uint32_t et0 = smem_u32(epi_s) + (uint32_t)(warp * 2 * EPI_TILE_BYTES);  // this warp's two exchange tiles
         // h_prev of a tile (independent of the MMAs): asynchronous coalesced copy into an exchange tile, issued one tile
@@ -896,7 +906,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                         tmem_ld8x4(t0 + j, t0 + nh + j, t0 + 2 * nh + j, t0 + 3 * nh + j, hn, ar, az, xn);
                         if (jb == 1) {  // both halves of this thread's accumulator columns are in registers
                             tc_fence_before();
-                            mbar_arrive(&acc_empty[buf]);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[buf]);
                             released = true;
                         }
                         const float4 h0 = lds128(et + (uint32_t)(lane * EPI_ROW_BYTES + jb * 32));
@@ -957,10 +968,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 released = true;
                 const bool relu = P.mode == MODE_CONV_RELU;
-                mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
+                if (P.out_bh == 1) mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
 #pragma unroll
                 for (int jb = 0; jb < 4; ++jb) {
                     const float4 b0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8));
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
 #pragma unroll
                         for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
                     }
-                    emit8((ch0 + j_lo) / 8 + jb, v);
+                    emit8((ch0 + j_lo) / 8 + jb, v, p, valid);
                 }
             } else if (P.ngroups == 2 && P.nhalf == 64 && P.acc_bufs == 1) {
                 // single accumulator buffer (3x3 conv): sum the four accumulator regions into registers first and hand
@@ -986,11 +998,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                     for (int q = 0; q < 8; ++q) o[jb * 8 + q] = (a[q] + a2[q]) + (b1[q] + b2[q]);
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 released = true;
                 if (P.out_bh) {
                     const bool relu = P.mode == MODE_CONV_RELU;
-                    mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
+                    if (P.out_bh == 1) mbar_wait_sleep(out_free, oph ^ 1, 32);  // the previous tile's stores have read the output tile
 #pragma unroll
                     for (int jb = 0; jb < 4; ++jb) {
                         const float4 b0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j_lo + jb * 8));
@@ -1001,7 +1014,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
 #pragma unroll
                             for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
                         }
-                        emit8((ch0 + j_lo) / 8 + jb, v);
+                        emit8((ch0 + j_lo) / 8 + jb, v, p, valid);
                     }
                 } else if (valid) {
                     const bool relu = P.mode == MODE_CONV_RELU;
@@ -1042,7 +1055,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                             }
                         }
                     }
-                    if (P.out_bh && j == j_lo) mbar_wait_sleep(out_free, oph ^ 1, 32);  // previous tile's stores have read out_s
+                    if (P.out_bh == 1 && j == j_lo) mbar_wait_sleep(out_free, oph ^ 1, 32);  // previous tile's stores have read out_s
                     if (valid || P.out_bh) {
                         float o[8];
                         const float4 bi0 = lds128(bias_u32 + 4u * (uint32_t)(ch0 + j));
@@ -1064,7 +1077,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
                             o[q] = relu ? fmaxf(v, 0.f) : v;
                         }
                         if (P.out_bh) {
-                            emit8((ch0 + j) / 8, o);
+                            emit8((ch0 + j) / 8, o, p, valid);
                         } else {
                             float4* op = reinterpret_cast<float4*>(P.out + p * P.cout + ch0 + j);
                             op[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -1075,9 +1088,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const __grid_constant__ 
             }
             if (!released) {
                 tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
-            if (P.out_bh) {
+            if (P.out_bh == 1) {
                 // the tile's [128 positions x (64 hi | 64 lo)] boxes are complete once all eight epilogue warps have
                 // arrived; the TMA store lane (second MMA warp) takes it from there
                 fence_proxy_async();
@@ -1154,7 +1168,7 @@ int pack_launch(const PackDesc& D, void* dst, cudaStream_t st) {
 static size_t smem_needed(const Params& P) {
     const size_t chunk2 = (size_t)2 * P.wchunk_rows * 128;
     const size_t wres = P.stream_b ? (size_t)P.b_stages * chunk2 : (size_t)P.n_wchunks * chunk2;
-    return 1024 + (P.out_bh ? (size_t)2 * OUT_BOX_BYTES : 0) + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 +
+    return 1024 + (P.out_bh == 1 ? (size_t)2 * OUT_BOX_BYTES : 0) + wres + (size_t)LOAD_WARPS * P.tb_depth * P.tb_bytes + 256 +
            2 * B_STAGES * 8 + BIAS_FLOATS * sizeof(float) + (P.mode == MODE_GRU ? (size_t)EPI_WARPS * 2 * EPI_TILE_BYTES : 0);
 }
 
@@ -1179,11 +1193,12 @@ static int launch(Params& P, cudaStream_t st) {
     // (tiles are separated by the accumulator hand-shake): ring depths must be even
     MRB_REQUIRE(P.im2col != 2 || P.nseg == LOAD_GROUPS, MRB_EUNSUPPORTED, "tensor-core conv: patch mode needs one K chunk per loader group");
     MRB_REQUIRE(!(P.src_bh || P.out_bh) || P.pos_padded, MRB_EINVAL, "tensor-core conv: BH tensors need padded positions");
-    MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1 && P.n_issuers == 1), MRB_EUNSUPPORTED,
-                "tensor-core conv: BH output needs 64 channels and one MMA issuer (the second MMA warp stores)");
+    MRB_REQUIRE(!P.out_bh || (P.cout == 64 && P.n_split == 1), MRB_EUNSUPPORTED, "tensor-core conv: BH output needs 64 channels");
+    MRB_REQUIRE(P.out_bh != 1 || P.n_issuers == 1, MRB_EUNSUPPORTED,
+                "tensor-core conv: the TMA-store variant needs one MMA issuer (the second MMA warp stores)");
     CUtensorMap tm_out;
     memset(&tm_out, 0, sizeof(tm_out));
-    if (P.out_bh) {
+    if (P.out_bh == 1) {
         int rc = tc2::make_bh_tmap(&tm_out, P.out, P.P, TILE_M);
         if (rc) return rc;
     }
@@ -1329,13 +1344,16 @@ static int tc_conv_launch(const void* x, const void* wpack, const void* bias, co
     // two accumulator groups, one per MMA issuer (the global segment stream alternates between them): fixed
     // accumulation order inside a group (bit-reproducible), half-length chains (see Params::ngroups); the epilogue
     // adds the groups.  A 1x1 kernel has a single segment per tile: one issuer, one group, two accumulator buffers.
-    // BH variant: ONE issuer.  Its staging tiles leave room for a 3-slot weight ring only, and a ring slot whose consecutive
-    // fills belong to different issuers breaks the parity waits (the issuer that is ahead sees the parity of the previous
-    // phase as "complete" and consumes the slot one fill early -- sporadic traps / hangs on the B200).  With K = 16 per MMA
-    // one issuing thread keeps the pipe fed (64 + 32 pipe cycles per k-step), and the 128-column accumulator can be
-    // double-buffered, so the epilogue overlaps the next tile.
-    P.n_issuers = (P.nseg >= 2 && !bh) ? 2 : 1;
+    // Ring depths must be EVEN with two issuers: a slot whose consecutive fills belong to different issuers breaks the parity
+    // waits (the issuer that is ahead sees the parity of the previous phase as "complete" and consumes the slot one fill
+    // early -- sporadic traps / hangs on the B200 with a 3-slot ring; launch() enforces it).
+    // BH variant: ONE issuer, output through the TMA store lane.  Measured alternative (MRB_TC_BH_2ISSUERS=1): two issuers
+    // with a 4-slot ring and plain st.global from the epilogue (out_bh = 2) -- 443 vs 371 us at B=16: the thread-per-position
+    // stores (32 cache lines per instruction) compete with the loaders' cp.async for L1 wavefronts.
+    const bool two = P.nseg >= 2 && (!bh || getenv("MRB_TC_BH_2ISSUERS"));
+    P.n_issuers = two ? 2 : 1;
     P.ngroups = P.n_issuers;
+    if (bh) P.out_bh = P.n_issuers == 2 ? 2 : 1;
     P.group_cols = 2 * cout;
     MRB_REQUIRE(P.ngroups * 2 * cout <= 512 - 2 * tc::A_STAGE_COLS, MRB_EUNSUPPORTED, "mrb_tc_conv_nhwc: accumulators exceed TMEM");
     P.acc_cols = P.ngroups * 2 * cout;  // per group: hi*hi chain + cross-term chain
