@@ -254,6 +254,12 @@ int mrb_tc_conv_bh(const void* x_bh, const void* wpack, const void* bias, void* 
 /* final RIM conv (rim_block.py:239-248) on a BH source with a valid border: out [B,H,W,2] = eta + conv3x3(x) (+ bias) */
 int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H,
                             int W, void* stream);
+/* the same final conv (rim_block.py:239-248, conv_layers.py:72-123) on the tensor core: the channel contraction runs once
+ * per position as a tap GEMM (T[pos][tap, o] = sum_c h[pos][c] w[o][c][tap], split-bf16 tcgen05), the nine taps are gathered
+ * in shared memory with their coordinates clamped to the image (= ReplicationPad2d(1)); the BH border of x_bh is never
+ * read, so a pointwise producer needs no mrb_bh_fix_border before this call */
+int mrb_tc2_final_conv(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H, int W,
+                       void* stream);
 /* edge pixels -> replicate border of a BH tensor (after a pointwise producer, before a spatial consumer) */
 int mrb_bh_fix_border(void* bh, int B, int H, int W, void* stream);
 /* ConvGRUCell, kernel size 1, 64 -> 64 (rnn_cells.py:93-127): x, h, out in BH layout; b_ih [192] or null; out must not
@@ -307,7 +313,8 @@ int mrb_abs_max_normalize(const void* x, long long n, int is_complex, void* out,
 /* gt, pred [B,H,W] fp32 -> res (device, 5 doubles) = mse, nmse, psnr, ssim, data range used.  maxval_mode 0: max(gt)
  * (reconstruction_metrics.py:23,35), 1: max(pred) - min(pred) (base.py:431,434), 2: `maxval`.  SSIM = skimage
  * structural_similarity defaults (7x7 uniform window, sample covariance, K1 0.01, K2 0.03, 3-px border crop, float64),
- * averaged over slices; PSNR = 10 log10(R^2 / mse). */
+ * averaged over slices; PSNR = 10 log10(R^2 / mse).  maxval_mode + 4 skips the SSIM kernels (res[3] = NaN; any H, W >= 1):
+ * the reference's mse / nmse / psnr accept images smaller than the SSIM window. */
 int mrb_recon_metrics(const void* gt, const void* pred, int B, int H, int W, int maxval_mode, double maxval, void* res,
                       void* ws, void* stream);
 

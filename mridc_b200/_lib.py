@@ -66,6 +66,7 @@ SIGNATURES = {
     "mrb_tc_conv_bh": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_conv_c2_bh_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrb_bh_fix_border": (_i, [_vp, _i, _i, _i, _vp]),
+    "mrb_tc2_final_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrb_tc2_gru_packed_bytes": (_sz, []),
     "mrb_tc2_pack_gru": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mrb_tc2_gru": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -131,6 +132,12 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
             "mridc_b200: %s is on %s; this package only runs on CUDA (sm_100a) -- there is no CPU fallback" % (name, t.device))
     if dtype is not None and t.dtype != dtype:
         raise TypeError("mridc_b200: %s must be %s (got %s)" % (name, dtype, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the current device's stream with raw pointers: a tensor of another GPU would be an illegal
+        # address (or, with peer access, silent remote execution)
+        raise RuntimeError("mridc_b200: %s lives on %s but the current CUDA device is cuda:%d; wrap the call in "
+                           "`with torch.cuda.device(t.device)` (one process per GPU is the supported layout)"
+                           % (name, t.device, torch.cuda.current_device()))
     return t
 
 

@@ -490,6 +490,237 @@ __global__ void bh_to_nhwc_kernel(const uint8_t* __restrict__ bh, float* __restr
     }
 }
 
+// ---- final RIM conv (64 -> 2, 3x3) as a tap GEMM + in-SM gather ------------------------------------------------------
+// out[y][x][o] = eta + bias[o] + sum_{tap, c} w[o][c][tap] * h[clamp(y + dy)][clamp(x + dx)][c]   (rim_block.py:239-248,
+// conv_layers.py:72-123 with ReplicationPad2d(1)).
+// The channel contraction does not depend on where a tap is read from, so it runs ONCE per position on the tensor core:
+//   T[pos][tap*2 + o] = sum_c h[pos][c] * w[o][c][tap]          (M = 128 positions, N = 18 padded to 32, K = 64)
+// and the spatial part is nine fp32 additions per output, out = sum_tap T[pos + tap][tap], done by the epilogue warps
+// through shared memory.  The CUDA-core kernel this replaces (conv_c2_k3_kernel<.., BH>) was FP32-pipe / latency bound at
+// ~4x the HBM time of reading h once.
+//   patch        16 x 16 positions (two M = 128 tiles) -> 14 x 14 outputs; one 3-D TMA box per operand half (hi / lo) lands
+//                in the UMMA SWIZZLE_128B layout, three patches in flight; overlapping halo positions are L2 hits
+//   MMA lane     per tile 4 k-steps x { h_hi x [w_hi ; w_lo] (N = 64: columns 0..31 hi*hi, 32..63 hi*lo), h_lo x w_hi (N = 32,
+//                onto the cross-term columns) }; main and cross terms are added in RN fp32 by the epilogue
+//   8 epilogue warps  T of their position -> shared memory, barrier, gather with the tap coordinates clamped to the image
+//                (the replicate padding: the BH border of the source is never used, so no border fix-up is needed), + eta
+constexpr int F2_PATCH = 16, F2_OUT = 14;
+constexpr int F2_STAGES = 3;
+constexpr int F2_STAGE_BYTES = 2 * 2 * SLOT_BYTES;  // hi box (2 tiles) | lo box (2 tiles)
+constexpr int F2_EPI_W = 8;
+constexpr int F2_THREADS = (F2_EPI_W + 2) * 32;
+constexpr int F2_TS = 18;                            // floats per position in the T exchange tile
+
+struct Fin2Params {
+    const float* w;     // [2][64][3][3]
+    const float* bias;  // [2] or null
+    const float* eta;   // [B][H][W][2]
+    float* out;         // [B][H][W][2]
+    int B, H, W;
+    int py, px;         // patches per image column / row
+    int n_patches;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+// 18 main + 18 cross-term columns of this thread's TMEM lane (columns [0,24) and [32,56) of the tile's accumulator)
+__device__ __forceinline__ void tmem_ld_fin2(uint32_t a, float* v) {
+    uint32_t r[48];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%48];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%49];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%50];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%51];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%32,%33,%34,%35,%36,%37,%38,%39}, [%52];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%40,%41,%42,%43,%44,%45,%46,%47}, [%53];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+        : "r"(a), "r"(a + 8), "r"(a + 16), "r"(a + 32), "r"(a + 40), "r"(a + 48)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < F2_TS; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r[24 + i]);
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+fin2_kernel(const __grid_constant__ CUtensorMap tm_h, const Fin2Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_s = smem;                                      // [F2_STAGES][hi 32 KB | lo 32 KB]
+    uint8_t* w_s = stage_s + F2_STAGES * F2_STAGE_BYTES;          // [w_hi 32 rows x 128 B | w_lo 32 rows x 128 B]
+    float* ts = (float*)(w_s + 2 * 32 * 128);                     // [256 positions][18]
+    uint64_t* full = (uint64_t*)(ts + 256 * F2_TS);               // [F2_STAGES]
+    uint64_t* empty = full + F2_STAGES;                           // [F2_STAGES] MMA commit
+    uint64_t* acc_full = empty + F2_STAGES;                       // [2]
+    uint64_t* acc_empty = acc_full + 2;                           // [2] one arrival per epilogue warp
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < F2_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], F2_EPI_W);
+        }
+        fence_barrier_init();
+    }
+    // weights: row n = tap*2 + o (18 used of 32), K = 64 input channels, split into bf16 hi / lo, SWIZZLE_128B rows
+    for (int i = threadIdx.x; i < 32 * 64; i += F2_THREADS) {
+        const int n = i >> 6, k = i & 63;
+        const float v = n < 18 ? P.w[((n & 1) * 64 + k) * 9 + (n >> 1)] : 0.f;
+        const uint16_t hb = bf16_rn_bits(v);
+        const float hf = __uint_as_float((uint32_t)hb << 16);
+        const uint16_t lb = bf16_rn_bits(v - hf);
+        const uint32_t off = swz(n, k >> 3) + (uint32_t)((k & 7) * 2);
+        *reinterpret_cast<uint16_t*>(w_s + off) = hb;
+        *reinterpret_cast<uint16_t*>(w_s + 32 * 128 + off) = lb;
+    }
+    if (warp == F2_EPI_W + 1) tmem_alloc(tmem_slot, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int Hp = P.H + 2 * PADB;
+    const int per_img = P.py * P.px;
+
+    if (warp == F2_EPI_W) {
+        // ============================== TMA PRODUCER ==============================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < P.n_patches; t += gridDim.x) {
+                const int b = t / per_img, r = t - b * per_img;
+                const int pi = r / P.px, pj = r - pi * P.px;
+                // patch origin in padded coordinates: outputs (14 pi .. +13) sit at padded rows 14 pi + 2 ..; one halo row above
+                const int y0 = b * Hp + F2_OUT * pi + PADB - 1, x0 = F2_OUT * pj + PADB - 1;
+                mbar_wait_sleep(&empty[s], ph ^ 1, 64);
+                mbar_expect_tx(&full[s], F2_STAGE_BYTES);
+                const uint32_t dst = smem_u32(stage_s + s * F2_STAGE_BYTES);
+                tma_load_3d(dst, &tm_h, 0, x0, y0, smem_u32(&full[s]));
+                tma_load_3d(dst + 2 * SLOT_BYTES, &tm_h, 64, x0, y0, smem_u32(&full[s]));
+                if (++s == F2_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == F2_EPI_W + 1) {
+        // ============================== MMA ISSUER ==============================
+        const uint32_t tmem_u = uni(tmem_base);
+        const uint64_t w_stack = make_desc(smem_u32(w_s));
+        constexpr uint32_t id64 = make_idesc(TILE, 64), id32 = make_idesc(TILE, 32);
+        int s = 0, buf = 0;
+        uint32_t ph = 0, acc_ph = 0;
+        for (int t = blockIdx.x; t < P.n_patches; t += gridDim.x) {
+            mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stage_s + s * F2_STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t d = tmem_u + (uint32_t)(buf * 128 + j * 64);
+                const uint64_t a_hi = make_desc(sb + (uint32_t)(j * SLOT_BYTES));
+                const uint64_t a_lo = make_desc(sb + (uint32_t)((2 + j) * SLOT_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_ss(d, a_hi + 2 * k, w_stack + 2 * k, id64, k > 0);
+                    umma_ss(d + 32, a_lo + 2 * k, w_stack + 2 * k, id32, 1);
+                }
+            }
+            umma_commit(&empty[s]);
+            umma_commit(&acc_full[buf]);
+            if (++s == F2_STAGES) { s = 0; ph ^= 1; }
+            if (++buf == 2) { buf = 0; acc_ph ^= 1; }
+        }
+    } else {
+        // ============================== EPILOGUE ==============================
+        const int quad = warp & 3, j = warp >> 2;
+        const int m = quad * 32 + lane;          // TMEM lane = row of M-tile j
+        const int pos = j * TILE + m;            // position inside the patch: row pos / 16, column pos % 16
+        const int r = pos >> 4, c = pos & 15;
+        const float b0 = P.bias ? P.bias[0] : 0.f, b1 = P.bias ? P.bias[1] : 0.f;
+        const uint32_t ts_u32 = smem_u32(ts);
+        int buf = 0;
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < P.n_patches; t += gridDim.x) {
+            const int b = t / per_img, rr = t - b * per_img;
+            const int pi = rr / P.px, pj = rr - pi * P.px;
+            const int y = F2_OUT * pi + r - 1, x = F2_OUT * pj + c - 1;  // output pixel of this thread
+            const bool valid = r >= 1 && r <= F2_OUT && c >= 1 && c <= F2_OUT && y < P.H && x < P.W;
+            const long long p = ((long long)b * P.H + y) * P.W + x;
+            float2 e = make_float2(0.f, 0.f);
+            if (valid) e = __ldg(reinterpret_cast<const float2*>(P.eta) + p);
+            mbar_wait_sleep(&acc_full[buf], acc_ph, 64);
+            tc_fence_after();
+            float v[F2_TS];
+            tmem_ld_fin2(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + j * 64), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            asm volatile("bar.sync 1, %0;" ::"n"(F2_EPI_W * 32) : "memory");  // the previous patch has been gathered
+#pragma unroll
+            for (int i = 0; i < F2_TS / 2; ++i)
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ts_u32 + (uint32_t)((pos * F2_TS + 2 * i) * 4)), "f"(v[2 * i]),
+                             "f"(v[2 * i + 1])
+                             : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(F2_EPI_W * 32) : "memory");
+            if (valid) {
+                // replicate padding = clamp the tap's image coordinates; a clamped tap is this thread's own row / column
+                const int rm = y > 0 ? r - 1 : r, rp = y < P.H - 1 ? r + 1 : r;
+                const int cm = x > 0 ? c - 1 : c, cp = x < P.W - 1 ? c + 1 : c;
+                const int rows[3] = {rm, r, rp}, cols[3] = {cm, c, cp};
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        float t0, t1;
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                                     : "=f"(t0), "=f"(t1)
+                                     : "r"(ts_u32 + (uint32_t)(((rows[dy] * F2_PATCH + cols[dx]) * F2_TS + 2 * (dy * 3 + dx)) * 4))
+                                     : "memory");
+                        s0 += t0;
+                        s1 += t1;
+                    }
+                reinterpret_cast<float2*>(P.out)[p] = make_float2(e.x + (s0 + b0), e.y + (s1 + b1));
+            }
+            if (++buf == 2) { buf = 0; acc_ph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == F2_EPI_W + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+static size_t fin2_smem() { return 1024 + F2_STAGES * F2_STAGE_BYTES + 2 * 32 * 128 + 256 * F2_TS * 4 + 16 * 8 + 16; }
+
+// A BH tensor as the 3-D array [B*(H+4) rows][W+4 columns][128 bf16]; box = 64 channels (hi or lo half) x 16 columns x 16 rows
+static int make_bh_tmap3(void* mp, const void* base, int B, int H, int W) {
+    CUtensorMap* m = reinterpret_cast<CUtensorMap*>(mp);
+    EncodeTiledFn fn = encode_fn();
+    MRB_REQUIRE(fn != nullptr, MRB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t Wp = (cuuint64_t)(W + 2 * PADB), rows = (cuuint64_t)B * (cuuint64_t)(H + 2 * PADB);
+    cuuint64_t dims[3] = {128, Wp, rows};
+    cuuint64_t strides[2] = {PX_BYTES, Wp * PX_BYTES};
+    cuuint32_t box[3] = {64, F2_PATCH, F2_PATCH};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRB_REQUIRE(r == CUDA_SUCCESS, MRB_ECUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return MRB_OK;
+}
+
 #ifdef MRB_TC_PROF
 int g_debug2 = 0;
 unsigned long long* g_prof2 = nullptr;
@@ -573,6 +804,38 @@ extern "C" int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack
     int grid = device_sm_count();
     if (grid > P.n_tiles) grid = P.n_tiles;
     tc2::gru2_kernel<<<grid, tc2::THREADS2, smem, (cudaStream_t)stream>>>(tm_h, tm_x, tm_o, P);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+/* final RIM conv on the tensor core (fin2_kernel): same contract as mrb_conv_c2_bh_residual except that the BH border of
+ * x_bh is never read (the replicate padding is applied to the tap coordinates) */
+extern "C" int mrb_tc2_final_conv(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H,
+                                  int W, void* stream) {
+    MRB_REQUIRE(x_bh && w && eta && out, MRB_EINVAL, "mrb_tc2_final_conv: null pointer");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_final_conv: bad shape");
+    MRB_REQUIRE((long long)B * (H + 2 * tc2::PADB) < 2147483647LL, MRB_EUNSUPPORTED, "mrb_tc2_final_conv: too many rows");
+    tc2::Fin2Params P;
+    P.w = (const float*)w; P.bias = (const float*)bias; P.eta = (const float*)eta; P.out = (float*)out;
+    P.B = B; P.H = H; P.W = W;
+    P.py = (H + tc2::F2_OUT - 1) / tc2::F2_OUT;
+    P.px = (W + tc2::F2_OUT - 1) / tc2::F2_OUT;
+    const long long np = (long long)B * P.py * P.px;
+    MRB_REQUIRE(np < 2147483647LL, MRB_EUNSUPPORTED, "mrb_tc2_final_conv: too many patches");
+    P.n_patches = (int)np;
+    CUtensorMap tm_h;
+    int rc = tc2::make_bh_tmap3(&tm_h, x_bh, B, H, W);
+    if (rc) return rc;
+    static bool attr_set = false;
+    const size_t smem = device_max_smem_optin();
+    if (!attr_set) {
+        MRB_REQUIRE(tc2::fin2_smem() <= smem, MRB_EUNSUPPORTED, "mrb_tc2_final_conv: shared memory");
+        MRB_CUDA(cudaFuncSetAttribute(tc2::fin2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = device_sm_count();
+    if (grid > P.n_patches) grid = P.n_patches;
+    tc2::fin2_kernel<<<grid, tc2::F2_THREADS, smem, (cudaStream_t)stream>>>(tm_h, P);
     MRB_LAUNCHED();
     return MRB_OK;
 }

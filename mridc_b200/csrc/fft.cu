@@ -247,6 +247,15 @@ static int choose_lines(const FftPlan& p, int want_min_threads_work, long long a
 int fft1d_launch(const float2* in, float2* out, long long outer, int n, long long inner, int inverse, int in_rot,
                  int out_rot, float scale, cudaStream_t st) {
     if (outer == 0 || inner == 0 || n == 0) return MRB_OK;
+    if (inner > 1 && outer > 65535) {
+        // the strided-axis kernels put `outer` in gridDim.y: more leading elements than that go in chunks
+        for (long long o = 0; o < outer; o += 65535) {
+            const long long cnt = outer - o < 65535 ? outer - o : 65535;
+            const int rcc = fft1d_launch(in + o * n * inner, out + o * n * inner, cnt, n, inner, inverse, in_rot, out_rot, scale, st);
+            if (rcc) return rcc;
+        }
+        return MRB_OK;
+    }
     FftPlan p;
     int rc = get_fft_plan(n, &p);
     if (rc) return rc;

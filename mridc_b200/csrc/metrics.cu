@@ -154,9 +154,12 @@ extern "C" int mrb_abs_max_normalize(const void* x, long long n, int is_complex,
 extern "C" int mrb_recon_metrics(const void* gt, const void* pred, int B, int H, int W, int maxval_mode, double maxval,
                                  void* res, void* ws, void* stream) {
     MRB_REQUIRE(gt && pred && res && ws, MRB_EINVAL, "mrb_recon_metrics: null pointer");
-    MRB_REQUIRE(B >= 1 && H >= SSIM_WIN && W >= SSIM_WIN, MRB_EINVAL,
+    const bool want_ssim = (maxval_mode & 4) == 0;  // + 4: MSE / NMSE / PSNR only (any image size, res[3] = NaN)
+    maxval_mode &= 3;
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_recon_metrics: bad shape");
+    MRB_REQUIRE(!want_ssim || (H >= SSIM_WIN && W >= SSIM_WIN), MRB_EINVAL,
                 "mrb_recon_metrics: win_size exceeds image extent (need H, W >= 7; got %d x %d)", H, W);
-    MRB_REQUIRE(maxval_mode >= 0 && maxval_mode <= 2, MRB_EINVAL, "mrb_recon_metrics: maxval_mode must be 0, 1 or 2");
+    MRB_REQUIRE(maxval_mode >= 0 && maxval_mode <= 2, MRB_EINVAL, "mrb_recon_metrics: maxval_mode must be 0, 1 or 2 (+ 4)");
     cudaStream_t st = (cudaStream_t)stream;
     // workspace: doubles [0,1] sums | ints at double slot 2..3: ext[4] | doubles [8 .. 8+B) per-slice SSIM sums
     struct Init { double sums[2]; int ext[4]; } init;
@@ -174,6 +177,11 @@ extern "C" int mrb_recon_metrics(const void* gt, const void* pred, int B, int H,
     MRB_LAUNCHED();
     metrics_finish_kernel<<<1, 1, 0, st>>>(wsd, (const int*)(wsd + 2), (double)n, maxval_mode, resd);
     MRB_LAUNCHED();
+    if (!want_ssim) {
+        const double qnan = __builtin_nan("");
+        MRB_CUDA(cudaMemcpyAsync(resd + 3, &qnan, sizeof(double), cudaMemcpyHostToDevice, st));
+        return MRB_OK;
+    }
     const int vw = W - SSIM_WIN + 1, vh = H - SSIM_WIN + 1;
     dim3 grid((vw + SSIM_TX - 1) / SSIM_TX, (vh + SSIM_TY - 1) / SSIM_TY, B);
     ssim_sum_kernel<<<grid, dim3(SSIM_TX, SSIM_TY), 0, st>>>((const float*)gt, (const float*)pred, H, W, resd + 4, wsd + 8);

@@ -49,18 +49,18 @@ def _as3d(gt, pred):
 
 def mse(gt: torch.Tensor, pred: torch.Tensor) -> float:
     """reconstruction_metrics.py:11-13."""
-    return float(_run(*_as3d(gt, pred), 0)[0])
+    return float(_run(*_as3d(gt, pred), 4)[0])
 
 
 def nmse(gt: torch.Tensor, pred: torch.Tensor) -> float:
     """reconstruction_metrics.py:16-18."""
-    return float(_run(*_as3d(gt, pred), 0)[1])
+    return float(_run(*_as3d(gt, pred), 4)[1])
 
 
 def psnr(gt: torch.Tensor, pred: torch.Tensor, maxval: Optional[float] = None) -> float:
     """reconstruction_metrics.py:21-25."""
     gt, pred = _as3d(gt, pred)
-    return float((_run(gt, pred, 0) if maxval is None else _run(gt, pred, 2, maxval))[2])
+    return float((_run(gt, pred, 4) if maxval is None else _run(gt, pred, 6, maxval))[2])
 
 
 def ssim(gt: torch.Tensor, pred: torch.Tensor, maxval: Optional[float] = None) -> float:

@@ -15,8 +15,10 @@ class HostPrefetcher:
     """Iterate over dictionaries of (pinned) host tensors, yielding the same dictionaries on ``device``.
 
     One batch is always in flight on a private copy stream; the consumer's stream waits on the upload's event.  The
-    device tensors are two persistent buffer sets that alternate, so a yielded batch is valid until the iterator is
-    advanced TWICE (clone what must live longer).  Non-tensor values are passed through untouched.
+    device tensors are two persistent buffer sets that alternate: a yielded batch is valid ONLY UNTIL THE NEXT ADVANCE of the
+    iterator.  Requesting batch i + 1 enqueues the upload of batch i + 2 into batch i's buffers, ordered after everything
+    the consumer's stream had been given before that advance -- work enqueued on batch i afterwards would race with the
+    overwrite, so clone what must live longer.  Non-tensor values are passed through untouched.
     """
 
     def __init__(self, batches: Iterable[Dict[str, object]], device):

@@ -21,6 +21,7 @@ def _enabled():
     return os.environ.get("MRIDC_B200_DISABLE_TC", "0") != "1"
 
 
+_FINAL_TC = os.environ.get("MRIDC_B200_FINAL_FP32", "0") != "1"  # =1: exact-fp32 CUDA-core final conv (conv.cu)
 _ZERO_STATE = {}
 _YH_STATIC = {}      # (B, C, H, W, device) -> [static hybrid k-space buffer, id of the tensor last copied into it]
 _GRAPH_POOL = {}     # device -> CUDA-graph memory pool shared by all cascades (they replay one after the other)
@@ -167,7 +168,7 @@ class RimTcEngine:
     # ---------------------------------------------------------------------------------------------
     def conv_stack_bh(self, g4, h, h_alt, xbuf, eta, packs, B, H, W):
         """One time step of the regulariser (rim_block.py:233-248) on BH buffers (conv_tc2.cu): conv5x5 -> ConvGRU -> border
-        -> conv3x3(dil) -> ConvGRU -> border -> final conv + eta update.  h / h_alt are ping-pong lists, swapped in place."""
+        -> conv3x3(dil) -> ConvGRU -> final conv (tap GEMM) + eta update.  h / h_alt are ping-pong lists, swapped in place."""
         lib = _lib.load()
         st = _lib.stream_ptr()
         b = self.block
@@ -185,10 +186,15 @@ class RimTcEngine:
         _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[1]), _lib.ptr(packs[1][1]), _lib.ptr(r1.ih.bias),
                                    _lib.ptr(h_alt[1]), B, H, W, st))
         h[1], h_alt[1] = h_alt[1], h[1]
-        _lib.check(lib.mrb_bh_fix_border(_lib.ptr(h[1]), B, H, W, st))  # the final 3x3 reads it spatially
         new_eta = torch.empty_like(eta)
-        _lib.check(lib.mrb_conv_c2_bh_residual(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight), _lib.ptr(fin.conv_layer.bias),
-                                               _lib.ptr(eta), _lib.ptr(new_eta), B, H, W, st))
+        if _FINAL_TC:
+            # tap GEMM on the tensor core + clamped gather: reads the interior of h[1] only, no border fix-up
+            _lib.check(lib.mrb_tc2_final_conv(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight), _lib.ptr(fin.conv_layer.bias),
+                                              _lib.ptr(eta), _lib.ptr(new_eta), B, H, W, st))
+        else:
+            _lib.check(lib.mrb_bh_fix_border(_lib.ptr(h[1]), B, H, W, st))  # the CUDA-core 3x3 reads it spatially
+            _lib.check(lib.mrb_conv_c2_bh_residual(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight),
+                                                   _lib.ptr(fin.conv_layer.bias), _lib.ptr(eta), _lib.ptr(new_eta), B, H, W, st))
         return new_eta
 
     def bench_step(self, B, H, W, dev):
@@ -208,7 +214,7 @@ class RimTcEngine:
             packs = self.packs(bh=True)
             return (lambda: self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W),
                     "split-bf16 tcgen05 ConvGRU stack of one time step on BH activations (conv5x5x4, TMA-fed ConvGRU, border, "
-                    "conv3x3d2, ConvGRU, border, conv3x3->2 + eta)")
+                    "conv3x3d2, ConvGRU, tap-GEMM conv3x3->2 + eta)")
         h = [torch.randn((B, H, W, 64), device=dev) * 0.1 for _ in range(2)]
         h_alt = [torch.empty_like(t) for t in h]
         xbuf = torch.empty((B, H, W, 64), device=dev)

@@ -71,6 +71,27 @@ def test_fft_complex_input_and_noncontiguous():
     assert rel_l2(mb.ifft2(xt.cuda(), False, "forward"), omri.ifft2(xt, False, "forward")) < 2e-6
 
 
+def test_fft_many_small_images_and_small_metrics():
+    """More than 65535 leading elements (gridDim.y of the strided-axis kernels) and metric getters on images smaller than
+    the SSIM window -- both fine in the reference."""
+    import mridc_b200 as mb
+    from mridc_b200 import metrics as mm
+    from oracle import metrics as ometrics, mri as omri
+
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(70000, 4, 6, 2, generator=g)
+    assert rel_l2(mb.fft2(x.cuda(), True, "ortho"), omri.fft2(x, True, "ortho")) < 2e-6
+    assert rel_l2(mb.ifft2(x.cuda(), False, "backward", spatial_dims=[1, 2]),
+                  omri.ifft2(x, False, "backward", [1, 2])) < 2e-6
+    a, b = torch.rand(2, 5, 6, generator=g), torch.rand(2, 5, 6, generator=g)
+    for name in ("mse", "nmse", "psnr"):
+        want = float(getattr(ometrics, name)(a.numpy(), b.numpy()))
+        got = getattr(mm, name)(a.cuda(), b.cuda())
+        assert abs(got - want) <= 1e-6 * max(1.0, abs(want)), (name, got, want)
+    with pytest.raises(ValueError, match="win_size"):
+        mm.ssim(a.cuda(), b.cuda())
+
+
 def test_shift_roll_bit_exact(golden):
     import mridc_b200 as mb
 

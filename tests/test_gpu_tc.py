@@ -310,6 +310,22 @@ def test_tc2_conv_ops_vs_oracle(B, H, W):
     e = rel_l2(o2, ref)
     print("[tc parity] %-16s rel-L2 %.2e" % ("conv_c2 (bh)", e))
     assert e < 5e-6  # exact fp32 arithmetic on x = hi + lo (2^-18 relative representation error)
+    # tensor-core tap GEMM + clamped gather: never reads the BH border (poisoned here), with and without bias
+    xp = xb.clone()
+    v = xp.view(torch.bfloat16).view(B, H + 4, W + 4, 128)
+    v[:, :2] = float("nan"); v[:, -2:] = float("nan"); v[:, :, :2] = float("nan"); v[:, :, -2:] = float("nan")
+    for bias in (None, torch.randn(2, generator=g)):
+        refb = ref if bias is None else ref + bias
+        o3 = torch.full((B, H, W, 2), float("nan"), device="cuda")
+        bdev = None if bias is None else bias.cuda()
+        bd = None if bias is None else _lib.ptr(bdev)
+        _lib.check(lib.mrb_tc2_final_conv(_lib.ptr(xp), _lib.ptr(w3d), bd, _lib.ptr(etad), _lib.ptr(o3), B, H, W, st))
+        e = rel_l2(o3, refb)
+        print("[tc parity] %-16s rel-L2 %.2e" % ("final conv (tc2)", e))
+        assert e < 1e-5
+        o4 = torch.empty_like(o3)
+        _lib.check(lib.mrb_tc2_final_conv(_lib.ptr(xp), _lib.ptr(w3d), bd, _lib.ptr(etad), _lib.ptr(o4), B, H, W, st))
+        assert torch.equal(o3, o4)
 
 
 def test_cirim_graph_replay_equals_eager(monkeypatch):
