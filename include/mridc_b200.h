@@ -251,6 +251,17 @@ int mrb_tc_conv5x5x4_bh(const void* x, const void* wpack, const void* bias, void
                         int relu, void* stream);
 int mrb_tc_conv_bh(const void* x_bh, const void* wpack, const void* bias, void* out_bh, int B, int H, int W, int cout, int k,
                    int dil, int relu, void* stream);
+/* First RIM conv fed by bulk copies.  "G8" input layout: the conv input [eta.re, eta.im, grad.re, grad.im] of a position as
+ * 4 hi + 4 lo bf16 (16 bytes), positions in the padded BH geometry [B][H+4][W+4] with a replicate border, plus guard
+ * positions before and after.  mrb_g8_bytes: allocation size (the caller zero-initialises the buffer ONCE; the guards are
+ * only ever read); mrb_g8_from_nhwc4: fp32 channels-last [B,H,W,4] (the output of mrb_dc_rim_grad with nhwc) -> G8;
+ * mrb_tc2_conv5x5x4: ConvNonlinear(4 -> 64, k = 5, replicate padding, optional ReLU; conv_layers.py:36-123) G8 -> BH with
+ * w [64,4,5,5] fp32 (split into bf16 hi/lo on the fly), bias [64] or null.  Every position of out_bh is written; its
+ * border is not a replicate copy. */
+size_t mrb_g8_bytes(int B, int H, int W);
+int mrb_g8_from_nhwc4(const void* x, void* g8, int B, int H, int W, void* stream);
+int mrb_tc2_conv5x5x4(const void* g8, const void* w, const void* bias, void* out_bh, int B, int H, int W, int relu,
+                      void* stream);
 /* final RIM conv (rim_block.py:239-248) on a BH source with a valid border: out [B,H,W,2] = eta + conv3x3(x) (+ bias) */
 int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H,
                             int W, void* stream);

@@ -721,6 +721,243 @@ static int make_bh_tmap3(void* mp, const void* base, int B, int H, int W) {
     return MRB_OK;
 }
 
+// ---- first RIM conv (4 -> 64, 5x5) fed by bulk copies ---------------------------------------------------------------
+// ConvNonlinear(4 -> 64, k = 5, ReplicationPad2d(2), ReLU) on the RIM input [eta.re, eta.im, grad.re, grad.im]
+// (rim_block.py:233-238, conv_layers.py:72-123).
+// Input format "G8": the 4 channels of a position as 4 bf16 hi + 4 bf16 lo = 16 bytes, positions in the padded BH geometry
+// [B][H+4][W+4] (replicate border written by the producer), with zeroed guard positions before and after the tensor.  In
+// the UMMA no-swizzle K-major layout a core matrix is 8 rows x 16 bytes stored contiguously, i.e. 8 consecutive positions of
+// a G8 row ARE a core matrix: the A operand of tap (dy, dx) for 128 consecutive (flat) positions is the contiguous G8 range
+// starting dy rows up / dx positions left.  Per tile the loader therefore issues five 1-D bulk copies (one per tap row,
+// 136 positions = 2176 B) and every tap of that row is the same shared-memory segment at a 16-byte offset: an MMA with
+// K = 16 takes two neighbouring taps (leading-dimension byte offset 16).  No im2col, no conversion, 10.6 KB of loads per
+// 128 outputs.  K per position: 8 = [hi | lo]; weights B1 = [w_hi | w_hi] (main term (a_hi + a_lo) w_hi) stacked on
+// B2 = [w_lo | 0] (cross term a_hi w_lo) -> one N = 128 MMA per tap pair, 15 per tile; the epilogue adds main + cross in RN
+// fp32, bias, ReLU, splits into the BH box layout, and a store lane issues the two TMA stores.
+// Pointwise in the flat padded position space like gru2_kernel: border positions of the output are written but are not
+// replicate copies (the ConvGRU that follows is pointwise).
+constexpr int C5_SEG_POS = 136;                      // 128 + 4 taps + pad tap, rounded to whole core matrices
+constexpr int C5_SEG_BYTES = C5_SEG_POS * 16;
+constexpr int C5_STAGE_BYTES = 5 * C5_SEG_BYTES;
+constexpr int C5_STAGES = 4;
+constexpr int C5_B_CHUNK = 128 * 16;                 // [128 rows][8 bf16] of one tap
+constexpr int C5_B_BYTES = 15 * 2 * C5_B_CHUNK;      // (tap row, tap pair) x 2 taps
+constexpr int C5_THREADS = (EPI_W + 3) * 32;
+
+struct Conv5Params {
+    const uint8_t* g8;   // first guard position
+    const float* w;      // [64][4][5][5]
+    const float* bias;   // [64] or null
+    long long Q;         // B * (H+4) * (W+4)
+    long long guard_lo;  // positions before position 0
+    int Wp;
+    int n_tiles;
+    int relu;
+};
+
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;  // byte distance between the two 16-byte K chunks of an MMA
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;  // byte distance between 8-row core matrices
+    d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell); layout type 0 = no swizzle
+    return d;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(C5_THREADS, 1)
+conv5g_kernel(const __grid_constant__ CUtensorMap tm_o, const Conv5Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* out_s = smem;                                         // [2 buffers][hi box | lo box], SWIZZLE_128B
+    uint8_t* w_s = out_s + 4 * SLOT_BYTES;                         // [15 pairs][2 taps][128 rows][16 B]
+    uint8_t* a_s = w_s + C5_B_BYTES;                               // [C5_STAGES][5 tap rows][136 positions][16 B]
+    float* bias_s = (float*)(a_s + C5_STAGES * C5_STAGE_BYTES);    // [64]
+    uint64_t* full = (uint64_t*)(bias_s + 64);                     // [C5_STAGES]
+    uint64_t* empty = full + C5_STAGES;                            // [C5_STAGES] MMA commit
+    uint64_t* acc_full = empty + C5_STAGES;                        // [4]
+    uint64_t* acc_empty = acc_full + 4;                            // [4] one arrival per epilogue warp
+    uint64_t* out_ready = acc_empty + 4;                           // [2] one arrival per epilogue warp
+    uint64_t* out_free = out_ready + 2;                            // [2] the TMA stores have read the buffer
+    uint32_t* tmem_slot = (uint32_t*)(out_free + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C5_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_W);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&out_ready[i], EPI_W);
+            mbar_init(&out_free[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 64) bias_s[threadIdx.x] = P.bias ? P.bias[threadIdx.x] : 0.f;
+    // weights: chunk (tap row dy, pair p, kc) = tap (dy, dx = 2p + kc) (dx = 5: zero pad tap); row n < 64: [w_hi | w_hi] of
+    // output channel n, row 64 + n: [w_lo | 0]
+    for (int i = threadIdx.x; i < 30 * 128; i += C5_THREADS) {
+        const int chunk = i >> 7, n = i & 127;
+        const int dy = chunk / 6, dx = chunk - dy * 6;
+        uint32_t hi01 = 0, hi23 = 0, lo01 = 0, lo23 = 0;
+        if (dx < 5) {
+            const float* wp = P.w + ((long long)(n & 63) * 4) * 25 + dy * 5 + dx;
+            split_bf16x2(wp[0], wp[25], hi01, lo01);
+            split_bf16x2(wp[50], wp[75], hi23, lo23);
+        }
+        const uint4 v = n < 64 ? make_uint4(hi01, hi23, hi01, hi23) : make_uint4(lo01, lo23, 0u, 0u);
+        *reinterpret_cast<uint4*>(w_s + (size_t)chunk * C5_B_CHUNK + n * 16) = v;
+    }
+    if (warp == EPI_W + 1) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EPI_W) {
+        // ============================== BULK-COPY PRODUCER ==============================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                mbar_wait_sleep(&empty[s], ph ^ 1, 64);
+                mbar_expect_tx(&full[s], C5_STAGE_BYTES);
+                const uint32_t dst = smem_u32(a_s + s * C5_STAGE_BYTES);
+                // tap row dy reads positions q0 + (dy - 2) Wp - 2 ... (+ 135)
+                const uint8_t* src = P.g8 + (P.guard_lo + (long long)tile * TILE - 2LL * P.Wp - 2) * 16;
+#pragma unroll
+                for (int dy = 0; dy < 5; ++dy)
+                    bulk_load_1d(dst + dy * C5_SEG_BYTES, src + (long long)dy * P.Wp * 16, C5_SEG_BYTES, smem_u32(&full[s]));
+                if (++s == C5_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == EPI_W + 1) {
+        // ============================== MMA ISSUER ==============================
+        const uint32_t tmem_u = uni(tmem_base);
+        const uint64_t bdesc0 = make_desc_ns(smem_u32(w_s), C5_B_CHUNK, 128);
+        const uint64_t adesc0 = make_desc_ns(smem_u32(a_s), 16, 128);
+        constexpr uint32_t id128 = make_idesc(TILE, 128);
+        int s = 0, buf = 0;
+        uint32_t ph = 0, acc_ph = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t d = tmem_u + (uint32_t)(buf * 128);
+            const uint64_t a_st = adesc0 + (uint64_t)((s * C5_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    umma_ss(d, a_st + (uint64_t)((dy * C5_SEG_BYTES + 2 * p * 16) >> 4),
+                            bdesc0 + (uint64_t)(((dy * 3 + p) * 2 * C5_B_CHUNK) >> 4), id128, (dy | p) != 0);
+            umma_commit(&empty[s]);
+            umma_commit(&acc_full[buf]);
+            if (++s == C5_STAGES) { s = 0; ph ^= 1; }
+            if (++buf == 4) { buf = 0; acc_ph ^= 1; }
+        }
+    } else if (warp == EPI_W + 2) {
+        // ============================== TMA STORE LANE ==============================
+        if (lane == 0) {
+            int it = 0;
+            const uint32_t out_u32 = smem_u32(out_s);
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int ob = it & 1;
+                mbar_wait_sleep(&out_ready[ob], (uint32_t)(it >> 1) & 1u, 64);
+                tma_store_2d(&tm_o, out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES), 0, tile * TILE);
+                tma_store_2d(&tm_o, out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES + SLOT_BYTES), 64, tile * TILE);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(&out_free[ob]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        // ============================== EPILOGUE ==============================
+        const int quad = warp & 3, cg = warp >> 2;
+        const int m = quad * 32 + lane;
+        const uint32_t ch0 = swz(m, 2 * cg), ch1 = swz(m, 2 * cg + 1);
+        const uint32_t out_u32 = smem_u32(out_s);
+        float bs[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bs[i] = bias_s[cg * 16 + i];
+        int buf = 0, it = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            mbar_wait_sleep(&acc_full[buf], acc_ph, 64);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cg * 16);
+            float m0[8], m1[8], c0[8], c1[8];
+            tmem_ld8x4(t0, t0 + 8, t0 + 64, t0 + 72, m0, m1, c0, c1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = (m0[i] + c0[i]) + bs[i];
+                o[8 + i] = (m1[i] + c1[i]) + bs[8 + i];
+            }
+            if (P.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = fmaxf(o[i], 0.f);
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_bf16x2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+            const int ob = it & 1;
+            mbar_wait_sleep(&out_free[ob], ((uint32_t)(it >> 1) & 1u) ^ 1u, 32);
+            const uint32_t ou = out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES);
+            sts128u(ou + ch0, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128u(ou + ch1, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+            sts128u(ou + SLOT_BYTES + ch0, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            sts128u(ou + SLOT_BYTES + ch1, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&out_ready[ob]);
+            if (++buf == 4) { buf = 0; acc_ph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_W + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+static size_t conv5g_smem() { return 1024 + 4 * SLOT_BYTES + C5_B_BYTES + C5_STAGES * C5_STAGE_BYTES + 64 * 4 + 24 * 8 + 16; }
+
+// guard positions of a G8 tensor (zeroed by the allocation): tap rows reach 2 rows + 2 positions before a tile, and the last
+// tile's segments 2 rows + 136 positions past the end
+__host__ __device__ inline long long g8_guard_lo(int W) { return 2LL * (W + 2 * PADB) + 2; }
+__host__ __device__ inline long long g8_guard_hi(int W) { return 2LL * (W + 2 * PADB) + C5_SEG_POS + TILE; }
+
+// fp32 channels-last [B,H,W,4] -> G8 (hi/lo split, replicate border)
+__global__ void g8_from_nhwc4_kernel(const float4* __restrict__ x, uint4* __restrict__ g8, int B, int H, int W) {
+    const int Hp = H + 2 * PADB, Wp = W + 2 * PADB;
+    const long long total = (long long)B * Hp * Wp;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(q % Wp);
+        const long long r = q / Wp;
+        const int yp = (int)(r % Hp), b = (int)(r / Hp);
+        const int xx = min(max(xp - PADB, 0), W - 1), yy = min(max(yp - PADB, 0), H - 1);
+        const float4 v = __ldg(x + ((long long)b * H + yy) * W + xx);
+        uint32_t h01, l01, h23, l23;
+        split_bf16x2(v.x, v.y, h01, l01);
+        split_bf16x2(v.z, v.w, h23, l23);
+        g8[q] = make_uint4(h01, h23, l01, l23);
+    }
+}
+
 #ifdef MRB_TC_PROF
 int g_debug2 = 0;
 unsigned long long* g_prof2 = nullptr;
@@ -804,6 +1041,53 @@ extern "C" int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack
     int grid = device_sm_count();
     if (grid > P.n_tiles) grid = P.n_tiles;
     tc2::gru2_kernel<<<grid, tc2::THREADS2, smem, (cudaStream_t)stream>>>(tm_h, tm_x, tm_o, P);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+/* G8: the RIM conv input [eta.re, eta.im, grad.re, grad.im] as 4 hi + 4 lo bf16 per position of the padded BH geometry,
+ * with guard positions before and after; the buffer must be ZERO-INITIALISED once by the caller (the guards are only read) */
+extern "C" size_t mrb_g8_bytes(int B, int H, int W) {
+    const long long Q = (long long)B * (H + 2 * tc2::PADB) * (W + 2 * tc2::PADB);
+    return (size_t)(Q + tc2::g8_guard_lo(W) + tc2::g8_guard_hi(W)) * 16;
+}
+
+extern "C" int mrb_g8_from_nhwc4(const void* x, void* g8, int B, int H, int W, void* stream) {
+    MRB_REQUIRE(x && g8 && B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_g8_from_nhwc4: bad argument");
+    const long long total = (long long)B * (H + 2 * tc2::PADB) * (W + 2 * tc2::PADB);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    tc2::g8_from_nhwc4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint4*)g8 + tc2::g8_guard_lo(W), B, H, W);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+/* ConvNonlinear 5x5, 4 -> 64 (conv_layers.py:36-123) from a G8 input to a BH output; w [64,4,5,5] fp32 (split on the fly),
+ * bias [64] or null.  Every position of out_bh is written; its border is not a replicate copy. */
+extern "C" int mrb_tc2_conv5x5x4(const void* g8, const void* w, const void* bias, void* out_bh, int B, int H, int W, int relu,
+                                 void* stream) {
+    MRB_REQUIRE(g8 && w && out_bh, MRB_EINVAL, "mrb_tc2_conv5x5x4: null pointer");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_conv5x5x4: bad shape");
+    tc2::Conv5Params P;
+    P.g8 = (const uint8_t*)g8; P.w = (const float*)w; P.bias = (const float*)bias;
+    P.Wp = W + 2 * tc2::PADB;
+    P.Q = (long long)B * (H + 2 * tc2::PADB) * P.Wp;
+    P.guard_lo = tc2::g8_guard_lo(W);
+    MRB_REQUIRE(P.Q < 2147483647LL - tc2::TILE, MRB_EUNSUPPORTED, "mrb_tc2_conv5x5x4: too many pixels");
+    P.n_tiles = (int)((P.Q + tc2::TILE - 1) / tc2::TILE);
+    P.relu = relu;
+    CUtensorMap tm_o;
+    int rc = tc2::make_bh_tmap(&tm_o, out_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    static bool attr_set = false;
+    const size_t smem = device_max_smem_optin();
+    if (!attr_set) {
+        MRB_REQUIRE(tc2::conv5g_smem() <= smem, MRB_EUNSUPPORTED, "mrb_tc2_conv5x5x4: shared memory");
+        MRB_CUDA(cudaFuncSetAttribute(tc2::conv5g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = device_sm_count();
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    tc2::conv5g_kernel<<<grid, tc2::C5_THREADS, smem, (cudaStream_t)stream>>>(tm_o, P);
     MRB_LAUNCHED();
     return MRB_OK;
 }

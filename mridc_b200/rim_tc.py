@@ -21,6 +21,7 @@ def _enabled():
     return os.environ.get("MRIDC_B200_DISABLE_TC", "0") != "1"
 
 
+_CONV5_G8 = os.environ.get("MRIDC_B200_CONV5_GEN1", "0") != "1"  # =1: first conv on the gen-1 loader-warp kernel (conv_tc.cu)
 _FINAL_TC = os.environ.get("MRIDC_B200_FINAL_FP32", "0") != "1"  # =1: exact-fp32 CUDA-core final conv (conv.cu)
 _ZERO_STATE = {}
 _YH_STATIC = {}      # (B, C, H, W, device) -> [static hybrid k-space buffer, id of the tensor last copied into it]
@@ -86,6 +87,13 @@ class RimTcEngine:
         c1, f = b.layers[1].convs, b.final_layer[0]
         return (not self._indrnn and os.environ.get("MRIDC_B200_TC_GEN1", "0") != "1" and W >= 28
                 and c1.dilation * (c1.kernel_size - 1) // 2 <= 2 and f.kernel_size == 3 and f.dilation == 1)
+
+    @staticmethod
+    def _g8(lib, B, H, W, dev):
+        """Zero-initialised G8 buffer (conv_tc2.cu) for the bulk-copy-fed first conv, or None for the gen-1 kernel."""
+        if not _CONV5_G8:
+            return None
+        return torch.zeros(lib.mrb_g8_bytes(B, H, W), dtype=torch.uint8, device=dev)
 
     def _params(self):
         b = self.block
@@ -166,7 +174,7 @@ class RimTcEngine:
         return new_eta
 
     # ---------------------------------------------------------------------------------------------
-    def conv_stack_bh(self, g4, h, h_alt, xbuf, eta, packs, B, H, W):
+    def conv_stack_bh(self, g4, h, h_alt, xbuf, eta, packs, B, H, W, g8=None):
         """One time step of the regulariser (rim_block.py:233-248) on BH buffers (conv_tc2.cu): conv5x5 -> ConvGRU -> border
         -> conv3x3(dil) -> ConvGRU -> final conv (tap GEMM) + eta update.  h / h_alt are ping-pong lists, swapped in place."""
         lib = _lib.load()
@@ -175,8 +183,14 @@ class RimTcEngine:
         c0, c1 = b.layers[0].convs, b.layers[1].convs
         r0, r1 = b.layers[0].rnn, b.layers[1].rnn
         fin = b.final_layer[0]
-        _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias), _lib.ptr(xbuf),
-                                           B, H, W, 64, 1, st))
+        if g8 is not None:
+            # bulk-copy-fed 5x5: the fp32 gradient is split once into the 16-byte G8 positions, taps are address offsets
+            _lib.check(lib.mrb_g8_from_nhwc4(_lib.ptr(g4), _lib.ptr(g8), B, H, W, st))
+            _lib.check(lib.mrb_tc2_conv5x5x4(_lib.ptr(g8), _lib.ptr(c0.conv_layer.weight), _lib.ptr(c0.conv_layer.bias),
+                                             _lib.ptr(xbuf), B, H, W, 1, st))
+        else:
+            _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias),
+                                               _lib.ptr(xbuf), B, H, W, 64, 1, st))
         _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[0]), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias),
                                    _lib.ptr(h_alt[0]), B, H, W, st))
         h[0], h_alt[0] = h_alt[0], h[0]
@@ -212,7 +226,8 @@ class RimTcEngine:
                 h.append(buf)
             xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
             packs = self.packs(bh=True)
-            return (lambda: self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W),
+            g8 = self._g8(lib, B, H, W, dev)
+            return (lambda: self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W, g8),
                     "split-bf16 tcgen05 ConvGRU stack of one time step on BH activations (conv5x5x4, TMA-fed ConvGRU, border, "
                     "conv3x3d2, ConvGRU, tap-GEMM conv3x3->2 + eta)")
         h = [torch.randn((B, H, W, 64), device=dev) * 0.1 for _ in range(2)]
@@ -234,11 +249,12 @@ class RimTcEngine:
         h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
         xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
         g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        g8 = self._g8(lib, B, H, W, dev)
         etas = []
         for step in range(b.time_steps):
             _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
                              ws=ws, nhwc=True, y_hybrid=y_hybrid)
-            eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W)
+            eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W, g8)
             if step == 0 and fresh_state:
                 # the ping-pong swap left the caller's / the shared zero buffers in h_alt: they must never be written
                 h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]

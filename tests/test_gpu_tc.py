@@ -284,6 +284,18 @@ def test_tc2_conv_ops_vs_oracle(B, H, W):
     ob = torch.full((nb,), 0x7f, dtype=torch.uint8, device="cuda")
     _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(x4d), _lib.ptr(p1), _lib.ptr(b1d), _lib.ptr(ob), B, H, W, 64, 1, st))
     _diag(from_bh(ob), ref, 1e-5, "conv5x5x4 (bh)")
+    # bulk-copy-fed variant: fp32 gradient -> G8 -> BH, weights split on the fly, with and without bias / ReLU
+    g8 = torch.zeros(lib.mrb_g8_bytes(B, H, W), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_g8_from_nhwc4(_lib.ptr(x4d), _lib.ptr(g8), B, H, W, st))
+    w1d = w1.cuda()
+    for bias, relu in ((b1d, 1), (None, 0)):
+        refg = onets.conv_nonlinear(x4, w1, None if bias is None else b1, 5, 1, "relu" if relu else None)
+        ob = torch.full((nb,), 0x7f, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.mrb_tc2_conv5x5x4(_lib.ptr(g8), _lib.ptr(w1d), _lib.ptr(bias), _lib.ptr(ob), B, H, W, relu, st))
+        _diag(from_bh(ob), refg, 1e-5, "conv5x5x4 (g8)")
+        ob2 = torch.empty_like(ob)
+        _lib.check(lib.mrb_tc2_conv5x5x4(_lib.ptr(g8), _lib.ptr(w1d), _lib.ptr(bias), _lib.ptr(ob2), B, H, W, relu, st))
+        assert torch.equal(from_bh(ob), from_bh(ob2))
 
     x = torch.randn(B, 64, H, W, generator=g)
     xd = x.permute(0, 2, 3, 1).contiguous().cuda()
