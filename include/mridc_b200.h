@@ -116,7 +116,9 @@ int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, const void* m
  *     ifft2(M * (fft2(x) - y)) = bs*H * V_W[ M * (fs * U_W x - yh) ],   yh = (1/H) * V_H y   (U/V: centred DFTs)
  * mrb_dc_hybrid_prepare computes yh once per slice batch (y is constant over the unrolled network): [B,C,H,W,2] buffer
  * whose rows hold the sampled columns packed at the front; ws as for mrb_sens_reduce (one [B,C,H,W] complex image).
- * mrb_dc_rim_grad_hybrid is then one kernel of row transforms per evaluation (same outputs as mrb_dc_rim_grad). */
+ * mrb_dc_rim_grad_hybrid is then one kernel of row transforms per evaluation (same outputs as mrb_dc_rim_grad).
+ * out_nhwc == 2 (W == 320, C <= 16 only): `out` is a G8 buffer (mrb_g8_bytes, zero-initialised once) and the kernel
+ * writes the regulariser's conv input directly -- 4 bf16 hi + 4 bf16 lo per position, replicate border included. */
 int mrb_dc_hybrid_prepare(const void* y, const void* mask, int mask_dtype, int mask_b, void* yh, int B, int C,
                           int H, int W, int centered, void* ws, size_t ws_bytes, void* stream);
 int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const void* S, const void* mask, int mask_dtype,

@@ -94,7 +94,9 @@ def dc_hybrid_prepare(y, mask, centered, ws=None):
 
 def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=None, nhwc=False, y_hybrid=None):
     """rim_utils.py:11-67 -> [B, 4, H, W] (or channels-last [B, H, W, 4] when nhwc).
-    y_hybrid: result of dc_hybrid_prepare(y, mask, centered) -> single-kernel row form (1-D masks only)."""
+    y_hybrid: result of dc_hybrid_prepare(y, mask, centered) -> single-kernel row form (1-D masks only).
+    nhwc == 2 (hybrid form, W == 320, C <= 16): ``out`` is a zero-initialised G8 byte buffer (mrb_g8_bytes) and receives the
+    split-bf16 conv input with its replicate border."""
     y = _check5(y, "masked_kspace")
     S = _check5(S, "sense")
     B, C, H, W, _ = y.shape
@@ -110,7 +112,8 @@ def dc_rim_grad(eta, y, S, mask, sigma, centered, normalization, out=None, ws=No
         if mh != 1 or y_hybrid.shape != y.shape:
             raise ValueError("y_hybrid needs a 1-D column mask and the shape of masked_kspace")
         _lib.check(lib.mrb_dc_rim_grad_hybrid(_lib.ptr(eta), _lib.ptr(y_hybrid), _lib.ptr(S), _lib.ptr(m), code, mb,
-                                              1.0 / (float(sigma) ** 2.0), _lib.ptr(out), int(bool(nhwc)), B, C, H, W,
+                                              1.0 / (float(sigma) ** 2.0), _lib.ptr(out), 2 if nhwc == 2 else int(bool(nhwc)),
+                                              B, C, H, W,
                                               int(bool(centered)), norm_code(normalization), _lib.stream_ptr()))
         return out
     if ws is None:

@@ -511,6 +511,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                  : "memory");
 }
 
+__device__ __forceinline__ uint32_t bf16x2_rn(float e0, float e1) {  // (e0 -> low half, e1 -> high half), round to nearest even
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+
 inline size_t smem_bytes(int C) {
     return (size_t)MAXC * CS * sizeof(float2) + (size_t)C * RS * sizeof(float2) + 3 * (size_t)N * sizeof(float2) +
            (size_t)N * sizeof(float) + (size_t)N * sizeof(unsigned short) + 16;
@@ -530,8 +536,13 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
     float* mval_s = reinterpret_cast<float*>(eta_s + N);                      // [N] mask value by un-centred k
     unsigned short* pos_s = reinterpret_cast<unsigned short*>(mval_s + N);    // [N] un-centred k -> packed index
     __shared__ int scan_s[THREADS / 32];
+    __shared__ __align__(8) unsigned long long yh_bar;  // transaction barrier of the hybrid k-space bulk copies
     const int tid = threadIdx.x;
     const int h = blockIdx.x, b = blockIdx.y;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&yh_bar)), "r"(C));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int c = tid / N2, t = tid - c * N2;
     const bool active = c < C;
     const long long cstride = (long long)H * N;
@@ -587,13 +598,20 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
         pos_s[tid] = mk != 0.f ? (unsigned short)(woff + __popc(bal & ((1u << lane) - 1u))) : (unsigned short)0;
     }
     const int ns2 = max(2, (ns + 1) & ~1);
-    if (active) {  // each coil's 20 threads prefetch that coil's packed hybrid k-space row (16-byte chunks)
-        const float2* ysrc = yh + rowoff + (long long)c * cstride;
-        float2* ydst = yh_s + (size_t)c * ns2;
-#pragma unroll 1
-        for (int q = 2 * t; q < ns2; q += 2 * N2) cp_async16(ydst + q, ysrc + q);
+    // TMA staging of the packed hybrid k-space rows: one bulk copy per coil (ns2 x 8 bytes, a multiple of 16) issued by the
+    // coil's first thread after its own arrive.expect_tx on a barrier of C arrivals (initialised before the scan's
+    // __syncthreads); the flight time overlaps pass 1
+    {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&yh_bar);
+        if (active && t == 0) {
+            const float2* ysrc = yh + rowoff + (long long)c * cstride;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(ns2 * 8)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(yh_s + (size_t)c * ns2)),
+                         "l"(ysrc), "r"((unsigned)(ns2 * 8)), "r"(bar)
+                         : "memory");
+        }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     float2* xc = xch + (size_t)c * CS;
     if (active) {
         cx v[N1];
@@ -610,7 +628,19 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
             xc[k1 * XS + t] = mulw<false>(upk(v[k1]), w.x, w.y);
         }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&yh_bar);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "YH_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra YH_DONE;\n\t"
+            "bra YH_WAIT;\n\t"
+            "YH_DONE:\n\t"
+            "}\n" ::"r"(bar)
+            : "memory");
+    }
     __syncthreads();
     // ---- pass 2: forward 20-point DFT, residual, inverse 20-point DFT.  Only 16 lines per coil: the threads are re-dealt as
     // (coil = tid / 16, k1 = tid % 16) so that the 16*C busy lanes fill whole warps (7.5 instead of 10 at C = 15) ----
@@ -670,7 +700,26 @@ __global__ void __launch_bounds__(THREADS, 2) row_dc320_kernel(const float2* __r
         }
         const int d = tid;
         const float2 e = eta_s[d];
-        if (OUT_MODE == 2) {
+        if (OUT_MODE == 3) {
+            // G8 (conv_tc2.cu): [eta.re, eta.im, g.re, g.im] as 4 bf16 hi + 4 bf16 lo = 16 bytes at padded position
+            // (h + 2, d + 2) of a [B][H+4][W+4] grid behind 2 (W+4) + 2 guard positions; edge threads / edge rows also write
+            // the replicate border (ReplicationPad2d(2) of the 5x5 conv)
+            const float gx = acc.x * oscale, gy = acc.y * oscale;
+            const uint32_t h01 = bf16x2_rn(e.x, e.y), h23 = bf16x2_rn(gx, gy);
+            const uint32_t l01 = bf16x2_rn(e.x - __uint_as_float(h01 << 16), e.y - __uint_as_float(h01 & 0xffff0000u));
+            const uint32_t l23 = bf16x2_rn(gx - __uint_as_float(h23 << 16), gy - __uint_as_float(h23 & 0xffff0000u));
+            const uint4 v = make_uint4(h01, h23, l01, l23);
+            constexpr int Wp = N + 4;
+            const int Hp = H + 4;
+            uint4* base = reinterpret_cast<uint4*>(out) + (2 * Wp + 2) + ((long long)b * Hp + h + 2) * Wp;
+            const int r0 = h == 0 ? -2 : 0, r1 = h == H - 1 ? 2 : 0;
+            for (int r = r0; r <= r1; ++r) {
+                uint4* row = base + (long long)r * Wp;
+                row[d + 2] = v;
+                if (d == 0) row[0] = row[1] = v;
+                if (d == N - 1) row[N + 2] = row[N + 3] = v;
+            }
+        } else if (OUT_MODE == 2) {
             reinterpret_cast<float4*>(out)[((long long)b * H + h) * N + d] = make_float4(e.x, e.y, acc.x * oscale, acc.y * oscale);
         } else {
             const long long HW = (long long)H * N;
@@ -846,7 +895,12 @@ extern "C" int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const voi
     if (W == r320::N && C <= r320::MAXC && !getenv("MRIDC_B200_DC_STOCKHAM")) {
         // register-resident two-pass row transforms (both fastMRI geometries have 320 columns)
         const size_t sm = r320::smem_bytes(C);
-        if (out_nhwc) {
+        if (out_nhwc == 2) {
+            if ((rc = set_smem(r320::row_dc320_kernel<3>))) return rc;
+            r320::row_dc320_kernel<3><<<dim3(H, B), r320::THREADS, sm, st>>>((const float2*)eta, (const float2*)S,
+                                                                             (const float2*)yh, (float*)out, C, H, g.pw.tw, rw,
+                                                                             fs, os, m);
+        } else if (out_nhwc) {
             if ((rc = set_smem(r320::row_dc320_kernel<2>))) return rc;
             r320::row_dc320_kernel<2><<<dim3(H, B), r320::THREADS, sm, st>>>((const float2*)eta, (const float2*)S,
                                                                              (const float2*)yh, (float*)out, C, H, g.pw.tw, rw,
@@ -860,6 +914,7 @@ extern "C" int mrb_dc_rim_grad_hybrid(const void* eta, const void* yh, const voi
         MRB_LAUNCHED();
         return MRB_OK;
     }
+    MRB_REQUIRE(out_nhwc != 2, MRB_EUNSUPPORTED, "mrb_dc_rim_grad_hybrid: the G8 output needs W == 320 and C <= 16");
     const bool keep = g.threads_row >= W && g.cc <= 8;
 #define MRB_ROW_DC(MODE, KEEP)                                                                                        \
     do {                                                                                                              \

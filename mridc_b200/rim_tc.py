@@ -185,7 +185,8 @@ class RimTcEngine:
         fin = b.final_layer[0]
         if g8 is not None:
             # bulk-copy-fed 5x5: the fp32 gradient is split once into the 16-byte G8 positions, taps are address offsets
-            _lib.check(lib.mrb_g8_from_nhwc4(_lib.ptr(g4), _lib.ptr(g8), B, H, W, st))
+            if g4 is not None:  # else: the DC kernel has written g8 itself
+                _lib.check(lib.mrb_g8_from_nhwc4(_lib.ptr(g4), _lib.ptr(g8), B, H, W, st))
             _lib.check(lib.mrb_tc2_conv5x5x4(_lib.ptr(g8), _lib.ptr(c0.conv_layer.weight), _lib.ptr(c0.conv_layer.bias),
                                              _lib.ptr(xbuf), B, H, W, 1, st))
         else:
@@ -248,12 +249,14 @@ class RimTcEngine:
         h = list(h)
         h_alt = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
         xbuf = torch.empty(nb, dtype=torch.uint8, device=dev)
-        g4 = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         g8 = self._g8(lib, B, H, W, dev)
+        # W = 320 row-form DC kernel writes the G8 conv input (split + replicate border) itself: no fp32 gradient tensor
+        direct = g8 is not None and y_hybrid is not None and W == 320 and C <= 16
+        g4 = None if direct else torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         etas = []
         for step in range(b.time_steps):
-            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization, out=g4,
-                             ws=ws, nhwc=True, y_hybrid=y_hybrid)
+            _ops.dc_rim_grad(eta, masked_kspace, sense, mask_can, sigma, b.fft_centered, b.fft_normalization,
+                             out=g8 if direct else g4, ws=ws, nhwc=2 if direct else True, y_hybrid=y_hybrid)
             eta = self.conv_stack_bh(g4, h, h_alt, xbuf, eta, packs, B, H, W, g8)
             if step == 0 and fresh_state:
                 # the ping-pong swap left the caller's / the shared zero buffers in h_alt: they must never be written

@@ -340,6 +340,30 @@ def test_tc2_conv_ops_vs_oracle(B, H, W):
         assert torch.equal(o3, o4)
 
 
+@pytest.mark.parametrize("centered", [False, True])
+def test_dc_direct_g8_output_equals_converter(centered):
+    """The W = 320 row-form DC kernel writing the regulariser's G8 input itself (split + replicate border) == fp32 output
+    followed by the converter, byte for byte (guards untouched)."""
+    from mridc_b200 import _lib, _ops
+
+    lib = _lib.load()
+    B, C, H, W = 2, 5, 9, 320
+    g = torch.Generator().manual_seed(11)
+    y = torch.randn(B, C, H, W, 2, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g)
+    eta = torch.randn(B, H, W, 2, generator=g)
+    m = (torch.rand(1, 1, 1, W, 1, generator=g) < 0.3).float()
+    y, S, eta, m = (y * m).cuda(), S.cuda(), eta.cuda(), m.cuda()
+    yh = _ops.dc_hybrid_prepare(y, m, centered)
+    g4 = _ops.dc_rim_grad(eta, y, S, m, 1.0, centered, "ortho", nhwc=True, y_hybrid=yh)
+    ga = torch.zeros(lib.mrb_g8_bytes(B, H, W), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_g8_from_nhwc4(_lib.ptr(g4), _lib.ptr(ga), B, H, W, _lib.stream_ptr()))
+    gb = torch.zeros_like(ga)
+    _ops.dc_rim_grad(eta, y, S, m, 1.0, centered, "ortho", out=gb, nhwc=2, y_hybrid=yh)
+    assert torch.equal(ga, gb)
+    assert int((ga != 0).sum()) > ga.numel() // 2
+
+
 def test_cirim_graph_replay_equals_eager(monkeypatch):
     """CUDA-graph replay of the time loop (third call with the same input tensors) == eager launches, bit for bit; new
     eta values, new k-space values in the same tensors and a different cascade state are all picked up."""
