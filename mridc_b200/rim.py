@@ -44,6 +44,53 @@ def _require_2d(conv_dim, who):
         raise NotImplementedError("mridc_b200: %s supports conv_dim == 2 only (got %s)" % (who, conv_dim))
 
 
+def _require_2d_or_3d(conv_dim, who):
+    if conv_dim not in (2, 3):
+        raise NotImplementedError("mridc_b200: %s supports conv_dim 2 and 3 (got %s)" % (who, conv_dim))
+
+
+def _conv3d_dchw(x, w5, bias, k, dil, pad_mode, act=_ops.ACT_NONE, slope=0.0, add=None, add_scale=None, residual=None):
+    """'same' 3-D convolution of the slice stack x [D, Cin, H, W] (torch's unbatched Conv3d input [Cin, D, H, W] with the
+    slice axis leading) with w5 [Cout, Cin, k, k, k]: the depth taps are k launches of the batched 2-D kernel over the
+    (replicate- or zero-) shifted stack, each adding the previous partial sum in its epilogue; bias, the optional
+    ``add_scale * add`` term, the activation and the channels-last residual belong to the last launch.
+    -> [D, Cout, H, W] (or [D, H, W, Cout] with ``residual``)."""
+    x = x.contiguous()
+    D = x.shape[0]
+    pad = _pad_amount(dil, k)
+    ar = torch.arange(D, device=x.device)
+    ones = None
+    acc = None
+    for kd in range(k):
+        off = kd * dil - pad
+        if off == 0:
+            xk = x
+        elif pad_mode == _ops.PAD_REPLICATE:
+            xk = x.index_select(0, (ar + off).clamp_(0, D - 1))
+        else:  # zero padding: slices outside the stack contribute nothing
+            lo, hi = max(0, -off), min(D, D - off)
+            if hi <= lo:
+                continue
+            xk = torch.zeros_like(x)
+            xk[lo:hi] = x[lo + off:hi + off]
+        last = kd == k - 1
+        a, a_s = acc, None
+        if acc is not None:
+            if ones is None:
+                ones = torch.ones(w5.shape[0], dtype=torch.float32, device=x.device)
+            a_s = ones
+        if last and add is not None:
+            extra = add.contiguous() * add_scale.reshape(1, -1, 1, 1)
+            a = extra if a is None else a + extra
+            if ones is None:
+                ones = torch.ones(w5.shape[0], dtype=torch.float32, device=x.device)
+            a_s = ones
+        acc = _ops.conv2d(xk, w5[:, :, kd].contiguous(), bias if last else None, k, dil, pad_mode,
+                          act if last else _ops.ACT_NONE, slope if last else 0.0, add=a, add_scale=a_s,
+                          residual=residual if last else None)
+    return acc
+
+
 class ConvRNNStack(nn.Module):
     """conv_layers.py:8-33."""
 
@@ -61,7 +108,7 @@ class ConvNonlinear(nn.Module):
 
     def __init__(self, input_size, features, conv_dim, kernel_size, dilation, bias, nonlinear="relu"):
         super().__init__()
-        _require_2d(conv_dim, "ConvNonlinear")
+        _require_2d_or_3d(conv_dim, "ConvNonlinear")
         if kernel_size % 2 != 1:
             raise NotImplementedError("mridc_b200: ConvNonlinear supports odd kernel sizes only")
         self.input_size = input_size
@@ -78,8 +125,9 @@ class ConvNonlinear(nn.Module):
             self._act, self._slope = _ops.ACT_NONE, 0.0
         else:
             raise ValueError("Please specify a proper nonlinearity")
-        self.conv_layer = nn.Conv2d(in_channels=input_size, out_channels=features, kernel_size=kernel_size, padding=0,
-                                    dilation=dilation, bias=bias)
+        conv_class = nn.Conv3d if conv_dim == 3 else nn.Conv2d  # conv_layers.py:96-104
+        self.conv_layer = conv_class(in_channels=input_size, out_channels=features, kernel_size=kernel_size, padding=0,
+                                     dilation=dilation, bias=bias)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -92,9 +140,27 @@ class ConvNonlinear(nn.Module):
             raise RuntimeError(f"input has inconsistent input_size: got {_input.size(1)}, expected {self.input_size}")
 
     def forward(self, _input, residual_nhwc: Optional[torch.Tensor] = None):
+        if self.conv_dim == 3:
+            # unbatched Conv3d input [C, D, H, W] (rim_block.py:230-231) -> [F, D, H, W]
+            out = self.forward_dchw(_input.permute(1, 0, 2, 3), residual_nhwc)
+            return out if residual_nhwc is not None else out.permute(1, 0, 2, 3)
         self.check_forward_input(_input)
         return _ops.conv2d(_input, self.conv_layer.weight, self.conv_layer.bias, self.kernel_size, self.dilation,
                            _ops.PAD_REPLICATE, self._act, self._slope, residual=residual_nhwc)
+
+    def forward_dchw(self, x, residual_nhwc: Optional[torch.Tensor] = None):
+        """conv_dim == 3 on the slice stack [D, C, H, W] (ReplicationPad3d + Conv3d, conv_layers.py:72-76,:123)."""
+        self.check_forward_input(x)
+        return _conv3d_dchw(x, self.conv_layer.weight, self.conv_layer.bias, self.kernel_size, self.dilation,
+                            _ops.PAD_REPLICATE, self._act, self._slope, residual=residual_nhwc)
+
+
+def _reject_3d_gates(conv_dim, _input):
+    """The reference builds the GRU / MGU gates as nn.Conv2d whatever conv_dim says (rnn_cells.py:23-38, :160-175) and
+    then feeds them the 5-D tensors of :114-116 / :249-251: the same failure, with the same text."""
+    if conv_dim == 3:
+        raise RuntimeError("Expected 3D (unbatched) or 4D (batched) input to conv2d, but got input of size: %s"
+                           % list(_input.unsqueeze(0).shape))
 
 
 class _CellBase(nn.Module):
@@ -120,7 +186,7 @@ class ConvGRUCell(_CellBase):
 
     def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
         super().__init__()
-        _require_2d(conv_dim, "ConvGRUCell")
+        _require_2d_or_3d(conv_dim, "ConvGRUCell")
         self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
         self.kernel_size, self.dilation = kernel_size, dilation
         pad = _pad_amount(dilation, kernel_size)
@@ -135,6 +201,7 @@ class ConvGRUCell(_CellBase):
             nn.init.zeros_(self.ih.bias)
 
     def forward(self, _input, hx):
+        _reject_3d_gates(self.conv_dim, _input)
         self.check_forward_input(_input)
         self.check_forward_hidden(_input, hx)
         lib = _lib.load()
@@ -158,7 +225,7 @@ class ConvMGUCell(_CellBase):
 
     def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
         super().__init__()
-        _require_2d(conv_dim, "ConvMGUCell")
+        _require_2d_or_3d(conv_dim, "ConvMGUCell")
         self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
         self.kernel_size, self.dilation = kernel_size, dilation
         pad = _pad_amount(dilation, kernel_size)
@@ -175,6 +242,7 @@ class ConvMGUCell(_CellBase):
             nn.init.zeros_(self.ih.bias)
 
     def forward(self, _input, hx):
+        _reject_3d_gates(self.conv_dim, _input)
         self.check_forward_input(_input)
         self.check_forward_hidden(_input, hx)
         _input, hx = _input.contiguous(), hx.contiguous()
@@ -192,13 +260,15 @@ class IndRNNCell(_CellBase):
 
     def __init__(self, input_size, hidden_size, conv_dim, kernel_size, dilation=1, bias=True):
         super().__init__()
-        _require_2d(conv_dim, "IndRNNCell")
+        _require_2d_or_3d(conv_dim, "IndRNNCell")
         self.input_size, self.hidden_size, self.bias, self.conv_dim = input_size, hidden_size, bias, conv_dim
         self.kernel_size, self.dilation = kernel_size, dilation
         pad = _pad_amount(dilation, kernel_size)
-        self.ih = nn.Conv2d(input_size, hidden_size, kernel_size, padding=pad, dilation=dilation, bias=bias)
+        conv_class = nn.Conv3d if conv_dim == 3 else nn.Conv2d  # rnn_cells.py:295-312
+        self.ih = conv_class(input_size, hidden_size, kernel_size, padding=pad, dilation=dilation, bias=bias)
         self.hh = nn.Parameter(
-            nn.init.normal_(torch.empty(1, hidden_size, 1, 1), std=1.0 / (hidden_size * (1 + kernel_size**2))))
+            nn.init.normal_(torch.empty(*((1, hidden_size) + (1,) * conv_dim)),
+                            std=1.0 / (hidden_size * (1 + kernel_size**2))))
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -208,6 +278,9 @@ class IndRNNCell(_CellBase):
             nn.init.zeros_(self.ih.bias)
 
     def forward(self, _input, hx):
+        if self.conv_dim == 3:
+            # rnn_cells.py:386-391: _input [C, D, H, W], hx [D, C, H, W] -> [1, C, D, H, W]
+            return self.forward_dchw(_input.permute(1, 0, 2, 3), hx).permute(1, 0, 2, 3).unsqueeze(0)
         self.check_forward_input(_input)
         self.check_forward_hidden(_input, hx)
         # ReLU(ih(x) + hh * h) with the recurrent term and ReLU fused into the conv epilogue (rnn_cells.py:391)
@@ -215,8 +288,21 @@ class IndRNNCell(_CellBase):
                            _ops.ACT_RELU, 0.0, add=hx.contiguous(), add_scale=self.hh.reshape(-1))
 
 
+def _indrnn_forward_dchw(self, x, hx):
+    """conv_dim == 3 on slice stacks [D, C, H, W]: ReLU(Conv3d(x) + hh * h), zero padding (rnn_cells.py:297-304,:391)."""
+    self.check_forward_input(x)
+    self.check_forward_hidden(x, hx)
+    return _conv3d_dchw(x, self.ih.weight, self.ih.bias, self.kernel_size, self.dilation, _ops.PAD_ZERO, _ops.ACT_RELU,
+                        0.0, add=hx, add_scale=self.hh.reshape(-1))
+
+
+IndRNNCell.forward_dchw = _indrnn_forward_dchw
+
+
 class RIMBlock(nn.Module):
-    """rim_block.py:15-269 (dimensionality 2)."""
+    """rim_block.py:15-269.  dimensionality == 3 (inputs [batch, slices, coils, H, W, 2], conv_dim == 3) runs like the
+    reference: folded to batch*slices for the data-consistency gradient (:168-180), the regulariser's 3-D convolutions
+    over the stack of batch*slices images (:230-246).  As in the reference only the IndRNN cell has a 3-D path."""
 
     def __init__(self, recurrent_layer=None, conv_filters=None, conv_kernels=None, conv_dilations=None,
                  conv_bias=None, recurrent_filters=None, recurrent_kernels=None, recurrent_dilations=None,
@@ -225,8 +311,7 @@ class RIMBlock(nn.Module):
                  spatial_dims: Optional[Tuple[int, int]] = None, coil_dim: int = 1, dimensionality: int = 2,
                  consecutive_slices: int = 1):
         super().__init__()
-        if dimensionality != 2 or consecutive_slices > 1:
-            raise NotImplementedError("mridc_b200: RIMBlock supports dimensionality == 2, consecutive_slices == 1")
+        self.conv_dim = conv_dim
         self.input_size = depth * 2
         self.time_steps = time_steps
         self.layers = nn.ModuleList()
@@ -282,6 +367,20 @@ class RIMBlock(nn.Module):
         _ops.check_spatial_dims(self.spatial_dims)
         if self.coil_dim != 1:
             raise NotImplementedError("mridc_b200: RIMBlock expects coil_dim == 1")
+        stack = self.dimensionality == 3 or self.consecutive_slices > 1
+        if stack:  # rim_block.py:168-180: [batch, slices, coils, H, W, 2] -> [batch * slices, coils, H, W, 2]
+            if self.conv_dim != 3:
+                # the reference hands [4, batch*slices, H, W] to its Conv2d layers here, which only type-checks when
+                # batch*slices happens to equal the channel count
+                raise NotImplementedError("mridc_b200: slice stacks (dimensionality 3 / consecutive_slices > 1) need "
+                                          "conv_dim == 3")
+            fold = lambda t: t.reshape([t.shape[0] * t.shape[1], *t.shape[2:]])
+            pred = pred[-1].detach() if isinstance(pred, (tuple, list)) else fold(pred)
+            masked_kspace, mask, sense = fold(masked_kspace), fold(mask), fold(sense)
+            if eta is not None and eta.dim() == 5:
+                eta = fold(eta)  # :213-214
+        elif self.conv_dim != 2:
+            raise NotImplementedError("mridc_b200: conv_dim == 3 needs dimensionality == 3")
         if isinstance(pred, list):
             pred = pred[-1].detach()  # rim_block.py:185-186
         masked_kspace = _lib.require_cuda(masked_kspace, "masked_kspace").contiguous()
@@ -321,6 +420,17 @@ class RIMBlock(nn.Module):
         for _ in range(0 if use_tc else self.time_steps):  # :217-249 (generic exact-fp32 kernels)
             grad_eta = _ops.dc_rim_grad(eta, masked_kspace, sense, mcan, sigma, self.fft_centered,
                                         self.fft_normalization, ws=ws, y_hybrid=yhyb)
+            if stack:
+                # [batch*slices, 4, H, W] is the slice stack [D, C, H, W] of the 3-D convolutions (:230-246)
+                for h, convrnn in enumerate(self.layers):
+                    grad_eta = convrnn.convs.forward_dchw(grad_eta)
+                    if not hasattr(convrnn.rnn, "forward_dchw"):
+                        _reject_3d_gates(3, grad_eta.permute(1, 0, 2, 3))  # GRU / MGU: fails like the reference
+                    hx[h] = convrnn.rnn.forward_dchw(grad_eta, hx[h])
+                    grad_eta = hx[h]
+                eta = final.forward_dchw(grad_eta, residual_nhwc=eta.contiguous())
+                etas.append(eta)
+                continue
             for h, convrnn in enumerate(self.layers):
                 hx[h] = convrnn(grad_eta, hx[h])
                 grad_eta = hx[h]

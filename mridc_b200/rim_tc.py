@@ -54,7 +54,7 @@ class RimTcEngine:
     def supported(block) -> bool:
         from .rim import ConvGRUCell, ConvNonlinear, IndRNNCell
 
-        if not _enabled() or len(block.layers) != 2:
+        if not _enabled() or len(block.layers) != 2 or getattr(block, "conv_dim", 2) != 2:
             return False
         for i, st in enumerate(block.layers):
             c, r = st.convs, st.rnn

@@ -223,6 +223,43 @@ def gen_rim(R):
     print("rim.npz: %d arrays" % len(out))
 
 
+def gen_rim3d(R):
+    """RIMBlock with dimensionality == 3 / conv_dim == 3 and the IndRNN cell -- the only cell whose 3-D path runs in the
+    reference (test_cirim.py:155-290 uses it): reference block -> oracle restatement -> rim3d.npz."""
+    out = {}
+    i = 0
+    for layer, (batch, slices), cen, nrm in [("IndRNN", (1, 3), True, "ortho"), ("IndRNN", (2, 2), False, "backward")]:
+        hp = dict(RIM_HP, recurrent_layer=layer, no_dc=True, fft_centered=cen, fft_normalization=nrm, time_steps=4,
+                  conv_dim=3, dimensionality=3)
+        torch.manual_seed(40 + i)
+        blk = R.rim_block.RIMBlock(recurrent_layer=layer, conv_filters=hp["conv_filters"], conv_kernels=hp["conv_kernels"],
+                                   conv_dilations=hp["conv_dilations"], conv_bias=hp["conv_bias"],
+                                   recurrent_filters=hp["recurrent_filters"], recurrent_kernels=hp["recurrent_kernels"],
+                                   recurrent_dilations=hp["recurrent_dilations"], recurrent_bias=hp["recurrent_bias"],
+                                   depth=2, time_steps=hp["time_steps"], conv_dim=3, no_dc=True, fft_centered=cen,
+                                   fft_normalization=nrm, spatial_dims=[-2, -1], coil_dim=1, dimensionality=3).eval()
+        sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+        y, S, _, m = small_inputs(batch * slices, 3, 15, 12, 300 + i, "1d", torch.float32)
+        y, S = y.reshape(batch, slices, *y.shape[1:]), S.reshape(batch, slices, *S.shape[1:])
+        m = m.reshape(1, 1, *m.shape[1:]).expand(batch, slices, *m.shape[1:]).contiguous()
+        with torch.no_grad():
+            etas, hx = blk(y.clone(), y, S, m, None, None, 1.0, False)
+            o_etas, o_hx = onets.rim_block_3d(sd, hp, y.clone(), y, S, m, None, None, 1.0, False)
+        for a, b in zip(o_etas, etas):
+            _close(a, b, "rim3d %s step" % layer, rtol=1e-5, atol=1e-6)
+        for a, b in zip(o_hx, hx):
+            _close(a, b, "rim3d %s hidden" % layer, rtol=1e-5, atol=1e-6)
+        out.update({"rim%d_%s" % (i, k): v for k, v in _np(dict(y=y, S=S, mask=m, last=etas[-1], first=etas[0],
+                                                                 h0=hx[0], h1=hx[1])).items()})
+        out.update({"rim%d_w_%s" % (i, k): v.numpy() for k, v in sd.items()})
+        out["rim%d_cfg" % i] = np.asarray([["GRU", "IndRNN", "MGU"].index(layer), int(cen),
+                                           ["backward", "ortho", "forward"].index(nrm), hp["time_steps"]])
+        i += 1
+    out["nrim"] = np.asarray(i)
+    np.savez_compressed(os.path.join(GOLDEN, "rim3d.npz"), **out)
+    print("rim3d.npz: %d arrays" % len(out))
+
+
 def gen_unet(R):
     out = {}
     i = 0
@@ -612,7 +649,8 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     R = Ref()
     only = set(sys.argv[1:])  # e.g. `python -m oracle.make_golden qmri` regenerates one fixture file
-    for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("unet", gen_unet),
+    for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("rim3d", gen_rim3d),
+                     ("unet", gen_unet),
                      ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens),
                      ("apply_mask", gen_apply_mask)):
         if not only or name in only:

@@ -133,6 +133,71 @@ def rim_block(sd, hp, pred, masked_kspace, sense, mask, eta=None, hx=None, sigma
     return ks, hx
 
 
+def rim_block_3d(sd, hp, pred, masked_kspace, sense, mask, eta=None, hx=None, sigma=1.0, keep_eta=False):
+    """rim/rim_block.py:168-254 with dimensionality == 3 and conv_dim == 3 (IndRNN cell, no_dc).
+
+    Inputs [batch, slices, coils, H, W, 2] are folded to [batch*slices, ...] (:168-180); in the time loop the gradient
+    [batch*slices, 4, H, W] becomes the UNBATCHED Conv3d input [4, D = batch*slices, H, W] (:230-231), ConvNonlinear pads
+    with ReplicationPad3d (conv_layers.py:72-76), the IndRNN cell runs its Conv3d on [1, C, D, H, W] with a
+    (1, C, 1, 1, 1) recurrent weight (rnn_cells.py:297-312, :386-391) and the block permutes the hidden states back to
+    [D, C, H, W] (:243-246).  Note that D mixes batch and slices: the 3-D convolutions see one stack of batch*slices.
+    The GRU / MGU cells cannot run in this mode in the reference: their gates are nn.Conv2d whatever conv_dim says
+    (rnn_cells.py:23-38, :160-175) and the 5-D tensors of :114-116 raise -- restated as the same RuntimeError.
+    """
+    cen, nrm = hp["fft_centered"], hp["fft_normalization"]
+    sdims, cdim = hp.get("spatial_dims") or [-2, -1], hp["coil_dim"]
+    batch, slices = masked_kspace.shape[0], masked_kspace.shape[1]
+    fold = lambda t: t.reshape([t.shape[0] * t.shape[1], *t.shape[2:]])
+    pred = pred[-1].detach() if isinstance(pred, (tuple, list)) else fold(pred)
+    masked_kspace, mask, sense = fold(masked_kspace), fold(mask), fold(sense)
+    if hx is None:
+        hx = [masked_kspace.new_zeros((masked_kspace.size(0), f, *masked_kspace.size()[2:-1]))
+              for f in hp["recurrent_filters"] if f != 0]
+    if eta is None or eta.ndim < 3:
+        eta = pred if keep_eta else torch.sum(
+            mri.complex_mul(mri.ifft2(pred, cen, nrm, sdims), mri.complex_conj(sense)), cdim)
+    if eta.dim() == 5:
+        eta = fold(eta)
+    rl = hp["recurrent_layer"].upper()
+    nlayers = sum(1 for f in hp["recurrent_filters"] if f != 0)
+
+    def conv3(x, w, b, k, dil, nonlinear):  # x [C, D, H, W]
+        pad = (dil * (k - 1)) // 2
+        if pad > 0:
+            x = F.pad(x.unsqueeze(0), (pad,) * 6, mode="replicate").squeeze(0)
+        x = F.conv3d(x.unsqueeze(0), w, b, padding=0, dilation=dil).squeeze(0)
+        return F.relu(x) if nonlinear == "relu" else x
+
+    etas = []
+    for _ in range(hp["time_steps"]):
+        g = log_likelihood_gradient(eta, masked_kspace, sense, mask, sigma, cen, nrm, sdims, cdim).contiguous()
+        g = g.view([batch * slices, 4, g.shape[2], g.shape[3]]).permute(1, 0, 2, 3)
+        for l in range(nlayers):
+            p = "layers.%d." % l
+            g = conv3(g, sd[p + "convs.conv_layer.weight"], sd.get(p + "convs.conv_layer.bias"),
+                      hp["conv_kernels"][l], hp["conv_dilations"][l], "relu")
+            k, d = hp["recurrent_kernels"][l], hp["recurrent_dilations"][l]
+            x5, h5 = g.unsqueeze(0), hx[l].permute(1, 0, 2, 3).unsqueeze(0)
+            if rl != "INDRNN":
+                raise RuntimeError("Expected 3D (unbatched) or 4D (batched) input to conv2d, but got input of size: %s"
+                                   % list(x5.shape))
+            h5 = F.relu(F.conv3d(x5, sd[p + "rnn.ih.weight"], sd.get(p + "rnn.ih.bias"), padding=(d * (k - 1)) // 2,
+                                 dilation=d) + sd[p + "rnn.hh"] * h5)
+            hx[l] = h5.squeeze(0)
+            g = hx[l]
+        L = nlayers
+        g = conv3(g, sd["final_layer.0.conv_layer.weight"], sd.get("final_layer.0.conv_layer.bias"),
+                  hp["conv_kernels"][L], hp["conv_dilations"][L], None)
+        g = g.permute(1, 2, 3, 0)
+        for l in range(len(hx)):
+            hx[l] = hx[l].permute(1, 0, 2, 3)
+        eta = eta + g
+        etas.append(eta)
+    if not hp["no_dc"]:
+        raise NotImplementedError("rim_block_3d restates the no_dc path")
+    return etas, hx
+
+
 # --------------------------------------------------------------------------------------------------
 # U-Net regulariser
 # --------------------------------------------------------------------------------------------------

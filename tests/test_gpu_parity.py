@@ -259,17 +259,43 @@ def test_apply_mask_on_device_golden(golden):
 
 
 # ---------------------------------------------------------------------------------------------- blocks
-def _rim_block(hp, sd):
+def _rim_block(hp, sd, dim=2):
     from mridc_b200.rim import RIMBlock
 
     blk = RIMBlock(recurrent_layer=hp["recurrent_layer"], conv_filters=hp["conv_filters"],
                    conv_kernels=hp["conv_kernels"], conv_dilations=hp["conv_dilations"], conv_bias=hp["conv_bias"],
                    recurrent_filters=hp["recurrent_filters"], recurrent_kernels=hp["recurrent_kernels"],
                    recurrent_dilations=hp["recurrent_dilations"], recurrent_bias=hp["recurrent_bias"], depth=2,
-                   time_steps=hp["time_steps"], conv_dim=2, no_dc=hp["no_dc"], fft_centered=hp["fft_centered"],
-                   fft_normalization=hp["fft_normalization"], spatial_dims=[-2, -1], coil_dim=1, dimensionality=2)
-    blk.load_state_dict(sd, strict=True)
+                   time_steps=hp["time_steps"], conv_dim=dim, no_dc=hp["no_dc"], fft_centered=hp["fft_centered"],
+                   fft_normalization=hp["fft_normalization"], spatial_dims=[-2, -1], coil_dim=1, dimensionality=dim)
+    if sd is not None:
+        blk.load_state_dict(sd, strict=True)
     return blk.cuda().eval()
+
+
+def test_rim_block_3d_golden(golden):
+    """dimensionality == 3 / conv_dim == 3 (rim_block.py:168-180,:230-246; the reference's test_cirim.py 3-D cases): inputs
+    [batch, slices, coils, H, W, 2], Conv3d weights loaded key-for-key, IndRNN cell; GRU / MGU fail like the reference."""
+    g = golden("rim3d")
+    for i in range(int(g["nrim"])):
+        layer, cen, nrm, steps = (int(v) for v in g["rim%d_cfg" % i])
+        hp = dict(RIM_HP, recurrent_layer=LAYERS[layer], no_dc=True, fft_centered=bool(cen), fft_normalization=NRM3[nrm],
+                  time_steps=steps)
+        blk = _rim_block(hp, golden.weights(g, "rim%d_w_" % i), dim=3)
+        y, S, m = cu(g["rim%d_y" % i]), cu(g["rim%d_S" % i]), cu(g["rim%d_mask" % i])
+        etas, hx = blk(y.clone(), y, S, m, None, None, 1.0, False)
+        assert len(etas) == steps and len(hx) == 2
+        assert etas[0].shape == (y.shape[0] * y.shape[1], y.shape[3], y.shape[4], 2)
+        assert rel_l2(etas[0], g["rim%d_first" % i]) < 1e-5, i
+        assert rel_l2(etas[-1], g["rim%d_last" % i]) < 1e-5, i
+        assert rel_l2(hx[0], g["rim%d_h0" % i]) < 1e-5, i
+        assert rel_l2(hx[1], g["rim%d_h1" % i]) < 1e-5, i
+        # second cascade convention: a list of etas as `pred` + keep_eta (cirim.py:149-160)
+        etas2, _ = blk(etas, y, S, m, None, None, 1.0, True)
+        assert etas2[-1].shape == etas[-1].shape and torch.isfinite(etas2[-1]).all()
+    hp = dict(RIM_HP, recurrent_layer="GRU", no_dc=True, fft_centered=True, fft_normalization="ortho", time_steps=8)
+    with pytest.raises(RuntimeError, match="input to conv2d, but got input of size"):
+        _rim_block(hp, None, dim=3)(y.clone(), y, S, m, None, None, 1.0, False)
 
 
 def test_rim_block_golden(golden):
@@ -287,6 +313,40 @@ def test_rim_block_golden(golden):
         assert rel_l2(etas[-1], g["rim%d_last" % i]) < 1e-5, i
         assert rel_l2(hx[0], g["rim%d_h0" % i]) < 1e-5, i
         assert rel_l2(hx[1], g["rim%d_h1" % i]) < 1e-5, i
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 3, 15, 12, 2), (2, 2, 4, 20, 16, 2)])
+def test_cirim_3d_like_reference_test(shape):
+    """The reference's own 3-D CIRIM test (tests/collections/reconstruction/models/test_cirim.py:155-370: IndRNN, conv_dim 3,
+    dimensionality 3, input [batch, slices, coils, H, W, 2], output [batch*slices, H, W]) + the cascades chained by hand
+    through the CPU oracle's 3-D block."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import nets as onets
+
+    cfg = dict(synth.cirim_cfg("IndRNN", num_cascades=2, centered=True, normalization="ortho"), conv_dim=3,
+               dimensionality=3, conv_filters=[16, 16, 2], recurrent_filters=[16, 16, 0])
+    torch.manual_seed(21)
+    model = mb.CIRIM(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(22)
+    y = torch.randn(*shape, generator=g)
+    S = torch.randn(*shape, generator=g) * 0.5
+    m = (torch.rand(1, 1, 1, 1, shape[4], 1, generator=g) < 0.4).float().expand(shape[0], shape[1], 1, 1, shape[4], 1)
+    y = y * m
+    tgt = torch.abs(torch.view_as_complex(y))
+    out = next(model.cuda()(y.cuda(), S.cuda(), m.contiguous().cuda(), None, tgt.cuda()))
+    assert len(out) == 2 and len(out[0]) == 8
+    assert out[-1][-1].shape == (shape[0] * shape[1], shape[3], shape[4]) and out[-1][-1].is_complex()
+    hp = dict(cfg, time_steps=8)
+    pred = y.clone()
+    with torch.no_grad():
+        for c in range(2):
+            sub = {k[len("cirim.%d." % c):]: v for k, v in sd.items() if k.startswith("cirim.%d." % c)}
+            pred, _ = onets.rim_block_3d(sub, hp, pred, y, S, m.contiguous(), None, None, 1.0, c > 0)
+    e = rel_l2(out[-1][-1], torch.view_as_complex(pred[-1].contiguous()))
+    print("[3-D CIRIM] rel-L2 vs oracle %.2e" % e)
+    assert e < 1e-5
 
 
 def test_conv_layers_vs_oracle():
