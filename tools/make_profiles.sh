@@ -7,7 +7,8 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file gpurun_out/${R}_bench_launches.csv \
     python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline > gpurun_out/${R}_bench_under_ncu.log 2>&1
 # (2) full capture of the hot kernels at the bench geometry (B=4, 15x320x320)
-ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|gru2_kernel|row_dc|conv_c2|bh_fix" -s 9 -c 9 \
+# one time step = row_dc320 (G8 output), conv5g, gru2, bh_fix_border, tc_kernel (conv3x3 d2), gru2, fin2: 7 launches
+ncu --set full --clock-control none --import-source on -k regex:"tc_kernel|gru2_kernel|row_dc|conv5g|fin2|bh_fix" -s 7 -c 7 \
     -o gpurun_out/${R}_hot python tools/prof_ops.py 4 2 all > gpurun_out/${R}_hot.log 2>&1
 ncu -i gpurun_out/${R}_hot.ncu-rep --page raw --csv > gpurun_out/${R}_hot_raw.csv 2>/dev/null
 # (3) the real bench line, outside any profiler

@@ -23,10 +23,11 @@ from mridc_b200.rim_tc import RimTcEngine
 eng = RimTcEngine(blk)
 conv_step, _ = eng.bench_step(B, H, W, dev)   # one time step of the regulariser in the engine's own layout
 yhyb = _ops.dc_hybrid_prepare(y, mask, False, ws=ws[0])
-g4o = torch.empty(B, H, W, 4, device=dev)
+from mridc_b200 import _lib
+g8o = torch.zeros(_lib.load().mrb_g8_bytes(B, H, W), dtype=torch.uint8, device=dev)
 for _ in range(reps):
-    if what in ("all", "dc"):
-        _ops.dc_rim_grad(eta, y, S, mask, 1.0, False, "backward", out=g4o, nhwc=True, y_hybrid=yhyb)
+    if what in ("all", "dc"):  # the production form at W = 320: G8 output (split-bf16 conv input with its border)
+        _ops.dc_rim_grad(eta, y, S, mask, 1.0, False, "backward", out=g8o, nhwc=2, y_hybrid=yhyb)
     if what in ("all", "conv"):
         conv_step()
     if what in ("all", "vn"):
