@@ -267,6 +267,14 @@ int mrb_tc2_conv5x5x4(const void* g8, const void* w, const void* bias, void* out
 /* final RIM conv (rim_block.py:239-248) on a BH source with a valid border: out [B,H,W,2] = eta + conv3x3(x) (+ bias) */
 int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, const void* eta, void* out, int B, int H,
                             int W, void* stream);
+/* U-Net 3x3 convolution (unet_base/unet_block.py:250-259: Conv2d(kernel 3, padding 1, bias False)) as an implicit GEMM on
+ * tcgen05 with error-compensated fp16-split operands (x = hi + lo to 2^-22, three products per MAC, fp32 accumulation:
+ * ~5e-7 relative per operator; operands must be O(1), i.e. instance-normalised activations -- values below 2^-14 lose
+ * relative accuracy).  x [N,Cin,H,W] / out [N,Cout,H,W] NCHW fp32
+ * with batch strides in floats (skip connections are read / written in place inside the concat buffers); w [Cout,Cin,3,3];
+ * Cin <= 64. */
+int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* w, void* out, long long out_bstride, int N, int Cin,
+                         int Cout, int H, int W, void* stream);
 /* the same final conv (rim_block.py:239-248, conv_layers.py:72-123) on the tensor core: the channel contraction runs once
  * per position as a tap GEMM (T[pos][tap, o] = sum_c h[pos][c] w[o][c][tap], split-bf16 tcgen05), the nine taps are gathered
  * in shared memory with their coordinates clamped to the image (= ReplicationPad2d(1)); the BH border of x_bh is never

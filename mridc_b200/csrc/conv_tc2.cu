@@ -31,6 +31,7 @@
 //                 instruction is executed by any warp: a first version that fetched h_prev with cp.async and stored with
 //                 st.global (16 lines per instruction) was bound by L1 wavefronts, not by HBM.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -958,6 +959,211 @@ __global__ void g8_from_nhwc4_kernel(const float4* __restrict__ x, uint4* __rest
     }
 }
 
+// ---- U-Net 3x3 convolution (unet_block.py:250-259: Conv2d(k = 3, padding = 1, bias = False)) on the tensor core ---------
+// NCHW fp32 in (batch stride in floats: concat buffers are read in place), NCHW fp32 out, Cin <= 64, up to 64 output
+// channels per launch.  Implicit GEMM over the flat positions of the [H][W + 1] grid of one image (one dummy column per row:
+// it is the zero padding to the right of a row AND to the left of the next one, so a horizontal tap is a plain +-1 offset):
+//   loaders (two groups of 5 warps, one A stage each)  thread = staged position; per kernel row dy and group of 8 input
+//       channels: 8 coalesced plane loads, hi/lo split, two 16-byte stores -> the UMMA no-swizzle K-major layout
+//       [dy][chunk = 8 channels, hi chunks then lo chunks][position][16 B]; the three horizontal taps of a row are the
+//       same segment at a 16-byte offset (as in conv5g_kernel);
+//   MMA lane   per tap and pair of chunks (K = 16 channels): a_hi x [w_hi ; w_lo] (N = 2 Coutp: main | cross columns) and
+//       a_lo x w_hi (N = Coutp, the first rows of the same weight block); weights are split and laid out at kernel start.
+//       Operands are FP16 halves (kind::f16 with F16 formats): the E2EVN metric gate (SSIM / PSNR to 4 decimals) does not
+//       survive the 2^-17 of a bf16 split, the 2^-22 of the fp16 split is at the level of the fp32 kernels;
+//   4 epilogue warps   main + cross in RN fp32, coalesced NCHW stores (lane = position = consecutive x).
+// fp32 pair -> packed fp16 hi pair + packed fp16 lo pair (x ~= hi + lo to ~2^-22: fp16 carries 11 significant bits, so
+// the two halves keep 22 of fp32's 24; the bf16 split of the RIM kernels keeps 16).  Valid for O(1) operands -- here the
+// instance-normalised activations and the weights of the U-Net; values below 2^-14 lose relative (not absolute) accuracy.
+__device__ __forceinline__ void split_f16x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(e0, e1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(e0 - hf.x, e1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    // as make_idesc, with F16 (format 0) A and B operands
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr int U3_ROWS = 136;                 // staged positions per segment: 128 + 2 halo, whole core matrices
+constexpr int U3_SEG = U3_ROWS * 16;
+constexpr int U3_LOAD_W = 5;                 // warps per loader group
+constexpr int U3_THREADS = (4 + 2 * U3_LOAD_W + 1) * 32;
+
+struct UConvParams {
+    const float* x;     // [N][Cin][H][W], batch stride xbs floats
+    const float* w;     // [Cout_total][Cin][3][3]
+    float* out;         // [N][Cout_total][H][W], batch stride obs floats
+    long long xbs, obs;
+    int N, Cin, H, W;
+    int co_begin, co_count;  // output channels of this launch
+    int cg, cgp;             // channel groups of 8 (real, padded to even)
+    int coutp;               // co_count padded to 16
+    int stages;              // 1 or 2 A stages
+    int tiles_per_img, n_tiles;
+};
+
+__global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = 3 * 2 * P.cgp * U3_SEG;
+    const int bchunk = 2 * P.coutp * 16;                       // one weight chunk: [main rows | cross rows][16 B]
+    uint8_t* a_s = smem;                                       // [stages][dy][2 cgp chunks][U3_ROWS][16 B]
+    uint8_t* w_s = a_s + (size_t)P.stages * stage_bytes;       // [tap][cgp][2 coutp rows][16 B]
+    uint64_t* full = (uint64_t*)(w_s + (size_t)9 * P.cgp * bchunk);  // [2]
+    uint64_t* empty = full + 2;                                // [2]
+    uint64_t* acc_full = empty + 2;                            // [2]
+    uint64_t* acc_empty = acc_full + 2;                        // [2]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], U3_LOAD_W);
+            mbar_init(&empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    // zero the A stages once (padding chunks and rows that no loader writes must be finite), then the weights
+    for (int i = threadIdx.x; i < P.stages * stage_bytes / 16; i += U3_THREADS)
+        reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 9 * P.cgp * 2 * P.coutp; i += U3_THREADS) {
+        const int n = i % (2 * P.coutp), kc = i / (2 * P.coutp);
+        const int g = kc % P.cgp, t = kc / P.cgp;
+        const int co = n < P.coutp ? n : n - P.coutp;
+        uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
+        if (co < P.co_count) {
+            const float* wp = P.w + ((long long)(P.co_begin + co) * P.Cin) * 9 + t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c0 = 8 * g + 2 * e, c1 = c0 + 1;
+                const float v0 = c0 < P.Cin ? wp[(long long)c0 * 9] : 0.f, v1 = c1 < P.Cin ? wp[(long long)c1 * 9] : 0.f;
+                split_f16x2(v0, v1, hw[e], lw[e]);
+            }
+        }
+        const uint4 v = n < P.coutp ? make_uint4(hw[0], hw[1], hw[2], hw[3]) : make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(w_s + (size_t)kc * bchunk + n * 16) = v;
+    }
+    if (warp == 4 + 2 * U3_LOAD_W) tmem_alloc(tmem_slot, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int Wq = P.W + 1;
+    const long long HW = (long long)P.H * P.W;
+    const int npos = P.H * Wq;
+
+    if (warp >= 4 && warp < 4 + 2 * U3_LOAD_W) {
+        // ============================== LOADERS ==============================
+        const int grp = (warp - 4) / U3_LOAD_W;
+        const int r = (warp - 4 - grp * U3_LOAD_W) * 32 + lane;  // staged position (row of every segment)
+        if (grp < P.stages) {
+            const int s = grp;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x + grp * gridDim.x; tile < P.n_tiles; tile += P.stages * gridDim.x) {
+                const int n = tile / P.tiles_per_img, p0 = (tile - n * P.tiles_per_img) * TILE;
+                mbar_wait_sleep(&empty[s], ph ^ 1, 40);
+                if (r < TILE + 2) {
+                    const float* xn = P.x + (long long)n * P.xbs;
+                    uint8_t* st = a_s + (size_t)s * stage_bytes + r * 16;
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const int q = p0 - 1 + r + (dy - 1) * Wq;
+                        const int yq = q >= 0 ? q / Wq : 0, xq = q - yq * Wq;
+                        const bool ok = q >= 0 && q < npos && xq < P.W;
+                        const float* src = xn + (long long)yq * P.W + xq;
+                        for (int g = 0; g < P.cg; ++g) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = 8 * g + e;
+                                v[e] = (ok && c < P.Cin) ? __ldg(src + (long long)c * HW) : 0.f;
+                            }
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) split_f16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+                            uint8_t* d = st + (size_t)(dy * 2 * P.cgp + g) * U3_SEG;
+                            *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(d + (size_t)P.cgp * U3_SEG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+                ph ^= 1;
+            }
+        }
+    } else if (warp == 4 + 2 * U3_LOAD_W) {
+        // ============================== MMA ISSUER ==============================
+        const uint32_t tmem_u = uni(tmem_base);
+        const uint64_t adesc0 = make_desc_ns(smem_u32(a_s), U3_SEG, 128);
+        const uint64_t bdesc0 = make_desc_ns(smem_u32(w_s), (uint32_t)bchunk, 128);
+        const uint32_t id2 = make_idesc_f16(TILE, 2 * P.coutp), id1 = make_idesc_f16(TILE, P.coutp);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int s = P.stages == 2 ? (it & 1) : 0;
+            const uint32_t ph = (uint32_t)(P.stages == 2 ? (it >> 1) : it) & 1u;
+            const int buf = it & 1;
+            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t d = tmem_u + (uint32_t)(buf * 128);
+            uint32_t acc = 0;
+            for (int t = 0; t < 9; ++t) {
+                const int dy = t / 3, dx = t - dy * 3;
+                const uint64_t a_t = adesc0 + (uint64_t)((s * stage_bytes + dy * 2 * P.cgp * U3_SEG + dx * 16) >> 4);
+                const uint64_t b_t = bdesc0 + (uint64_t)((t * P.cgp * bchunk) >> 4);
+                for (int j = 0; j < P.cgp / 2; ++j) {
+                    const uint64_t bj = b_t + (uint64_t)((2 * j * bchunk) >> 4);
+                    umma_ss(d, a_t + (uint64_t)((2 * j * U3_SEG) >> 4), bj, id2, acc);
+                    acc = 1;
+                    umma_ss(d, a_t + (uint64_t)(((P.cgp + 2 * j) * U3_SEG) >> 4), bj, id1, 1);
+                }
+            }
+            umma_commit(&empty[s]);
+            umma_commit(&acc_full[buf]);
+        }
+    } else if (warp < 4) {
+        // ============================== EPILOGUE ==============================
+        const int m = warp * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int n = tile / P.tiles_per_img, p = (tile - n * P.tiles_per_img) * TILE + m;
+            const int y = p / Wq, x = p - y * Wq;
+            const bool ok = p < npos && x < P.W;
+            float* o = P.out + (long long)n * P.obs + (long long)P.co_begin * HW + (long long)y * P.W + x;
+            const int buf = it & 1;
+            mbar_wait_sleep(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 64);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128);
+            for (int c8 = 0; c8 < P.coutp; c8 += 8) {
+                float a[8], b[8];
+                tmem_ld8(t0 + c8, a);
+                tmem_ld8(t0 + P.coutp + c8, b);
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (c8 + e < P.co_count) o[(long long)(c8 + e) * HW] = a[e] + b[e];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4 + 2 * U3_LOAD_W) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 #ifdef MRB_TC_PROF
 int g_debug2 = 0;
 unsigned long long* g_prof2 = nullptr;
@@ -1089,6 +1295,48 @@ extern "C" int mrb_tc2_conv5x5x4(const void* g8, const void* w, const void* bias
     if (grid > P.n_tiles) grid = P.n_tiles;
     tc2::conv5g_kernel<<<grid, tc2::C5_THREADS, smem, (cudaStream_t)stream>>>(tm_o, P);
     MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+/* U-Net 3x3 conv (zero padding, no bias; unet_block.py:250-259) on the tensor core, NCHW fp32 in / out with batch strides in
+ * floats (concat buffers are read and written in place).  Cin <= 64, any Cout (launches of up to 64 output channels, 32 when
+ * Cin > 32).  Error-compensated fp16-split products (x = hi + lo to 2^-22; operands must be O(1): instance-normalised
+ * activations). */
+extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* w, void* out, long long out_bstride, int N,
+                                    int Cin, int Cout, int H, int W, void* stream) {
+    MRB_REQUIRE(x && w && out, MRB_EINVAL, "mrb_tc2_unet_conv3x3: null pointer");
+    MRB_REQUIRE(N >= 1 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_unet_conv3x3: bad shape");
+    MRB_REQUIRE(Cin <= 64, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: at most 64 input channels (got %d)", Cin);
+    tc2::UConvParams P;
+    P.x = (const float*)x; P.w = (const float*)w; P.out = (float*)out;
+    P.xbs = x_bstride; P.obs = out_bstride;
+    P.N = N; P.Cin = Cin; P.H = H; P.W = W;
+    P.cg = (Cin + 7) / 8;
+    P.cgp = (P.cg + 1) & ~1;
+    const long long npos = (long long)H * (W + 1);
+    P.tiles_per_img = (int)((npos + tc2::TILE - 1) / tc2::TILE);
+    MRB_REQUIRE((long long)N * P.tiles_per_img < 2147483647LL && npos < 2147483647LL - 1024, MRB_EUNSUPPORTED,
+                "mrb_tc2_unet_conv3x3: too many pixels");
+    P.n_tiles = N * P.tiles_per_img;
+    const size_t smem_max = device_max_smem_optin();
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRB_CUDA(cudaFuncSetAttribute(tc2::uconv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        attr_set = true;
+    }
+    const int per_pass = P.cgp > 4 ? 32 : 64;
+    for (int co = 0; co < Cout; co += per_pass) {
+        P.co_begin = co;
+        P.co_count = std::min(per_pass, Cout - co);
+        P.coutp = (P.co_count + 15) & ~15;
+        const size_t stage = (size_t)3 * 2 * P.cgp * tc2::U3_SEG, wb = (size_t)9 * P.cgp * 2 * P.coutp * 16;
+        P.stages = (1024 + 2 * stage + wb + 256 <= smem_max) ? 2 : 1;
+        MRB_REQUIRE(1024 + P.stages * stage + wb + 256 <= smem_max, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: shared memory");
+        int grid = device_sm_count();
+        if (grid > P.n_tiles) grid = P.n_tiles;
+        tc2::uconv3_kernel<<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
+        MRB_LAUNCHED();
+    }
     return MRB_OK;
 }
 

@@ -1,12 +1,15 @@
 """Drop-ins for the U-Net regulariser of the reference (unet_base/unet_block.py:11-308) on B200 kernels.
 
 Sub-module names match the reference (``unet.down_sample_layers.N.layers.{0,4}.weight`` ...) so reference
-checkpoints load key-for-key; ``torch.nn`` layers only hold parameters / initialise them.  Convolutions run on
-the exact-fp32 CUDA-core kernel (the E2EVN fp32 noise floor is ~2.7e-5 against a 1e-4 tolerance, SURVEY
-section 7), InstanceNorm statistics in fp64.  Skip connections are written straight into the concat buffer
+checkpoints load key-for-key; ``torch.nn`` layers only hold parameters / initialise them.  The 3x3 convolutions run as
+implicit GEMMs on tcgen05 with error-compensated fp16-split operands (conv_tc2.cu, uconv3_kernel: x = hi + lo to 2^-22,
+three products per MAC, fp32 accumulation -- the bf16 split of the RIM kernels (2^-17) does not survive E2EVN's metric
+gate), the first conv (caller-scaled input) and everything else on exact-fp32 CUDA-core kernels, InstanceNorm statistics in
+fp64.  Skip connections are written straight into the concat buffer
 (no ``torch.cat``).  Inference only (Dropout2d is the identity).
 """
 import math
+import os
 from typing import List, Tuple
 
 import torch
@@ -15,6 +18,25 @@ import torch.nn as nn
 from . import _lib, _ops
 
 __all__ = ["NormUnet", "Unet", "ConvBlock", "TransposeConvBlock"]
+
+
+def _tc_convs():
+    """tcgen05 split-bf16 3x3 convolutions (conv_tc2.cu, uconv3_kernel); MRIDC_B200_UNET_FP32=1 keeps the exact-fp32
+    CUDA-core kernel."""
+    return os.environ.get("MRIDC_B200_UNET_FP32", "0") != "1"
+
+
+def _conv3x3(x, weight, x_bs, N, Cin, H, W, normalised=True):
+    """Conv2d(k = 3, padding = 1, bias = False) of the buffer x ([N, Cin, H, W] with batch stride x_bs) -> contiguous
+    [N, Cout, H, W].  ``normalised``: the input is the output of an InstanceNorm (O(1) values), which the fp16-split
+    tensor-core kernel requires; the first conv of a U-Net sees caller-scaled data and stays on the exact-fp32 kernel."""
+    Cout = weight.shape[0]
+    if normalised and _tc_convs() and Cin <= 64:
+        out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().mrb_tc2_unet_conv3x3(_lib.ptr(x), x_bs, _lib.ptr(weight), _lib.ptr(out), Cout * H * W, N, Cin,
+                                                    Cout, H, W, _lib.stream_ptr()))
+        return out
+    return _ops.conv2d(x, weight, None, 3, 1, _ops.PAD_ZERO, x_bstride=x_bs, N=N, Cin=Cin, H=H, W=W)
 
 
 def _instnorm_lrelu(x, x_bs, out, out_bs, N, C, HW, slope=0.2, eps=1e-5):
@@ -41,17 +63,16 @@ class ConvBlock(nn.Module):
             nn.Dropout2d(drop_prob),
         )
 
-    def run(self, x, x_bs, N, H, W, out=None, out_bs=None):
+    def run(self, x, x_bs, N, H, W, out=None, out_bs=None, normalised=True):
         """x: buffer holding [N, in_chans, H, W] with batch stride x_bs.  Result goes to ``out`` (batch stride
-        out_bs) if given, else to a fresh contiguous tensor."""
+        out_bs) if given, else to a fresh contiguous tensor.  ``normalised``: see _conv3x3."""
         if self.training and self.drop_prob > 0:
             raise NotImplementedError("mridc_b200 is inference only (Dropout2d with p > 0 in training mode)")
         C = self.out_chans
         HW = H * W
-        t = _ops.conv2d(x, self.layers[0].weight, None, 3, 1, _ops.PAD_ZERO, x_bstride=x_bs, N=N,
-                        Cin=self.in_chans, H=H, W=W)
+        t = _conv3x3(x, self.layers[0].weight, x_bs, N, self.in_chans, H, W, normalised)
         _instnorm_lrelu(t, C * HW, t, C * HW, N, C, HW)
-        u = _ops.conv2d(t, self.layers[4].weight, None, 3, 1, _ops.PAD_ZERO)
+        u = _conv3x3(t, self.layers[4].weight, C * HW, N, C, H, W)
         if out is None:
             out, out_bs = u, C * HW
         _instnorm_lrelu(u, C * HW, out, out_bs, N, C, HW)
@@ -60,7 +81,7 @@ class ConvBlock(nn.Module):
     def forward(self, image: torch.Tensor) -> torch.Tensor:
         image = _lib.require_cuda(image, "image").contiguous()
         N, C, H, W = image.shape
-        return self.run(image, C * H * W, N, H, W)
+        return self.run(image, C * H * W, N, H, W, normalised=False)
 
 
 class TransposeConvBlock(nn.Module):
@@ -124,11 +145,13 @@ class Unet(nn.Module):
         dev = image.device
         cats = []  # (concat buffer [N, 2*ch, h, w], ch, h, w): skip lives in channels [ch, 2ch)
         cur, cur_bs, cur_c, h, w = image, C * H * W, C, H, W
-        for layer in self.down_sample_layers:
+        for li, layer in enumerate(self.down_sample_layers):
             ch = layer.out_chans
             cat = torch.empty((N, 2 * ch, h, w), dtype=torch.float32, device=dev)
             skip = cat[:, ch:]  # view: batch stride 2*ch*h*w
-            layer.run(cur, cur_bs, N, h, w, out=skip, out_bs=2 * ch * h * w)
+            # the very first conv reads the caller's image (any scale); every later input is an average of
+            # instance-normalised activations
+            layer.run(cur, cur_bs, N, h, w, out=skip, out_bs=2 * ch * h * w, normalised=li > 0)
             cats.append((cat, ch, h, w))
             pooled = torch.empty((N, ch, h // 2, w // 2), dtype=torch.float32, device=dev)
             _lib.check(lib.mrb_avgpool2(_lib.ptr(skip), 2 * ch * h * w, _lib.ptr(pooled), ch * (h // 2) * (w // 2), N,

@@ -4,7 +4,7 @@ on seeded inputs at sizes it finishes in seconds, (3) size-independent propertie
 Tolerances (fp32 path; north star: relative L2 <= 1e-4 on the reconstructed image, SSIM/PSNR to 4 decimals,
 masks / indices / crops bit-exact):
   per-operator  rel-L2 <= 2e-6   (FFT, DC gradient, sens_reduce / expand, elementwise)
-  blocks        rel-L2 <= 1e-5   (RIM block 8 steps, NormUnet, VarNet block)
+  blocks        rel-L2 <= 1e-5   (RIM block 8 steps, NormUnet, VarNet block; 3e-5 on the split-bf16 tensor-core kernels)
   models        rel-L2 <= 1e-4   (CIRIM 5x8, E2EVN 12 cascades at 15x320x320)
 """
 import numpy as np
@@ -377,10 +377,14 @@ def test_conv_layers_vs_oracle():
             assert rel_l2(mod.cuda()(x.cuda(), h.cuda()), ref) < 2e-6, (cls.__name__, cx, ch, k)
 
 
-def test_unet_varnet_golden(golden):
+@pytest.mark.parametrize("conv_path,tol", [("tc", 1e-5), ("fp32", 1e-5)])
+def test_unet_varnet_golden(golden, monkeypatch, conv_path, tol):
+    """NormUnet / VarNetBlock against the reference vectors, on both convolution paths: tcgen05 with fp16-split operands and
+    exact fp32, same block tolerance."""
     from mridc_b200.unet import NormUnet
     from mridc_b200.varnet import VarNetBlock
 
+    monkeypatch.setenv("MRIDC_B200_UNET_FP32", "1" if conv_path == "fp32" else "0")
     g = golden("unet_vn")
     for i in range(int(g["nunet"])):
         chans, pools, padsz = (int(v) for v in g["unet%d_cfg" % i])
@@ -388,7 +392,9 @@ def test_unet_varnet_golden(golden):
         nu.load_state_dict(golden.weights(g, "unet%d_w_" % i), strict=True)
         out = nu.cuda().eval()(cu(g["unet%d_x" % i]))
         assert out.shape == g["unet%d_out" % i].shape
-        assert rel_l2(out, g["unet%d_out" % i]) < 1e-5, i
+        e = rel_l2(out, g["unet%d_out" % i])
+        print("[unet %s] NormUnet %d rel-L2 %.2e (tol %.0e)" % (conv_path, i, e, tol))
+        assert e < tol, i
     for j in range(int(g["nvn"])):
         cen, nrm, no_dc = (int(v) for v in g["vn%d_cfg" % j])
         vb = VarNetBlock(NormUnet(chans=4, num_pools=2, padding_size=11, normalize=True), bool(cen), NRM3[nrm],
@@ -396,7 +402,9 @@ def test_unet_varnet_golden(golden):
         vb.load_state_dict(golden.weights(g, "vn%d_w_" % j), strict=True)
         vb = vb.cuda().eval()
         out = vb(cu(g["vn%d_pred" % j]), cu(g["vn%d_y" % j]), cu(g["vn%d_S" % j]), cu(g["vn%d_mask" % j]))
-        assert rel_l2(out, g["vn%d_out" % j]) < 1e-5, j
+        e = rel_l2(out, g["vn%d_out" % j])
+        print("[unet %s] VarNetBlock %d rel-L2 %.2e (tol %.0e)" % (conv_path, j, e, tol))
+        assert e < tol, j
 
 
 # ---------------------------------------------------------------------------------------------- models
@@ -437,7 +445,9 @@ def test_models_golden(golden):
                       fft_normalization="ortho", spatial_dims=[-2, -1], coil_dim=1, coil_combination_method="SENSE"))
     un.load_state_dict(golden.weights(g, "unet_w_"), strict=True)
     o = un.cuda().eval()(y, S, m, None, tgt)
-    assert rel_l2(o, torch.view_as_complex(torch.from_numpy(g["unet_out"]))) < 1e-5
+    e = rel_l2(o, torch.view_as_complex(torch.from_numpy(g["unet_out"])))
+    print("[models golden] UNet rel-L2 %.2e" % e)
+    assert e < 1e-5
 
 
 def _metrics(pred, target):
@@ -685,6 +695,7 @@ def test_sensitivity_model_golden(golden):
         out = net(y, m, nlf)
         assert out.shape == y.shape
         e = rel_l2(out, g["sens%d_out" % i])
+        print("[sens golden] %d rel-L2 %.2e" % (i, e))
         assert e < 1e-5, (i, e)
         if hp["sens_normalize"]:  # maps have unit root-sum-of-squares over coils
             assert torch.allclose(mb.rss_complex(out, dim=1), torch.ones_like(out[:, 0, ..., 0]), atol=1e-5)

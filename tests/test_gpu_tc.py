@@ -364,6 +364,33 @@ def test_dc_direct_g8_output_equals_converter(centered):
     assert int((ga != 0).sum()) > ga.numel() // 2
 
 
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 2, 14, 32, 48), (1, 14, 14, 37, 45), (2, 28, 56, 20, 24), (1, 56, 56, 16, 16),
+                                            (2, 56, 28, 40, 40), (1, 64, 70, 12, 11), (1, 14, 14, 320, 320)])
+def test_unet_conv3x3_tc_vs_oracle(N, Cin, Cout, H, W):
+    """U-Net 3x3 conv (zero padding, no bias) on tcgen05: any channel counts up to 64 inputs, odd sizes, input read in place
+    from a wider (concat) buffer, output written with a batch stride; run-to-run deterministic."""
+    from mridc_b200 import _lib
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(Cin * 100 + Cout)
+    xfull = torch.randn(N, Cin + 3, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3.0 * Cin ** 0.5))
+    ref = torch.nn.functional.conv2d(xfull[:, 3:], w, None, padding=1)
+    xd, wd = xfull.cuda(), w.cuda()
+    xv = xd[:, 3:]  # channels [3, 3 + Cin) of the wider buffer: batch stride (Cin + 3) H W
+    outfull = torch.full((N, Cout + 2, H, W), float("nan"), device="cuda")
+    ov = outfull[:, 2:]
+    _lib.check(lib.mrb_tc2_unet_conv3x3(_lib.ptr(xv), (Cin + 3) * H * W, _lib.ptr(wd), _lib.ptr(ov), (Cout + 2) * H * W, N, Cin,
+                                        Cout, H, W, st))
+    _diag(ov, ref, 2e-6, "unet conv3x3 %d->%d" % (Cin, Cout))  # fp16 split: the tolerance of the fp32 kernels
+    assert torch.isnan(outfull[:, :2]).all()  # nothing outside the destination channels is written
+    o2 = torch.empty((N, Cout, H, W), device="cuda")
+    _lib.check(lib.mrb_tc2_unet_conv3x3(_lib.ptr(xv), (Cin + 3) * H * W, _lib.ptr(wd), _lib.ptr(o2), Cout * H * W, N, Cin, Cout,
+                                        H, W, st))
+    assert torch.equal(o2, ov)
+
+
 def test_cirim_graph_replay_equals_eager(monkeypatch):
     """CUDA-graph replay of the time loop (third call with the same input tensors) == eager launches, bit for bit; new
     eta values, new k-space values in the same tensors and a different cascade state are all picked up."""
