@@ -271,10 +271,14 @@ int mrb_conv_c2_bh_residual(const void* x_bh, const void* w, const void* bias, c
  * tcgen05 with error-compensated fp16-split operands (x = hi + lo to 2^-22, three products per MAC, fp32 accumulation:
  * ~5e-7 relative per operator; operands must be O(1), i.e. instance-normalised activations -- values below 2^-14 lose
  * relative accuracy).  x [N,Cin,H,W] / out [N,Cout,H,W] NCHW fp32
- * with batch strides in floats (skip connections are read / written in place inside the concat buffers); w [Cout,Cin,3,3];
- * Cin <= 64. */
-int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* w, void* out, long long out_bstride, int N, int Cin,
-                         int Cout, int H, int W, void* stream);
+ * with batch strides in floats (skip connections are read / written in place inside the concat buffers); wpack from
+ * mrb_tc2_unet_pack (mrb_tc2_unet_packed_bytes bytes); Cin <= 64. */
+size_t mrb_tc2_unet_packed_bytes(int Cin, int Cout);
+/* w [Cout,Cin,3,3] fp32 -> the kernel's weight image (fp16 hi / lo rows per tap and group of 8 input channels); once per
+ * parameter version */
+int mrb_tc2_unet_pack(const void* w, void* dst, int Cin, int Cout, void* stream);
+int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* wpack, void* out, long long out_bstride, int N,
+                         int Cin, int Cout, int H, int W, void* stream);
 /* the same final conv (rim_block.py:239-248, conv_layers.py:72-123) on the tensor core: the channel contraction runs once
  * per position as a tap GEMM (T[pos][tap, o] = sum_c h[pos][c] w[o][c][tap], split-bf16 tcgen05), the nine taps are gathered
  * in shared memory with their coordinates clamped to the image (= ReplicationPad2d(1)); the BH border of x_bh is never

@@ -67,6 +67,8 @@ SIGNATURES = {
     "mrb_conv_c2_bh_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrb_bh_fix_border": (_i, [_vp, _i, _i, _i, _vp]),
     "mrb_tc2_final_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mrb_tc2_unet_packed_bytes": (_sz, [_i, _i]),
+    "mrb_tc2_unet_pack": (_i, [_vp, _vp, _i, _i, _vp]),
     "mrb_tc2_unet_conv3x3": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "mrb_g8_bytes": (_sz, [_i, _i, _i]),
     "mrb_g8_from_nhwc4": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -986,6 +986,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     // as make_idesc, with F16 (format 0) A and B operands
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+constexpr float U3_WSCALE = 256.f;           // power of two applied to the weights before the fp16 split
 constexpr int U3_ROWS = 136;                 // staged positions per segment: 128 + 2 halo, whole core matrices
 constexpr int U3_SEG = U3_ROWS * 16;
 constexpr int U3_LOAD_W = 5;                 // warps per loader group
@@ -993,33 +994,40 @@ constexpr int U3_THREADS = (4 + 2 * U3_LOAD_W + 1) * 32;
 
 struct UConvParams {
     const float* x;     // [N][Cin][H][W], batch stride xbs floats
-    const float* w;     // [Cout_total][Cin][3][3]
+    const void* wpack;  // this launch's packed weights (uconv3_pack_kernel)
     float* out;         // [N][Cout_total][H][W], batch stride obs floats
     long long xbs, obs;
     int N, Cin, H, W;
     int co_begin, co_count;  // output channels of this launch
     int cg, cgp;             // channel groups of 8 (real, padded to even)
     int coutp;               // co_count padded to 16
-    int stages;              // 1 or 2 A stages
+    int stages;              // 1 .. 4 A stages
     int tiles_per_img, n_tiles;
+#ifdef MRB_TC_PROF
+    int debug;               // role switches (tools build): 1 no global loads, 2 no MMAs, 4 no stores, 8 no split / staging stores
+    unsigned long long* prof;  // [grid][16] cycle counters
+#endif
 };
 
+template <int PAIRS>  // pairs of 8-channel groups: cgp = 2 * PAIRS (compile-time: the loader and issue loops unroll)
 __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams P) {
+    constexpr int CGP = 2 * PAIRS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = 3 * 2 * P.cgp * U3_SEG;
+    const int stage_bytes = 3 * 2 * CGP * U3_SEG;
     const int bchunk = 2 * P.coutp * 16;                       // one weight chunk: [main rows | cross rows][16 B]
     uint8_t* a_s = smem;                                       // [stages][dy][2 cgp chunks][U3_ROWS][16 B]
     uint8_t* w_s = a_s + (size_t)P.stages * stage_bytes;       // [tap][cgp][2 coutp rows][16 B]
-    uint64_t* full = (uint64_t*)(w_s + (size_t)9 * P.cgp * bchunk);  // [2]
-    uint64_t* empty = full + 2;                                // [2]
-    uint64_t* acc_full = empty + 2;                            // [2]
-    uint64_t* acc_empty = acc_full + 2;                        // [2]
-    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    uint64_t* full = (uint64_t*)(w_s + (size_t)9 * CGP * bchunk);  // [4]
+    uint64_t* empty = full + 4;                                // [4]
+    uint64_t* acc_full = empty + 4;                            // [4]
+    uint64_t* acc_empty = acc_full + 4;                        // [4]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 4);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    T2P(const long long t_k0 = clock64();)
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&full[i], U3_LOAD_W);
             mbar_init(&empty[i], 1);
             mbar_init(&acc_full[i], 1);
@@ -1030,29 +1038,17 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
     // zero the A stages once (padding chunks and rows that no loader writes must be finite), then the weights
     for (int i = threadIdx.x; i < P.stages * stage_bytes / 16; i += U3_THREADS)
         reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x; i < 9 * P.cgp * 2 * P.coutp; i += U3_THREADS) {
-        const int n = i % (2 * P.coutp), kc = i / (2 * P.coutp);
-        const int g = kc % P.cgp, t = kc / P.cgp;
-        const int co = n < P.coutp ? n : n - P.coutp;
-        uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
-        if (co < P.co_count) {
-            const float* wp = P.w + ((long long)(P.co_begin + co) * P.Cin) * 9 + t;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c0 = 8 * g + 2 * e, c1 = c0 + 1;
-                const float v0 = c0 < P.Cin ? wp[(long long)c0 * 9] : 0.f, v1 = c1 < P.Cin ? wp[(long long)c1 * 9] : 0.f;
-                split_f16x2(v0, v1, hw[e], lw[e]);
-            }
-        }
-        const uint4 v = n < P.coutp ? make_uint4(hw[0], hw[1], hw[2], hw[3]) : make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(w_s + (size_t)kc * bchunk + n * 16) = v;
+    {   // weights: packed once per parameter version by uconv3_pack_kernel, [tap][group][main rows | cross rows][16 B]
+        const uint4* g = reinterpret_cast<const uint4*>(P.wpack);
+        for (int i = threadIdx.x; i < 9 * CGP * 2 * P.coutp; i += U3_THREADS) reinterpret_cast<uint4*>(w_s)[i] = __ldg(g + i);
     }
-    if (warp == 4 + 2 * U3_LOAD_W) tmem_alloc(tmem_slot, 256);
+    if (warp == 4 + 2 * U3_LOAD_W) tmem_alloc(tmem_slot, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    T2P(if (P.prof && threadIdx.x == 0) P.prof[blockIdx.x * 16 + 15] = clock64() - t_k0;)
     const int Wq = P.W + 1;
     const long long HW = (long long)P.H * P.W;
     const int npos = P.H * Wq;
@@ -1061,42 +1057,65 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
         // ============================== LOADERS ==============================
         const int grp = (warp - 4) / U3_LOAD_W;
         const int r = (warp - 4 - grp * U3_LOAD_W) * 32 + lane;  // staged position (row of every segment)
-        if (grp < P.stages) {
-            const int s = grp;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x + grp * gridDim.x; tile < P.n_tiles; tile += P.stages * gridDim.x) {
+        // tile number `it` of this CTA lives in A stage it % stages; the two loader groups alternate tiles (one group when
+        // there is a single stage), so up to `stages` tiles are in flight between the loaders and the MMA lane.
+        // (A software-pipelined variant -- loads of the next (tile, row) step issued before the current one is converted --
+        // was measured slower: the loaders are bound by their own instruction stream, ~450 per thread and tile, not by the
+        // three global round trips; see DESIGN.md.)
+        const int ngrp = P.stages >= 2 ? 2 : 1;
+        T2P(long long t_l0 = clock64(), t_lw = 0, t_lld = 0, c0;)
+        if (grp < ngrp) {
+            for (int it = grp; blockIdx.x + (long long)it * gridDim.x < P.n_tiles; it += ngrp) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int s = it % P.stages;
+                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
                 const int n = tile / P.tiles_per_img, p0 = (tile - n * P.tiles_per_img) * TILE;
+                T2P(c0 = clock64();)
                 mbar_wait_sleep(&empty[s], ph ^ 1, 40);
+                T2P(t_lw += clock64() - c0; c0 = clock64();)
                 if (r < TILE + 2) {
                     const float* xn = P.x + (long long)n * P.xbs;
                     uint8_t* st = a_s + (size_t)s * stage_bytes + r * 16;
+                    // per kernel row: the loads of up to four channel groups (32 planes) are issued before the first value is
+                    // used -- one global round trip per (row, 32 channels); plane pointers advance by H*W
+                    const int hw32 = (int)HW;
+#pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         const int q = p0 - 1 + r + (dy - 1) * Wq;
                         const int yq = q >= 0 ? q / Wq : 0, xq = q - yq * Wq;
-                        const bool ok = q >= 0 && q < npos && xq < P.W;
-                        const float* src = xn + (long long)yq * P.W + xq;
-                        for (int g = 0; g < P.cg; ++g) {
-                            float v[8];
+                        const bool ok = q >= 0 && q < npos && xq < P.W && !T2_DBG(P, 1);
+                        const float* src = xn + (ok ? yq * P.W + xq : 0);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int c = 8 * g + e;
-                                v[e] = (ok && c < P.Cin) ? __ldg(src + (long long)c * HW) : 0.f;
+                        for (int g0 = 0; g0 < CGP; g0 += 4) {
+                            constexpr int NG = CGP < 4 ? CGP : 4;
+                            float v[8 * NG];
+#pragma unroll
+                            for (int e = 0; e < 8 * NG; ++e) {
+                                const int c = 8 * g0 + e;
+                                v[e] = (ok && c < P.Cin) ? __ldg(src + c * hw32) : 0.f;
                             }
-                            uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) split_f16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-                            uint8_t* d = st + (size_t)(dy * 2 * P.cgp + g) * U3_SEG;
-                            *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(d + (size_t)P.cgp * U3_SEG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            for (int gg = 0; gg < NG; ++gg) {
+                                if (g0 + gg < P.cg && !T2_DBG(P, 8)) {
+                                    uint32_t hi[4], lo[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        split_f16x2(v[8 * gg + 2 * e], v[8 * gg + 2 * e + 1], hi[e], lo[e]);
+                                    uint8_t* d = st + (size_t)(dy * 2 * CGP + g0 + gg) * U3_SEG;
+                                    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                    *reinterpret_cast<uint4*>(d + (size_t)CGP * U3_SEG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                }
+                            }
                         }
                     }
                 }
+                T2P(t_lld += clock64() - c0;)
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's operand reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[s]);
-                ph ^= 1;
             }
         }
+        T2P(if (P.prof && lane == 0 && (warp - 4) % U3_LOAD_W == 0) { unsigned long long* o = P.prof + blockIdx.x * 16 + 4 * grp; o[0] = clock64() - t_l0; o[1] = t_lw; o[2] = t_lld; })
     } else if (warp == 4 + 2 * U3_LOAD_W) {
         // ============================== MMA ISSUER ==============================
         const uint32_t tmem_u = uni(tmem_base);
@@ -1104,64 +1123,127 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
         const uint64_t bdesc0 = make_desc_ns(smem_u32(w_s), (uint32_t)bchunk, 128);
         const uint32_t id2 = make_idesc_f16(TILE, 2 * P.coutp), id1 = make_idesc_f16(TILE, P.coutp);
         int it = 0;
+        T2P(long long t_m0 = clock64(), t_mwa = 0, t_mwf = 0, c0;)
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-            const int s = P.stages == 2 ? (it & 1) : 0;
-            const uint32_t ph = (uint32_t)(P.stages == 2 ? (it >> 1) : it) & 1u;
+            const int s = it % P.stages;
+            const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
             const int buf = it & 1;
             const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            T2P(c0 = clock64();)
             mbar_wait(&acc_empty[buf], acc_ph ^ 1);
+            T2P(t_mwa += clock64() - c0; c0 = clock64();)
             mbar_wait(&full[s], ph);
+            T2P(t_mwf += clock64() - c0;)
             tc_fence_after();
-            const uint32_t d = tmem_u + (uint32_t)(buf * 128);
-            uint32_t acc = 0;
-            for (int t = 0; t < 9; ++t) {
-                const int dy = t / 3, dx = t - dy * 3;
-                const uint64_t a_t = adesc0 + (uint64_t)((s * stage_bytes + dy * 2 * P.cgp * U3_SEG + dx * 16) >> 4);
-                const uint64_t b_t = bdesc0 + (uint64_t)((t * P.cgp * bchunk) >> 4);
-                for (int j = 0; j < P.cgp / 2; ++j) {
-                    const uint64_t bj = b_t + (uint64_t)((2 * j * bchunk) >> 4);
-                    umma_ss(d, a_t + (uint64_t)((2 * j * U3_SEG) >> 4), bj, id2, acc);
-                    acc = 1;
-                    umma_ss(d, a_t + (uint64_t)(((P.cgp + 2 * j) * U3_SEG) >> 4), bj, id1, 1);
+            // accumulator buffer = three groups (one per kernel row) of [main coutp | cross coutp] columns: the tensor core's
+            // fp32 accumulation truncates, so the error of a chain grows with its length -- the long hi*hi chain is cut into
+            // three (3 * PAIRS accumulations each), the small cross terms (hi*lo, lo*hi) go to their own columns, and the
+            // epilogue adds the six partial sums in RN fp32
+            const uint32_t d0 = tmem_u + (uint32_t)(buf * 192);
+            const uint64_t a_s0 = adesc0 + (uint64_t)((s * stage_bytes) >> 4);
+            const uint32_t bc16 = (uint32_t)(bchunk >> 4);
+            if (!T2_DBG(P, 2)) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3, dx = t - dy * 3;
+                    const uint64_t a_t = a_s0 + (uint64_t)((dy * 2 * CGP * U3_SEG + dx * 16) >> 4);
+                    const uint32_t d = d0 + (uint32_t)(dy * 2 * P.coutp);
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) {
+                        const uint64_t bj = bdesc0 + (uint64_t)((t * CGP + 2 * j) * bc16);
+                        umma_ss(d, a_t + (uint64_t)((2 * j * U3_SEG) >> 4), bj, id2, (dx | j) != 0);
+                        const uint64_t a_lo = a_t + (uint64_t)(((CGP + 2 * j) * U3_SEG) >> 4);
+                        umma_ss(d + P.coutp, a_lo, bj, id1, 1);                                   // a_lo * w_hi
+                        umma_ss(d + P.coutp, a_lo, bj + (uint64_t)((P.coutp * 16) >> 4), id1, 1);  // a_lo * w_lo: the issue lane
+                        // has slack, so the fourth product is kept and the sum is exact to the 2^-22 of the operand split
+                    }
                 }
             }
             umma_commit(&empty[s]);
             umma_commit(&acc_full[buf]);
         }
+        T2P(if (P.prof && lane == 0) { unsigned long long* o = P.prof + blockIdx.x * 16 + 8; o[0] = clock64() - t_m0; o[1] = t_mwa; o[2] = t_mwf; })
     } else if (warp < 4) {
         // ============================== EPILOGUE ==============================
         const int m = warp * 32 + lane;
         int it = 0;
+        T2P(long long t_e0 = clock64(), t_ew = 0, c0;)
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
             const int n = tile / P.tiles_per_img, p = (tile - n * P.tiles_per_img) * TILE + m;
             const int y = p / Wq, x = p - y * Wq;
             const bool ok = p < npos && x < P.W;
             float* o = P.out + (long long)n * P.obs + (long long)P.co_begin * HW + (long long)y * P.W + x;
             const int buf = it & 1;
+            T2P(c0 = clock64();)
             mbar_wait_sleep(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 64);
+            T2P(t_ew += clock64() - c0;)
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128);
-            for (int c8 = 0; c8 < P.coutp; c8 += 8) {
-                float a[8], b[8];
-                tmem_ld8(t0 + c8, a);
-                tmem_ld8(t0 + P.coutp + c8, b);
-                if (ok) {
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 192);
+            for (int c8 = 0; c8 < P.coutp; c8 += 8) {  // 8 channels per step: main + cross columns of the three row groups
+                float m0[8], x0[8], m1[8], x1[8], m2[8], x2[8], dum[8];
+                const uint32_t g0 = t0 + c8, g1 = g0 + 2 * P.coutp, g2 = g1 + 2 * P.coutp;
+                tmem_ld8x4(g0, g0 + P.coutp, g1, g1 + P.coutp, m0, x0, m1, x1);
+                tmem_ld8x4(g2, g2 + P.coutp, g2, g2 + P.coutp, m2, x2, dum, dum);
+                if (ok && !T2_DBG(P, 4)) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if (c8 + e < P.co_count) o[(long long)(c8 + e) * HW] = a[e] + b[e];
+                        if (c8 + e < P.co_count)
+                            o[(long long)(c8 + e) * HW] =
+                                (((m0[e] + m1[e]) + m2[e]) + ((x0[e] + x1[e]) + x2[e])) * (1.f / U3_WSCALE);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        T2P(if (P.prof && threadIdx.x == 0) { unsigned long long* o = P.prof + blockIdx.x * 16 + 12; o[0] = clock64() - t_e0; o[1] = t_ew; })
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 4 + 2 * U3_LOAD_W) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
+}
+
+// weights [Cout][Cin][3][3] fp32 -> the kernel's shared-memory image of one launch (output channels co_begin .. +co_count):
+// [tap][group of 8 input channels][rows: coutp x w_hi | coutp x w_lo][8 fp16]
+__global__ void uconv3_pack_kernel(const float* __restrict__ w, uint4* __restrict__ dst, int Cin, int cgp, int co_begin,
+                                   int co_count, int coutp) {
+    const int total = 9 * cgp * 2 * coutp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i % (2 * coutp), kc = i / (2 * coutp);
+        const int g = kc % cgp, t = kc / cgp;
+        const int co = n < coutp ? n : n - coutp;
+        uint32_t hw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
+        if (co < co_count) {
+            const float* wp = w + ((long long)(co_begin + co) * Cin) * 9 + t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c0 = 8 * g + 2 * e, c1 = c0 + 1;
+                const float v0 = c0 < Cin ? wp[(long long)c0 * 9] : 0.f, v1 = c1 < Cin ? wp[(long long)c1 * 9] : 0.f;
+                // weights of a 3x3 conv are O(1/sqrt(9 Cin)): times 2^8 (exact) their lo halves leave fp16's subnormal range;
+                // the epilogue multiplies the sums by 2^-8
+                split_f16x2(v0 * U3_WSCALE, v1 * U3_WSCALE, hw[e], lw[e]);
+            }
+        }
+        dst[i] = n < coutp ? make_uint4(hw[0], hw[1], hw[2], hw[3]) : make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
+// launches of one convolution: output channels per launch and the byte offset of each launch's packed weights
+struct UConvPlan {
+    int cg, cgp, per_pass, n_pass;
+};
+static UConvPlan uconv3_plan(int Cin, int Cout) {
+    UConvPlan pl;
+    pl.cg = (Cin + 7) / 8;
+    pl.cgp = pl.cg <= 2 ? 2 : pl.cg <= 4 ? 4 : 8;
+    pl.per_pass = 32;  // <= 32 output channels per launch: three accumulator groups x [main | cross] x 2 buffers of TMEM
+    pl.n_pass = (Cout + pl.per_pass - 1) / pl.per_pass;
+    return pl;
+}
+static size_t uconv3_pass_bytes(const UConvPlan& pl, int co_count) {
+    return (size_t)9 * pl.cgp * 2 * ((co_count + 15) & ~15) * 16;
 }
 
 #ifdef MRB_TC_PROF
@@ -1299,20 +1381,45 @@ extern "C" int mrb_tc2_conv5x5x4(const void* g8, const void* w, const void* bias
 }
 
 /* U-Net 3x3 conv (zero padding, no bias; unet_block.py:250-259) on the tensor core, NCHW fp32 in / out with batch strides in
- * floats (concat buffers are read and written in place).  Cin <= 64, any Cout (launches of up to 64 output channels, 32 when
- * Cin > 32).  Error-compensated fp16-split products (x = hi + lo to 2^-22; operands must be O(1): instance-normalised
- * activations). */
-extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* w, void* out, long long out_bstride, int N,
-                                    int Cin, int Cout, int H, int W, void* stream) {
-    MRB_REQUIRE(x && w && out, MRB_EINVAL, "mrb_tc2_unet_conv3x3: null pointer");
+ * floats (concat buffers are read and written in place).  Cin <= 64, any Cout (launches of up to 32 output channels).  Error-compensated fp16-split products (x = hi + lo to 2^-22; operands must be O(1): instance-normalised
+ * activations).  wpack = mrb_tc2_unet_pack of the layer's weight. */
+extern "C" size_t mrb_tc2_unet_packed_bytes(int Cin, int Cout) {
+    if (Cin < 1 || Cin > 64 || Cout < 1) return 0;
+    const tc2::UConvPlan pl = tc2::uconv3_plan(Cin, Cout);
+    size_t tot = 0;
+    for (int p = 0; p < pl.n_pass; ++p) tot += tc2::uconv3_pass_bytes(pl, std::min(pl.per_pass, Cout - p * pl.per_pass));
+    return tot;
+}
+
+extern "C" int mrb_tc2_unet_pack(const void* w, void* dst, int Cin, int Cout, void* stream) {
+    MRB_REQUIRE(w && dst, MRB_EINVAL, "mrb_tc2_unet_pack: null pointer");
+    MRB_REQUIRE(Cin >= 1 && Cin <= 64 && Cout >= 1, MRB_EUNSUPPORTED, "mrb_tc2_unet_pack: 1 <= Cin <= 64 (got %d)", Cin);
+    const tc2::UConvPlan pl = tc2::uconv3_plan(Cin, Cout);
+    size_t off = 0;
+    for (int p = 0; p < pl.n_pass; ++p) {
+        const int cnt = std::min(pl.per_pass, Cout - p * pl.per_pass), coutp = (cnt + 15) & ~15;
+        const int total = 9 * pl.cgp * 2 * coutp;
+        tc2::uconv3_pack_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+            (const float*)w, (uint4*)((uint8_t*)dst + off), Cin, pl.cgp, p * pl.per_pass, cnt, coutp);
+        MRB_LAUNCHED();
+        off += tc2::uconv3_pass_bytes(pl, cnt);
+    }
+    return MRB_OK;
+}
+
+extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const void* wpack, void* out, long long out_bstride,
+                                    int N, int Cin, int Cout, int H, int W, void* stream) {
+    MRB_REQUIRE(x && wpack && out, MRB_EINVAL, "mrb_tc2_unet_conv3x3: null pointer");
     MRB_REQUIRE(N >= 1 && Cin >= 1 && Cout >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_unet_conv3x3: bad shape");
     MRB_REQUIRE(Cin <= 64, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: at most 64 input channels (got %d)", Cin);
+    MRB_REQUIRE((long long)H * W * 64 < 2147483647LL, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: image too large");
+    const tc2::UConvPlan pl = tc2::uconv3_plan(Cin, Cout);
     tc2::UConvParams P;
-    P.x = (const float*)x; P.w = (const float*)w; P.out = (float*)out;
+    P.x = (const float*)x; P.out = (float*)out;
     P.xbs = x_bstride; P.obs = out_bstride;
     P.N = N; P.Cin = Cin; P.H = H; P.W = W;
-    P.cg = (Cin + 7) / 8;
-    P.cgp = (P.cg + 1) & ~1;
+    P.cg = pl.cg;
+    P.cgp = pl.cgp;
     const long long npos = (long long)H * (W + 1);
     P.tiles_per_img = (int)((npos + tc2::TILE - 1) / tc2::TILE);
     MRB_REQUIRE((long long)N * P.tiles_per_img < 2147483647LL && npos < 2147483647LL - 1024, MRB_EUNSUPPORTED,
@@ -1321,20 +1428,29 @@ extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const vo
     const size_t smem_max = device_max_smem_optin();
     static bool attr_set = false;
     if (!attr_set) {
-        MRB_CUDA(cudaFuncSetAttribute(tc2::uconv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        MRB_CUDA(cudaFuncSetAttribute(tc2::uconv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        MRB_CUDA(cudaFuncSetAttribute(tc2::uconv3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        MRB_CUDA(cudaFuncSetAttribute(tc2::uconv3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         attr_set = true;
     }
-    const int per_pass = P.cgp > 4 ? 32 : 64;
-    for (int co = 0; co < Cout; co += per_pass) {
-        P.co_begin = co;
-        P.co_count = std::min(per_pass, Cout - co);
+#ifdef MRB_TC_PROF
+    P.debug = tc2::g_debug2; P.prof = tc2::g_prof2;
+#endif
+    size_t off = 0;
+    for (int p = 0; p < pl.n_pass; ++p) {
+        P.co_begin = p * pl.per_pass;
+        P.co_count = std::min(pl.per_pass, Cout - P.co_begin);
         P.coutp = (P.co_count + 15) & ~15;
+        P.wpack = (const uint8_t*)wpack + off;
+        off += tc2::uconv3_pass_bytes(pl, P.co_count);
         const size_t stage = (size_t)3 * 2 * P.cgp * tc2::U3_SEG, wb = (size_t)9 * P.cgp * 2 * P.coutp * 16;
-        P.stages = (1024 + 2 * stage + wb + 256 <= smem_max) ? 2 : 1;
-        MRB_REQUIRE(1024 + P.stages * stage + wb + 256 <= smem_max, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: shared memory");
+        MRB_REQUIRE(1024 + stage + wb + 512 <= smem_max, MRB_EUNSUPPORTED, "mrb_tc2_unet_conv3x3: shared memory");
+        P.stages = (int)std::min<size_t>(4, (smem_max - 1024 - wb - 512) / stage);
         int grid = device_sm_count();
         if (grid > P.n_tiles) grid = P.n_tiles;
-        tc2::uconv3_kernel<<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
+        if (pl.cgp == 2) tc2::uconv3_kernel<1><<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
+        else if (pl.cgp == 4) tc2::uconv3_kernel<2><<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
+        else tc2::uconv3_kernel<4><<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
         MRB_LAUNCHED();
     }
     return MRB_OK;

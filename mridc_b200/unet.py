@@ -26,6 +26,26 @@ def _tc_convs():
     return os.environ.get("MRIDC_B200_UNET_FP32", "0") != "1"
 
 
+_PACKS = {}  # id(parameter) -> (data_ptr, version, device, packed weights); rebuilt when the parameter changes
+
+
+def _packed(weight):
+    """fp16 hi / lo weight image of uconv3_kernel, packed once per parameter version."""
+    key = (weight.data_ptr(), weight._version, str(weight.device))
+    hit = _PACKS.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    lib = _lib.load()
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().contiguous()
+    pk = torch.empty(lib.mrb_tc2_unet_packed_bytes(Cin, Cout), dtype=torch.uint8, device=weight.device)
+    _lib.check(lib.mrb_tc2_unet_pack(_lib.ptr(w), _lib.ptr(pk), Cin, Cout, _lib.stream_ptr()))
+    if len(_PACKS) > 4096:
+        _PACKS.clear()
+    _PACKS[id(weight)] = (key, pk)
+    return pk
+
+
 def _conv3x3(x, weight, x_bs, N, Cin, H, W, normalised=True):
     """Conv2d(k = 3, padding = 1, bias = False) of the buffer x ([N, Cin, H, W] with batch stride x_bs) -> contiguous
     [N, Cout, H, W].  ``normalised``: the input is the output of an InstanceNorm (O(1) values), which the fp16-split
@@ -33,8 +53,8 @@ def _conv3x3(x, weight, x_bs, N, Cin, H, W, normalised=True):
     Cout = weight.shape[0]
     if normalised and _tc_convs() and Cin <= 64:
         out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().mrb_tc2_unet_conv3x3(_lib.ptr(x), x_bs, _lib.ptr(weight), _lib.ptr(out), Cout * H * W, N, Cin,
-                                                    Cout, H, W, _lib.stream_ptr()))
+        _lib.check(_lib.load().mrb_tc2_unet_conv3x3(_lib.ptr(x), x_bs, _lib.ptr(_packed(weight)), _lib.ptr(out), Cout * H * W,
+                                                    N, Cin, Cout, H, W, _lib.stream_ptr()))
         return out
     return _ops.conv2d(x, weight, None, 3, 1, _ops.PAD_ZERO, x_bstride=x_bs, N=N, Cin=Cin, H=H, W=W)
 
@@ -138,7 +158,9 @@ class Unet(nn.Module):
                                           nn.Conv2d(ch, self.out_chans, kernel_size=1, stride=1)))
 
     @torch.no_grad()
-    def forward(self, image: torch.Tensor) -> torch.Tensor:
+    def forward(self, image: torch.Tensor, normalised_input: bool = False) -> torch.Tensor:
+        """unet_block.py:187-227.  ``normalised_input`` (not in the reference signature): the caller guarantees O(1) input
+        values (NormUnet with normalize=True), so the first convolution may use the fp16-split tensor-core kernel too."""
         lib = _lib.load()
         image = _lib.require_cuda(image, "image").contiguous()
         N, C, H, W = image.shape
@@ -151,7 +173,7 @@ class Unet(nn.Module):
             skip = cat[:, ch:]  # view: batch stride 2*ch*h*w
             # the very first conv reads the caller's image (any scale); every later input is an average of
             # instance-normalised activations
-            layer.run(cur, cur_bs, N, h, w, out=skip, out_bs=2 * ch * h * w, normalised=li > 0)
+            layer.run(cur, cur_bs, N, h, w, out=skip, out_bs=2 * ch * h * w, normalised=li > 0 or normalised_input)
             cats.append((cat, ch, h, w))
             pooled = torch.empty((N, ch, h // 2, w // 2), dtype=torch.float32, device=dev)
             _lib.check(lib.mrb_avgpool2(_lib.ptr(skip), 2 * ch * h * w, _lib.ptr(pooled), ch * (h // 2) * (w // 2), N,
@@ -217,7 +239,7 @@ class NormUnet(nn.Module):
                                      2 * C, H, W, h_mult, w_mult, h_pad[0], w_pad[0], 0, st))
         else:
             padded = planar
-        y = self.unet(padded)
+        y = self.unet(padded, normalised_input=bool(self.normalize))  # group-normalised: zero mean, unit std
         Co = y.shape[1]
         if (h_mult, w_mult) != (H, W):
             un = torch.empty((B, Co, H, W), dtype=torch.float32, device=dev)

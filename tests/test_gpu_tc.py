@@ -377,7 +377,9 @@ def test_unet_conv3x3_tc_vs_oracle(N, Cin, Cout, H, W):
     xfull = torch.randn(N, Cin + 3, H, W, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3.0 * Cin ** 0.5))
     ref = torch.nn.functional.conv2d(xfull[:, 3:], w, None, padding=1)
-    xd, wd = xfull.cuda(), w.cuda()
+    xd, wraw = xfull.cuda(), w.cuda()
+    wd = torch.empty(lib.mrb_tc2_unet_packed_bytes(Cin, Cout), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mrb_tc2_unet_pack(_lib.ptr(wraw), _lib.ptr(wd), Cin, Cout, st))
     xv = xd[:, 3:]  # channels [3, 3 + Cin) of the wider buffer: batch stride (Cin + 3) H W
     outfull = torch.full((N, Cout + 2, H, W), float("nan"), device="cuda")
     ov = outfull[:, 2:]
