@@ -990,7 +990,8 @@ constexpr float U3_WSCALE = 256.f;           // power of two applied to the weig
 constexpr int U3_ROWS = 136;                 // staged positions per segment: 128 + 2 halo, whole core matrices
 constexpr int U3_SEG = U3_ROWS * 16;
 constexpr int U3_LOAD_W = 5;                 // warps per loader group
-constexpr int U3_THREADS = (4 + 2 * U3_LOAD_W + 1) * 32;
+constexpr int U3_LOAD_G = 3;                 // loader groups: every tile is split three ways (one kernel row per group)
+constexpr int U3_THREADS = (4 + U3_LOAD_G * U3_LOAD_W + 1) * 32;
 
 struct UConvParams {
     const float* x;     // [N][Cin][H][W], batch stride xbs floats
@@ -1002,6 +1003,7 @@ struct UConvParams {
     int cg, cgp;             // channel groups of 8 (real, padded to even)
     int coutp;               // co_count padded to 16
     int stages;              // 1 .. 4 A stages
+    int nbuf;                // accumulator buffers of 6 coutp TMEM columns: 4 (coutp 16) or 2 (coutp 32)
     int tiles_per_img, n_tiles;
 #ifdef MRB_TC_PROF
     int debug;               // role switches (tools build): 1 no global loads, 2 no MMAs, 4 no stores, 8 no split / staging stores
@@ -1028,7 +1030,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
     T2P(const long long t_k0 = clock64();)
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&full[i], U3_LOAD_W);
+            mbar_init(&full[i], U3_LOAD_G * U3_LOAD_W);
             mbar_init(&empty[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 4);
@@ -1042,7 +1044,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
         const uint4* g = reinterpret_cast<const uint4*>(P.wpack);
         for (int i = threadIdx.x; i < 9 * CGP * 2 * P.coutp; i += U3_THREADS) reinterpret_cast<uint4*>(w_s)[i] = __ldg(g + i);
     }
-    if (warp == 4 + 2 * U3_LOAD_W) tmem_alloc(tmem_slot, 512);
+    if (warp == 4 + U3_LOAD_G * U3_LOAD_W) tmem_alloc(tmem_slot, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1053,70 +1055,89 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
     const long long HW = (long long)P.H * P.W;
     const int npos = P.H * Wq;
 
-    if (warp >= 4 && warp < 4 + 2 * U3_LOAD_W) {
+    if (warp >= 4 && warp < 4 + U3_LOAD_G * U3_LOAD_W) {
         // ============================== LOADERS ==============================
         const int grp = (warp - 4) / U3_LOAD_W;
         const int r = (warp - 4 - grp * U3_LOAD_W) * 32 + lane;  // staged position (row of every segment)
-        // tile number `it` of this CTA lives in A stage it % stages; the two loader groups alternate tiles (one group when
-        // there is a single stage), so up to `stages` tiles are in flight between the loaders and the MMA lane.
-        // (A software-pipelined variant -- loads of the next (tile, row) step issued before the current one is converted --
-        // was measured slower: the loaders are bound by their own instruction stream, ~450 per thread and tile, not by the
-        // three global round trips; see DESIGN.md.)
-        const int ngrp = P.stages >= 2 ? 2 : 1;
+        // Tile number `it` of this CTA lives in A stage it % stages.  The three loader groups split EVERY tile: group g stages
+        // kernel row dy = g (all channel groups), so a tile costs each thread one global round trip per 32 channels and a third
+        // of the conversion work, and a single-stage configuration (56 input channels) still has 15 warps loading.
+        // The loads of the next tile are issued before the current one is converted (register ping-pong) when a step is at
+        // most 16 channels; wider steps do not fit the register budget twice.
+        const int dy = grp;
+        const bool active = r < TILE + 2;
+        constexpr int NG = CGP < 4 ? CGP : 4;   // channel groups per step
+        constexpr int NB = CGP > 4 ? 2 : 1;     // steps per tile and group
+        const int hw32 = (int)HW;
         T2P(long long t_l0 = clock64(), t_lw = 0, t_lld = 0, c0;)
-        if (grp < ngrp) {
-            for (int it = grp; blockIdx.x + (long long)it * gridDim.x < P.n_tiles; it += ngrp) {
-                const int tile = blockIdx.x + it * gridDim.x;
-                const int s = it % P.stages;
-                const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-                const int n = tile / P.tiles_per_img, p0 = (tile - n * P.tiles_per_img) * TILE;
-                T2P(c0 = clock64();)
-                mbar_wait_sleep(&empty[s], ph ^ 1, 40);
-                T2P(t_lw += clock64() - c0; c0 = clock64();)
-                if (r < TILE + 2) {
-                    const float* xn = P.x + (long long)n * P.xbs;
-                    uint8_t* st = a_s + (size_t)s * stage_bytes + r * 16;
-                    // per kernel row: the loads of up to four channel groups (32 planes) are issued before the first value is
-                    // used -- one global round trip per (row, 32 channels); plane pointers advance by H*W
-                    const int hw32 = (int)HW;
+        auto issue = [&](int it, int g0, float* v) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int n = tile / P.tiles_per_img, p0 = (tile - n * P.tiles_per_img) * TILE;
+            const int q = p0 - 1 + r + (dy - 1) * Wq;
+            const int yq = q >= 0 ? q / Wq : 0, xq = q - yq * Wq;
+            const bool ok = active && q >= 0 && q < npos && xq < P.W && !T2_DBG(P, 1);
+            const float* src = P.x + (long long)n * P.xbs + (ok ? yq * P.W + xq : 0) + 8 * g0 * hw32;
+            const int cleft = P.Cin - 8 * g0;
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const int q = p0 - 1 + r + (dy - 1) * Wq;
-                        const int yq = q >= 0 ? q / Wq : 0, xq = q - yq * Wq;
-                        const bool ok = q >= 0 && q < npos && xq < P.W && !T2_DBG(P, 1);
-                        const float* src = xn + (ok ? yq * P.W + xq : 0);
+            for (int e = 0; e < 8 * NG; ++e) v[e] = (ok && e < cleft) ? __ldg(src + e * hw32) : 0.f;
+        };
+        auto convert = [&](int it, int g0, const float* v) {
+            const int s = it % P.stages;
+            uint8_t* st = a_s + (size_t)s * stage_bytes + r * 16 + (size_t)(dy * 2 * CGP + g0) * U3_SEG;
 #pragma unroll
-                        for (int g0 = 0; g0 < CGP; g0 += 4) {
-                            constexpr int NG = CGP < 4 ? CGP : 4;
-                            float v[8 * NG];
+            for (int gg = 0; gg < NG; ++gg) {
+                if (active && g0 + gg < P.cg && !T2_DBG(P, 8)) {
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int e = 0; e < 8 * NG; ++e) {
-                                const int c = 8 * g0 + e;
-                                v[e] = (ok && c < P.Cin) ? __ldg(src + c * hw32) : 0.f;
-                            }
-#pragma unroll
-                            for (int gg = 0; gg < NG; ++gg) {
-                                if (g0 + gg < P.cg && !T2_DBG(P, 8)) {
-                                    uint32_t hi[4], lo[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        split_f16x2(v[8 * gg + 2 * e], v[8 * gg + 2 * e + 1], hi[e], lo[e]);
-                                    uint8_t* d = st + (size_t)(dy * 2 * CGP + g0 + gg) * U3_SEG;
-                                    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                    *reinterpret_cast<uint4*>(d + (size_t)CGP * U3_SEG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                                }
-                            }
-                        }
-                    }
+                    for (int e = 0; e < 4; ++e) split_f16x2(v[8 * gg + 2 * e], v[8 * gg + 2 * e + 1], hi[e], lo[e]);
+                    uint8_t* d = st + (size_t)gg * U3_SEG;
+                    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(d + (size_t)CGP * U3_SEG) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                T2P(t_lld += clock64() - c0;)
-                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's operand reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        };
+        auto acquire = [&](int it) {
+            T2P(c0 = clock64();)
+            mbar_wait_sleep(&empty[it % P.stages], ((uint32_t)(it / P.stages) & 1u) ^ 1u, 40);
+            T2P(t_lw += clock64() - c0;)
+        };
+        auto publish = [&](int it) {
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's operand reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[it % P.stages]);
+        };
+        const int my_tiles = (int)blockIdx.x < P.n_tiles ? (P.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        if (NB == 1 && NG <= 2) {
+            float va[8 * NG], vb[8 * NG];
+            if (my_tiles > 0) issue(0, 0, va);
+            for (int it = 0; it < my_tiles; it += 2) {
+                if (it + 1 < my_tiles) issue(it + 1, 0, vb);
+                acquire(it);
+                convert(it, 0, va);
+                publish(it);
+                if (it + 2 < my_tiles) issue(it + 2, 0, va);
+                if (it + 1 < my_tiles) {
+                    acquire(it + 1);
+                    convert(it + 1, 0, vb);
+                    publish(it + 1);
+                }
+            }
+        } else {
+            for (int it = 0; it < my_tiles; ++it) {
+                float v[8 * NG];
+                issue(it, 0, v);
+                acquire(it);
+                convert(it, 0, v);
+                if (NB == 2) {
+                    issue(it, 4, v);
+                    convert(it, 4, v);
+                }
+                publish(it);
             }
         }
-        T2P(if (P.prof && lane == 0 && (warp - 4) % U3_LOAD_W == 0) { unsigned long long* o = P.prof + blockIdx.x * 16 + 4 * grp; o[0] = clock64() - t_l0; o[1] = t_lw; o[2] = t_lld; })
-    } else if (warp == 4 + 2 * U3_LOAD_W) {
+        T2P(t_lld = clock64() - t_l0 - t_lw;)
+        T2P(if (P.prof && lane == 0 && (warp - 4) % U3_LOAD_W == 0) { unsigned long long* o = P.prof + blockIdx.x * 16 + 4 * (grp < 2 ? grp : 0); if (grp < 2) { o[0] = clock64() - t_l0; o[1] = t_lw; o[2] = t_lld; } })
+    } else if (warp == 4 + U3_LOAD_G * U3_LOAD_W) {
         // ============================== MMA ISSUER ==============================
         const uint32_t tmem_u = uni(tmem_base);
         const uint64_t adesc0 = make_desc_ns(smem_u32(a_s), U3_SEG, 128);
@@ -1127,8 +1148,8 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
             const int s = it % P.stages;
             const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-            const int buf = it & 1;
-            const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+            const int buf = it % P.nbuf;
+            const uint32_t acc_ph = (uint32_t)(it / P.nbuf) & 1u;
             T2P(c0 = clock64();)
             mbar_wait(&acc_empty[buf], acc_ph ^ 1);
             T2P(t_mwa += clock64() - c0; c0 = clock64();)
@@ -1139,7 +1160,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
             // fp32 accumulation truncates, so the error of a chain grows with its length -- the long hi*hi chain is cut into
             // three (3 * PAIRS accumulations each), the small cross terms (hi*lo, lo*hi) go to their own columns, and the
             // epilogue adds the six partial sums in RN fp32
-            const uint32_t d0 = tmem_u + (uint32_t)(buf * 192);
+            const uint32_t d0 = tmem_u + (uint32_t)(buf * 6 * P.coutp);
             const uint64_t a_s0 = adesc0 + (uint64_t)((s * stage_bytes) >> 4);
             const uint32_t bc16 = (uint32_t)(bchunk >> 4);
             if (!T2_DBG(P, 2)) {
@@ -1173,12 +1194,12 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
             const int y = p / Wq, x = p - y * Wq;
             const bool ok = p < npos && x < P.W;
             float* o = P.out + (long long)n * P.obs + (long long)P.co_begin * HW + (long long)y * P.W + x;
-            const int buf = it & 1;
+            const int buf = it % P.nbuf;
             T2P(c0 = clock64();)
-            mbar_wait_sleep(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 64);
+            mbar_wait_sleep(&acc_full[buf], (uint32_t)(it / P.nbuf) & 1u, 64);
             T2P(t_ew += clock64() - c0;)
             tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 192);
+            const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 6 * P.coutp);
             for (int c8 = 0; c8 < P.coutp; c8 += 8) {  // 8 channels per step: main + cross columns of the three row groups
                 float m0[8], x0[8], m1[8], x1[8], m2[8], x2[8], dum[8];
                 const uint32_t g0 = t0 + c8, g1 = g0 + 2 * P.coutp, g2 = g1 + 2 * P.coutp;
@@ -1200,7 +1221,7 @@ __global__ void __launch_bounds__(U3_THREADS, 1) uconv3_kernel(const UConvParams
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4 + 2 * U3_LOAD_W) {
+    if (warp == 4 + U3_LOAD_G * U3_LOAD_W) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -1441,6 +1462,7 @@ extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const vo
         P.co_begin = p * pl.per_pass;
         P.co_count = std::min(pl.per_pass, Cout - P.co_begin);
         P.coutp = (P.co_count + 15) & ~15;
+        P.nbuf = P.coutp <= 16 ? 4 : 2;
         P.wpack = (const uint8_t*)wpack + off;
         off += tc2::uconv3_pass_bytes(pl, P.co_count);
         const size_t stage = (size_t)3 * 2 * P.cgp * tc2::U3_SEG, wb = (size_t)9 * P.cgp * 2 * P.coutp * 16;
