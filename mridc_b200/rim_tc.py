@@ -202,7 +202,7 @@ class RimTcEngine:
                                    _lib.ptr(h_alt[1]), B, H, W, st))
         h[1], h_alt[1] = h_alt[1], h[1]
         new_eta = torch.empty_like(eta)
-        if _FINAL_TC:
+        if _FINAL_TC and B * (H + 4) >= 16:  # the 3-D TMA box of the tap GEMM spans 16 rows of the [B (H+4)] x (W+4) grid
             # tap GEMM on the tensor core + clamped gather: reads the interior of h[1] only, no border fix-up
             _lib.check(lib.mrb_tc2_final_conv(_lib.ptr(h[1]), _lib.ptr(fin.conv_layer.weight), _lib.ptr(fin.conv_layer.bias),
                                               _lib.ptr(eta), _lib.ptr(new_eta), B, H, W, st))

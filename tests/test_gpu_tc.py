@@ -259,7 +259,7 @@ def test_tc2_gru_vs_oracle(B, H, W):
     assert torch.equal(ob, ob2)
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 64, 32), (2, 33, 28), (1, 320, 320)])
+@pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 64, 32), (2, 33, 28), (1, 320, 320), (1, 12, 30)])
 def test_tc2_conv_ops_vs_oracle(B, H, W):
     """The convolutions of the time step on BH activations: conv5x5 (fp32 gradient -> BH), conv3x3 (BH -> BH, replicate
     padding = the BH border), final conv (BH -> eta)."""
@@ -391,6 +391,27 @@ def test_unet_conv3x3_tc_vs_oracle(N, Cin, Cout, H, W):
     _lib.check(lib.mrb_tc2_unet_conv3x3(_lib.ptr(xv), (Cin + 3) * H * W, _lib.ptr(wd), _lib.ptr(o2), Cout * H * W, N, Cin, Cout,
                                         H, W, st))
     assert torch.equal(o2, ov)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 32), (1, 12, 28), (3, 5, 40)])
+def test_cirim_tiny_images_on_the_bh_engine(B, H, W):
+    """Images smaller than a tile / a TMA box (the final tap GEMM falls back to the CUDA-core kernel below 16 padded rows)."""
+    import mridc_b200 as mb
+    from mridc_b200 import synth
+    from oracle import models as omodels
+
+    cfg = synth.cirim_cfg("GRU", num_cascades=1, centered=True, normalization="ortho")
+    batch = synth.make_batch(B, 3, H, W, centered=True, normalization="ortho")
+    torch.manual_seed(5)
+    model = mb.CIRIM(cfg).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = omodels.cirim_forward(sd, cfg, batch["y"], batch["sensitivity_maps"], batch["mask"], None, batch["target"])
+    out = next(model.cuda()(batch["y"].cuda(), batch["sensitivity_maps"].cuda(), batch["mask"].cuda(), None,
+                            batch["target"].cuda()))
+    e = rel_l2(out[-1][-1], ref[-1][-1])
+    print("[tc parity] tiny CIRIM %dx%dx%d rel-L2 %.2e" % (B, H, W, e))
+    assert e < 3e-5
 
 
 def test_cirim_graph_replay_equals_eager(monkeypatch):
