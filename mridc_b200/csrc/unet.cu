@@ -3,9 +3,12 @@
 // Reference behaviour: mridc/collections/reconstruction/models/unet_base/unet_block.py:11-308.
 // Statistics are accumulated in fp64 (sum, sum of squares) so the fp32 result is independent of the
 // reduction order to well below fp32 round-off (E2EVN's fp32 noise floor is only ~4x under the tolerance).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace mrb {
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -59,6 +62,87 @@ __global__ void instnorm_apply_kernel(const float* __restrict__ x, long long xbs
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
         float v = (p[i] - m) * rstd;
         o[i] = v > 0.f ? v : v * slope;
+    }
+}
+
+// InstanceNorm2d + LeakyReLU in ONE pass over global memory: a thread-block cluster owns one (n, c) plane, every CTA keeps
+// its share of the plane in shared memory while it accumulates the fp64 sums, the per-CTA sums are exchanged through
+// distributed shared memory (fixed rank order: the statistics do not depend on scheduling, unlike the atomics of the
+// two-kernel form), and the normalised values are written from shared memory.  1 read + 1 write per element instead of
+// 2 reads + 1 write and three launches (memset, statistics, apply).  In-place use (out == x) is safe: an element is
+// read before its own CTA writes it.
+constexpr int IN_THREADS = 512;
+__global__ void __launch_bounds__(IN_THREADS) instnorm_cluster_kernel(const float* __restrict__ x, long long xbs, float* out,
+                                                                      long long obs, int C, int HW, int chunk, float eps,
+                                                                      float slope) {
+    extern __shared__ __align__(16) float in_buf[];
+    __shared__ double part[2];
+    __shared__ double sh[2][IN_THREADS / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int plane = blockIdx.x / cs;
+    const int n = plane / C, c = plane - n * C;
+    const float* p = x + (long long)n * xbs + (long long)c * HW;
+    float* o = out + (long long)n * obs + (long long)c * HW;
+    const int beg = rank * chunk, end = min(HW, beg + chunk);  // chunk is a multiple of 4
+    const int cnt = max(0, end - beg);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p + beg) | reinterpret_cast<uintptr_t>(o + beg)) & 15) == 0 && (cnt & 3) == 0;
+    double s = 0.0, ss = 0.0;
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(p + beg);
+        for (int i = threadIdx.x; i < cnt / 4; i += IN_THREADS) {
+            const float4 v = __ldg(p4 + i);
+            reinterpret_cast<float4*>(in_buf)[i] = v;
+            s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+            ss += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += IN_THREADS) {
+            const float v = p[beg + i];
+            in_buf[i] = v;
+            s += (double)v;
+            ss += (double)v * v;
+        }
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = s; sh[1][wid] = ss; }
+    __syncthreads();
+    if (wid == 0) {
+        s = lane < IN_THREADS / 32 ? sh[0][lane] : 0.0;
+        ss = lane < IN_THREADS / 32 ? sh[1][lane] : 0.0;
+        s = warp_sum(s);
+        ss = warp_sum(ss);
+        if (lane == 0) { part[0] = s; part[1] = ss; }
+    }
+    cluster.sync();  // every CTA's partial sums are published
+    double ts = 0.0, tss = 0.0;
+    for (int r = 0; r < cs; ++r) {
+        const double* rp = cluster.map_shared_rank(part, r);
+        ts += rp[0];
+        tss += rp[1];
+    }
+    cluster.sync();  // remote reads done before any CTA of the cluster may exit
+    const double mean = ts / (double)HW;
+    double var = tss / (double)HW - mean * mean;  // biased variance (InstanceNorm2d)
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (vec) {
+        float4* o4 = reinterpret_cast<float4*>(o + beg);
+        for (int i = threadIdx.x; i < cnt / 4; i += IN_THREADS) {
+            float4 v = reinterpret_cast<const float4*>(in_buf)[i];
+            v.x = (v.x - m) * rstd; v.y = (v.y - m) * rstd; v.z = (v.z - m) * rstd; v.w = (v.w - m) * rstd;
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            o4[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += IN_THREADS) {
+            const float v = (in_buf[i] - m) * rstd;
+            o[beg + i] = v > 0.f ? v : v * slope;
+        }
     }
 }
 
@@ -250,6 +334,37 @@ extern "C" int mrb_instnorm_lrelu(const void* x, long long x_bstride, void* out,
     MRB_REQUIRE(N >= 1 && C >= 1 && HW >= 1 && (long long)N * C <= 65535, MRB_EINVAL, "mrb_instnorm_lrelu: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     const int planes = N * C;
+    if (HW < 2147483647LL / 4 && !getenv("MRIDC_B200_INSTNORM_2PASS")) {
+        // single-pass cluster form: 2 .. 8 CTAs per plane, each holding <= 64 KB of it in shared memory (one CTA for
+        // planes up to 64 KB; planes above 8 x 200 KB take the two-kernel form below)
+        int cs = 1;
+        while (cs < 8 && (HW * 4 + cs - 1) / cs > 65536) cs *= 2;
+        const int chunk = (int)((((HW + cs - 1) / cs) + 3) & ~3LL);
+        const size_t smem = (size_t)chunk * 4;
+        if (smem <= 200 * 1024 && (long long)planes * cs < 2147483647LL) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                MRB_CUDA(cudaFuncSetAttribute(instnorm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(planes * cs));
+            cfg.blockDim = dim3(IN_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            MRB_CUDA(cudaLaunchKernelEx(&cfg, instnorm_cluster_kernel, (const float*)x, x_bstride, (float*)out, out_bstride, C,
+                                        (int)HW, chunk, eps, slope));
+            MRB_LAUNCHED();
+            return MRB_OK;
+        }
+    }
     MRB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * planes, st));
     dim3 grid(split_grid(HW, planes), planes);
     plane_stats_kernel<<<grid, 256, 0, st>>>((const float*)x, x_bstride, C, HW, (double*)stats);

@@ -10,6 +10,7 @@ fp64.  Skip connections are written straight into the concat buffer
 """
 import math
 import os
+import weakref
 from typing import List, Tuple
 
 import torch
@@ -26,23 +27,26 @@ def _tc_convs():
     return os.environ.get("MRIDC_B200_UNET_FP32", "0") != "1"
 
 
-_PACKS = {}  # id(parameter) -> (data_ptr, version, device, packed weights); rebuilt when the parameter changes
+_PACKS = {}  # id(parameter) -> (weak reference, key, packed weights); rebuilt when the parameter changes
 
 
 def _packed(weight):
-    """fp16 hi / lo weight image of uconv3_kernel, packed once per parameter version."""
+    """fp16 hi / lo weight image of uconv3_kernel, packed once per parameter version.  The entry holds a weak reference to
+    the parameter: ids and device addresses are recycled once a model is freed, so (id, data_ptr, version) alone could hand
+    a new model the packed weights of a dead one."""
     key = (weight.data_ptr(), weight._version, str(weight.device))
     hit = _PACKS.get(id(weight))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0]() is weight and hit[1] == key:
+        return hit[2]
     lib = _lib.load()
     Cout, Cin = weight.shape[0], weight.shape[1]
     w = weight.detach().contiguous()
     pk = torch.empty(lib.mrb_tc2_unet_packed_bytes(Cin, Cout), dtype=torch.uint8, device=weight.device)
     _lib.check(lib.mrb_tc2_unet_pack(_lib.ptr(w), _lib.ptr(pk), Cin, Cout, _lib.stream_ptr()))
-    if len(_PACKS) > 4096:
-        _PACKS.clear()
-    _PACKS[id(weight)] = (key, pk)
+    if len(_PACKS) > 1024:  # drop the entries of freed parameters
+        for k in [k for k, v in _PACKS.items() if v[0]() is None]:
+            del _PACKS[k]
+    _PACKS[id(weight)] = (weakref.ref(weight), key, pk)
     return pk
 
 
