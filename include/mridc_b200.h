@@ -185,6 +185,11 @@ int mrb_instnorm_lrelu(const void* x, long long x_bstride, void* out, long long 
 int mrb_avgpool2(const void* x, long long x_bstride, void* out, long long out_bstride, int N, int C, int H,
                  int W, void* stream);
 
+/* Conv2d(kernel 1) with bias (the last layer of the U-Net, unet_block.py:185): x [N,Cin,HW] -> out [N,Cout,HW], batch
+ * strides in floats; w [Cout,Cin]; bias [Cout] or null.  HW and the strides must be multiples of 4 (16-byte loads). */
+int mrb_conv1x1(const void* x, long long x_bstride, const void* w, const void* bias, void* out, long long out_bstride, int N,
+                int Cin, int Cout, long long HW, void* stream);
+
 /* ConvTranspose2d(kernel 2, stride 2, bias False) (unet_block.py:293): x [N,Cin,H,W], w [Cin,Cout,2,2]
  * -> out [N,Cout,2H,2W] */
 int mrb_conv_transpose2x2(const void* x, long long x_bstride, const void* w, void* out,

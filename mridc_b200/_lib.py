@@ -46,6 +46,7 @@ SIGNATURES = {
     "mrb_gru_gates": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
     "mrb_mgu_gates": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp]),
     "mrb_instnorm_lrelu": (_i, [_vp, _ll, _vp, _ll, _i, _i, _ll, _f, _f, _vp, _vp]),
+    "mrb_conv1x1": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _ll, _vp]),
     "mrb_avgpool2": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
     "mrb_conv_transpose2x2": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "mrb_pad2d": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

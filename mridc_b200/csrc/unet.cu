@@ -5,6 +5,8 @@
 // reduction order to well below fp32 round-off (E2EVN's fp32 noise floor is only ~4x under the tolerance).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mrb {
@@ -143,6 +145,39 @@ __global__ void __launch_bounds__(IN_THREADS) instnorm_cluster_kernel(const floa
             const float v = (in_buf[i] - m) * rstd;
             o[beg + i] = v > 0.f ? v : v * slope;
         }
+    }
+}
+
+// 1x1 convolution with bias (the last layer of the U-Net, unet_block.py:185: Conv2d(ch, out_chans, kernel_size=1)): one
+// thread = four consecutive pixels x up to four output channels; every input plane is read once with 16-byte loads.
+__global__ void conv1x1_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ out, long long obs, int Cin, int Cout,
+                               long long HW4) {
+    const int n = blockIdx.z, co0 = blockIdx.y * 4;
+    const int nco = min(4, Cout - co0);
+    const float4* p = reinterpret_cast<const float4*>(x + (long long)n * xbs);
+    float4* o = reinterpret_cast<float4*>(out + (long long)n * obs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW4; i += (long long)gridDim.x * blockDim.x) {
+        float4 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float b = (bias && j < nco) ? bias[co0 + j] : 0.f;
+            acc[j] = make_float4(b, b, b, b);
+        }
+        for (int c = 0; c < Cin; ++c) {
+            const float4 v = __ldg(p + (long long)c * HW4 + i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nco) {
+                    const float wv = __ldg(w + (long long)(co0 + j) * Cin + c);
+                    acc[j].x = fmaf(v.x, wv, acc[j].x); acc[j].y = fmaf(v.y, wv, acc[j].y);
+                    acc[j].z = fmaf(v.z, wv, acc[j].z); acc[j].w = fmaf(v.w, wv, acc[j].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nco) o[(long long)(co0 + j) * HW4 + i] = acc[j];
     }
 }
 
@@ -371,6 +406,21 @@ extern "C" int mrb_instnorm_lrelu(const void* x, long long x_bstride, void* out,
     MRB_LAUNCHED();
     instnorm_apply_kernel<<<grid, 256, 0, st>>>((const float*)x, x_bstride, (float*)out, out_bstride, C, HW,
                                                 (const double*)stats, eps, slope);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
+
+extern "C" int mrb_conv1x1(const void* x, long long x_bstride, const void* w, const void* bias, void* out,
+                           long long out_bstride, int N, int Cin, int Cout, long long HW, void* stream) {
+    MRB_REQUIRE(x && w && out, MRB_EINVAL, "mrb_conv1x1: null pointer");
+    MRB_REQUIRE(N >= 1 && N <= 65535 && Cin >= 1 && Cout >= 1 && Cout <= 4 * 65535 && HW >= 1, MRB_EINVAL, "mrb_conv1x1: bad shape");
+    MRB_REQUIRE((HW & 3) == 0 && (x_bstride & 3) == 0 && (out_bstride & 3) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                MRB_EUNSUPPORTED, "mrb_conv1x1: planes must be 16-byte aligned (H*W and the batch strides multiples of 4)");
+    const long long HW4 = HW / 4;
+    const unsigned gx = (unsigned)std::min<long long>((HW4 + 255) / 256, (long long)device_sm_count() * 8);
+    conv1x1_kernel<<<dim3(gx, (unsigned)((Cout + 3) / 4), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, x_bstride, (const float*)w, (const float*)bias, (float*)out, out_bstride, Cin, Cout, HW4);
     MRB_LAUNCHED();
     return MRB_OK;
 }

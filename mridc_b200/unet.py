@@ -197,7 +197,14 @@ class Unet(nn.Module):
             block = conv if isinstance(conv, ConvBlock) else conv[0]
             out = block.run(cat, 2 * ch * h * w, N, h, w)
             if not isinstance(conv, ConvBlock):
-                out = _ops.conv2d(out, conv[1].weight, conv[1].bias, 1, 1, _ops.PAD_ZERO)
+                fin = conv[1]  # unet_block.py:185: 1x1 conv with bias
+                if (h * w) % 4 == 0:
+                    res = torch.empty((N, fin.out_channels, h, w), dtype=torch.float32, device=dev)
+                    _lib.check(lib.mrb_conv1x1(_lib.ptr(out), ch * h * w, _lib.ptr(fin.weight), _lib.ptr(fin.bias), _lib.ptr(res),
+                                               fin.out_channels * h * w, N, ch, fin.out_channels, h * w, _lib.stream_ptr()))
+                    out = res
+                else:
+                    out = _ops.conv2d(out, fin.weight, fin.bias, 1, 1, _ops.PAD_ZERO)
         return out
 
 
