@@ -298,6 +298,11 @@ int mrb_bh_fix_border(void* bh, int B, int H, int W, void* stream);
  * interior result. */
 int mrb_tc2_gru(const void* x_bh, const void* h_bh, const void* wpack, const void* b_ih, void* out_bh, int B, int H, int W,
                 void* stream);
+/* IndRNNCell, kernel size 1, 64 -> 64 (rnn_cells.py:264-391, the cell base_cirim_run.yaml ships) on BH tensors:
+ * out = ReLU(W_ih x + b_ih + hh * h); wpack = mrb_tc_pack_conv(ih.weight, 64, 64, 1); b_ih [64] or null; hh [64]; out must
+ * not alias x or h.  Pointwise over all positions like mrb_tc2_gru. */
+int mrb_tc2_indrnn(const void* x_bh, const void* h_bh, const void* wpack, const void* b_ih, const void* hh, void* out_bh, int B,
+                   int H, int W, void* stream);
 /* Final RIM conv (rim_block.py:239-248): k x k (odd), dilation dil, replicate padding, cin -> 2 channels, no bias,
  * x [B,H,W,cin] channels-last, out [B,H,W,2] = eta + conv(x). */
 int mrb_conv_c2_nhwc_residual(const void* x, const void* w, const void* bias, const void* eta, void* out, int B,

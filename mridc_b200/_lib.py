@@ -77,6 +77,7 @@ SIGNATURES = {
     "mrb_tc2_gru_packed_bytes": (_sz, []),
     "mrb_tc2_pack_gru": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mrb_tc2_gru": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mrb_tc2_indrnn": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrb_conv_c2_nhwc_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mrb_metrics_workspace_bytes": (_sz, [_i]),
     "mrb_abs_max_normalize": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),

@@ -491,6 +491,197 @@ __global__ void bh_to_nhwc_kernel(const uint8_t* __restrict__ bh, float* __restr
     }
 }
 
+// ---- IndRNN cell on BH activations ------------------------------------------------------------------------------------
+// IndRNNCell with kernel size 1 (rnn_cells.py:264-391, the cell base_cirim_run.yaml ships): h' = ReLU(W_ih x + b + hh * h),
+// hh one recurrent weight per channel.  Same skeleton as gru2_kernel with a third of the tensor work: the x boxes feed
+// 8 MMAs per tile (x_hi x [w_hi ; w_lo], N = 128: main | cross columns; x_lo x w_hi, N = 64 onto the cross columns), the h
+// boxes are only read by the epilogue (h_prev from the TMA-landed slots), four accumulator buffers, double-buffered output
+// tile.  Pointwise over all (H+4)(W+4) positions; HBM-bound like the ConvGRU (768 B per position).
+struct Ind2Params {
+    const void* wpack;   // mrb_tc_pack_conv(ih.weight, 64, 64, 1): [hi 64 x 128 B | lo 64 x 128 B], SWIZZLE_128B
+    const float* bias;   // b_ih [64] or null
+    const float* hh;     // [64]
+    long long Q;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS2, 1)
+ind2_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_x,
+            const __grid_constant__ CUtensorMap tm_o, const Ind2Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_s = smem;                                  // [hi 64 rows | lo 64 rows] x 128 B
+    uint8_t* hring = w_s + SLOT_BYTES;                    // [2 tiles][h_hi | h_lo]
+    uint8_t* xring = hring + 4 * SLOT_BYTES;              // [2 tiles][x_hi | x_lo]
+    uint8_t* out_s = xring + 4 * SLOT_BYTES;              // [2 buffers][hi box | lo box]
+    float* bias_s = (float*)(out_s + 4 * SLOT_BYTES);     // [64] bias | [64] hh
+    uint64_t* hfull = (uint64_t*)(bias_s + 128);          // [2]
+    uint64_t* hempty = hfull + 2;                         // [2] one arrival per epilogue warp
+    uint64_t* xfull = hempty + 2;                         // [2]
+    uint64_t* xempty = xfull + 2;                         // [2] MMA commit
+    uint64_t* acc_full = xempty + 2;                      // [4]
+    uint64_t* acc_empty = acc_full + 4;                   // [4]
+    uint64_t* out_ready = acc_empty + 4;                  // [2]
+    uint64_t* out_free = out_ready + 2;                   // [2]
+    uint32_t* tmem_slot = (uint32_t*)(out_free + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&hfull[i], 1);
+            mbar_init(&hempty[i], EPI_W);
+            mbar_init(&xfull[i], 1);
+            mbar_init(&xempty[i], 1);
+            mbar_init(&out_ready[i], EPI_W);
+            mbar_init(&out_free[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], EPI_W);
+        }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 64) {
+        bias_s[threadIdx.x] = P.bias ? P.bias[threadIdx.x] : 0.f;
+        bias_s[64 + threadIdx.x] = P.hh[threadIdx.x];
+    }
+    if (warp == EPI_W + 1) tmem_alloc(tmem_slot, 512);
+    {
+        const float4* g = reinterpret_cast<const float4*>(P.wpack);
+        const uint32_t sa = smem_u32(w_s);
+        for (int i = threadIdx.x; i < SLOT_BYTES / 16; i += THREADS2) sts128(sa + 16u * (uint32_t)i, __ldg(g + i));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EPI_W) {
+        // ============================== TMA PRODUCER ==============================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int p = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait_sleep(&xempty[p], ph ^ 1, 64);
+                mbar_expect_tx(&xfull[p], 2 * SLOT_BYTES);
+                tma_load_2d(smem_u32(xring + (2 * p) * SLOT_BYTES), &tm_x, 0, tile * TILE, smem_u32(&xfull[p]));
+                tma_load_2d(smem_u32(xring + (2 * p + 1) * SLOT_BYTES), &tm_x, 64, tile * TILE, smem_u32(&xfull[p]));
+                mbar_wait_sleep(&hempty[p], ph ^ 1, 64);
+                mbar_expect_tx(&hfull[p], 2 * SLOT_BYTES);
+                tma_load_2d(smem_u32(hring + (2 * p) * SLOT_BYTES), &tm_h, 0, tile * TILE, smem_u32(&hfull[p]));
+                tma_load_2d(smem_u32(hring + (2 * p + 1) * SLOT_BYTES), &tm_h, 64, tile * TILE, smem_u32(&hfull[p]));
+            }
+        }
+    } else if (warp == EPI_W + 1) {
+        // ============================== MMA ISSUER ==============================
+        const uint32_t tmem_u = uni(tmem_base);
+        const uint64_t w_stack = make_desc(smem_u32(w_s));  // N = 128: [w_hi ; w_lo]; N = 64: w_hi
+        constexpr uint32_t id128 = make_idesc(TILE, 128), id64 = make_idesc(TILE, 64);
+        const uint32_t xs = smem_u32(xring);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int p = it & 1, buf = it & 3;
+            mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 2) & 1u) ^ 1u);
+            mbar_wait(&xfull[p], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t d = tmem_u + (uint32_t)(buf * 128);
+            const uint64_t a_hi = make_desc(xs + (uint32_t)((2 * p) * SLOT_BYTES));
+            const uint64_t a_lo = make_desc(xs + (uint32_t)((2 * p + 1) * SLOT_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d, a_hi + 2 * k, w_stack + 2 * k, id128, k > 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(d + 64, a_lo + 2 * k, w_stack + 2 * k, id64, 1);
+            umma_commit(&xempty[p]);
+            umma_commit(&acc_full[buf]);
+        }
+    } else if (warp == EPI_W + 2) {
+        // ============================== TMA STORE LANE ==============================
+        if (lane == 0) {
+            int it = 0;
+            const uint32_t out_u32 = smem_u32(out_s);
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+                const int ob = it & 1;
+                mbar_wait_sleep(&out_ready[ob], (uint32_t)(it >> 1) & 1u, 64);
+                tma_store_2d(&tm_o, out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES), 0, tile * TILE);
+                tma_store_2d(&tm_o, out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES + SLOT_BYTES), 64, tile * TILE);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(&out_free[ob]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        // ============================== EPILOGUE ==============================
+        const int quad = warp & 3, cg = warp >> 2;
+        const int m = quad * 32 + lane;
+        const uint32_t ch0 = swz(m, 2 * cg), ch1 = swz(m, 2 * cg + 1);
+        const uint32_t hring_u32 = smem_u32(hring), out_u32 = smem_u32(out_s);
+        float bs[16], hw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            bs[i] = bias_s[cg * 16 + i];
+            hw[i] = bias_s[64 + cg * 16 + i];
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+            const int p = it & 1, buf = it & 3;
+            float hp[16];
+            {
+                mbar_wait_sleep(&hfull[p], (uint32_t)(it >> 1) & 1u, 32);
+                const uint32_t hb = hring_u32 + (uint32_t)((2 * p) * SLOT_BYTES);
+                const uint4 h0 = lds128u(hb + ch0), h1 = lds128u(hb + ch1);
+                const uint4 l0 = lds128u(hb + SLOT_BYTES + ch0), l1 = lds128u(hb + SLOT_BYTES + ch1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hempty[p]);
+                const uint32_t hw_[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                const uint32_t lw_[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    hp[2 * i] = bf_lo(hw_[i]) + bf_lo(lw_[i]);
+                    hp[2 * i + 1] = bf_hi(hw_[i]) + bf_hi(lw_[i]);
+                }
+            }
+            mbar_wait_sleep(&acc_full[buf], (uint32_t)(it >> 2) & 1u, 64);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 128 + cg * 16);
+            float m0[8], m1[8], c0[8], c1[8];
+            tmem_ld8x4(t0, t0 + 8, t0 + 64, t0 + 72, m0, m1, c0, c1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // rnn_cells.py:391: ReLU(ih(x) + hh * h)
+                o[i] = fmaxf(fmaf(hw[i], hp[i], (m0[i] + c0[i]) + bs[i]), 0.f);
+                o[8 + i] = fmaxf(fmaf(hw[8 + i], hp[8 + i], (m1[i] + c1[i]) + bs[8 + i]), 0.f);
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_bf16x2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+            const int ob = it & 1;
+            mbar_wait_sleep(&out_free[ob], ((uint32_t)(it >> 1) & 1u) ^ 1u, 32);
+            const uint32_t ou = out_u32 + (uint32_t)(ob * 2 * SLOT_BYTES);
+            sts128u(ou + ch0, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128u(ou + ch1, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+            sts128u(ou + SLOT_BYTES + ch0, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            sts128u(ou + SLOT_BYTES + ch1, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&out_ready[ob]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_W + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+static size_t ind2_smem() { return 1024 + 13 * SLOT_BYTES + 128 * 4 + 24 * 8 + 16; }
+
 // ---- final RIM conv (64 -> 2, 3x3) as a tap GEMM + in-SM gather ------------------------------------------------------
 // out[y][x][o] = eta + bias[o] + sum_{tap, c} w[o][c][tap] * h[clamp(y + dy)][clamp(x + dx)][c]   (rim_block.py:239-248,
 // conv_layers.py:72-123 with ReplicationPad2d(1)).
@@ -1475,6 +1666,39 @@ extern "C" int mrb_tc2_unet_conv3x3(const void* x, long long x_bstride, const vo
         else tc2::uconv3_kernel<4><<<grid, tc2::U3_THREADS, smem_max, (cudaStream_t)stream>>>(P);
         MRB_LAUNCHED();
     }
+    return MRB_OK;
+}
+
+/* IndRNNCell, kernel size 1, 64 -> 64 (rnn_cells.py:264-391) on BH tensors: out = ReLU(W_ih x + b_ih + hh * h); wpack =
+ * mrb_tc_pack_conv(ih.weight, 64, 64, 1); hh [64]; out must not alias x or h; pointwise over all positions like mrb_tc2_gru */
+extern "C" int mrb_tc2_indrnn(const void* x_bh, const void* h_bh, const void* wpack, const void* b_ih, const void* hh,
+                              void* out_bh, int B, int H, int W, void* stream) {
+    MRB_REQUIRE(x_bh && h_bh && wpack && hh && out_bh, MRB_EINVAL, "mrb_tc2_indrnn: null pointer");
+    MRB_REQUIRE(out_bh != h_bh && out_bh != x_bh, MRB_EINVAL, "mrb_tc2_indrnn: the output must not alias an input");
+    MRB_REQUIRE(B >= 1 && H >= 1 && W >= 1, MRB_EINVAL, "mrb_tc2_indrnn: bad shape");
+    tc2::Ind2Params P;
+    P.wpack = wpack; P.bias = (const float*)b_ih; P.hh = (const float*)hh;
+    P.Q = (long long)B * (H + 2 * tc2::PADB) * (W + 2 * tc2::PADB);
+    MRB_REQUIRE(P.Q < 2147483647LL - tc2::TILE, MRB_EUNSUPPORTED, "mrb_tc2_indrnn: too many pixels");
+    P.n_tiles = (int)((P.Q + tc2::TILE - 1) / tc2::TILE);
+    CUtensorMap tm_h, tm_x, tm_o;
+    int rc = tc2::make_bh_tmap(&tm_h, h_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    rc = tc2::make_bh_tmap(&tm_x, x_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    rc = tc2::make_bh_tmap(&tm_o, out_bh, P.Q, tc2::TILE);
+    if (rc) return rc;
+    static bool attr_set = false;
+    const size_t smem = device_max_smem_optin();
+    if (!attr_set) {
+        MRB_REQUIRE(tc2::ind2_smem() <= smem, MRB_EUNSUPPORTED, "mrb_tc2_indrnn: shared memory");
+        MRB_CUDA(cudaFuncSetAttribute(tc2::ind2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = device_sm_count();
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    tc2::ind2_kernel<<<grid, tc2::THREADS2, smem, (cudaStream_t)stream>>>(tm_h, tm_x, tm_o, P);
+    MRB_LAUNCHED();
     return MRB_OK;
 }
 

@@ -81,11 +81,11 @@ class RimTcEngine:
 
     # ---------------------------------------------------------------------------------------------
     def use_bh(self, W) -> bool:
-        """BH-layout engine: ConvGRU, second conv with a receptive field inside the 2-pixel border, final conv 3x3, and
-        rows of at least 32 positions (W + 4 >= 32)."""
+        """BH-layout engine (ConvGRU and IndRNN cells): second conv with a receptive field inside the 2-pixel border, final
+        conv 3x3, and rows of at least 32 positions (W + 4 >= 32)."""
         b = self.block
         c1, f = b.layers[1].convs, b.final_layer[0]
-        return (not self._indrnn and os.environ.get("MRIDC_B200_TC_GEN1", "0") != "1" and W >= 28
+        return (os.environ.get("MRIDC_B200_TC_GEN1", "0") != "1" and W >= 28
                 and c1.dilation * (c1.kernel_size - 1) // 2 <= 2 and f.kernel_size == 3 and f.dilation == 1)
 
     @staticmethod
@@ -147,6 +147,15 @@ class RimTcEngine:
             _lib.check(lib.mrb_tc_gru_nhwc(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pack), _lib.ptr(rnn.ih.bias),
                                            _lib.ptr(h_out), B, H, W, 64, st))
 
+    def _cell_bh(self, lib, x, h, pack, rnn, h_out, B, H, W, st):
+        """The same cells on BH buffers (conv_tc2.cu: gru2_kernel / ind2_kernel)."""
+        if self._indrnn:
+            _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pack), _lib.ptr(rnn.ih.bias),
+                                          _lib.ptr(rnn.hh.detach().reshape(-1)), _lib.ptr(h_out), B, H, W, st))
+        else:
+            _lib.check(lib.mrb_tc2_gru(_lib.ptr(x), _lib.ptr(h), _lib.ptr(pack), _lib.ptr(rnn.ih.bias), _lib.ptr(h_out),
+                                       B, H, W, st))
+
     # ---------------------------------------------------------------------------------------------
     def conv_stack(self, g4, h, h_alt, xbuf, eta, packs=None):
         """One time step of the regulariser (rim_block.py:233-248) on channels-last buffers: conv5x5 -> GRU ->
@@ -192,14 +201,12 @@ class RimTcEngine:
         else:
             _lib.check(lib.mrb_tc_conv5x5x4_bh(_lib.ptr(g4), _lib.ptr(packs[0][0]), _lib.ptr(c0.conv_layer.bias),
                                                _lib.ptr(xbuf), B, H, W, 64, 1, st))
-        _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[0]), _lib.ptr(packs[0][1]), _lib.ptr(r0.ih.bias),
-                                   _lib.ptr(h_alt[0]), B, H, W, st))
+        self._cell_bh(lib, xbuf, h[0], packs[0][1], r0, h_alt[0], B, H, W, st)
         h[0], h_alt[0] = h_alt[0], h[0]
         _lib.check(lib.mrb_bh_fix_border(_lib.ptr(h[0]), B, H, W, st))  # the dilated 3x3 reads it spatially
         _lib.check(lib.mrb_tc_conv_bh(_lib.ptr(h[0]), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias), _lib.ptr(xbuf),
                                       B, H, W, 64, c1.kernel_size, c1.dilation, 1, st))
-        _lib.check(lib.mrb_tc2_gru(_lib.ptr(xbuf), _lib.ptr(h[1]), _lib.ptr(packs[1][1]), _lib.ptr(r1.ih.bias),
-                                   _lib.ptr(h_alt[1]), B, H, W, st))
+        self._cell_bh(lib, xbuf, h[1], packs[1][1], r1, h_alt[1], B, H, W, st)
         h[1], h_alt[1] = h_alt[1], h[1]
         new_eta = torch.empty_like(eta)
         if _FINAL_TC and B * (H + 4) >= 16:  # the 3-D TMA box of the tap GEMM spans 16 rows of the [B (H+4)] x (W+4) grid

@@ -259,6 +259,39 @@ def test_tc2_gru_vs_oracle(B, H, W):
     assert torch.equal(ob, ob2)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (1, 320, 320)])
+def test_tc2_indrnn_vs_oracle(B, H, W):
+    """IndRNN cell on BH activations (ind2_kernel): ReLU(W_ih x + b + hh * h), with and without bias; deterministic."""
+    from mridc_b200 import _lib
+    from oracle import nets as onets
+
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(W + 7)
+    x = torch.randn(B, 64, H, W, generator=g)
+    h = torch.randn(B, 64, H, W, generator=g)
+    wih = torch.randn(64, 64, 1, 1, generator=g) * 0.1
+    bih = torch.randn(64, generator=g)
+    hh = torch.randn(1, 64, 1, 1, generator=g) * 0.5
+    xb, _ = _bh_roundtrip(x.permute(0, 2, 3, 1).contiguous().cuda())
+    hb, _ = _bh_roundtrip(h.permute(0, 2, 3, 1).contiguous().cuda())
+    pk = _pack(0, wih.cuda().contiguous(), k=1)
+    hhd = hh.reshape(-1).cuda()
+    for bias in (bih, None):
+        ref = onets.indrnn_cell(x, h, wih, bias, hh, 1, 1)
+        bd = None if bias is None else bias.cuda()
+        ob = torch.full((lib.mrb_bh_bytes(B, H, W),), 0x7f, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(hhd), _lib.ptr(ob), B, H, W,
+                                      st))
+        out = torch.empty(B, H, W, 64, device="cuda")
+        _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(ob), _lib.ptr(out), B, H, W, st))
+        _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "indrnn (tc2)")
+        ob2 = torch.empty_like(ob)
+        _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(hhd), _lib.ptr(ob2), B, H, W,
+                                      st))
+        assert torch.equal(ob, ob2)
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 64, 32), (2, 33, 28), (1, 320, 320), (1, 12, 30)])
 def test_tc2_conv_ops_vs_oracle(B, H, W):
     """The convolutions of the time step on BH activations: conv5x5 (fp32 gradient -> BH), conv3x3 (BH -> BH, replicate

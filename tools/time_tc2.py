@@ -60,3 +60,10 @@ u_new = t(lambda: _lib.check(lib.mrb_tc2_conv5x5x4(_lib.ptr(g8), _lib.ptr(c0.con
 print("conv5x5 B=%d: gen-1 %.1f us; G8 converter %.1f us + bulk-copy kernel %.1f us (%.0f GB/s at 272 B/px)" % (B, u_old, u_cv, u_new, px * 272 / u_new / 1e3))
 u3 = t(lambda: _lib.check(lib.mrb_tc_conv_bh(_lib.ptr(hb), _lib.ptr(packs[1][0]), _lib.ptr(c1.conv_layer.bias), _lib.ptr(ob), B, H, W, 64, 3, 2, 1, st)))
 print("conv3x3 d2 B=%d: %.1f us (%.1f TFLOP/s algorithmic)" % (B, u3, px * 2 * 64 * 64 * 9 / u3 / 1e6))
+# IndRNN cell on BH activations
+wi = torch.randn(64, 64, 1, 1, device=dev) * 0.1
+pki = torch.empty(lib.mrb_tc_packed_floats(0, 64, 64, 1), device=dev)
+_lib.check(lib.mrb_tc_pack_conv(_lib.ptr(wi), _lib.ptr(pki), 64, 64, 1, st))
+bi = torch.randn(64, device=dev); hhv = torch.randn(64, device=dev)
+ui = t(lambda: _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pki), _lib.ptr(bi), _lib.ptr(hhv), _lib.ptr(ob), B, H, W, st)))
+print("tc2 indrnn B=%d: %.1f us  (%.0f GB/s at 768 B/px)" % (B, ui, px * 768 / ui / 1e3))
