@@ -336,6 +336,7 @@ gru2_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CU
                 mbar_wait_sleep(&hfull[2 * p + 1], hph, 32);
                 hl[0] = lds128u(ring_u32 + (uint32_t)((2 * p + 1) * SLOT_BYTES) + ch0);
                 hl[1] = lds128u(ring_u32 + (uint32_t)((2 * p + 1) * SLOT_BYTES) + ch1);
+                fence_proxy_async();  // the loads complete before the TMA may refill the boxes (see ind2_kernel)
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&hempty[2 * p]);
@@ -633,6 +634,10 @@ ind2_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CU
                 const uint32_t hb = hring_u32 + (uint32_t)((2 * p) * SLOT_BYTES);
                 const uint4 h0 = lds128u(hb + ch0), h1 = lds128u(hb + ch1);
                 const uint4 l0 = lds128u(hb + SLOT_BYTES + ch0), l1 = lds128u(hb + SLOT_BYTES + ch1);
+                // generic-proxy reads -> async-proxy (TMA) overwrite of the same boxes: the proxy fence makes the loads
+                // complete before the release; without it the refill of the slot overtook the last loads of a late warp
+                // (second 16-byte chunk of a few rows, about once per 800 tiles)
+                fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hempty[p]);
                 const uint32_t hw_[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
