@@ -19,6 +19,12 @@ from .sensitivity import BaseSensitivityModel  # noqa: F401
 from .qrim import (  # noqa: F401
     RescaleByMax, SignalForwardModel, expand_op, analytical_log_likelihood_gradient, qRIMBlock,
 )
+from .data_consistency import (  # noqa: F401
+    DataIDLayer, DataGDLayer, DataProxCGLayer, ConjugateGradient, DataVSLayer, DCLayer,
+)
+from .cascadenet import CascadeNetBlock  # noqa: F401
+from .recurrentvarnet import Conv2dGRU, RecurrentInit, RecurrentVarNetBlock  # noqa: F401
+from .qvarnet import qVarNetBlock  # noqa: F401
 from .models import CIRIM, VarNet, UNet, ZF, qCIRIM  # noqa: F401
 from .pipeline import HostPrefetcher  # noqa: F401
 from . import metrics  # noqa: F401

@@ -644,6 +644,126 @@ def gen_apply_mask(R):
     print("apply_mask: %d cases" % len(cases))
 
 
+def gen_consumers(R):
+    """The other consumers of the DC operator: sigmanet DC layers in the sigmanet layout
+    ([B, C, sets, H, W, 2] maps) and in DUNet's ([1, C, H, W, 2] maps, dunet.py:177-186), CascadeNetBlock,
+    RecurrentInit / RecurrentVarNetBlock, qVarNetBlock.  Reference modules run unmodified; the oracle restatement
+    (oracle/consumers.py) is checked against them."""
+    from . import consumers as oc
+
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    sd_ = [-2, -1]
+    # ---- sigmanet layers, sigmanet layout: x [B, sets, H, W, 2], y [B, C, 1, H, W, 2], smaps [B, C, sets, H, W, 2]
+    i = 0
+    for B, C, S, H, W, cen, nrm in [(2, 3, 1, 12, 10, True, "ortho"), (1, 4, 2, 9, 14, False, "backward")]:
+        x, smaps = rn(B, S, H, W, 2), rn(B, C, S, H, W, 2) * 0.5
+        mask = (torch.rand(1, 1, 1, 1, W, 1, generator=g) < 0.45).float()
+        y = rn(B, C, 1, H, W, 2) * mask
+        gd = R.dc_layers.DataGDLayer(0.7, fft_centered=cen, fft_normalization=nrm, spatial_dims=sd_)
+        vs = R.dc_layers.DataVSLayer(0.3, 0.6, fft_centered=cen, fft_normalization=nrm, spatial_dims=sd_)
+        with torch.no_grad():
+            r_gd, r_vs = gd(x, y, smaps, mask), vs(x, y, smaps, mask)
+        _close(oc.data_gd(x, y, smaps, mask, 0.7, cen, nrm, sd_), r_gd, "DataGDLayer %d" % i)
+        _close(oc.data_vs(x, y, smaps, mask, 0.3, 0.6, cen, nrm, sd_), r_vs, "DataVSLayer %d" % i)
+        case = dict(x=x, y=y, smaps=smaps, mask=mask, gd=r_gd, vs=r_vs)
+        if B == 1:  # the prox layer broadcasts x over the coil axis with expand_as: batch size 1 upstream
+            cg = R.dc_layers.DataProxCGLayer(0.5, tol=1e-6, iter=6, fft_centered=cen, fft_normalization=nrm, spatial_dims=sd_)
+            with torch.no_grad():
+                r_cg = cg(x, y, smaps, mask)
+            _close(oc.prox_cg(x, 0.5, y, smaps, mask, 1e-6, 6, cen, nrm, sd_), r_cg, "DataProxCGLayer %d" % i, rtol=1e-5, atol=1e-6)
+            case["cg"] = r_cg
+        out.update({"sig%d_%s" % (i, k): v for k, v in _np(case).items()})
+        out["sig%d_cfg" % i] = np.asarray([int(cen), ["backward", "ortho", "forward"].index(nrm)])
+        i += 1
+    out["nsig"] = np.asarray(i)
+    # ---- DUNet layout, two iterations of the gradient layer (the image becomes per-coil after the first, dunet.py:186)
+    C, H, W = 3, 10, 12
+    x, smaps = rn(1, H, W, 2), rn(1, C, H, W, 2) * 0.5
+    mask = (torch.rand(1, 1, 1, W, 1, generator=g) < 0.5).float()
+    y = rn(1, C, H, W, 2) * mask
+    gd = R.dc_layers.DataGDLayer(0.4, fft_centered=True, fft_normalization="ortho", spatial_dims=sd_)
+    vs = R.dc_layers.DataVSLayer(0.2, 0.5, fft_centered=True, fft_normalization="ortho", spatial_dims=sd_)
+    with torch.no_grad():
+        x1 = gd(x, y, smaps, mask)
+        x2 = gd(x1, y, smaps, mask)
+        v1 = vs(x, y, smaps, mask)
+    _close(oc.data_gd(oc.data_gd(x, y, smaps, mask, 0.4, True, "ortho", sd_), y, smaps, mask, 0.4, True, "ortho", sd_), x2, "GD dunet")
+    _close(oc.data_vs(x, y, smaps, mask, 0.2, 0.5, True, "ortho", sd_), v1, "VS dunet")
+    out.update({"dun_" + k: v for k, v in _np(dict(x=x, y=y, smaps=smaps, mask=mask, gd1=x1, gd2=x2, vs=v1)).items()})
+    # ---- DCLayer (single coil)
+    x, mask = rn(2, 1, 8, 10, 2), (torch.rand(2, 1, 8, 10, 1, generator=g) < 0.4).float()
+    y = rn(2, 1, 8, 10, 2) * mask
+    dl = R.dc_layers.DCLayer(0.25, fft_centered=False, fft_normalization="ortho", spatial_dims=sd_)
+    with torch.no_grad():
+        r = dl(x, y, mask)
+    _close(oc.dc_layer(x, y, mask, 0.25, False, "ortho", sd_), r, "DCLayer")
+    out.update({"dcl_" + k: v for k, v in _np(dict(x=x, y=y, mask=mask, out=r)).items()})
+    # ---- CascadeNetBlock around a two-conv regulariser
+    torch.manual_seed(5)
+    reg = torch.nn.Sequential(torch.nn.Conv2d(2, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 2, 3, padding=1))
+    i = 0
+    for no_dc, md in [(False, torch.float32), (True, torch.uint8)]:
+        y, S, _, m = small_inputs(2, 3, 12, 10, 300 + i, "1d", md)
+        pred = y + 0.1 * rn(*y.shape)
+        blk = R.ccnn_block.CascadeNetBlock(reg, True, "ortho", sd_, 1, no_dc)
+        blk.dc_weight.data.fill_(0.8)
+        with torch.no_grad():
+            r = blk(pred, y, S, m)
+            _close(oc.cascadenet_block(reg, blk.dc_weight, pred, y, S, m, True, "ortho", sd_, 1, no_dc), r, "CascadeNetBlock %d" % i)
+        out.update({"ccnn%d_%s" % (i, k): v for k, v in _np(dict(pred=pred, y=y, S=S, mask=m, out=r)).items()})
+        i += 1
+    out.update({"ccnn_w_" + k.replace(".", "_"): v.numpy() for k, v in reg.state_dict().items()})
+    # ---- RecurrentInit + two RecurrentVarNetBlock steps (hidden state carried)
+    torch.manual_seed(6)
+    init = R.recurrentvarnet.RecurrentInit(2, 8, (8, 8), (1, 2), depth=2, multiscale_depth=2).eval()
+    blk = R.recurrentvarnet.RecurrentVarNetBlock(2, 8, 2, True, "ortho", sd_, 1).eval()
+    blk.learning_rate.data.fill_(0.9)
+    y, S, _, m = small_inputs(2, 3, 12, 10, 310, "1d", torch.float32)
+    cur = y + 0.1 * rn(*y.shape)
+    with torch.no_grad():
+        img0 = R.utils.complex_mul(R.fft.ifft2(y, True, "ortho", sd_), R.utils.complex_conj(S)).sum(1).permute(0, 3, 1, 2)
+        h0 = init(img0)
+        k1, h1 = blk(cur, y, m, S, h0)
+        k2, h2 = blk(k1, y, m, S, h1)
+        k1n, h1n = blk(cur, y, m, S, None)
+    isd, bsd = init.state_dict(), blk.state_dict()
+    _close(oc.recurrent_init(isd, (1, 2), 2, 2, img0), h0, "RecurrentInit")
+    o1, oh1 = oc.recurrentvarnet_block(bsd, 2, 8, cur, y, m, S, h0, True, "ortho", sd_)
+    o2, oh2 = oc.recurrentvarnet_block(bsd, 2, 8, o1, y, m, S, oh1, True, "ortho", sd_)
+    _close(o2, k2, "RecurrentVarNetBlock k-space", rtol=1e-5, atol=1e-6)
+    _close(oh2, h2, "RecurrentVarNetBlock state", rtol=1e-5, atol=1e-6)
+    out.update({"rvn_" + k: v for k, v in _np(dict(y=y, S=S, mask=m, cur=cur, img0=img0, h0=h0, k1=k1, h1=h1, k2=k2, h2=h2,
+                                                  k1n=k1n, h1n=h1n)).items()})
+    out.update({"rvn_init_" + k.replace(".", "_"): v.numpy() for k, v in isd.items()})
+    out.update({"rvn_blk_" + k.replace(".", "_"): v.numpy() for k, v in bsd.items()})
+    # ---- qVarNetBlock (batch 1, 4 echoes, coil_dim 2) around a NormUnet(8 -> 8 channels)
+    torch.manual_seed(7)
+    E, C, H, W = 4, 3, 16, 12
+    unet = R.unet_block.NormUnet(chans=4, num_pools=2, in_chans=2 * E, out_chans=2 * E, padding_size=3, normalize=True)
+    qb = R.qvn_block.qVarNetBlock(unet, True, "ortho", sd_, 2, False).eval()
+    qb.dc_weight.data.fill_(0.7)
+    maps = [rn(1, H, W).abs() * s for s in (30.0, 1.0, 10.0, 0.5)]
+    maps[0][0, :2] = -1.0  # negative R2* estimates are clipped on the way out (:156-158)
+    S = rn(1, C, H, W, 2) * 0.5
+    sm = (torch.rand(1, 1, 1, H, W, 1, generator=g) < 0.4).float()
+    yq = rn(1, E, C, H, W, 2) * sm
+    TEs = [3.0, 11.5, 20.0, 28.5]
+    gamma = torch.tensor([150.0, 150.0, 1000.0, 150.0])
+    with torch.no_grad():
+        r = qb(yq.clone(), yq, *[m_ / gamma[j] for j, m_ in enumerate(maps)], TEs, S, sm, gamma)
+        o = oc.qvarnet_block({k[len("model."):]: v for k, v in qb.state_dict().items() if k.startswith("model.")},
+                             dict(num_pools=2, padding_size=3, normalize=True), qb.dc_weight, yq,
+                             *[m_ / gamma[j] for j, m_ in enumerate(maps)], TEs, S, sm, gamma, True, "ortho", sd_, 2)
+    _close(o, r, "qVarNetBlock", rtol=1e-5, atol=1e-6)
+    out.update({"qvn_" + k: v for k, v in _np(dict(y=yq, S=S, mask=sm, gamma=gamma, R2=maps[0] / gamma[0], S0=maps[1] / gamma[1],
+                                                  B0=maps[2] / gamma[2], phi=maps[3] / gamma[3], out=r)).items()})
+    out.update({"qvn_w_" + k.replace(".", "_"): v.numpy() for k, v in qb.state_dict().items()})
+    np.savez_compressed(os.path.join(GOLDEN, "consumers.npz"), **out)
+    print("consumers.npz: %d arrays" % len(out))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
@@ -652,7 +772,7 @@ def main():
     for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("rim3d", gen_rim3d),
                      ("unet", gen_unet),
                      ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens),
-                     ("apply_mask", gen_apply_mask)):
+                     ("apply_mask", gen_apply_mask), ("consumers", gen_consumers)):
         if not only or name in only:
             fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))

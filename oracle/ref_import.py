@@ -28,6 +28,10 @@ _PKGS = [
     "mridc.collections.quantitative",
     "mridc.collections.quantitative.models",
     "mridc.collections.quantitative.models.qrim",
+    "mridc.collections.reconstruction.models.sigmanet",
+    "mridc.collections.reconstruction.models.cascadenet",
+    "mridc.collections.reconstruction.models.recurrentvarnet",
+    "mridc.collections.quantitative.models.qvarnet",
 ]
 
 
@@ -86,6 +90,23 @@ class Ref:
         self.unet_block = ref("reconstruction.models.unet_base.unet_block")
         self.qrim_utils = ref("quantitative.models.qrim.utils")
         self.qrim_block = ref("quantitative.models.qrim.qrim_block")
+
+    # the other consumers of the DC operator, imported on first use
+    @property
+    def dc_layers(self):
+        return ref("reconstruction.models.sigmanet.dc_layers")
+
+    @property
+    def ccnn_block(self):
+        return ref("reconstruction.models.cascadenet.ccnn_block")
+
+    @property
+    def recurrentvarnet(self):
+        return ref("reconstruction.models.recurrentvarnet.recurrentvarnet")
+
+    @property
+    def qvn_block(self):
+        return ref("quantitative.models.qvarnet.qvn_block")
 
 
 def ref_class_from_source(rel_path: str, class_name: str, namespace: dict):
