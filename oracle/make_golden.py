@@ -764,6 +764,67 @@ def gen_consumers(R):
     print("consumers.npz: %d arrays" % len(out))
 
 
+TRANSFORM_CASES = [
+    # name, ctor keyword arguments (mask functions by name), extra inputs
+    ("sense_norm", dict(coil_combination_method="SENSE", mask_func=["equi"], normalize_inputs=True, fft_centered=True,
+                        fft_normalization="ortho", coil_dim=1), {}),
+    ("rss_crop", dict(coil_combination_method="RSS", mask_func=["rand", "equi"], crop_size=(10, 8), normalize_inputs=False,
+                      fft_centered=False, fft_normalization="backward", coil_dim=1), {}),
+    # cropping after masking needs a 2-D mask upstream (center_crop of the squeezed mask, :524): a precomputed one
+    ("kcrop_after", dict(coil_combination_method="SENSE", mask_func=None, crop_size=(12, 10), kspace_crop=True,
+                         crop_before_masking=False, normalize_inputs=True, fft_centered=True, fft_normalization="backward",
+                         coil_dim=1), {"eta": True, "mask": True}),
+    # a tuple of mask functions takes the single-mask branch (:485-496)
+    ("single_func", dict(coil_combination_method="SENSE", mask_func=("equi",), crop_size=(12, 10), kspace_crop=False,
+                         normalize_inputs=True, fft_centered=True, fft_normalization="ortho", coil_dim=1), {"eta": True}),
+    ("zero_fill_full", dict(coil_combination_method="SENSE", mask_func=None, kspace_zero_filling_size=(20, 18),
+                            normalize_inputs=True, fft_centered=True, fft_normalization="ortho", coil_dim=1), {}),
+    ("given_mask", dict(coil_combination_method="SENSE", mask_func=None, shift_mask=True, normalize_inputs=True,
+                        fft_centered=False, fft_normalization="forward", coil_dim=1), {"mask": True}),
+    ("none_norm", dict(coil_combination_method="RSS", mask_func=["equi"], normalize_inputs=True, fft_centered=False,
+                       fft_normalization="none", coil_dim=1), {}),
+]
+
+
+def transform_inputs(seed, C=4, H=16, W=14):
+    rng = np.random.RandomState(seed)
+    k = (rng.randn(C, H, W) + 1j * rng.randn(C, H, W)).astype(np.complex64)
+    S = (rng.randn(C, H, W) + 1j * rng.randn(C, H, W)).astype(np.complex64) * 0.5
+    eta = (rng.randn(H, W) + 1j * rng.randn(H, W)).astype(np.complex64)
+    m = (rng.rand(H, W) < 0.4).astype(np.float32)
+    return k, S, eta, m
+
+
+def gen_transforms(R):
+    """MRIDataTransforms (reconstruction/parts/transforms.py:155-619) run unmodified on small slices: every output of the
+    9-tuple is stored.  Mask functions are the reference's; the product is fed the bit-identical restatements."""
+    sub = R.subsample
+    mk = {"equi": lambda: sub.Equispaced1DMaskFunc([0.08], [4]), "rand": lambda: sub.RandomMaskFunc([0.1], [3])}
+    out = {}
+    for idx, (name, kw, extra) in enumerate(TRANSFORM_CASES):
+        kw = dict(kw)
+        if kw.get("mask_func"):
+            kw["mask_func"] = type(kw["mask_func"])(mk[n]() for n in kw["mask_func"])
+        tr = R.transforms.MRIDataTransforms(**kw)
+        k, S, eta, m = transform_inputs(500 + idx)
+        res = tr(k, S, [m] if extra.get("mask") else None, eta if extra.get("eta") else None, None, {}, "file%d.h5" % idx, 3)
+        kspace, masked, sens, mask, eta_o, target, fname, sl, acc = res
+        d = dict(kspace=kspace, sens=sens, target=target)
+        if isinstance(masked, list):
+            for j, (y_, m_) in enumerate(zip(masked, mask)):
+                d["masked%d" % j], d["mask%d" % j] = y_, m_
+            d["acc"] = np.asarray([float(a) for a in acc])
+        else:
+            d["masked0"], d["mask0"] = masked, mask
+            d["acc"] = np.asarray([float(torch.as_tensor(acc).reshape(-1)[0])])
+        if extra.get("eta"):
+            d["eta"] = eta_o
+        out.update({"tr%d_%s" % (idx, k_): v for k_, v in _np(d).items()})
+        assert fname == "file%d.h5" % idx and sl == 3
+    np.savez_compressed(os.path.join(GOLDEN, "transforms.npz"), **out)
+    print("transforms.npz: %d arrays" % len(out))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
@@ -772,7 +833,7 @@ def main():
     for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("rim3d", gen_rim3d),
                      ("unet", gen_unet),
                      ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens),
-                     ("apply_mask", gen_apply_mask), ("consumers", gen_consumers)):
+                     ("apply_mask", gen_apply_mask), ("consumers", gen_consumers), ("transforms", gen_transforms)):
         if not only or name in only:
             fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))

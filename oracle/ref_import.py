@@ -32,6 +32,7 @@ _PKGS = [
     "mridc.collections.reconstruction.models.cascadenet",
     "mridc.collections.reconstruction.models.recurrentvarnet",
     "mridc.collections.quantitative.models.qvarnet",
+    "mridc.collections.reconstruction.parts",
 ]
 
 
@@ -103,6 +104,10 @@ class Ref:
     @property
     def recurrentvarnet(self):
         return ref("reconstruction.models.recurrentvarnet.recurrentvarnet")
+
+    @property
+    def transforms(self):
+        return ref("reconstruction.parts.transforms")
 
     @property
     def qvn_block(self):
