@@ -24,7 +24,7 @@ def _enabled():
 _CONV5_G8 = os.environ.get("MRIDC_B200_CONV5_GEN1", "0") != "1"  # =1: first conv on the gen-1 loader-warp kernel (conv_tc.cu)
 _FINAL_TC = os.environ.get("MRIDC_B200_FINAL_FP32", "0") != "1"  # =1: exact-fp32 CUDA-core final conv (conv.cu)
 _ZERO_STATE = {}
-_YH_STATIC = {}      # (B, C, H, W, device) -> [static hybrid k-space buffer, id of the tensor last copied into it]
+_YH_STATIC = {}      # (B, C, H, W, device) -> [static hybrid k-space buffer, version of the tensor last copied into it]
 _GRAPH_POOL = {}     # device -> CUDA-graph memory pool shared by all cascades (they replay one after the other)
 
 
@@ -305,10 +305,12 @@ class RimTcEngine:
             ent = _YH_STATIC.get(ykey)
             if ent is None:
                 ent = _YH_STATIC[ykey] = [torch.empty_like(y_hybrid), None]
-            tag = (y_hybrid.data_ptr(), y_hybrid._version, id(y_hybrid))
-            if ent[1] != tag:  # once per forward: the five cascades share one hybrid k-space tensor
+            # once per forward: the cascades share ONE hybrid k-space tensor object, which is marked after the copy.  (An
+            # (address, version, id) tag is not enough: the next forward's tensor can reuse all three.)
+            if getattr(y_hybrid, "_mrb_static_copy", None) is not ent[0] or y_hybrid._version != ent[1]:
                 ent[0].copy_(y_hybrid)
-                ent[1] = tag
+                y_hybrid._mrb_static_copy = ent[0]
+                ent[1] = y_hybrid._version
             yh = ent[0]
             pkey = tuple((p.data_ptr(), p._version) for p in self._params())
             gkey = (masked_kspace.data_ptr(), sense.data_ptr(), mask_can.data_ptr(), tuple(masked_kspace.shape),
