@@ -133,5 +133,5 @@ def test_device_transforms_feed_cirim_full_size():
     assert y.is_cuda and m.dtype == torch.uint8 and float(target.max()) == 1.0
     assert float((y * (1 - m.float())).abs().max()) < 1e-5 * float(y.abs().max())
     model = mb.CIRIM(synth.cirim_cfg(num_cascades=1, centered=True, normalization="ortho")).cuda()
-    out = list(model.forward(y.unsqueeze(0), sens.unsqueeze(0), m.unsqueeze(0), None, target.unsqueeze(0)))
-    assert torch.isfinite(torch.view_as_real(out[-1][-1])).all()
+    out = next(model.forward(y.unsqueeze(0), sens.unsqueeze(0), m.unsqueeze(0), None, target.unsqueeze(0)))
+    assert out[-1][-1].shape == (1, H, W) and torch.isfinite(torch.view_as_real(out[-1][-1])).all()
