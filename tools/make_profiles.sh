@@ -14,3 +14,9 @@ ncu -i gpurun_out/${R}_hot.ncu-rep --page raw --csv > gpurun_out/${R}_hot_raw.cs
 # (3) the real bench line, outside any profiler
 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 tail -c 600 gpurun_out/${R}_bench.json
+# (4) the IndRNN cell on BH activations (the cell base_cirim_run.yaml ships): one full capture + the tool's own timing
+ncu --set full --clock-control none --import-source on -k regex:"ind2_kernel" -s 5 -c 1 -o gpurun_out/${R}_ind2 \
+    python tools/time_tc2.py > gpurun_out/${R}_ind2.log 2>&1
+ncu -i gpurun_out/${R}_ind2.ncu-rep --page raw --csv > gpurun_out/${R}_ind2_raw.csv 2>/dev/null
+python tools/time_tc2.py > gpurun_out/${R}_time_tc2.log 2>&1
+tail -6 gpurun_out/${R}_time_tc2.log
