@@ -252,11 +252,12 @@ def test_tc2_gru_vs_oracle(B, H, W):
     inner = rawo[:, 2:-2, 2:-2]
     pad = torch.nn.functional.pad(inner.permute(0, 3, 1, 2), (2, 2, 2, 2), mode="replicate").permute(0, 2, 3, 1)
     assert torch.equal(pad, rawo)  # the replicate border of the output is complete and exact
-    # run-to-run determinism
-    ob2 = torch.empty_like(ob)
-    _lib.check(lib.mrb_tc2_gru(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(ob2), B, H, W, st))
-    _lib.check(lib.mrb_bh_fix_border(_lib.ptr(ob2), B, H, W, st))
-    assert torch.equal(ob, ob2)
+    # run-to-run determinism (eight launches at the full size, see the IndRNN twin below)
+    for rep in range(8 if H >= 320 else 2):
+        ob2 = torch.full_like(ob, 0x11 if rep % 2 else 0x7f)
+        _lib.check(lib.mrb_tc2_gru(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(ob2), B, H, W, st))
+        _lib.check(lib.mrb_bh_fix_border(_lib.ptr(ob2), B, H, W, st))
+        assert torch.equal(ob, ob2), rep
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 37, 45), (1, 320, 320)])
@@ -286,10 +287,13 @@ def test_tc2_indrnn_vs_oracle(B, H, W):
         out = torch.empty(B, H, W, 64, device="cuda")
         _lib.check(lib.mrb_bh_to_nhwc(_lib.ptr(ob), _lib.ptr(out), B, H, W, st))
         _diag(out.permute(0, 3, 1, 2), ref, 1e-5, "indrnn (tc2)")
-        ob2 = torch.empty_like(ob)
-        _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(hhd), _lib.ptr(ob2), B, H, W,
-                                      st))
-        assert torch.equal(ob, ob2)
+        # bit-reproducible run to run: eight launches (the refill of an h box once overtook the epilogue's last loads of it,
+        # about one tile in 800 -- DESIGN 4.3)
+        for rep in range(8 if H >= 320 else 2):
+            ob2 = torch.full_like(ob, 0x11 if rep % 2 else 0x7f)
+            _lib.check(lib.mrb_tc2_indrnn(_lib.ptr(xb), _lib.ptr(hb), _lib.ptr(pk), _lib.ptr(bd), _lib.ptr(hhd), _lib.ptr(ob2), B, H,
+                                          W, st))
+            assert torch.equal(ob, ob2), rep
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 37, 45), (1, 64, 32), (2, 33, 28), (1, 320, 320), (1, 12, 30)])

@@ -11,6 +11,13 @@ run() { # name tool args...
   tail -2 gpurun_out/sanitizer/${name}.out >> gpurun_out/sanitizer/${name}.log
   echo "== $name"; cat gpurun_out/sanitizer/${name}.log
 }
+ONLY=${1:-}   # optional substring filter on the run name (e.g. `indrnn`)
+_run() { run "$@"; }
+run_if() { case "$1" in *"$ONLY"*) _run "$@";; esac; }
+run_if memcheck_indrnn_b2 memcheck python tools/sanitize_run.py 2 320 indrnn
+run_if synccheck_indrnn_b1 synccheck python tools/sanitize_run.py 1 64 indrnn
+run_if racecheck_indrnn_b1_64x320 racecheck python tools/sanitize_run.py 1 64 indrnn
+[ -n "$ONLY" ] && exit 0
 run memcheck_cirim_b2 memcheck python tools/sanitize_run.py 2 320 cirim
 run memcheck_e2evn_b2 memcheck python tools/sanitize_run.py 2 320 vn
 # initcheck is 100x+ slower than the others: run it alone with a longer limit if needed
