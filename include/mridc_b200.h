@@ -333,7 +333,8 @@ int mrb_qrim_eta_update(void* eta, int eta_channels, int eta_offset, const void*
                         long long HW, void* stream);
 /* RescaleByMax.reverse (qrim/utils.py:25-28): out[b] = x[b] * scales[b], or |x[b]| * scales[b] when take_abs
  * (qcirim.py:287-289 applies it to torch.abs(pred)); the reference indexes its 4 regularisation factors by BATCH
- * index, so B <= 4.  scales: host pointer, B floats. */
+ * index (four in every shipped config), so one call takes B <= 4; longer batches are chunked by the caller.  scales:
+ * host pointer, B floats. */
 int mrb_scale_batch(const void* x, void* out, int B, long long per_batch, const float* scales, int take_abs,
                     void* stream);
 

@@ -66,13 +66,13 @@ class RescaleByMax:
         B = data.shape[0]
         if B > len(gamma):
             raise IndexError("index %d is out of bounds for dimension 0 with size %d" % (len(gamma), len(gamma)))
-        if B > 4:
-            raise NotImplementedError("mridc_b200: RescaleByMax.reverse supports batch <= 4")
         data = data.contiguous()
         out = torch.empty_like(data)
-        scales = _c_floats([float(gamma[i]) for i in range(B)])
-        _lib.check(_lib.load().mrb_scale_batch(_lib.ptr(data), _lib.ptr(out), B, data[0].numel() if B else 0, scales,
-                                               int(_take_abs), _lib.stream_ptr()))
+        for b0 in range(0, B, 4):  # the entry point takes up to four per-sample factors by value
+            nb = min(4, B - b0)
+            scales = _c_floats([float(gamma[b0 + i]) for i in range(nb)])
+            _lib.check(_lib.load().mrb_scale_batch(_lib.ptr(data[b0:]), _lib.ptr(out[b0:]), nb, data[0].numel(), scales,
+                                                   int(_take_abs), _lib.stream_ptr()))
         return out
 
     @staticmethod

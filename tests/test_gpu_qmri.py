@@ -69,6 +69,9 @@ def test_signal_model_api_and_errors():
     assert torch.equal(r.cpu(), torch.stack([x.cpu()[i] * torch.tensor(QGAMMA)[i] for i in range(2)], 0))
     with pytest.raises(IndexError):
         mb.RescaleByMax.reverse(torch.randn(5, 4, 3, 3).cuda(), torch.tensor(QGAMMA))
+    g6 = torch.tensor([2.0, 3.0, 5.0, 7.0, 11.0, 13.0])  # more factors than the four the entry point takes per call
+    x = torch.randn(6, 4, 3, 3).cuda()
+    assert torch.equal(mb.RescaleByMax.reverse(x, g6).cpu(), torch.stack([x.cpu()[i] * g6[i] for i in range(6)], 0))
 
 
 @pytest.mark.parametrize("B,E,C,H,W,mk", [(1, 2, 1, 4, 3, "2d"), (2, 4, 3, 17, 13, "2db"), (3, 2, 5, 16, 24, "1d"),
