@@ -279,6 +279,25 @@ def run_extras(model, d, dev, e0, e1):
                                       "(BASELINE.json configs[3], one GPU's share of the batch)",
                           "dc_gradient": {"ms": dcb_ms, "algorithmic_bytes": bytes_b, "achieved_gbs": bytes_b / dcb_ms / 1e6,
                                           "frac": bytes_b / dcb_ms / 1e6 / peaks["hbm_gbs"]}}
+    # ---- configs[3]: E2EVN on the same brain-shaped slices ----
+    torch.manual_seed(1)
+    vnb = mb.VarNet(synth.varnet_cfg()).eval().to(dev)
+    msvb = timed(lambda: vnb(gb["y"], gb["sensitivity_maps"], gb["mask"], None, gb["target"]), 5, 2)
+    out["brain_e2evn"] = {"metric": "e2evn_640x320x16coil_slices_per_sec", "value": Bb / msvb * 1e3, "unit": "slices/s",
+                          "slices_per_step": Bb,
+                          "workload": "E2EVN 12 cascades, 16-coil 640x320 brain-shaped slices, 8x equispaced mask "
+                                      "(BASELINE.json configs[3], one GPU's share of the batch)"}
+    del vnb, gb
+    # ---- the IndRNN variant of the headline network (the cell base_cirim_run.yaml ships) ----
+    torch.manual_seed(1)
+    mi = mb.CIRIM(synth.cirim_cfg("IndRNN")).eval().to(dev)
+    Bi = min(16, d["y"].shape[0])
+    di = {k: (d[k][:Bi].contiguous() if d[k].shape[0] > 1 else d[k]) for k in ("y", "sensitivity_maps", "mask", "target")}
+    msi = timed(lambda: next(mi(di["y"], di["sensitivity_maps"], di["mask"], None, di["target"]))[-1][-1], 5, 2)
+    out["cirim_indrnn"] = {"metric": "cirim_indrnn_320x320x15coil_slices_per_sec", "value": Bi / msi * 1e3, "unit": "slices/s",
+                           "slices_per_step": Bi,
+                           "workload": "CIRIM 5x8 with IndRNN cells (base_cirim_run.yaml), 15x320x320, same inputs as the "
+                                       "headline"}
     return out
 
 
