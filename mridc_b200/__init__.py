@@ -25,6 +25,7 @@ from .data_consistency import (  # noqa: F401
 from .cascadenet import CascadeNetBlock  # noqa: F401
 from .recurrentvarnet import Conv2dGRU, RecurrentInit, RecurrentVarNetBlock  # noqa: F401
 from .qvarnet import qVarNetBlock  # noqa: F401
+from .jrscirim import JRSCIRIMBlock  # noqa: F401
 from .models import CIRIM, VarNet, UNet, ZF, qCIRIM  # noqa: F401
 from .pipeline import HostPrefetcher  # noqa: F401
 from .transforms import MRIDataTransforms, assemble_reconstructions, save_reconstructions  # noqa: F401

@@ -6,6 +6,7 @@ functionally on PyTorch-CPU.
   conv2dgru / recurrent_init /
   recurrentvarnet_block                    .../recurrentvarnet/conv2gru.py:119-163, recurrentvarnet.py:89-109,:176-240
   qvarnet_block                            mridc/collections/quantitative/models/qvarnet/qvn_block.py:103-160
+  jrscirim_block                           mridc/collections/segmentation/models/jrscirim_base/jrscirim_block.py:200-377
 
 Pinned by oracle/make_golden.py::gen_consumers against the unmodified reference modules (tests/golden/consumers.npz).
 Not imported by the product package.
@@ -16,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import mri
-from .nets import norm_unet
+from .nets import conv_nonlinear, norm_unet, rim_block, unet
 from .qnets import megre_signal
 
 
@@ -178,3 +179,60 @@ def qvarnet_block(model_sd, unet_hp, dc_weight, masked_kspace, R2, S0, B0, phi, 
     e0[e0 < 0] = 0
     eta[:, 0, ...] = e0
     return eta
+
+
+def jrscirim_block(sd, rim_hp, num_cascades, keep_eta, seg_kind, seg_hp, input_channels, magnitude_input, consecutive_slices,
+                   y, sens, mask, init_pred, target, normalize_output=True):
+    """JRSCIRIMBlock.forward, jrscirim_block.py:200-333, for no_dc reconstruction modules of dimensionality 2.
+    ``sd``: reconstruction_module.<i>.* + segmentation_module.*; returns (list[cascades][time steps] of complex images,
+    segmentation)."""
+
+    def cascades(y_, S_, m_, init_, tgt_, hx):
+        pred, out = y_.clone(), []
+        for i in range(num_cascades):
+            bsd = {k[len("reconstruction_module.%d." % i):]: v for k, v in sd.items()
+                   if k.startswith("reconstruction_module.%d." % i)}
+            pred, hx = rim_block(bsd, rim_hp, pred, y_, S_, m_, init_, hx, 1.0, keep_eta=False if i == 0 else keep_eta)
+            steps = []
+            for p in pred:  # process_intermediate_pred (:335-377) with no_dc: view + crop to the target
+                p = torch.view_as_complex(p)
+                t = torch.view_as_complex(tgt_) if tgt_.shape[-1] == 2 else tgt_
+                steps.append(mri.center_crop_to_smallest(t, p)[1])
+            out.append(steps)
+        return out, hx
+
+    hx = None
+    if consecutive_slices > 1:
+        per_slice = []
+        for s_ in range(consecutive_slices):
+            init_s = init_pred[:, s_, ...]
+            cas, hx = cascades(y[:, s_, ...], sens[:, s_, ...], mask[:, 0, ...], None if init_s.dim() < 4 else init_s,
+                               target[:, s_, ...], hx)
+            per_slice.append(torch.stack([torch.stack(c, 0) for c in cas], 0))
+        preds = torch.stack(per_slice, dim=3)
+        etas = [[preds[c, t] for t in range(preds.shape[1])] for c in range(preds.shape[0])]
+    else:
+        etas, hx = cascades(y, sens, mask, None if init_pred is None or init_pred.dim() < 4 else init_pred, target, hx)
+    x = etas[-1][-1]
+    if x.shape[-1] != 2:
+        x = torch.view_as_real(x)
+    if consecutive_slices > 1 and x.dim() == 5:
+        x = x.reshape(x.shape[0] * x.shape[1], *x.shape[2:])
+    if input_channels == 1:
+        x = torch.view_as_complex(x).unsqueeze(1)
+        if magnitude_input:
+            x = torch.abs(x)
+    else:
+        x = x.permute(0, 3, 1, 2)
+    x = F.group_norm(x, num_groups=1)
+    seg_sd = {k[len("segmentation_module."):]: v for k, v in sd.items() if k.startswith("segmentation_module.")}
+    if seg_kind == "unet":
+        seg = unet(x, seg_sd, seg_hp["pooling_layers"])
+    else:
+        seg = conv_nonlinear(x, seg_sd["0.conv_layer.weight"], None, 3, 1, None)
+    seg = torch.abs(seg)
+    if normalize_output:
+        seg = seg / torch.max(seg)
+    if consecutive_slices > 1:
+        seg = seg.view([y.shape[0], y.shape[1], *seg.shape[1:]])
+    return etas, seg

@@ -825,6 +825,61 @@ def gen_transforms(R):
     print("transforms.npz: %d arrays" % len(out))
 
 
+JRS_RIM = dict(recurrent_layer="GRU", conv_filters=[8, 8, 2], conv_kernels=[5, 3, 3], conv_dilations=[1, 2, 1],
+               conv_bias=[True, True, False], recurrent_filters=[8, 8, 0], recurrent_kernels=[1, 1, 0],
+               recurrent_dilations=[1, 1, 0], recurrent_bias=[True, True, False], depth=2, time_steps=8, conv_dim=2,
+               num_cascades=2, no_dc=True, keep_eta=True, dimensionality=2, pretrained=False, accumulate_estimates=True)
+JRS_CASES = [
+    # name, segmentation params, input channels, magnitude input, consecutive slices
+    ("unet_mag", dict(segmentation_module="UNet", output_channels=3, channels=4, pooling_layers=2, dropout=0.0), 1, True, 1),
+    ("conv_cplx", dict(segmentation_module="ConvLayer", output_channels=2, conv_dim=2), 2, False, 1),
+    ("unet_slices", dict(segmentation_module="UNet", output_channels=2, channels=4, pooling_layers=1, dropout=0.0), 1, True, 2),
+]
+
+
+def jrs_inputs(idx, slices):
+    g = torch.Generator().manual_seed(900 + idx)
+    B, C, H, W = 2, 3, 16, 12
+    lead = (B, slices) if slices > 1 else (B,)
+    y = torch.randn(*lead, C, H, W, 2, generator=g)
+    S = torch.randn(*lead, C, H, W, 2, generator=g) * 0.5
+    m = (torch.rand(1, 1, 1, W, 1, generator=g) < 0.45).float()
+    m[..., W // 2, :] = 1
+    m = m.reshape(1, 1, 1, 1, W, 1) if slices > 1 else m
+    y = y * m
+    init = torch.randn(*lead, H, W, 2, generator=g)
+    target = torch.randn(*lead, H, W, 2, generator=g)
+    return y, S, m, init, target
+
+
+def gen_jrscirim(R):
+    """JRSCIRIMBlock (segmentation/models/jrscirim_base/jrscirim_block.py) run unmodified: CIRIM cascades + UNet / ConvLayer
+    segmentation heads, single slices and the per-slice loop of consecutive_slices = 2."""
+    from . import consumers as oc
+
+    out = {}
+    for idx, (name, sp, in_ch, mag, slices) in enumerate(JRS_CASES):
+        torch.manual_seed(40 + idx)
+        blk = R.jrscirim_block.JRSCIRIMBlock(dict(JRS_RIM), dict(sp), in_ch, mag, True, "ortho", [-2, -1], 2, 2, slices,
+                                             "SENSE", True).eval()
+        y, S, m, init, target = jrs_inputs(idx, slices)
+        use_init = idx == 1  # one case starts every cascade from a given image (rim_block.py:195)
+        no_init = torch.zeros(2, slices) if slices > 1 else torch.zeros(1)  # < 4-D: ignored (:243-247, :277-281)
+        with torch.no_grad():
+            rec, seg, _ = blk(y, S, m, init if use_init else no_init, target)
+            hp = dict(JRS_RIM, fft_centered=True, fft_normalization="ortho", spatial_dims=[-2, -1], coil_dim=1)
+            orec, oseg = oc.jrscirim_block(blk.state_dict(), hp, 2, True, "unet" if "UNet" in sp["segmentation_module"] else "conv",
+                                           sp, in_ch, mag, slices, y, S, m, init if use_init else no_init, target)
+        _close(torch.stack([torch.stack(c) for c in orec]), torch.stack([torch.stack(c) for c in rec]), "JRSCIRIM rec " + name,
+               rtol=1e-5, atol=1e-6)
+        _close(oseg, seg, "JRSCIRIM seg " + name, rtol=1e-4, atol=1e-5)
+        d = dict(y=y, S=S, mask=m, init=init, target=target, rec=torch.stack([torch.stack(c) for c in rec]), seg=seg)
+        out.update({"jrs%d_%s" % (idx, k): v for k, v in _np(d).items()})
+        out.update({"jrs%d_w_%s" % (idx, k.replace(".", "_")): v.numpy() for k, v in blk.state_dict().items()})
+    np.savez_compressed(os.path.join(GOLDEN, "jrscirim.npz"), **out)
+    print("jrscirim.npz: %d arrays" % len(out))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(GOLDEN, exist_ok=True)
@@ -833,7 +888,8 @@ def main():
     for name, fn in (("masks", gen_masks), ("prims", gen_prims), ("dc", gen_dc), ("rim", gen_rim), ("rim3d", gen_rim3d),
                      ("unet", gen_unet),
                      ("models", gen_models), ("qmri", gen_qmri), ("poisson", gen_poisson), ("sens", gen_sens),
-                     ("apply_mask", gen_apply_mask), ("consumers", gen_consumers), ("transforms", gen_transforms)):
+                     ("apply_mask", gen_apply_mask), ("consumers", gen_consumers), ("transforms", gen_transforms),
+                     ("jrscirim", gen_jrscirim)):
         if not only or name in only:
             fn(R)
     tot = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))

@@ -33,6 +33,12 @@ _PKGS = [
     "mridc.collections.reconstruction.models.recurrentvarnet",
     "mridc.collections.quantitative.models.qvarnet",
     "mridc.collections.reconstruction.parts",
+    "mridc.collections.segmentation",
+    "mridc.collections.segmentation.models",
+    "mridc.collections.segmentation.models.jrscirim_base",
+    "mridc.collections.segmentation.models.attention_unet_base",
+    "mridc.collections.segmentation.models.lambda_unet_base",
+    "mridc.collections.segmentation.models.vnet_base",
 ]
 
 
@@ -104,6 +110,10 @@ class Ref:
     @property
     def recurrentvarnet(self):
         return ref("reconstruction.models.recurrentvarnet.recurrentvarnet")
+
+    @property
+    def jrscirim_block(self):
+        return ref("segmentation.models.jrscirim_base.jrscirim_block")
 
     @property
     def transforms(self):

@@ -206,3 +206,26 @@ def test_initialisers_follow_the_reference_rng_order():
     torch.manual_seed(12)
     b = mb.RecurrentInit(2, 8, (8, 8, 16), (1, 2, 4), depth=3, multiscale_depth=2).state_dict()
     assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_oracle_jrscirim_golden(golden):
+    """JRSCIRIMBlock restatement (CIRIM cascades + segmentation head) against the reference's own outputs."""
+    from oracle.make_golden import JRS_CASES, JRS_RIM
+
+    g = golden("jrscirim")
+    hp = dict(JRS_RIM, fft_centered=True, fft_normalization="ortho", spatial_dims=SD, coil_dim=1)
+    for idx, (name, sp, in_ch, mag, slices) in enumerate(JRS_CASES):
+        p = "jrs%d_" % idx
+        y, S, m, init, target = (T(g[p + k]) for k in ("y", "S", "mask", "init", "target"))
+        sd = {k[len(p + "w_"):]: T(v) for k, v in g.items() if k.startswith(p + "w_")}
+        # stored keys have '.' replaced by '_': rebuild the dotted names from a reference-shaped module
+        import mridc_b200 as mb
+        blk = mb.JRSCIRIMBlock(dict(JRS_RIM), dict(sp), in_ch, mag, True, "ortho", SD, 2, 2, slices, "SENSE", True)
+        sd = {k: sd[k.replace(".", "_")] for k in blk.state_dict().keys()}
+        no_init = torch.zeros(2, slices) if slices > 1 else torch.zeros(1)
+        with torch.no_grad():
+            rec, seg = oc.jrscirim_block(sd, hp, 2, True, "unet" if "UNet" in sp["segmentation_module"] else "conv", sp, in_ch,
+                                         mag, slices, y, S, m, init if idx == 1 else no_init, target)
+        rec = torch.view_as_real(torch.stack([torch.stack(c) for c in rec]))
+        assert rel_l2(rec, g[p + "rec"]) < 1e-5, name
+        assert rel_l2(seg, g[p + "seg"]) < 1e-4, name

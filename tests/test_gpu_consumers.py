@@ -148,3 +148,30 @@ def test_qvarnet_block_golden(golden):
     assert out.shape == g["qvn_out"].shape
     assert rel_l2(out, g["qvn_out"]) < 1e-5, rel_l2(out, g["qvn_out"])
     assert float(out[:, 0].min()) >= 0.0  # negative R2* estimates are clipped (qvn_block.py:156-158)
+
+
+def test_jrscirim_block_golden(golden):
+    """JRSCIRIMBlock: CIRIM cascades on the fused DC operator + UNet / ConvLayer segmentation heads, single slices, a given
+    initial image, and the per-slice loop of consecutive_slices = 2 -- against the reference's own outputs.  The 8-channel
+    ConvGRU of the fixture runs on the exact-fp32 kernels: blocks <= 1e-5, segmentation (after group-norm + U-Net) <= 1e-4."""
+    import mridc_b200 as mb
+    from oracle.make_golden import JRS_CASES, JRS_RIM
+
+    g = golden("jrscirim")
+    for idx, (name, sp, in_ch, mag, slices) in enumerate(JRS_CASES):
+        p = "jrs%d_" % idx
+        blk = load_sd(mb.JRSCIRIMBlock(dict(JRS_RIM), dict(sp), in_ch, mag, True, "ortho", SD, 2, 2, slices, "SENSE", True), g,
+                      p + "w_")
+        y, S, m, init, target = (cu(g[p + k]) for k in ("y", "S", "mask", "init", "target"))
+        no_init = torch.zeros(2, slices).cuda() if slices > 1 else torch.zeros(1).cuda()
+        rec, seg, hx = blk(y, S, m, init if idx == 1 else no_init, target)
+        rec = torch.view_as_real(torch.stack([torch.stack(c) for c in rec]))
+        assert rec.shape == g[p + "rec"].shape and seg.shape == g[p + "seg"].shape, name
+        e_r, e_s = rel_l2(rec, g[p + "rec"]), rel_l2(seg, g[p + "seg"])
+        print("[jrscirim] %s rec %.2e seg %.2e" % (name, e_r, e_s))
+        assert e_r < 1e-5 and e_s < 1e-4, (name, e_r, e_s)
+        assert len(hx) == 2 and hx[0].shape[1] == 8
+    with pytest.raises(NotImplementedError):
+        mb.JRSCIRIMBlock(dict(JRS_RIM), dict(segmentation_module="AttentionUNet", output_channels=2), 1)
+    with pytest.raises(ValueError, match="not implemented"):
+        mb.JRSCIRIMBlock(dict(JRS_RIM), dict(segmentation_module="nope", output_channels=2), 1)
