@@ -7,8 +7,11 @@ One slice of raw k-space goes to the GPU once; zero filling, target formation (R
 ``normalize_inputs`` then run on the device with this package's FFT / coil-combination kernels, so the slice that enters
 ``CIRIM.forward`` never returns to the host.  Same constructor arguments, call signature and 9-tuple as the reference.
 Masks are still drawn on the host by the reference's mask functions (bit-exact inputs).
-Noise pre-whitening and geometric coil compression (transforms.py:622-905; an SVD per read-out position) are not built.
+Noise pre-whitening (``NoisePreWhitening``, transforms.py:622-663) runs on the device too: the C x C whitening matrix from
+a noise patch, applied as a 1 x 1 channel-mixing convolution.  Geometric coil compression (transforms.py:666-905; an SVD per
+read-out position) is not built.
 """
+import math
 import os
 from collections import defaultdict
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -16,9 +19,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import fft, utils
+from . import _ops, fft, utils
 
-__all__ = ["MRIDataTransforms", "assemble_reconstructions", "save_reconstructions"]
+__all__ = ["MRIDataTransforms", "NoisePreWhitening", "assemble_reconstructions", "save_reconstructions"]
 
 
 def _unset(v) -> bool:
@@ -27,6 +30,32 @@ def _unset(v) -> bool:
 
 def _device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
+
+
+class NoisePreWhitening:
+    """transforms.py:622-663: coil decorrelation.  psi = inv(chol(N N^T / (n - 1))) * sqrt(2 scale) from the noise patch
+    ``data[:, x0:x1, y0:y1]`` of the (re, im)-stacked view -- a REAL C x C matrix, as upstream computes it -- then
+    ``psi @ data``.  The C x C factorisation is a few hundred flops (torch.linalg on the device, no host round trip); the
+    product over the slice is this package's convolution kernel with psi as a 1 x 1 kernel."""
+
+    def __init__(self, patch_size: List[int], scale_factor: float = 1.0):
+        self.patch_size = patch_size
+        self.scale_factor = scale_factor
+
+    @torch.no_grad()
+    def __call__(self, data):
+        if not self.patch_size:
+            raise ValueError("Patch size must be defined for noise prewhitening.")
+        if data.shape[-1] != 2:
+            data = torch.view_as_real(data)
+        noise = data[:, self.patch_size[0]: self.patch_size[1], self.patch_size[-2]: self.patch_size[-1]]
+        noise_int = torch.reshape(noise, (noise.shape[0], int(torch.numel(noise) / noise.shape[0])))
+        deformation_matrix = (1 / (float(noise_int.shape[1]) - 1)) * torch.mm(noise_int, noise_int.t())
+        psi = torch.linalg.inv(torch.linalg.cholesky(deformation_matrix)) * math.sqrt(2) * math.sqrt(self.scale_factor)
+        C = data.shape[0]
+        flat = data.contiguous().reshape(1, C, data.shape[1], -1)  # pointwise: any 2-D arrangement of the samples works
+        out = _ops.conv2d(flat, psi.reshape(C, C, 1, 1).contiguous(), None, 1, 1, _ops.PAD_ZERO)
+        return out.reshape(data.shape)
 
 
 class MRIDataTransforms:
@@ -39,8 +68,8 @@ class MRIDataTransforms:
                  crop_before_masking: bool = True, kspace_zero_filling_size: Optional[Tuple] = None,
                  normalize_inputs: bool = False, fft_centered: bool = True, fft_normalization: str = "ortho",
                  max_norm: bool = True, spatial_dims: Sequence[int] = None, coil_dim: int = 0, use_seed: bool = True):
-        if apply_prewhitening or apply_gcc:
-            raise NotImplementedError("mridc_b200: noise pre-whitening / geometric coil compression are not built")
+        if apply_gcc:
+            raise NotImplementedError("mridc_b200: geometric coil compression is not built")
         if dimensionality != 2:
             raise NotImplementedError("mridc_b200: MRIDataTransforms handles dimensionality == 2 (one slice per call)")
         self.coil_combination_method = coil_combination_method
@@ -60,8 +89,11 @@ class MRIDataTransforms:
         self.max_norm = max_norm
         self.spatial_dims = spatial_dims if spatial_dims is not None else [-2, -1]
         self.coil_dim = coil_dim - 1  # transforms.py:130 (2-D data: the batch axis is not there yet)
-        self.apply_prewhitening = False
-        self.prewhitening = None
+        self.apply_prewhitening = apply_prewhitening
+        self.prewhitening = NoisePreWhitening(  # transforms.py:132-143
+            patch_size=[prewhitening_patch_start, prewhitening_patch_length + prewhitening_patch_start,
+                        prewhitening_patch_start, prewhitening_patch_length + prewhitening_patch_start],
+            scale_factor=prewhitening_scale_factor) if apply_prewhitening else None
         self.gcc = None
         self.use_seed = use_seed
 
@@ -102,6 +134,8 @@ class MRIDataTransforms:
         have_sens = sensitivity_map is not None and sensitivity_map.size != 0
         if have_sens:
             sensitivity_map = utils.to_tensor(sensitivity_map).to(dev)
+        if self.apply_prewhitening:  # :223-224
+            kspace = self.prewhitening(kspace)
 
         if not _unset(self.kspace_zero_filling_size):  # :229-262
             top = int(np.floor_divide(abs(int(self.kspace_zero_filling_size[0]) - kspace.shape[1]), 2))

@@ -781,6 +781,9 @@ TRANSFORM_CASES = [
                             normalize_inputs=True, fft_centered=True, fft_normalization="ortho", coil_dim=1), {}),
     ("given_mask", dict(coil_combination_method="SENSE", mask_func=None, shift_mask=True, normalize_inputs=True,
                         fft_centered=False, fft_normalization="forward", coil_dim=1), {"mask": True}),
+    ("prewhiten", dict(apply_prewhitening=True, prewhitening_scale_factor=1.5, prewhitening_patch_start=2,
+                       prewhitening_patch_length=6, coil_combination_method="SENSE", mask_func=["equi"], normalize_inputs=True,
+                       fft_centered=True, fft_normalization="ortho", coil_dim=1), {}),
     ("none_norm", dict(coil_combination_method="RSS", mask_func=["equi"], normalize_inputs=True, fft_centered=False,
                        fft_normalization="none", coil_dim=1), {}),
 ]

@@ -1,6 +1,6 @@
 """MRIDataTransforms on the device against the outputs of the unmodified reference class
 (tests/golden/transforms.npz, oracle/make_golden.py::gen_transforms): every element of the 9-tuple, for SENSE / RSS
-targets, image- and k-space crops before / after masking, zero filling, fully sampled data, precomputed and generated
+targets, image- and k-space crops before / after masking, zero filling, noise pre-whitening, fully sampled data, precomputed and generated
 masks, all normalisation modes.
 
 CPU part: the transform's host logic with the CUDA wrappers swapped for the oracle's CPU functions (test scaffolding; the
@@ -62,10 +62,19 @@ class _OracleUtils:
     complex_abs = staticmethod(omri.complex_abs)
 
 
+class _OracleOps:
+    PAD_ZERO = 0
+
+    @staticmethod
+    def conv2d(x, weight, bias, k, dil, pad_mode, **kw):
+        return torch.nn.functional.conv2d(x, weight, bias)
+
+
 def test_host_logic_against_reference_vectors(golden, monkeypatch):
     import mridc_b200 as mb
     import mridc_b200.transforms as tm
 
+    monkeypatch.setattr(tm, "_ops", _OracleOps)
     monkeypatch.setattr(tm, "fft", omri)
     monkeypatch.setattr(tm, "utils", _OracleUtils(tm.utils))
     monkeypatch.setattr(tm, "_device", lambda: torch.device("cpu"))
@@ -79,8 +88,6 @@ def test_unbuilt_options_raise():
 
     with pytest.raises(NotImplementedError):
         mb.MRIDataTransforms(apply_gcc=True)
-    with pytest.raises(NotImplementedError):
-        mb.MRIDataTransforms(apply_prewhitening=True)
     with pytest.raises(NotImplementedError):
         mb.MRIDataTransforms(dimensionality=3)
 
