@@ -964,6 +964,154 @@ __global__ void __launch_bounds__(S_THREADS, 2) row_dc320s_kernel(const float2* 
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 320-point forms of the VarNet-side operators (vn_block.py:51-87,109-119): the same register-resident 16 x 20 transform as
+// fft.cu's fft320_kernel (16 lines per CTA, one shared-memory transpose) with the surrounding arithmetic in its loads and
+// stores.  Centring is the pair of thread-constant signs of that kernel, so every tensor stays in STORAGE order:
+//   expand_row320:  T1[b,c,h,:]  = FFT_W(S[b,c,h,:] * img[b,h,:])            lines = the C <= 16 coils of one image row
+//   col_softdc320:  out[b,c,:,w] = base - where(mask, pred - y, 0) dcw - fs FFT_H(T1[b,c,:,w])   lines = 16 columns
+//   reduce_row320:  out[b,h,:]   = scale * sum_c conj(S[b,c,h,:]) IFFT_W(T2[b,c,h,:])            lines = the coils
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int VXS = 22, VLINES = 16;
+
+// One CTA of 320 threads transforms up to 16 lines: ld(l, j) -> element j of line l, st(l, k, X) <- bin k of line l.
+// ROWS: thread (l = tid / 20, t = tid % 20); COLS: thread (t = tid / 16, l = tid % 16) -- see fft320_kernel.
+template <bool INV, bool COLS, class Load, class Store>
+__device__ __forceinline__ void fft320_cta(float2* xch, float2* tw1_s, const float2* __restrict__ tw, int nvalid, int in_sign,
+                                           int out_sign, float scale, Load ld, Store st) {
+    constexpr int CS = COLS ? N1 * VXS + 1 : N1 * VXS + 4;
+    const int tid = threadIdx.x;
+    const int l = COLS ? (tid & 15) : tid / N2, t = COLS ? (tid >> 4) : tid - (tid / N2) * N2;
+    cx v[N1];
+    if (l < nvalid) {
+        float2 x[N1];
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) x[n1] = ld(l, N2 * n1 + t);
+        const float sg = (in_sign && (t & 1)) ? -1.f : 1.f;
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) v[n1] = pk(x[n1].x * sg, x[n1].y * sg);
+    }
+    {
+        const int a = tid / N2, b = tid - a * N2;
+        tw1_s[tid] = __ldg(&tw[a * b]);  // tid = 20*k1 + t
+    }
+    __syncthreads();
+    float2* xl = xch + (size_t)l * CS;
+    if (l < nvalid) {
+        dft16<INV>(v);
+        xl[t] = upk(v[0]);
+#pragma unroll
+        for (int k1 = 1; k1 < N1; ++k1) {
+            const float2 w = tw1_s[k1 * N2 + t];
+            xl[k1 * VXS + t] = mulw<INV>(upk(v[k1]), w.x, w.y);
+        }
+    }
+    __syncthreads();
+    if (tid < VLINES * N1) {
+        const int l2 = COLS ? (tid & 15) : (tid >> 4), k1 = COLS ? (tid >> 4) : (tid & 15);
+        if (l2 < nvalid) {
+            cx u[N2];
+            const float2* row = xch + (size_t)l2 * CS + k1 * VXS;
+            if (COLS) {
+#pragma unroll
+                for (int i = 0; i < N2; ++i) u[i] = pk(row[i]);
+            } else {
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+                for (int i = 0; i < N2 / 2; ++i) {
+                    const float4 q = row4[i];
+                    u[2 * i] = pk(q.x, q.y);
+                    u[2 * i + 1] = pk(q.z, q.w);
+                }
+            }
+            dft20<INV>(u);
+            const float sc = (out_sign && (k1 & 1)) ? -scale : scale;
+#pragma unroll
+            for (int k2 = 0; k2 < N2; ++k2) {
+                const float2 r = upk(u[k2]);
+                st(l2, k1 + N1 * k2, make_float2(r.x * sc, r.y * sc));
+            }
+        }
+    }
+}
+inline size_t v320_smem(bool cols, bool reduce) {
+    return (size_t)(VLINES * (N1 * VXS + (cols ? 1 : 4)) + N + (reduce ? MAXC * (N + 4) : 0)) * sizeof(float2);
+}
+
+// K1 (VarNet expand, W = 320): grid (H, B)
+__global__ void __launch_bounds__(THREADS, 3) expand_row320_kernel(const float2* __restrict__ img, const float2* __restrict__ S,
+                                                                   float2* __restrict__ T1, int C, int H,
+                                                                   const float2* __restrict__ tw, int rw) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + VLINES * (N1 * VXS + 4);
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float2* irow = img + ((long long)b * H + h) * N;
+    const long long cstride = (long long)H * N, rowoff = ((long long)b * C * H + h) * N;
+    auto ld = [&](int c, int j) {
+        const float2 e = __ldg(&irow[j]), s0 = LDSTREAM(S + rowoff + (long long)c * cstride + j);
+        return make_float2(e.x * s0.x - e.y * s0.y, e.x * s0.y + e.y * s0.x);  // vn_block.py:66 complex_mul(x, sens)
+    };
+    auto st = [&](int c, int k, float2 v) { T1[rowoff + (long long)c * cstride + k] = v; };
+    fft320_cta<false, false>(xch, tw1_s, tw, C, rw != 0, rw != 0, 1.f, ld, st);
+}
+
+// K2' (VarNet soft DC, H = 320): grid (W / 16 rounded up, C, B); the column transform of 16 adjacent k_w
+__global__ void __launch_bounds__(THREADS, 3) col_softdc320_kernel(const float2* __restrict__ T1, const float2* __restrict__ base,
+                                                                   const float2* __restrict__ pred, const float2* __restrict__ y,
+                                                                   float2* __restrict__ out, MaskDesc mask, int C, int W,
+                                                                   const float2* __restrict__ tw, int rh, float fscale,
+                                                                   const float* __restrict__ dcw_p, int no_dc) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + VLINES * (N1 * VXS + 1);
+    const int w0 = blockIdx.x * VLINES, c = blockIdx.y, b = blockIdx.z;
+    const long long plane = ((long long)b * C + c) * N * W;
+    const float dcw = no_dc ? 0.f : *dcw_p;
+    auto ld = [&](int l, int j) { return T1[plane + (long long)j * W + w0 + l]; };
+    auto st = [&](int l, int kh, float2 E) {
+        const long long o = plane + (long long)kh * W + w0 + l;
+        if (no_dc) {
+            out[o] = E;
+        } else {
+            const float2 bv = base[o];
+            float2 sd = make_float2(0.f, 0.f);
+            if (mask_value(mask, b, kh, w0 + l) != 0.f) {  // vn_block.py:110 torch.where(mask.bool(), pred - ref, 0)
+                const float2 pv = pred[o], yv = y[o];
+                sd = make_float2(pv.x - yv.x, pv.y - yv.y);
+            }
+            out[o] = make_float2((bv.x - sd.x * dcw) - E.x, (bv.y - sd.y * dcw) - E.y);  // :110,117
+        }
+    };
+    fft320_cta<false, true>(xch, tw1_s, tw, min(VLINES, W - w0), rh != 0, rh != 0, fscale, ld, st);
+}
+
+// K3 (VarNet reduce, W = 320): grid (H, B); out [B, H, W] complex
+__global__ void __launch_bounds__(THREADS, 2) reduce_row320_kernel(const float2* __restrict__ T2, const float2* __restrict__ S,
+                                                                   float2* __restrict__ out, int C, int H,
+                                                                   const float2* __restrict__ tw, int rw, float scale) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + VLINES * (N1 * VXS + 4);
+    float2* red = tw1_s + N;  // [C][N + 4] conj(S) * IFFT_W(T2) per coil
+    const int h = blockIdx.x, b = blockIdx.y;
+    const long long cstride = (long long)H * N, rowoff = ((long long)b * C * H + h) * N;
+    auto ld = [&](int c, int j) { return LDSTREAM(T2 + rowoff + (long long)c * cstride + j); };
+    auto st = [&](int c, int n, float2 x) {
+        const float2 s0 = LDSTREAM(S + rowoff + (long long)c * cstride + n);
+        red[(size_t)c * (N + 4) + n] = make_float2(x.x * s0.x + x.y * s0.y, x.y * s0.x - x.x * s0.y);  // x * conj(S)
+    };
+    fft320_cta<true, false>(xch, tw1_s, tw, C, rw != 0, rw != 0, 1.f, ld, st);
+    __syncthreads();
+    float2 acc = make_float2(0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+        const float2 r = red[(size_t)c * (N + 4) + threadIdx.x];
+        acc.x += r.x;
+        acc.y += r.y;
+    }
+    out[((long long)b * H + h) * N + threadIdx.x] = make_float2(acc.x * scale, acc.y * scale);
+}
 }  // namespace r320
 
 struct DcGeom {
@@ -1200,6 +1348,14 @@ extern "C" int mrb_sens_reduce(const void* x, const void* S, void* out, int B, i
     // inverse FFT along H (strided lines), rotations applied on both sides; W axis untouched (still centred)
     rc = fft1d_launch((const float2*)x, T2, (long long)B * C, H, W, 1, rh, rh, 1.0f, st);
     if (rc) return rc;
+    if (W == r320::N && C <= r320::MAXC && !getenv("MRIDC_B200_DC_STOCKHAM")) {
+        // register-resident row transform + conj(S) + coil sum (both fastMRI geometries have 320 columns)
+        const size_t sm = r320::v320_smem(false, true);
+        MRB_CUDA(cudaFuncSetAttribute(r320::reduce_row320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        r320::reduce_row320_kernel<<<dim3(H, B), r320::THREADS, sm, st>>>(T2, (const float2*)S, (float2*)out, C, H, g.pw.tw, rw, bs);
+        MRB_LAUNCHED();
+        return MRB_OK;
+    }
     if ((rc = set_smem(rowifft_reduce_kernel<0, false>))) return rc;
     MaskDesc nomask;
     memset(&nomask, 0, sizeof(nomask));
@@ -1234,14 +1390,33 @@ extern "C" int mrb_sens_expand_softdc(const void* img, const void* S, const void
     float2* T1 = (float2*)ws;
     const int rh = centered ? H / 2 : 0, rw = centered ? W / 2 : 0;
     const float fs = norm_scale(norm, 0, (double)H * W);
-    if ((rc = set_smem(expand_rowfft_kernel<false>))) return rc;
-    if ((rc = set_smem(col_softdc_kernel))) return rc;
-    expand_rowfft_kernel<false><<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)img, (const float2*)S, T1,
-                                                                               C, H, W, g.cc, g.pw, rw, m, 0);
+    const bool fast = !getenv("MRIDC_B200_DC_STOCKHAM");
+    // T1's k_w axis: storage (centred) order after the 320-point row kernel, un-centred after the Stockham one
+    const bool row320 = fast && W == r320::N && C <= r320::MAXC;
+    if (row320) {
+        const size_t sm = r320::v320_smem(false, false);
+        MRB_CUDA(cudaFuncSetAttribute(r320::expand_row320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        r320::expand_row320_kernel<<<dim3(H, B), r320::THREADS, sm, st>>>((const float2*)img, (const float2*)S, T1, C, H,
+                                                                          g.pw.tw, rw);
+    } else {
+        if ((rc = set_smem(expand_rowfft_kernel<false>))) return rc;
+        expand_rowfft_kernel<false><<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)img, (const float2*)S, T1,
+                                                                                   C, H, W, g.cc, g.pw, rw, m, 0);
+    }
     MRB_LAUNCHED();
-    col_softdc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(
-        T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.tsh, g.ph, rh, rw, fs,
-        (const float*)dc_weight, no_dc);
+    if (fast && H == r320::N && row320) {
+        const size_t sm = r320::v320_smem(true, false);
+        MRB_CUDA(cudaFuncSetAttribute(r320::col_softdc320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        r320::col_softdc320_kernel<<<dim3(ceil_div(W, r320::VLINES), C, B), r320::THREADS, sm, st>>>(
+            T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, W, g.ph.tw, rh, fs,
+            (const float*)dc_weight, no_dc);
+    } else {
+        if ((rc = set_smem(col_softdc_kernel))) return rc;
+        // after the 320-point row kernel the columns already sit at their storage position: no W rotation left
+        col_softdc_kernel<<<dim3(ceil_div(W, g.ti), C, B), 256, g.smem_col, st>>>(
+            T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, H, W, g.tsh, g.ph, rh,
+            row320 ? 0 : rw, fs, (const float*)dc_weight, no_dc);
+    }
     MRB_LAUNCHED();
     return MRB_OK;
 }

@@ -187,6 +187,41 @@ def test_dc_shapes_vs_oracle(B, C, H, W):
             assert rel_l2(a, b) < 2e-6
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 15, 320, 320), (1, 16, 640, 320), (1, 5, 320, 200), (2, 3, 64, 320)])
+def test_sens_reduce_expand_softdc_fastmri_widths_vs_oracle(B, C, H, W, monkeypatch):
+    """The VarNet-side operators at the fastMRI sizes: 320-point row kernels (W = 320: expand_row320 / reduce_row320) and the
+    320-point column kernel with the soft-DC epilogue (H = 320: col_softdc320), their mixes with the Stockham kernels
+    (H = 640 or 64: fast rows + Stockham columns; W = 200: all Stockham), centred and not, every normalisation, uint8 /
+    float masks, no_dc; and the fast path equals the Stockham path to rounding."""
+    from mridc_b200 import _ops
+    from oracle import nets as onets
+
+    g = torch.Generator().manual_seed(B + C + H + W)
+    pred = torch.randn(B, C, H, W, 2, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g) * 0.3
+    img = torch.randn(B, 1, H, W, 2, generator=g)
+    m1 = (torch.rand(1, 1, 1, W, 1, generator=g) < 0.3)
+    m2 = (torch.rand(B, 1, H, W, 1, generator=g) < 0.3)
+    y = torch.randn(B, C, H, W, 2, generator=g) * m1
+    dcw = torch.tensor([0.8])
+    pc, Sc, ic, yc = pred.cuda(), S.cuda(), img.cuda(), y.cuda()
+    for cen, nrm, mask in ((True, "ortho", m1.to(torch.uint8)), (False, "backward", m2.float()), (True, "forward", m1.float())):
+        red = _ops.sens_reduce(pc, Sc, cen, nrm)
+        ref_red = onets.sens_reduce(pred, S, cen, nrm, [-2, -1], 1)[:, 0]
+        assert rel_l2(red, ref_red) < 2e-6, (cen, nrm, rel_l2(red, ref_red))
+        E = onets.sens_expand(img, S, cen, nrm, [-2, -1])
+        out_nodc = _ops.sens_expand_softdc(ic, Sc, None, None, None, None, None, True, cen, nrm)
+        assert rel_l2(out_nodc, E) < 2e-6, (cen, nrm, rel_l2(out_nodc, E))
+        ref = pred - torch.where(mask.bool(), pred - y, torch.zeros(1)) * dcw - E
+        out = _ops.sens_expand_softdc(ic, Sc, pc, pc, yc, mask.cuda(), dcw.cuda(), False, cen, nrm)
+        assert rel_l2(out, ref) < 2e-6, (cen, nrm, rel_l2(out, ref))
+        monkeypatch.setenv("MRIDC_B200_DC_STOCKHAM", "1")
+        red_s = _ops.sens_reduce(pc, Sc, cen, nrm)
+        out_s = _ops.sens_expand_softdc(ic, Sc, pc, pc, yc, mask.cuda(), dcw.cuda(), False, cen, nrm)
+        monkeypatch.delenv("MRIDC_B200_DC_STOCKHAM")
+        assert rel_l2(red, red_s) < 1e-6 and rel_l2(out, out_s) < 1e-6
+
+
 def test_dc_float_valued_mask_multiplies():
     """RIM multiplies by the mask VALUE (rim_utils.py:54); VarNet tests truthiness (vn_block.py:110)."""
     import mridc_b200 as mb
