@@ -1035,7 +1035,7 @@ __device__ __forceinline__ void fft320_cta(float2* xch, float2* tw1_s, const flo
         }
     }
 }
-inline size_t v320_smem(bool cols, bool reduce) {
+inline size_t v320_smem(bool cols, bool reduce) {  // reduce: + the [16][N + 4] coil-sum / residual buffer
     return (size_t)(VLINES * (N1 * VXS + (cols ? 1 : 4)) + N + (reduce ? MAXC * (N + 4) : 0)) * sizeof(float2);
 }
 
@@ -1087,10 +1087,13 @@ __global__ void __launch_bounds__(THREADS, 3) col_softdc320_kernel(const float2*
     fft320_cta<false, true>(xch, tw1_s, tw, min(VLINES, W - w0), rh != 0, rh != 0, fscale, ld, st);
 }
 
-// K3 (VarNet reduce, W = 320): grid (H, B); out [B, H, W] complex
+// K3 (W = 320): grid (H, B).  OUT_MODE 0 (VarNet reduce): out [B, H, W] complex = acc * scale; 1 (RIM gradient): out
+// [B, 4, H, W] = (eta_re, eta_im, acc * scale); 2: the same channels-last [B, H, W, 4]
+template <int OUT_MODE>
 __global__ void __launch_bounds__(THREADS, 2) reduce_row320_kernel(const float2* __restrict__ T2, const float2* __restrict__ S,
-                                                                   float2* __restrict__ out, int C, int H,
-                                                                   const float2* __restrict__ tw, int rw, float scale) {
+                                                                   const float2* __restrict__ eta, float* __restrict__ out,
+                                                                   int C, int H, const float2* __restrict__ tw, int rw,
+                                                                   float scale) {
     extern __shared__ float2 smem[];
     float2* xch = smem;
     float2* tw1_s = xch + VLINES * (N1 * VXS + 4);
@@ -1110,7 +1113,52 @@ __global__ void __launch_bounds__(THREADS, 2) reduce_row320_kernel(const float2*
         acc.x += r.x;
         acc.y += r.y;
     }
-    out[((long long)b * H + h) * N + threadIdx.x] = make_float2(acc.x * scale, acc.y * scale);
+    const int d = threadIdx.x;
+    if (OUT_MODE == 0) {
+        reinterpret_cast<float2*>(out)[((long long)b * H + h) * N + d] = make_float2(acc.x * scale, acc.y * scale);
+    } else {
+        const float2 e = eta[((long long)b * H + h) * N + d];  // rim_utils.py:67: channels 0-1 are eta itself
+        if (OUT_MODE == 2) {
+            reinterpret_cast<float4*>(out)[((long long)b * H + h) * N + d] = make_float4(e.x, e.y, acc.x * scale, acc.y * scale);
+        } else {
+            const long long HW = (long long)H * N;
+            float* o = out + (long long)b * 4 * HW + (long long)h * N + d;
+            o[0] = e.x;
+            o[HW] = e.y;
+            o[2 * HW] = acc.x * scale;
+            o[3 * HW] = acc.y * scale;
+        }
+    }
+}
+
+// K2 (RIM gradient, H = 320, any mask): per 16 adjacent columns of one (b, c) plane  P = fs FFT_H(T1),
+// r = mask * (P - y) (rim_utils.py:54), T2 = IFFT_H(r); the residual crosses from the bin-owning threads of the first
+// transform to the sample-owning threads of the second through shared memory.  grid (W / 16 rounded up, C, B)
+__global__ void __launch_bounds__(THREADS, 2) col_dc320_kernel(const float2* __restrict__ T1, const float2* __restrict__ y,
+                                                               float2* __restrict__ T2, MaskDesc mask, int C, int W,
+                                                               const float2* __restrict__ tw, int rh, float fscale) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + VLINES * (N1 * VXS + 1);
+    float2* res = tw1_s + N;  // [16][N + 1]
+    const int w0 = blockIdx.x * VLINES, c = blockIdx.y, b = blockIdx.z;
+    const long long plane = ((long long)b * C + c) * N * W;
+    const int nv = min(VLINES, W - w0);
+    auto ld = [&](int l, int j) { return LDSTREAM(T1 + plane + (long long)j * W + w0 + l); };
+    auto st = [&](int l, int kh, float2 P) {
+        const float m = mask_value(mask, b, kh, w0 + l);
+        float2 r = make_float2(0.f, 0.f);
+        if (m != 0.f) {  // unsampled entries contribute exactly 0 whatever y holds: skip the read
+            const float2 yv = __ldg(&y[plane + (long long)kh * W + w0 + l]);
+            r = make_float2(m * (P.x - yv.x), m * (P.y - yv.y));
+        }
+        res[(size_t)l * (N + 1) + kh] = r;
+    };
+    fft320_cta<false, true>(xch, tw1_s, tw, nv, rh != 0, rh != 0, fscale, ld, st);
+    __syncthreads();
+    auto ld2 = [&](int l, int j) { return res[(size_t)l * (N + 1) + j]; };
+    auto st2 = [&](int l, int d, float2 v) { T2[plane + (long long)d * W + w0 + l] = v; };
+    fft320_cta<true, true>(xch, tw1_s, tw, nv, rh != 0, rh != 0, 1.f, ld2, st2);
 }
 }  // namespace r320
 
@@ -1217,6 +1265,29 @@ extern "C" int mrb_dc_rim_grad(const void* eta, const void* y, const void* S, co
     if ((rc = set_smem(rowifft_reduce_kernel<1, true>))) return rc;
     if ((rc = set_smem(rowifft_reduce_kernel<2, true>))) return rc;
     const int prune = (mask_h == 1) ? 1 : 0;  // 1-D masks: only sampled k_w columns are transformed along H
+    if (!prune && W == r320::N && H == r320::N && C <= r320::MAXC && !getenv("MRIDC_B200_DC_STOCKHAM")) {
+        // 2-D masks at 320 x 320: the three passes on the register-resident 320-point transform, every tensor in storage order
+        const size_t sm_r = r320::v320_smem(false, false), sm_c = r320::v320_smem(true, true), sm_o = r320::v320_smem(false, true);
+        MRB_CUDA(cudaFuncSetAttribute(r320::expand_row320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_r));
+        MRB_CUDA(cudaFuncSetAttribute(r320::col_dc320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        r320::expand_row320_kernel<<<dim3(H, B), r320::THREADS, sm_r, st>>>((const float2*)eta, (const float2*)S, T1, C, H,
+                                                                            g.pw.tw, rw);
+        MRB_LAUNCHED();
+        r320::col_dc320_kernel<<<dim3(ceil_div(W, r320::VLINES), C, B), r320::THREADS, sm_c, st>>>(
+            T1, (const float2*)y, T2, m, C, W, g.ph.tw, rh, fs);
+        MRB_LAUNCHED();
+        if (out_nhwc) {
+            MRB_CUDA(cudaFuncSetAttribute(r320::reduce_row320_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_o));
+            r320::reduce_row320_kernel<2><<<dim3(H, B), r320::THREADS, sm_o, st>>>(T2, (const float2*)S, (const float2*)eta,
+                                                                                   (float*)out, C, H, g.pw.tw, rw, bs * inv_sigma2);
+        } else {
+            MRB_CUDA(cudaFuncSetAttribute(r320::reduce_row320_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_o));
+            r320::reduce_row320_kernel<1><<<dim3(H, B), r320::THREADS, sm_o, st>>>(T2, (const float2*)S, (const float2*)eta,
+                                                                                   (float*)out, C, H, g.pw.tw, rw, bs * inv_sigma2);
+        }
+        MRB_LAUNCHED();
+        return MRB_OK;
+    }
     expand_rowfft_kernel<true><<<dim3(H, B), g.threads_row, g.smem_row, st>>>((const float2*)eta, (const float2*)S, T1,
                                                                               C, H, W, g.cc, g.pw, rw, m, prune);
     MRB_LAUNCHED();
@@ -1351,8 +1422,9 @@ extern "C" int mrb_sens_reduce(const void* x, const void* S, void* out, int B, i
     if (W == r320::N && C <= r320::MAXC && !getenv("MRIDC_B200_DC_STOCKHAM")) {
         // register-resident row transform + conj(S) + coil sum (both fastMRI geometries have 320 columns)
         const size_t sm = r320::v320_smem(false, true);
-        MRB_CUDA(cudaFuncSetAttribute(r320::reduce_row320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        r320::reduce_row320_kernel<<<dim3(H, B), r320::THREADS, sm, st>>>(T2, (const float2*)S, (float2*)out, C, H, g.pw.tw, rw, bs);
+        MRB_CUDA(cudaFuncSetAttribute(r320::reduce_row320_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        r320::reduce_row320_kernel<0><<<dim3(H, B), r320::THREADS, sm, st>>>(T2, (const float2*)S, nullptr, (float*)out, C, H,
+                                                                             g.pw.tw, rw, bs);
         MRB_LAUNCHED();
         return MRB_OK;
     }

@@ -222,6 +222,35 @@ def test_sens_reduce_expand_softdc_fastmri_widths_vs_oracle(B, C, H, W, monkeypa
         assert rel_l2(red, red_s) < 1e-6 and rel_l2(out, out_s) < 1e-6
 
 
+def test_dc_three_pass_320_two_d_masks_vs_oracle(monkeypatch):
+    """RIM gradient with 2-D masks at 15 x 320 x 320 (Gaussian2D / Poisson2D style sampling): the three passes on the
+    register-resident 320-point transform (expand_row320 -> col_dc320 -> reduce_row320) vs the oracle and vs the Stockham
+    operator; shared and per-slice masks, uint8 / float-valued masks, both output layouts."""
+    import mridc_b200 as mb
+    from mridc_b200 import _ops
+    from oracle import nets as onets
+
+    g = torch.Generator().manual_seed(320)
+    B, C, H, W = 2, 15, 320, 320
+    y = torch.randn(B, C, H, W, 2, generator=g)
+    S = torch.randn(B, C, H, W, 2, generator=g) * 0.3
+    eta = torch.randn(B, H, W, 2, generator=g)
+    masks = [(torch.rand(1, 1, H, W, 1, generator=g) < 0.2).to(torch.uint8),
+             (torch.rand(B, 1, H, W, 1, generator=g) < 0.2).float() * 0.5]  # float-valued: the RIM multiplies by the value
+    for (cen, nrm), m in zip(((True, "ortho"), (False, "backward")), masks):
+        ref = onets.log_likelihood_gradient(eta, y, S, m.float(), 0.7, cen, nrm, [-2, -1], 1)
+        a = mb.log_likelihood_gradient(eta.cuda(), y.cuda(), S.cuda(), m.cuda(), 0.7, cen, nrm, [-2, -1], 1)
+        e = rel_l2(a, ref)
+        assert e < 2e-6, (cen, nrm, e)
+        assert torch.equal(a[:, :2].cpu(), eta.permute(0, 3, 1, 2))  # eta passes through bit-exactly
+        nh = _ops.dc_rim_grad(eta.cuda(), y.cuda(), S.cuda(), m.cuda(), 0.7, cen, nrm, nhwc=True)
+        assert torch.equal(nh.permute(0, 3, 1, 2), a)
+        monkeypatch.setenv("MRIDC_B200_DC_STOCKHAM", "1")
+        b = mb.log_likelihood_gradient(eta.cuda(), y.cuda(), S.cuda(), m.cuda(), 0.7, cen, nrm, [-2, -1], 1)
+        monkeypatch.delenv("MRIDC_B200_DC_STOCKHAM")
+        assert rel_l2(a, b) < 1e-6
+
+
 def test_dc_float_valued_mask_multiplies():
     """RIM multiplies by the mask VALUE (rim_utils.py:54); VarNet tests truthiness (vn_block.py:110)."""
     import mridc_b200 as mb

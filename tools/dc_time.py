@@ -27,6 +27,13 @@ for B in (1, 4, 8):
         print("B=%d centered=%s rim_grad (hybrid) %7.1f us  -> %6.0f GB/s algorithmic" % (B, cen, us, bytes_alg / us / 1e3))
         us = t(lambda: _ops.dc_hybrid_prepare(y, mask, cen, ws=ws[0]))
         print("B=%d centered=%s hybrid prepare   %7.1f us (once per slice batch)" % (B, cen, us))
+    m2 = (torch.rand(1, 1, H, W, 1, device=dev) < 0.25).to(torch.uint8)  # 2-D mask: the general three-pass operator
+    us = t(lambda: _ops.dc_rim_grad(eta, y, S, m2, 1.0, True, "ortho", out=out, ws=ws, nhwc=True))
+    os.environ["MRIDC_B200_DC_STOCKHAM"] = "1"
+    us_s = t(lambda: _ops.dc_rim_grad(eta, y, S, m2, 1.0, True, "ortho", out=out, ws=ws, nhwc=True))
+    del os.environ["MRIDC_B200_DC_STOCKHAM"]
+    print("B=%d 2-D mask rim_grad (3-pass, 320-point kernels) %7.1f us -> %6.0f GB/s algorithmic   (Stockham kernels: %7.1f us)"
+          % (B, us, bytes_alg / us / 1e3, us_s))
     us = t(lambda: _ops.sens_reduce(y, S, False, "backward", ws=ws))
     print("B=%d sens_reduce %7.1f us" % (B, us))
     us = t(lambda: _ops.sens_expand_softdc(eta, S, None, None, None, None, None, True, False, "backward", ws=ws))
