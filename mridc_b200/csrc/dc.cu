@@ -973,68 +973,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) row_dc320s_kernel(const float2* 
 //   col_softdc320:  out[b,c,:,w] = base - where(mask, pred - y, 0) dcw - fs FFT_H(T1[b,c,:,w])   lines = 16 columns
 //   reduce_row320:  out[b,h,:]   = scale * sum_c conj(S[b,c,h,:]) IFFT_W(T2[b,c,h,:])            lines = the coils
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int VXS = 22, VLINES = 16;
+constexpr int VLINES = CTA_LINES, VXS = CTA_XS;
 
-// One CTA of 320 threads transforms up to 16 lines: ld(l, j) -> element j of line l, st(l, k, X) <- bin k of line l.
-// ROWS: thread (l = tid / 20, t = tid % 20); COLS: thread (t = tid / 16, l = tid % 16) -- see fft320_kernel.
-template <bool INV, bool COLS, class Load, class Store>
-__device__ __forceinline__ void fft320_cta(float2* xch, float2* tw1_s, const float2* __restrict__ tw, int nvalid, int in_sign,
-                                           int out_sign, float scale, Load ld, Store st) {
-    constexpr int CS = COLS ? N1 * VXS + 1 : N1 * VXS + 4;
-    const int tid = threadIdx.x;
-    const int l = COLS ? (tid & 15) : tid / N2, t = COLS ? (tid >> 4) : tid - (tid / N2) * N2;
-    cx v[N1];
-    if (l < nvalid) {
-        float2 x[N1];
-#pragma unroll
-        for (int n1 = 0; n1 < N1; ++n1) x[n1] = ld(l, N2 * n1 + t);
-        const float sg = (in_sign && (t & 1)) ? -1.f : 1.f;
-#pragma unroll
-        for (int n1 = 0; n1 < N1; ++n1) v[n1] = pk(x[n1].x * sg, x[n1].y * sg);
-    }
-    {
-        const int a = tid / N2, b = tid - a * N2;
-        tw1_s[tid] = __ldg(&tw[a * b]);  // tid = 20*k1 + t
-    }
-    __syncthreads();
-    float2* xl = xch + (size_t)l * CS;
-    if (l < nvalid) {
-        dft16<INV>(v);
-        xl[t] = upk(v[0]);
-#pragma unroll
-        for (int k1 = 1; k1 < N1; ++k1) {
-            const float2 w = tw1_s[k1 * N2 + t];
-            xl[k1 * VXS + t] = mulw<INV>(upk(v[k1]), w.x, w.y);
-        }
-    }
-    __syncthreads();
-    if (tid < VLINES * N1) {
-        const int l2 = COLS ? (tid & 15) : (tid >> 4), k1 = COLS ? (tid >> 4) : (tid & 15);
-        if (l2 < nvalid) {
-            cx u[N2];
-            const float2* row = xch + (size_t)l2 * CS + k1 * VXS;
-            if (COLS) {
-#pragma unroll
-                for (int i = 0; i < N2; ++i) u[i] = pk(row[i]);
-            } else {
-                const float4* row4 = reinterpret_cast<const float4*>(row);
-#pragma unroll
-                for (int i = 0; i < N2 / 2; ++i) {
-                    const float4 q = row4[i];
-                    u[2 * i] = pk(q.x, q.y);
-                    u[2 * i + 1] = pk(q.z, q.w);
-                }
-            }
-            dft20<INV>(u);
-            const float sc = (out_sign && (k1 & 1)) ? -scale : scale;
-#pragma unroll
-            for (int k2 = 0; k2 < N2; ++k2) {
-                const float2 r = upk(u[k2]);
-                st(l2, k1 + N1 * k2, make_float2(r.x * sc, r.y * sc));
-            }
-        }
-    }
-}
 inline size_t v320_smem(bool cols, bool reduce) {  // reduce: + the [16][N + 4] coil-sum / residual buffer
     return (size_t)(VLINES * (N1 * VXS + (cols ? 1 : 4)) + N + (reduce ? MAXC * (N + 4) : 0)) * sizeof(float2);
 }
@@ -1085,6 +1025,39 @@ __global__ void __launch_bounds__(THREADS, 3) col_softdc320_kernel(const float2*
         }
     };
     fft320_cta<false, true>(xch, tw1_s, tw, min(VLINES, W - w0), rh != 0, rh != 0, fscale, ld, st);
+}
+
+// K2' at H = 640 (brain geometry): 8 adjacent k_w columns per CTA on the 640-point column transform (fft640_cols_cta);
+// grid (W / 8 rounded up, C, B)
+__global__ void __launch_bounds__(THREADS, 2) col_softdc640_kernel(const float2* __restrict__ T1, const float2* __restrict__ base,
+                                                                   const float2* __restrict__ pred, const float2* __restrict__ y,
+                                                                   float2* __restrict__ out, MaskDesc mask, int C, int W,
+                                                                   const float2* __restrict__ tw320,
+                                                                   const float2* __restrict__ tw640, int rh, float fscale,
+                                                                   const float* __restrict__ dcw_p, int no_dc) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + VLINES * (N1 * VXS + 1);
+    float2* buf = tw1_s + N;
+    const int w0 = blockIdx.x * 8, c = blockIdx.y, b = blockIdx.z;
+    const long long plane = ((long long)b * C + c) * (2 * N) * W;
+    const float dcw = no_dc ? 0.f : *dcw_p;
+    auto ld = [&](int cl, int j) { return T1[plane + (long long)j * W + w0 + cl]; };
+    auto st = [&](int cl, int kh, float2 E) {
+        const long long o = plane + (long long)kh * W + w0 + cl;
+        if (no_dc) {
+            out[o] = E;
+        } else {
+            const float2 bv = base[o];
+            float2 sd = make_float2(0.f, 0.f);
+            if (mask_value(mask, b, kh, w0 + cl) != 0.f) {
+                const float2 pv = pred[o], yv = y[o];
+                sd = make_float2(pv.x - yv.x, pv.y - yv.y);
+            }
+            out[o] = make_float2((bv.x - sd.x * dcw) - E.x, (bv.y - sd.y * dcw) - E.y);
+        }
+    };
+    fft640_cols_cta<false>(xch, tw1_s, buf, tw320, tw640, min(8, W - w0), rh != 0, rh != 0, fscale, ld, st);
 }
 
 // K3 (W = 320): grid (H, B).  OUT_MODE 0 (VarNet reduce): out [B, H, W] complex = acc * scale; 1 (RIM gradient): out
@@ -1481,6 +1454,12 @@ extern "C" int mrb_sens_expand_softdc(const void* img, const void* S, const void
         MRB_CUDA(cudaFuncSetAttribute(r320::col_softdc320_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         r320::col_softdc320_kernel<<<dim3(ceil_div(W, r320::VLINES), C, B), r320::THREADS, sm, st>>>(
             T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, W, g.ph.tw, rh, fs,
+            (const float*)dc_weight, no_dc);
+    } else if (fast && H == 2 * r320::N && row320) {
+        const size_t sm = r320::v320_smem(true, true);
+        MRB_CUDA(cudaFuncSetAttribute(r320::col_softdc640_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        r320::col_softdc640_kernel<<<dim3(ceil_div(W, 8), C, B), r320::THREADS, sm, st>>>(
+            T1, (const float2*)base, (const float2*)pred, (const float2*)y, (float2*)out, m, C, W, g.pw.tw, g.ph.tw, rh, fs,
             (const float*)dc_weight, no_dc);
     } else {
         if ((rc = set_smem(col_softdc_kernel))) return rc;

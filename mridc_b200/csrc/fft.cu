@@ -233,6 +233,37 @@ static int launch_fft320(const float2* in, float2* out, long long outer, long lo
     MRB_LAUNCHED();
     return MRB_OK;
 }
+
+// 640-point transform along a strided axis (the H = 640 columns of the brain geometry): 8 adjacent columns per CTA,
+// fft640_cols_cta (two 320-point transforms + one radix-2 combine).  grid (inner / 8 rounded up, outer)
+template <bool INV>
+__global__ void __launch_bounds__(FTHREADS, 2) fft640_cols_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                  long long inner, const float2* __restrict__ tw320,
+                                                                  const float2* __restrict__ tw640, int in_mod, int out_sign,
+                                                                  float scale) {
+    extern __shared__ float2 smem[];
+    float2* xch = smem;
+    float2* tw1_s = xch + CTA_LINES * (CTA_N1 * CTA_XS + 1);
+    float2* buf = tw1_s + CTA_N;
+    const long long c0 = (long long)blockIdx.x * 8;
+    const long long base = (long long)blockIdx.y * (2 * CTA_N) * inner + c0;
+    const int ncols = (int)(inner - c0 < 8 ? inner - c0 : 8);
+    auto ld = [&](int cl, int n) { return __ldg(in + base + (long long)n * inner + cl); };
+    auto st = [&](int cl, int k, float2 v) { out[base + (long long)k * inner + cl] = v; };
+    fft640_cols_cta<INV>(xch, tw1_s, buf, tw320, tw640, ncols, in_mod, out_sign, scale, ld, st);
+}
+inline size_t fft640_smem() { return (size_t)(CTA_LINES * (CTA_N1 * CTA_XS + 1) + CTA_N + CTA_LINES * (CTA_N + 1)) * sizeof(float2); }
+
+template <bool INV>
+static int launch_fft640_cols(const float2* in, float2* out, long long outer, long long inner, const float2* tw320,
+                              const float2* tw640, int in_mod, int out_sign, float scale, cudaStream_t st) {
+    auto k = fft640_cols_kernel<INV>;
+    MRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft640_smem()));
+    k<<<dim3((unsigned)((inner + 7) / 8), (unsigned)outer), FTHREADS, fft640_smem(), st>>>(in, out, inner, tw320, tw640, in_mod,
+                                                                                          out_sign, scale);
+    MRB_LAUNCHED();
+    return MRB_OK;
+}
 }  // namespace r320
 
 static int choose_lines(const FftPlan& p, int want_min_threads_work, long long avail_lines, size_t max_smem) {
@@ -274,6 +305,14 @@ int fft1d_launch(const float2* in, float2* out, long long outer, int n, long lon
             return inverse ? r320::launch_fft320<true, true>(in, out, outer, inner, p.tw, in_sign, out_sign, scale, st)
                            : r320::launch_fft320<false, true>(in, out, outer, inner, p.tw, in_sign, out_sign, scale, st);
         }
+    }
+    if (n == 2 * r320::FN && inner > 1 && (in_rot == 0 || in_rot == n / 2) && (out_rot == 0 || out_rot == n / 2) &&
+        outer <= 65535 && (inner + 7) / 8 <= 2147483647LL && !getenv("MRIDC_B200_FFT_STOCKHAM")) {
+        FftPlan p320;
+        int rc = get_fft_plan(r320::FN, &p320);
+        if (rc) return rc;
+        return inverse ? r320::launch_fft640_cols<true>(in, out, outer, inner, p320.tw, p.tw, out_rot != 0, in_rot != 0, scale, st)
+                       : r320::launch_fft640_cols<false>(in, out, outer, inner, p320.tw, p.tw, out_rot != 0, in_rot != 0, scale, st);
     }
     const int threads = 256;
     if (inner == 1) {

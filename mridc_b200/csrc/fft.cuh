@@ -406,6 +406,106 @@ __device__ __forceinline__ void dft20(cx* v) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-level 320-point transform with caller-supplied loads and stores (the body of fft.cu's fft320_kernel): 320 threads,
+// up to 16 lines, shared memory = [16][16*22 + (COLS ? 1 : 4)] float2 exchange buffer + 320 float2 twiddles.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CTA_N = 320, CTA_N1 = 16, CTA_N2 = 20, CTA_XS = 22, CTA_LINES = 16;
+
+// One CTA of 320 threads transforms up to 16 lines: ld(l, j) -> element j of line l, st(l, k, X) <- bin k of line l.
+// ROWS: thread (l = tid / 20, t = tid % 20); COLS: thread (t = tid / 16, l = tid % 16) -- see fft320_kernel.
+template <bool INV, bool COLS, class Load, class Store>
+__device__ __forceinline__ void fft320_cta(float2* xch, float2* tw1_s, const float2* __restrict__ tw, int nvalid, int in_sign,
+                                           int out_sign, float scale, Load ld, Store st) {
+    constexpr int CS = COLS ? CTA_N1 * CTA_XS + 1 : CTA_N1 * CTA_XS + 4;
+    const int tid = threadIdx.x;
+    const int l = COLS ? (tid & 15) : tid / CTA_N2, t = COLS ? (tid >> 4) : tid - (tid / CTA_N2) * CTA_N2;
+    cx v[CTA_N1];
+    if (l < nvalid) {
+        float2 x[CTA_N1];
+#pragma unroll
+        for (int n1 = 0; n1 < CTA_N1; ++n1) x[n1] = ld(l, CTA_N2 * n1 + t);
+        const float sg = (in_sign && (t & 1)) ? -1.f : 1.f;
+#pragma unroll
+        for (int n1 = 0; n1 < CTA_N1; ++n1) v[n1] = pk(x[n1].x * sg, x[n1].y * sg);
+    }
+    {
+        const int a = tid / CTA_N2, b = tid - a * CTA_N2;
+        tw1_s[tid] = __ldg(&tw[a * b]);  // tid = 20*k1 + t
+    }
+    __syncthreads();
+    float2* xl = xch + (size_t)l * CS;
+    if (l < nvalid) {
+        dft16<INV>(v);
+        xl[t] = upk(v[0]);
+#pragma unroll
+        for (int k1 = 1; k1 < CTA_N1; ++k1) {
+            const float2 w = tw1_s[k1 * CTA_N2 + t];
+            xl[k1 * CTA_XS + t] = mulw<INV>(upk(v[k1]), w.x, w.y);
+        }
+    }
+    __syncthreads();
+    if (tid < CTA_LINES * CTA_N1) {
+        const int l2 = COLS ? (tid & 15) : (tid >> 4), k1 = COLS ? (tid >> 4) : (tid & 15);
+        if (l2 < nvalid) {
+            cx u[CTA_N2];
+            const float2* row = xch + (size_t)l2 * CS + k1 * CTA_XS;
+            if (COLS) {
+#pragma unroll
+                for (int i = 0; i < CTA_N2; ++i) u[i] = pk(row[i]);
+            } else {
+                const float4* row4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+                for (int i = 0; i < CTA_N2 / 2; ++i) {
+                    const float4 q = row4[i];
+                    u[2 * i] = pk(q.x, q.y);
+                    u[2 * i + 1] = pk(q.z, q.w);
+                }
+            }
+            dft20<INV>(u);
+            const float sc = (out_sign && (k1 & 1)) ? -scale : scale;
+#pragma unroll
+            for (int k2 = 0; k2 < CTA_N2; ++k2) {
+                const float2 r = upk(u[k2]);
+                st(l2, k1 + CTA_N1 * k2, make_float2(r.x * sc, r.y * sc));
+            }
+        }
+    }
+}
+
+// 640-point COLUMN transform of 8 adjacent columns per CTA: radix-2 decimation in time over two 320-point transforms (the
+// even and the odd samples of a column are two of the 16 lines of fft320_cta), combined through shared memory:
+// X[k] = E[k] + w640^k O[k], X[k + 320] = E[k] - w640^k O[k].  Centring: a half-length rotation of the input is the sign
+// (-1)^k on the output (k and k + 320 have the same parity); a half-length rotation of the output is the modulation
+// (-1)^n of the input, i.e. a minus sign on the odd-sample lines.  ld(col, n) -> sample n < 640 of column col < 8,
+// st(col, k, X) <- bin k < 640.  buf: [16][321] float2.
+template <bool INV, class Load, class Store>
+__device__ __forceinline__ void fft640_cols_cta(float2* xch, float2* tw1_s, float2* buf, const float2* __restrict__ tw320,
+                                                const float2* __restrict__ tw640, int ncols, int in_mod, int out_sign,
+                                                float scale, Load ld, Store st) {
+    auto ld2 = [&](int l, int j) {
+        const int e = l >> 3, cl = l & 7;
+        float2 v = make_float2(0.f, 0.f);
+        if (cl < ncols) v = ld(cl, 2 * j + e);
+        if (in_mod && e) v = make_float2(-v.x, -v.y);
+        return v;
+    };
+    auto st2 = [&](int l, int k, float2 v) { buf[(size_t)l * (CTA_N + 1) + k] = v; };
+    fft320_cta<INV, true>(xch, tw1_s, tw320, CTA_LINES, 0, 0, 1.f, ld2, st2);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 8 * CTA_N; idx += blockDim.x) {
+        const int cl = idx & 7, k = idx >> 3;
+        if (cl >= ncols) continue;
+        const float2 E = buf[(size_t)cl * (CTA_N + 1) + k], O = buf[(size_t)(8 + cl) * (CTA_N + 1) + k];
+        const float2 w = __ldg(&tw640[k]);
+        const float2 T = mulw<INV>(O, w.x, w.y);
+        const float sc = (out_sign && (k & 1)) ? -scale : scale;
+        st(cl, k, make_float2((E.x + T.x) * sc, (E.y + T.y) * sc));
+        st(cl, k + CTA_N, make_float2((E.x - T.x) * sc, (E.y - T.y) * sc));
+    }
+}
+
 }  // namespace r320
 
 }  // namespace mrb
