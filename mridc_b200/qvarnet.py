@@ -32,15 +32,16 @@ class qVarNetBlock(nn.Module):
         self.no_dc = no_dc
         self.dc_weight = nn.Parameter(torch.ones(1))
 
+    def _kw(self):
+        return dict(centered=self.fft_centered, normalization=self.fft_normalization, spatial_dims=self.spatial_dims)
+
     def sens_expand(self, x: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
-        """qvn_block.py:63-82."""
-        return fft.fft2(utils.complex_mul(x, sens_maps), centered=self.fft_centered, normalization=self.fft_normalization,
-                        spatial_dims=self.spatial_dims)
+        """qvn_block.py:63-82: image(s) -> coil k-space, F(S x)."""
+        return fft.fft2(utils.complex_mul(x, sens_maps), **self._kw())
 
     def sens_reduce(self, x: torch.Tensor, sens_maps: torch.Tensor) -> torch.Tensor:
-        """qvn_block.py:84-101 (no keepdim)."""
-        x = fft.ifft2(x, centered=self.fft_centered, normalization=self.fft_normalization, spatial_dims=self.spatial_dims)
-        return utils.complex_mul(x, sens_maps, _conj_y=True).sum(dim=self.coil_dim)
+        """qvn_block.py:84-101: coil k-space -> image, sum over the coil axis of conj(S) F^-1 x (no keepdim)."""
+        return utils.complex_mul(fft.ifft2(x, **self._kw()), sens_maps, _conj_y=True).sum(dim=self.coil_dim)
 
     @torch.no_grad()
     def forward(self, prediction: torch.Tensor, masked_kspace: torch.Tensor, R2star_map_init: torch.Tensor,
